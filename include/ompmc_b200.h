@@ -1,0 +1,210 @@
+/*
+ * ompmc_b200.h -- C-ABI of the B200-native replacement for ompMC's shower() hot path.
+ *
+ * The reference (edoerner/ompMC) has no plugin/FFI layer: its "API" is link-time C symbols between
+ * a user code (ucodes/omc_dosxyz/omc_dosxyz.c, ucodes/omc_matrad/omc_matrad.c) and src/ompmc.c plus
+ * shared global structs.  Per-step host callbacks (howfar/hownear/ausgab, src/ompmc.h:37-39) cannot
+ * cross a device boundary, so the drop-in boundary sits at the *batch loop*
+ * (omc_dosxyz.c:1237-1263, omc_matrad.c:1389-1414):
+ *
+ *     for ibatch { omp parallel for ihist { initHistory(); shower(); }  accumEndep(); }
+ *
+ * Everything above that loop (ini parsing, .egsphant reader, table initialisation, statistics,
+ * .3ddose writer) stays host C and hands its already-built global structs to this library as
+ * plain pointers.  No torch / C++ types appear in any signature.  All functions return 0 on
+ * success and a non-zero code otherwise; omc_gpu_last_error() returns the message the reference
+ * would have printf'ed before exit(EXIT_FAILURE).
+ *
+ * Array layouts are exactly the reference's (same strides, same 0-based C indexing), so a user
+ * code can pass e.g. photon_data.gmfp0 directly.
+ */
+#ifndef OMPMC_B200_H
+#define OMPMC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* compile-time table dimensions, src/ompmc.h:104,129-130,256-259,283-285,325-326 */
+#define OMC_MXGE       2000   /* MXGE    */
+#define OMC_MXEKE      500    /* MXEKE   */
+#define OMC_MXRAYFF    100    /* MXRAYFF == RAYCDFSIZE */
+#define OMC_MXMED      9      /* MXMED   */
+#define OMC_SPIN_NE    32     /* MXE_SPIN1+1 */
+#define OMC_SPIN_NQ    16     /* MXQ_SPIN+1  */
+#define OMC_SPIN_NU    32     /* MXU_SPIN+1  */
+#define OMC_MS_NL      64     /* MXL_MS+1 */
+#define OMC_MS_NQ      8      /* MXQ_MS+1 */
+#define OMC_MS_NU      32     /* MXU_MS+1 */
+#define OMC_RM         0.5109989461   /* src/ompmc.h:46 */
+
+/*
+ * Physics tables == the output of initMediaData() (src/ompmc.c:5450-5482).
+ * Field <-> reference global:
+ *   ge*..cohe*     struct Photon   photon_data    (src/ompmc.h:105-112)
+ *   ray_*          struct Rayleigh rayleigh_data  (src/ompmc.h:134-143)
+ *   dl1..zbrang    struct Pair     pair_data      (src/ompmc.h:155-167)
+ *   esig0..blcc    struct Electron electron_data  (src/ompmc.h:207-249)
+ *   spin_*         struct Spin     spin_data      (src/ompmc.h:261-269)
+ *   ums..dqmsi     struct Mscat    mscat_data     (src/ompmc.h:292-300)
+ *   pegs_*         struct Pegs     pegs_data      (src/ompmc.h:379-404)
+ */
+typedef struct omc_media_tables {
+    int nmed;
+    /* photon, [nmed] and [nmed*OMC_MXGE] */
+    const double *ge0, *ge1;
+    const double *gmfp0, *gmfp1, *gbr10, *gbr11, *gbr20, *gbr21, *cohe0, *cohe1;
+    /* Rayleigh, [nmed*OMC_MXRAYFF] / [nmed*OMC_MXGE] */
+    const double *ray_xgrid, *ray_fcum, *ray_b_array, *ray_c_array;
+    const int    *ray_i_array;
+    const double *ray_pmax0, *ray_pmax1;
+    /* pair + brems screening, [nmed*8] and [nmed] */
+    const double *dl1, *dl2, *dl3, *dl4, *dl5, *dl6;
+    const double *bpar0, *bpar1, *delcm, *zbrang;
+    /* electron PWL tables, [nmed*OMC_MXEKE] */
+    const double *esig0, *esig1, *psig0, *psig1, *ededx0, *ededx1, *pdedx0, *pdedx1;
+    const double *ebr10, *ebr11, *pbr10, *pbr11, *pbr20, *pbr21, *tmxs0, *tmxs1;
+    const double *blcce0, *blcce1, *etae_ms0, *etae_ms1, *etap_ms0, *etap_ms1;
+    const double *q1ce_ms0, *q1ce_ms1, *q1cp_ms0, *q1cp_ms1;
+    const double *q2ce_ms0, *q2ce_ms1, *q2cp_ms0, *q2cp_ms1;
+    const double *range_ep;        /* [2*nmed*OMC_MXEKE], qel-major */
+    const double *e_array;         /* [nmed*OMC_MXEKE] */
+    const double *eke0, *eke1;     /* [nmed] */
+    const int    *sig_ismonotone;  /* [2*nmed], qel-major */
+    const double *esig_e, *psig_e, *xcc, *blcc;   /* [nmed] */
+    /* spin (Mott) rejection, spin_rej[nmed][2][32][16][32] */
+    double b2spin_min, dbeta2i, espml, dleneri, dqq1i;
+    const double *spin_rej;
+    /* screened-Rutherford MS alias tables [64][8][32] */
+    const double *ums, *fms, *wms;
+    const int    *ims;
+    double dllambi, dqmsi;
+    /* PEGS4 scalars, [nmed] */
+    const double *pegs_ap, *pegs_ae, *pegs_te, *pegs_thmoll, *pegs_rho;
+    const int    *pegs_meke;
+} omc_media_tables;
+
+/*
+ * Voxel geometry + per-region transport data: struct Geom (omc_dosxyz.c:46-59) and
+ * struct Region (src/ompmc.h:412-418).  nreg = isize*jsize*ksize + 1; region 0 = outside.
+ */
+typedef struct omc_geometry {
+    int isize, jsize, ksize;
+    const double *xbounds, *ybounds, *zbounds;   /* [isize+1],[jsize+1],[ksize+1] */
+    const int    *med;                           /* [nreg] 0-based medium, -1 = vacuum */
+    const double *rhof, *pcut, *ecut;            /* [nreg] */
+} omc_geometry;
+
+/* struct Source of omc_dosxyz.c:342-366 as filled by initSource() (:368-632). */
+typedef struct omc_source_dosxyz {
+    int spectrum;            /* 0 mono-energetic, 1 spectrum */
+    int charge;              /* 0 photon, -1 e-, +1 e+ */
+    double energy;           /* mono energy */
+    double deltak;           /* number of inverse-CDF bins (INVDIM = 1000) */
+    const double *cdfinv1, *cdfinv2;   /* [(int)deltak] */
+    double ssd;
+    double xinl, xinu, yinl, yinu, xsize, ysize;
+    int ixinl, ixinu, iyinl, iyinu;
+} omc_source_dosxyz;
+
+/* struct Source of omc_matrad.c:514-541 (bixel arrays), as filled by initSource() (:543-751). */
+typedef struct omc_source_matrad {
+    int spectrum, charge;
+    double energy, deltak;
+    const double *cdfinv1, *cdfinv2;
+    int nbeams, nbixels;
+    const int    *ibeam;                         /* [nbixels] beam of each bixel */
+    const double *xsource, *ysource, *zsource;   /* [nbeams]  */
+    const double *xcorner, *ycorner, *zcorner;   /* [nbixels] */
+    const double *xside1, *yside1, *zside1;      /* [nbixels] */
+    const double *xside2, *yside2, *zside2;      /* [nbixels] */
+} omc_source_matrad;
+
+/* Per-history debug record (lock-step parity with the instrumented reference). */
+typedef struct omc_history_record {
+    unsigned int ndraws;     /* random numbers consumed by initHistory()+shower() */
+    int          ir_start;   /* region index chosen by initHistory() */
+    unsigned int ndeposit;   /* number of ausgab() calls */
+    unsigned int flags;      /* bit0: stack overflow, bit1: invalid lambda drop (Q8) */
+    double       edep;       /* sum of wt*edep over all ausgab() calls (incl. region 0) */
+} omc_history_record;
+
+/* Work counters of the last run (filled on the device). */
+typedef struct omc_gpu_counters {
+    unsigned long long histories;      /* histories started                           */
+    unsigned long long kernel_launches;/* kernels of this library launched            */
+    unsigned long long photon_steps;   /* howfar() calls from photon()                */
+    unsigned long long electron_steps; /* hownear() calls (ustep-loop iterations)     */
+    unsigned long long deposits;       /* ausgab() calls                              */
+    unsigned long long rng_draws;      /* random numbers consumed                     */
+    unsigned long long errors;         /* stack/queue overflows, invalid-lambda drops */
+    unsigned long long reserved[9];
+} omc_gpu_counters;
+
+typedef struct omc_gpu_ctx *omc_gpu_handle;
+
+/* kernel selection for omc_gpu_set_option("kernel", ...) */
+#define OMC_KERNEL_LOCKSTEP  0   /* one history per thread, reference draw order (parity anchor) */
+#define OMC_KERNEL_WAVEFRONT 1   /* particle-queue production kernels                            */
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+/* replaces initStack()/initRandom() per thread (omc_dosxyz.c:1184-1191) */
+int  omc_gpu_create(omc_gpu_handle *h, int device_id);
+/* replaces clean*() (omc_dosxyz.c:1285-1300) */
+void omc_gpu_destroy(omc_gpu_handle h);
+const char *omc_gpu_last_error(omc_gpu_handle h);
+
+/* ---- problem upload (arrays are borrowed for the duration of the call and copied) -------- */
+int omc_gpu_set_media(omc_gpu_handle h, const omc_media_tables *t);        /* initMediaData() output, src/ompmc.c:5450 */
+int omc_gpu_set_geometry(omc_gpu_handle h, const omc_geometry *g);        /* initPhantom()+initRegions(), omc_dosxyz.c:62,890 */
+int omc_gpu_set_source_dosxyz(omc_gpu_handle h, const omc_source_dosxyz *s); /* initSource(), omc_dosxyz.c:368 */
+int omc_gpu_set_source_matrad(omc_gpu_handle h, const omc_source_matrad *s); /* initSource(), omc_matrad.c:543 */
+int omc_gpu_set_vrt(omc_gpu_handle h, int nsplit);                         /* initVrt(), src/ompmc.c:5964 */
+int omc_gpu_set_seed(omc_gpu_handle h, int ixx, int jxx);                  /* "rng seeds", src/omc_random.c:58-82 */
+/* tuning / debug knobs: "kernel", "threads_per_block", "stack_depth", "pool_size", "record_histories" */
+int omc_gpu_set_option(omc_gpu_handle h, const char *key, long long value);
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+/*
+ * {initHistory(); shower();} for history ids [first_history, first_history+nhist)
+ * (omc_dosxyz.c:1252-1259; omc_matrad.c:1393-1400 when ibeamlet >= 0), scoring into the batch
+ * grid score.endep.  History id -> RNG stream, so results do not depend on scheduling or on how
+ * ids are split over GPUs.  Asynchronous: returns after enqueueing on the context's stream.
+ */
+int omc_gpu_run_histories(omc_gpu_handle h, long long first_history, long long nhist, int ibeamlet);
+/* accumEndep() (omc_dosxyz.c:696-717): accum += e, accum2 += e*e, zero the batch grid. */
+int omc_gpu_accum_batch(omc_gpu_handle h);
+/* convenience: run_histories + accum_batch == one iteration of the reference batch loop */
+int omc_gpu_run_batch(omc_gpu_handle h, long long first_history, long long nhist, int ibeamlet);
+int omc_gpu_synchronize(omc_gpu_handle h);
+
+/* ---- results ----------------------------------------------------------------------------- */
+/* score.accum_endep / score.accum_endep2 / score.ensrc (omc_dosxyz.c:636-645); each [nreg] fp64; any may be NULL */
+int omc_gpu_get_tallies(omc_gpu_handle h, double *accum_endep, double *accum_endep2, double *ensrc);
+/* score.endep of the running batch, [nreg] fp64 (before accum_batch) */
+int omc_gpu_get_batch_grid(omc_gpu_handle h, double *endep);
+/* memset of the three grids (initScore(), omc_dosxyz.c:647-665; omc_matrad.c:1482 zeroes accum only: which = 1) */
+int omc_gpu_reset_tallies(omc_gpu_handle h, int which /* 0 = all, 1 = accum_endep only */);
+/* device addresses + element counts, for an NCCL reduce driven by the host plumbing (multi-GPU) */
+int omc_gpu_device_ptrs(omc_gpu_handle h, void **endep, void **accum_endep, void **accum_endep2, long long *nreg);
+/* cudaStream_t the context launches on (so callers can time with events on the right stream) */
+void *omc_gpu_stream(omc_gpu_handle h);
+int omc_gpu_get_counters(omc_gpu_handle h, omc_gpu_counters *c);
+/* debug: copy per-history records of the last run_histories (needs option record_histories=1) */
+int omc_gpu_get_history_records(omc_gpu_handle h, omc_history_record *out, long long n);
+
+/* ---- unit-test hooks: run single device functions on explicit inputs --------------------- */
+/*
+ * howfar()/hownear() (omc_dosxyz.c:187-334) for n particles: in x,y,z,u,v,w,ustep_in,ir -> out
+ * idisc, irnew, ustep, tperp.
+ */
+int omc_gpu_test_geometry(omc_gpu_handle h, int n, const double *xyzuvw /* [6*n] */, const int *ir,
+                          const double *ustep_in, int *idisc, int *irnew, double *ustep_out,
+                          double *tperp);
+/* n raw Philox draws of history `hist` as the transport sees them (double in [0,1)) */
+int omc_gpu_test_rng(omc_gpu_handle h, long long hist, int n, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMPMC_B200_H */

@@ -1,0 +1,173 @@
+"""ctypes driver for the two CPU checkers.  TEST INFRASTRUCTURE (oracle/).
+
+* ``RefTransport``    -> oracle/_ref/libompmc_ref[_omp].so : the unmodified reference + harness
+                         (oracle/ref_harness.c)
+* ``OracleTransport`` -> oracle/libomc_oracle.so            : this repo's plain-C restatement
+                         (oracle/omc_oracle.c)
+Both export the same entry points under a different prefix (``ref_`` / ``orc_``).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class HistoryRecord(C.Structure):
+    _fields_ = [("ndraws", C.c_uint), ("ir_start", C.c_int), ("ndeposit", C.c_uint), ("flags", C.c_uint),
+                ("edep", C.c_double)]
+
+
+RECORD_DTYPE = np.dtype([("ndraws", "<u4"), ("ir_start", "<i4"), ("ndeposit", "<u4"), ("flags", "<u4"), ("edep", "<f8")])
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class _CpuTransport:
+    prefix = ""
+
+    def __init__(self, libpath: str):
+        if not os.path.exists(libpath):
+            raise FileNotFoundError(libpath)
+        self.lib = C.CDLL(libpath)
+        self.path = libpath
+        f = self._f
+        f("load_problem").argtypes = [C.c_char_p]; f("load_problem").restype = C.c_int
+        f("set_rng").argtypes = [C.c_int, C.c_int, C.c_int]
+        f("set_nsplit").argtypes = [C.c_int]
+        f("nreg").restype = C.c_int
+        f("run_histories").argtypes = [C.c_longlong, C.c_longlong, C.c_void_p]
+        f("get_endep").argtypes = [C.c_void_p]
+        f("get_accum").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        f("time_batches").argtypes = [C.c_longlong, C.c_longlong, C.c_int]; f("time_batches").restype = C.c_double
+        f("num_threads").restype = C.c_int
+        f("set_num_threads").argtypes = [C.c_int]
+        f("test_geometry").argtypes = [C.c_int] + [C.c_void_p] * 7
+        f("test_rng").argtypes = [C.c_longlong, C.c_int, C.c_void_p]
+        f("run_particle").argtypes = [C.c_longlong, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+
+    def _f(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    # -- problem ---------------------------------------------------------------------------
+    def load_problem(self, problem, seeds=(97, 33)):
+        """problem: path of a full blob, or a dict as built by ompmc_b200.problem.build_problem()."""
+        self._f("set_rng")(1, int(seeds[0]), int(seeds[1]))
+        if isinstance(problem, dict):
+            from ompmc_b200.problem import save_blob
+            fd, path = tempfile.mkstemp(suffix=".blob"); os.close(fd)
+            try:
+                save_blob(path, problem)
+                rc = self._f("load_problem")(path.encode())
+            finally:
+                os.unlink(path)
+        else:
+            rc = self._f("load_problem")(str(problem).encode())
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}load_problem failed rc={rc}")
+        self.nreg = self._f("nreg")()
+
+    def set_rng(self, mode: str, seeds=(97, 33)):
+        self._f("set_rng")({"ranmar": 0, "philox": 1}[mode], int(seeds[0]), int(seeds[1]))
+
+    def set_nsplit(self, n: int):
+        self._f("set_nsplit")(int(n))
+
+    # -- hot path --------------------------------------------------------------------------
+    def run_histories(self, first: int, n: int, records: bool = False):
+        rec = np.zeros(n, dtype=RECORD_DTYPE) if records else None
+        self._f("run_histories")(first, n, rec.ctypes.data if records else None)
+        return rec
+
+    def accum_endep(self):
+        self._f("accum_endep")()
+
+    def reset_score(self):
+        self._f("reset_score")()
+
+    def get_endep(self) -> np.ndarray:
+        out = np.zeros(self.nreg)
+        self._f("get_endep")(out.ctypes.data)
+        return out
+
+    def get_accum(self):
+        a = np.zeros(self.nreg); a2 = np.zeros(self.nreg); e = C.c_double(0.0)
+        self._f("get_accum")(a.ctypes.data, a2.ctypes.data, C.byref(e))
+        return a, a2, e.value
+
+    def time_batches(self, first: int, nperbatch: int, nbatch: int) -> float:
+        return float(self._f("time_batches")(first, nperbatch, nbatch))
+
+    def num_threads(self) -> int:
+        return int(self._f("num_threads")())
+
+    def set_num_threads(self, n: int):
+        self._f("set_num_threads")(int(n))
+
+    # -- unit hooks ------------------------------------------------------------------------
+    def test_geometry(self, xyzuvw, ir, ustep_in):
+        xyzuvw = np.ascontiguousarray(xyzuvw, dtype=np.float64); ir = np.ascontiguousarray(ir, dtype=np.int32)
+        ustep_in = np.ascontiguousarray(ustep_in, dtype=np.float64)
+        n = len(ir)
+        idisc = np.zeros(n, np.int32); irnew = np.zeros(n, np.int32); us = np.zeros(n); tp = np.zeros(n)
+        self._f("test_geometry")(n, xyzuvw.ctypes.data, ir.ctypes.data, ustep_in.ctypes.data, idisc.ctypes.data,
+                                 irnew.ctypes.data, us.ctypes.data, tp.ctypes.data)
+        return idisc, irnew, us, tp
+
+    def test_rng(self, hist: int, n: int) -> np.ndarray:
+        out = np.zeros(n)
+        self._f("test_rng")(hist, n, out.ctypes.data)
+        return out
+
+    def run_particle(self, hist: int, iq: int, e: float, xyzuvw, ir: int, wt: float = 1.0):
+        xyzuvw = np.ascontiguousarray(xyzuvw, dtype=np.float64)
+        rec = np.zeros(1, dtype=RECORD_DTYPE)
+        self._f("run_particle")(hist, iq, e, xyzuvw.ctypes.data, ir, wt, rec.ctypes.data)
+        return rec[0]
+
+
+class RefTransport(_CpuTransport):
+    prefix = "ref_"
+
+    def __init__(self, omp: bool = False):
+        super().__init__(ref_lib_path(omp))
+        self.lib.ref_init_from_inp.argtypes = [C.c_char_p]
+        self.lib.ref_dump_problem.argtypes = [C.c_char_p]
+
+    def init_from_inp(self, stem: str):
+        self.lib.ref_init_from_inp(stem.encode())
+        self.nreg = self.lib.ref_nreg()
+
+    def dump_problem(self, path: str):
+        if self.lib.ref_dump_problem(path.encode()) != 0:
+            raise RuntimeError("ref_dump_problem failed")
+
+
+class OracleTransport(_CpuTransport):
+    prefix = "orc_"
+
+    def __init__(self):
+        super().__init__(oracle_lib_path())
+
+
+def ref_lib_path(omp: bool = False) -> str:
+    return os.path.join(HERE, "_ref", "libompmc_ref_omp.so" if omp else "libompmc_ref.so")
+
+
+def oracle_lib_path() -> str:
+    return os.path.join(HERE, "libomc_oracle.so")
+
+
+def have_ref(omp: bool = False) -> bool:
+    return os.path.exists(ref_lib_path(omp))
