@@ -193,6 +193,10 @@ int omc_gpu_get_counters(omc_gpu_handle h, omc_gpu_counters *c);
 /* debug: copy per-history records of the last run_histories (needs option record_histories=1) */
 int omc_gpu_get_history_records(omc_gpu_handle h, omc_history_record *out, long long n);
 
+/* sizeof() of the structs above as this library was compiled (0 media, 1 geometry, 2 source_dosxyz,
+ * 3 source_matrad, 4 history_record, 5 counters): lets a foreign-language binding check its layout */
+int omc_gpu_abi_sizeof(int what);
+
 /* ---- unit-test hooks: run single device functions on explicit inputs --------------------- */
 /*
  * howfar()/hownear() (omc_dosxyz.c:187-334) for n particles: in x,y,z,u,v,w,ustep_in,ir -> out

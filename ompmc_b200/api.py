@@ -1,0 +1,266 @@
+"""ctypes binding of the C-ABI (include/ompmc_b200.h) -- the reference-facing entry points.
+
+``GpuTransport`` mirrors, call for call, what a reference user code does around its batch loop
+(ucodes/omc_dosxyz/omc_dosxyz.c:1155-1283):
+
+    init*()                       -> GpuTransport.load_problem(problem dict)
+    for ibatch: {initHistory(); shower();} x nperbatch; accumEndep()
+                                  -> run_batch(first_history, nperbatch)
+    accumulateResults()/output    -> get_tallies() + ompmc_b200.problem.accumulate_results()
+
+There is no CPU fallback: if the CUDA library is missing or no GPU is present, construction fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import problem as P
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libompmc_b200.so")
+
+RECORD_DTYPE = np.dtype([("ndraws", "<u4"), ("ir_start", "<i4"), ("ndeposit", "<u4"), ("flags", "<u4"), ("edep", "<f8")])
+COUNTER_NAMES = ["histories", "kernel_launches", "photon_steps", "electron_steps", "deposits", "rng_draws", "errors"]
+
+PD = C.POINTER(C.c_double)
+PI = C.POINTER(C.c_int)
+
+_MEDIA_F64 = ["ge0", "ge1", "gmfp0", "gmfp1", "gbr10", "gbr11", "gbr20", "gbr21", "cohe0", "cohe1",
+              "ray_xgrid", "ray_fcum", "ray_b_array", "ray_c_array"]
+
+
+class MediaTables(C.Structure):
+    """omc_media_tables -- field order must match include/ompmc_b200.h."""
+    _fields_ = (
+        [("nmed", C.c_int)]
+        + [(n, PD) for n in ["ge0", "ge1", "gmfp0", "gmfp1", "gbr10", "gbr11", "gbr20", "gbr21", "cohe0", "cohe1"]]
+        + [(n, PD) for n in ["ray_xgrid", "ray_fcum", "ray_b_array", "ray_c_array"]]
+        + [("ray_i_array", PI)]
+        + [(n, PD) for n in ["ray_pmax0", "ray_pmax1"]]
+        + [(n, PD) for n in ["dl1", "dl2", "dl3", "dl4", "dl5", "dl6", "bpar0", "bpar1", "delcm", "zbrang"]]
+        + [(n, PD) for n in ["esig0", "esig1", "psig0", "psig1", "ededx0", "ededx1", "pdedx0", "pdedx1",
+                             "ebr10", "ebr11", "pbr10", "pbr11", "pbr20", "pbr21", "tmxs0", "tmxs1",
+                             "blcce0", "blcce1", "etae_ms0", "etae_ms1", "etap_ms0", "etap_ms1",
+                             "q1ce_ms0", "q1ce_ms1", "q1cp_ms0", "q1cp_ms1", "q2ce_ms0", "q2ce_ms1", "q2cp_ms0", "q2cp_ms1",
+                             "range_ep", "e_array", "eke0", "eke1"]]
+        + [("sig_ismonotone", PI)]
+        + [(n, PD) for n in ["esig_e", "psig_e", "xcc", "blcc"]]
+        + [(n, C.c_double) for n in ["b2spin_min", "dbeta2i", "espml", "dleneri", "dqq1i"]]
+        + [("spin_rej", PD)]
+        + [(n, PD) for n in ["ums", "fms", "wms"]]
+        + [("ims", PI)]
+        + [(n, C.c_double) for n in ["dllambi", "dqmsi"]]
+        + [(n, PD) for n in ["pegs_ap", "pegs_ae", "pegs_te", "pegs_thmoll", "pegs_rho"]]
+        + [("pegs_meke", PI)]
+    )
+
+
+class Geometry(C.Structure):
+    _fields_ = [("isize", C.c_int), ("jsize", C.c_int), ("ksize", C.c_int), ("xbounds", PD), ("ybounds", PD), ("zbounds", PD),
+                ("med", PI), ("rhof", PD), ("pcut", PD), ("ecut", PD)]
+
+
+class SourceDosxyz(C.Structure):
+    _fields_ = [("spectrum", C.c_int), ("charge", C.c_int), ("energy", C.c_double), ("deltak", C.c_double),
+                ("cdfinv1", PD), ("cdfinv2", PD), ("ssd", C.c_double),
+                ("xinl", C.c_double), ("xinu", C.c_double), ("yinl", C.c_double), ("yinu", C.c_double),
+                ("xsize", C.c_double), ("ysize", C.c_double),
+                ("ixinl", C.c_int), ("ixinu", C.c_int), ("iyinl", C.c_int), ("iyinu", C.c_int)]
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_ulonglong) for n in COUNTER_NAMES] + [("reserved", C.c_ulonglong * 9)]
+
+
+EXPORTS = ["omc_gpu_create", "omc_gpu_destroy", "omc_gpu_last_error", "omc_gpu_set_media", "omc_gpu_set_geometry",
+           "omc_gpu_set_source_dosxyz", "omc_gpu_set_source_matrad", "omc_gpu_set_vrt", "omc_gpu_set_seed", "omc_gpu_set_option",
+           "omc_gpu_run_histories", "omc_gpu_accum_batch", "omc_gpu_run_batch", "omc_gpu_synchronize", "omc_gpu_get_tallies",
+           "omc_gpu_get_batch_grid", "omc_gpu_reset_tallies", "omc_gpu_device_ptrs", "omc_gpu_stream", "omc_gpu_get_counters",
+           "omc_gpu_get_history_records", "omc_gpu_test_geometry", "omc_gpu_test_rng", "omc_gpu_abi_sizeof"]
+
+
+def load_library() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -m ompmc_b200.build` (no CPU fallback exists)")
+    lib = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    lib.omc_gpu_create.argtypes = [C.POINTER(H), C.c_int]
+    lib.omc_gpu_destroy.argtypes = [H]; lib.omc_gpu_destroy.restype = None
+    lib.omc_gpu_last_error.argtypes = [H]; lib.omc_gpu_last_error.restype = C.c_char_p
+    lib.omc_gpu_set_media.argtypes = [H, C.POINTER(MediaTables)]
+    lib.omc_gpu_set_geometry.argtypes = [H, C.POINTER(Geometry)]
+    lib.omc_gpu_set_source_dosxyz.argtypes = [H, C.POINTER(SourceDosxyz)]
+    lib.omc_gpu_set_vrt.argtypes = [H, C.c_int]
+    lib.omc_gpu_set_seed.argtypes = [H, C.c_int, C.c_int]
+    lib.omc_gpu_set_option.argtypes = [H, C.c_char_p, C.c_longlong]
+    lib.omc_gpu_run_histories.argtypes = [H, C.c_longlong, C.c_longlong, C.c_int]
+    lib.omc_gpu_accum_batch.argtypes = [H]
+    lib.omc_gpu_run_batch.argtypes = [H, C.c_longlong, C.c_longlong, C.c_int]
+    lib.omc_gpu_synchronize.argtypes = [H]
+    lib.omc_gpu_get_tallies.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.omc_gpu_get_batch_grid.argtypes = [H, C.c_void_p]
+    lib.omc_gpu_reset_tallies.argtypes = [H, C.c_int]
+    lib.omc_gpu_device_ptrs.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
+    lib.omc_gpu_stream.argtypes = [H]; lib.omc_gpu_stream.restype = C.c_void_p
+    lib.omc_gpu_get_counters.argtypes = [H, C.POINTER(Counters)]
+    lib.omc_gpu_get_history_records.argtypes = [H, C.c_void_p, C.c_longlong]
+    lib.omc_gpu_test_geometry.argtypes = [H, C.c_int] + [C.c_void_p] * 7
+    lib.omc_gpu_test_rng.argtypes = [H, C.c_longlong, C.c_int, C.c_void_p]
+    lib.omc_gpu_abi_sizeof.argtypes = [C.c_int]
+    return lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class OmcGpuError(RuntimeError):
+    pass
+
+
+class GpuTransport:
+    """One GPU context == one ``omc_gpu_handle``."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        rc = self.lib.omc_gpu_create(C.byref(self.h), device)
+        if rc != 0:
+            raise OmcGpuError(f"omc_gpu_create(device={device}) failed rc={rc}: CUDA device required, no CPU fallback")
+        self.device = device
+        self._keep = []
+        self.nreg = 0
+
+    def close(self):
+        if self.h:
+            self.lib.omc_gpu_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int, what: str):
+        if rc != 0:
+            raise OmcGpuError(f"{what} failed (rc={rc}): {self.lib.omc_gpu_last_error(self.h).decode()}")
+
+    # -- problem upload ----------------------------------------------------------------------
+    def load_problem(self, prob: dict, seeds=(97, 33)):
+        keep = []
+
+        def pd(name):
+            a = _f64(prob[name]); keep.append(a)
+            return a.ctypes.data_as(PD)
+
+        def pi(name):
+            a = _i32(prob[name]); keep.append(a)
+            return a.ctypes.data_as(PI)
+        mt = MediaTables()
+        mt.nmed = int(prob["nmed"][0])
+        for name, typ in MediaTables._fields_[1:]:
+            if typ is PD:
+                setattr(mt, name, pd(name))
+            elif typ is PI:
+                setattr(mt, name, pi(name))
+            else:
+                setattr(mt, name, float(prob[name][0]))
+        self._ck(self.lib.omc_gpu_set_media(self.h, C.byref(mt)), "omc_gpu_set_media")
+        g = Geometry()
+        g.isize, g.jsize, g.ksize = int(prob["isize"][0]), int(prob["jsize"][0]), int(prob["ksize"][0])
+        g.xbounds, g.ybounds, g.zbounds = pd("xbounds"), pd("ybounds"), pd("zbounds")
+        g.med, g.rhof, g.pcut, g.ecut = pi("region_med"), pd("region_rhof"), pd("region_pcut"), pd("region_ecut")
+        self._ck(self.lib.omc_gpu_set_geometry(self.h, C.byref(g)), "omc_gpu_set_geometry")
+        self.nreg = g.isize * g.jsize * g.ksize + 1
+        s = SourceDosxyz()
+        s.spectrum, s.charge = int(prob["src_spectrum"][0]), int(prob["src_charge"][0])
+        s.energy, s.deltak = float(prob["src_energy"][0]), float(prob["src_deltak"][0])
+        s.cdfinv1, s.cdfinv2 = pd("src_cdfinv1"), pd("src_cdfinv2")
+        for k in ["ssd", "xinl", "xinu", "yinl", "yinu", "xsize", "ysize"]:
+            setattr(s, k, float(prob["src_" + k][0]))
+        for k in ["ixinl", "ixinu", "iyinl", "iyinu"]:
+            setattr(s, k, int(prob["src_" + k][0]))
+        self._ck(self.lib.omc_gpu_set_source_dosxyz(self.h, C.byref(s)), "omc_gpu_set_source_dosxyz")
+        self._ck(self.lib.omc_gpu_set_vrt(self.h, int(prob["nsplit"][0])), "omc_gpu_set_vrt")
+        self._ck(self.lib.omc_gpu_set_seed(self.h, int(seeds[0]), int(seeds[1])), "omc_gpu_set_seed")
+        del keep   # arrays were copied to the device by the set_* calls
+
+    def set_option(self, key: str, value: int):
+        self._ck(self.lib.omc_gpu_set_option(self.h, key.encode(), int(value)), f"omc_gpu_set_option({key})")
+
+    def set_nsplit(self, n: int):
+        self._ck(self.lib.omc_gpu_set_vrt(self.h, int(n)), "omc_gpu_set_vrt")
+
+    # -- hot path ----------------------------------------------------------------------------
+    def run_histories(self, first: int, n: int, records: bool = False, ibeamlet: int = -1):
+        self.set_option("record_histories", 1 if records else 0)
+        self._ck(self.lib.omc_gpu_run_histories(self.h, first, n, ibeamlet), "omc_gpu_run_histories")
+        if records:
+            rec = np.zeros(n, dtype=RECORD_DTYPE)
+            self._ck(self.lib.omc_gpu_get_history_records(self.h, rec.ctypes.data, n), "omc_gpu_get_history_records")
+            return rec
+        return None
+
+    def accum_batch(self):
+        self._ck(self.lib.omc_gpu_accum_batch(self.h), "omc_gpu_accum_batch")
+
+    accum_endep = accum_batch
+
+    def run_batch(self, first: int, n: int, ibeamlet: int = -1):
+        self._ck(self.lib.omc_gpu_run_batch(self.h, first, n, ibeamlet), "omc_gpu_run_batch")
+
+    def synchronize(self):
+        self._ck(self.lib.omc_gpu_synchronize(self.h), "omc_gpu_synchronize")
+
+    def get_endep(self) -> np.ndarray:
+        out = np.zeros(self.nreg)
+        self._ck(self.lib.omc_gpu_get_batch_grid(self.h, out.ctypes.data), "omc_gpu_get_batch_grid")
+        return out
+
+    def get_tallies(self):
+        a = np.zeros(self.nreg); a2 = np.zeros(self.nreg); e = C.c_double(0.0)
+        self._ck(self.lib.omc_gpu_get_tallies(self.h, a.ctypes.data, a2.ctypes.data, C.addressof(e)), "omc_gpu_get_tallies")
+        return a, a2, e.value
+
+    get_accum = get_tallies
+
+    def reset_tallies(self, which: int = 0):
+        self._ck(self.lib.omc_gpu_reset_tallies(self.h, which), "omc_gpu_reset_tallies")
+
+    reset_score = reset_tallies
+
+    def counters(self) -> dict:
+        c = Counters()
+        self._ck(self.lib.omc_gpu_get_counters(self.h, C.byref(c)), "omc_gpu_get_counters")
+        return {n: int(getattr(c, n)) for n in COUNTER_NAMES}
+
+    def stream_ptr(self) -> int:
+        return int(self.lib.omc_gpu_stream(self.h) or 0)
+
+    def device_ptrs(self):
+        e, a, a2, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_longlong()
+        self._ck(self.lib.omc_gpu_device_ptrs(self.h, C.byref(e), C.byref(a), C.byref(a2), C.byref(n)), "omc_gpu_device_ptrs")
+        return int(e.value), int(a.value), int(a2.value), int(n.value)
+
+    # -- unit hooks --------------------------------------------------------------------------
+    def test_geometry(self, xyzuvw, ir, ustep_in):
+        xyzuvw = _f64(xyzuvw); ir = _i32(ir); ustep_in = _f64(ustep_in)
+        n = len(ir)
+        idisc = np.zeros(n, np.int32); irnew = np.zeros(n, np.int32); us = np.zeros(n); tp = np.zeros(n)
+        self._ck(self.lib.omc_gpu_test_geometry(self.h, n, xyzuvw.ctypes.data, ir.ctypes.data, ustep_in.ctypes.data,
+                                                idisc.ctypes.data, irnew.ctypes.data, us.ctypes.data, tp.ctypes.data),
+                 "omc_gpu_test_geometry")
+        return idisc, irnew, us, tp
+
+    def test_rng(self, hist: int, n: int) -> np.ndarray:
+        out = np.zeros(n)
+        self._ck(self.lib.omc_gpu_test_rng(self.h, hist, n, out.ctypes.data), "omc_gpu_test_rng")
+        return out

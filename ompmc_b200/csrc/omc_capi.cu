@@ -1,0 +1,458 @@
+// omc_capi.cu -- C-ABI of libompmc_b200.so (declared in include/ompmc_b200.h).
+//
+// Host side only: packs the reference-layout tables into the device records of omc_types.cuh,
+// owns device memory / the stream, launches the kernels.  There is NO CPU transport path in this
+// library: every entry point that does physics launches a CUDA kernel or fails.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "omc_kernels.h"
+
+using namespace omc;
+
+struct omc_gpu_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    DevProblem P{};
+    std::vector<void *> media_bufs, geom_bufs, source_bufs;
+    bool have_media = false, have_geom = false, have_source = false;
+    double *accum = nullptr, *accum2 = nullptr;
+    // options
+    int kernel = OMC_KERNEL_LOCKSTEP;
+    int threads_per_block = 128;
+    int stack_depth = 0;          // 0 = auto from nsplit
+    int max_blocks = 0;           // 0 = auto (SMs x occupancy)
+    int record = 0;
+    // scratch
+    Part *stack = nullptr;
+    size_t stack_bytes = 0;
+    omc_history_record *records = nullptr;
+    long long records_cap = 0, last_nhist = 0;
+    unsigned long long launches = 0;
+};
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+            return 1;                                                                                    \
+        }                                                                                                \
+    } while (0)
+
+static int fail(omc_gpu_handle h, const char *msg) {
+    h->err = msg;
+    return 2;
+}
+
+template <typename T>
+static int upload(omc_gpu_handle h, std::vector<void *> &pool, const T *host, size_t n, const T **dev) {
+    void *d = nullptr;
+    CK(cudaMalloc(&d, (n ? n : 1) * sizeof(T)));
+    pool.push_back(d);
+    if (n) CK(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *dev = static_cast<const T *>(d);
+    return 0;
+}
+
+static void free_pool(std::vector<void *> &pool) {
+    for (void *p : pool) cudaFree(p);
+    pool.clear();
+}
+
+extern "C" {
+
+int omc_gpu_create(omc_gpu_handle *out, int device_id) {
+    if (!out) return 2;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        fprintf(stderr, "ompmc_b200: no CUDA device available; this library has no CPU fallback\n");
+        return 3;
+    }
+    if (device_id < 0 || device_id >= ndev) return 4;
+    omc_gpu_handle h = new omc_gpu_ctx();
+    h->device = device_id;
+    if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return 5;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    h->P.nsplit = 1;
+    h->P.seed0 = 97; h->P.seed1 = 33;
+    void *c = nullptr, *e = nullptr;
+    if (cudaMalloc(&c, sizeof(Counters)) != cudaSuccess || cudaMalloc(&e, sizeof(double)) != cudaSuccess) {
+        delete h;
+        return 6;
+    }
+    cudaMemset(c, 0, sizeof(Counters));
+    cudaMemset(e, 0, sizeof(double));
+    h->P.counters = static_cast<Counters *>(c);
+    h->P.ensrc = static_cast<double *>(e);
+    *out = h;
+    return 0;
+}
+
+void omc_gpu_destroy(omc_gpu_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_pool(h->media_bufs); free_pool(h->geom_bufs); free_pool(h->source_bufs);
+    cudaFree(h->P.endep); cudaFree(h->P.endep32); cudaFree(h->accum); cudaFree(h->accum2);
+    cudaFree(h->P.counters); cudaFree(h->P.ensrc); cudaFree(h->stack); cudaFree(h->records);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char *omc_gpu_last_error(omc_gpu_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+int omc_gpu_set_media(omc_gpu_handle h, const omc_media_tables *t) {
+    if (!h || !t) return 2;
+    if (t->nmed < 1 || t->nmed > OMC_MXMED) return fail(h, "nmed out of range (MXMED = 9, src/ompmc.h:356)");
+    CK(cudaSetDevice(h->device));
+    free_pool(h->media_bufs);
+    const int nmed = t->nmed;
+    DevProblem &P = h->P;
+    P.nmed = nmed;
+    // per-medium scalars
+    std::vector<MedRec> med(nmed);
+    for (int m = 0; m < nmed; m++) {
+        MedRec &r = med[m];
+        memset(&r, 0, sizeof r);
+        r.ge1 = t->ge1[m]; r.ge0 = t->ge0[m]; r.eke1 = t->eke1[m]; r.eke0 = t->eke0[m];
+        r.xcc = t->xcc[m]; r.blcc = t->blcc[m]; r.esig_e = t->esig_e[m]; r.psig_e = t->psig_e[m];
+        r.te = t->pegs_te[m]; r.thmoll = t->pegs_thmoll[m]; r.ap = t->pegs_ap[m];
+        r.delcm = t->delcm[m]; r.zbrang = t->zbrang[m]; r.bpar0 = t->bpar0[m]; r.bpar1 = t->bpar1[m];
+        const double *dl[6] = {t->dl1, t->dl2, t->dl3, t->dl4, t->dl5, t->dl6};
+        for (int a = 0; a < 6; a++)
+            for (int k = 0; k < 8; k++) r.dl[a][k] = dl[a][m * 8 + k];
+        r.sig_ismonotone[0] = t->sig_ismonotone[0 * nmed + m];
+        r.sig_ismonotone[1] = t->sig_ismonotone[1 * nmed + m];
+    }
+    if (upload(h, h->media_bufs, med.data(), med.size(), &P.med)) return 1;
+    // photon bins
+    std::vector<PhotBin> pb((size_t)nmed * MXGE);
+    for (size_t i = 0; i < pb.size(); i++) {
+        PhotBin &b = pb[i];
+        b.gmfp1 = t->gmfp1[i]; b.gmfp0 = t->gmfp0[i]; b.cohe1 = t->cohe1[i]; b.cohe0 = t->cohe0[i];
+        b.gbr11 = t->gbr11[i]; b.gbr10 = t->gbr10[i]; b.gbr21 = t->gbr21[i]; b.gbr20 = t->gbr20[i];
+        b.pmax1 = t->ray_pmax1[i]; b.pmax0 = t->ray_pmax0[i];
+    }
+    if (upload(h, h->media_bufs, pb.data(), pb.size(), &P.phot)) return 1;
+    // electron bins, [qel][imed][lelke]
+    std::vector<ElecBin> eb((size_t)2 * nmed * MXEKE);
+    for (int q = 0; q < 2; q++)
+        for (size_t i = 0; i < (size_t)nmed * MXEKE; i++) {
+            ElecBin &b = eb[(size_t)q * nmed * MXEKE + i];
+            memset(&b, 0, sizeof b);
+            if (q == 0) {
+                b.sig1 = t->esig1[i]; b.sig0 = t->esig0[i]; b.dedx1 = t->ededx1[i]; b.dedx0 = t->ededx0[i];
+                b.eta1 = t->etae_ms1[i]; b.eta0 = t->etae_ms0[i]; b.q1c1 = t->q1ce_ms1[i]; b.q1c0 = t->q1ce_ms0[i];
+                b.q2c1 = t->q2ce_ms1[i]; b.q2c0 = t->q2ce_ms0[i]; b.bra1 = t->ebr11[i]; b.bra0 = t->ebr10[i];
+            } else {
+                b.sig1 = t->psig1[i]; b.sig0 = t->psig0[i]; b.dedx1 = t->pdedx1[i]; b.dedx0 = t->pdedx0[i];
+                b.eta1 = t->etap_ms1[i]; b.eta0 = t->etap_ms0[i]; b.q1c1 = t->q1cp_ms1[i]; b.q1c0 = t->q1cp_ms0[i];
+                b.q2c1 = t->q2cp_ms1[i]; b.q2c0 = t->q2cp_ms0[i]; b.bra1 = t->pbr11[i]; b.bra0 = t->pbr10[i];
+                b.brb1 = t->pbr21[i]; b.brb0 = t->pbr20[i];
+            }
+            b.tmxs1 = t->tmxs1[i]; b.tmxs0 = t->tmxs0[i]; b.blcce1 = t->blcce1[i]; b.blcce0 = t->blcce0[i];
+            b.range_ep = t->range_ep[(size_t)q * nmed * MXEKE + i];
+            b.e_array = t->e_array[i];
+        }
+    if (upload(h, h->media_bufs, eb.data(), eb.size(), &P.ebin)) return 1;
+    // Rayleigh form-factor tables (only medium 0 is ever indexed by the reference, Q3; all are uploaded)
+    if (upload(h, h->media_bufs, t->ray_xgrid, (size_t)nmed * OMC_MXRAYFF, &P.ray_xgrid)) return 1;
+    if (upload(h, h->media_bufs, t->ray_fcum, (size_t)nmed * OMC_MXRAYFF, &P.ray_fcum)) return 1;
+    if (upload(h, h->media_bufs, t->ray_b_array, (size_t)nmed * OMC_MXRAYFF, &P.ray_b)) return 1;
+    if (upload(h, h->media_bufs, t->ray_c_array, (size_t)nmed * OMC_MXRAYFF, &P.ray_c)) return 1;
+    if (upload(h, h->media_bufs, t->ray_i_array, (size_t)nmed * OMC_MXRAYFF, &P.ray_i)) return 1;
+    // spin
+    P.b2spin_min = t->b2spin_min; P.dbeta2i = t->dbeta2i; P.espml = t->espml; P.dleneri = t->dleneri; P.dqq1i = t->dqq1i;
+    if (upload(h, h->media_bufs, t->spin_rej, (size_t)nmed * 2 * OMC_SPIN_NE * OMC_SPIN_NQ * OMC_SPIN_NU, &P.spin_rej)) return 1;
+    // mscat
+    const size_t nms = (size_t)OMC_MS_NL * OMC_MS_NQ * OMC_MS_NU;
+    std::vector<MsEntry> ms(nms);
+    for (size_t i = 0; i < nms; i++) {
+        ms[i].ums = t->ums[i]; ms[i].fms = t->fms[i]; ms[i].wms = t->wms[i]; ms[i].ims = t->ims[i]; ms[i].pad = 0;
+    }
+    if (upload(h, h->media_bufs, ms.data(), nms, &P.ms)) return 1;
+    P.dllambi = t->dllambi; P.dqmsi = t->dqmsi;
+    h->have_media = true;
+    return 0;
+}
+
+int omc_gpu_set_geometry(omc_gpu_handle h, const omc_geometry *g) {
+    if (!h || !g) return 2;
+    if (g->isize < 1 || g->jsize < 1 || g->ksize < 1) return fail(h, "empty voxel grid");
+    const long long nvox = (long long)g->isize * g->jsize * g->ksize;
+    if (nvox + 1 > 2147483647LL) return fail(h, "region index must fit the reference's 32-bit int");
+    CK(cudaSetDevice(h->device));
+    free_pool(h->geom_bufs);
+    DevProblem &P = h->P;
+    P.isize = g->isize; P.jsize = g->jsize; P.ksize = g->ksize;
+    P.ijmax = g->isize * g->jsize;
+    P.nreg = (int)(nvox + 1);
+    if (upload(h, h->geom_bufs, g->xbounds, (size_t)g->isize + 1, &P.xb)) return 1;
+    if (upload(h, h->geom_bufs, g->ybounds, (size_t)g->jsize + 1, &P.yb)) return 1;
+    if (upload(h, h->geom_bufs, g->zbounds, (size_t)g->ksize + 1, &P.zb)) return 1;
+    std::vector<RegionRec> reg((size_t)P.nreg);
+    for (int i = 0; i < P.nreg; i++) {
+        reg[i].rhof = g->rhof[i]; reg[i].ecut = g->ecut[i]; reg[i].pcut = g->pcut[i]; reg[i].med = g->med[i]; reg[i].pad = 0;
+        if (g->med[i] < -1 || g->med[i] >= OMC_MXMED) return fail(h, "region medium index out of range");
+    }
+    if (upload(h, h->geom_bufs, reg.data(), reg.size(), &P.reg)) return 1;
+    cudaFree(P.endep); cudaFree(P.endep32); cudaFree(h->accum); cudaFree(h->accum2);
+    P.endep = nullptr; P.endep32 = nullptr; h->accum = h->accum2 = nullptr;
+    CK(cudaMalloc((void **)&P.endep, (size_t)P.nreg * sizeof(double)));
+    CK(cudaMalloc((void **)&P.endep32, (size_t)P.nreg * sizeof(float)));
+    CK(cudaMalloc((void **)&h->accum, (size_t)P.nreg * sizeof(double)));
+    CK(cudaMalloc((void **)&h->accum2, (size_t)P.nreg * sizeof(double)));
+    h->have_geom = true;
+    return omc_gpu_reset_tallies(h, 0);
+}
+
+int omc_gpu_set_source_dosxyz(omc_gpu_handle h, const omc_source_dosxyz *s) {
+    if (!h || !s) return 2;
+    if (s->charge < -1 || s->charge > 1) return fail(h, "Particle kind not recognized.");          // omc_dosxyz.c:602-605
+    if (s->ssd < 0) return fail(h, "SSD must be greater than zero.");                              // omc_dosxyz.c:614-617
+    CK(cudaSetDevice(h->device));
+    free_pool(h->source_bufs);
+    SourceDosxyz &S = h->P.src;
+    S.spectrum = s->spectrum; S.charge = s->charge; S.energy = s->energy; S.deltak = s->deltak;
+    S.ssd = s->ssd; S.xinl = s->xinl; S.yinl = s->yinl; S.xsize = s->xsize; S.ysize = s->ysize;
+    S.ixinl = s->ixinl; S.iyinl = s->iyinl;
+    S.cdfinv1 = S.cdfinv2 = nullptr;
+    if (s->spectrum) {
+        const size_t n = (size_t)s->deltak;
+        if (n < 1 || !s->cdfinv1 || !s->cdfinv2) return fail(h, "spectrum source without inverse-CDF tables");
+        if (upload(h, h->source_bufs, s->cdfinv1, n, &S.cdfinv1)) return 1;
+        if (upload(h, h->source_bufs, s->cdfinv2, n, &S.cdfinv2)) return 1;
+    }
+    h->have_source = true;
+    return 0;
+}
+
+int omc_gpu_set_source_matrad(omc_gpu_handle h, const omc_source_matrad *s) {
+    (void)s;
+    return fail(h, "omc_gpu_set_source_matrad: beamlet source not implemented in this build");
+}
+
+int omc_gpu_set_vrt(omc_gpu_handle h, int nsplit) {
+    if (!h) return 2;
+    if (nsplit < 1) nsplit = 1;   // "Photon splitting disabled" (src/ompmc.c:5973-5978); nsplit <= 0 would divide by zero in photon()
+    h->P.nsplit = nsplit;
+    return 0;
+}
+
+int omc_gpu_set_seed(omc_gpu_handle h, int ixx, int jxx) {
+    if (!h) return 2;
+    h->P.seed0 = (uint32_t)ixx; h->P.seed1 = (uint32_t)jxx;
+    return 0;
+}
+
+int omc_gpu_set_option(omc_gpu_handle h, const char *key, long long value) {
+    if (!h || !key) return 2;
+    std::string k(key);
+    if (k == "kernel") h->kernel = (int)value;
+    else if (k == "threads_per_block") h->threads_per_block = (int)value;
+    else if (k == "stack_depth") h->stack_depth = (int)value;
+    else if (k == "max_blocks") h->max_blocks = (int)value;
+    else if (k == "record_histories") h->record = (int)value;
+    else return fail(h, "unknown option");
+    return 0;
+}
+
+int omc_gpu_run_histories(omc_gpu_handle h, long long first, long long nhist, int ibeamlet) {
+    if (!h) return 2;
+    if (!h->have_media || !h->have_geom || !h->have_source) return fail(h, "media, geometry and source must be set first");
+    if (ibeamlet >= 0) return fail(h, "beamlet sources not implemented in this build");
+    if (nhist <= 0) return 0;
+    CK(cudaSetDevice(h->device));
+    DevProblem &P = h->P;
+    if (h->record) {
+        if (h->records_cap < nhist) {
+            cudaFree(h->records);
+            h->records = nullptr;
+            CK(cudaMalloc((void **)&h->records, (size_t)nhist * sizeof(omc_history_record)));
+            h->records_cap = nhist;
+        }
+        P.records = h->records;
+    } else {
+        P.records = nullptr;
+    }
+    h->last_nhist = nhist;
+    if (h->kernel == OMC_KERNEL_LOCKSTEP) {
+        const int tpb = h->threads_per_block;
+        int blocks_cap = h->max_blocks > 0 ? h->max_blocks : h->sm_count * lockstep_blocks_per_sm(tpb);
+        long long want = (nhist + tpb - 1) / tpb;
+        const int blocks = (int)(want < blocks_cap ? want : blocks_cap);
+        const int depth = h->stack_depth > 0 ? h->stack_depth : (P.nsplit <= 1 ? 32 : 64 + 24 * P.nsplit);
+        const size_t need = (size_t)depth * blocks * tpb * sizeof(Part);
+        if (need > h->stack_bytes) {
+            cudaFree(h->stack);
+            h->stack = nullptr; h->stack_bytes = 0;
+            CK(cudaMalloc((void **)&h->stack, need));
+            h->stack_bytes = need;
+        }
+        launch_lockstep(P, h->stack, depth, blocks, tpb, first, nhist, h->stream);
+        h->launches += 1;
+        CK(cudaGetLastError());
+    } else {
+        return fail(h, "wavefront kernels not built yet");
+    }
+    return 0;
+}
+
+int omc_gpu_accum_batch(omc_gpu_handle h) {
+    if (!h || !h->have_geom) return 2;
+    CK(cudaSetDevice(h->device));
+    launch_accum(h->P.endep, h->accum, h->accum2, h->P.nreg, h->stream);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int omc_gpu_run_batch(omc_gpu_handle h, long long first, long long nhist, int ibeamlet) {
+    int rc = omc_gpu_run_histories(h, first, nhist, ibeamlet);
+    if (rc) return rc;
+    return omc_gpu_accum_batch(h);
+}
+
+int omc_gpu_synchronize(omc_gpu_handle h) {
+    if (!h) return 2;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    Counters c;
+    CK(cudaMemcpy(&c, h->P.counters, sizeof c, cudaMemcpyDeviceToHost));
+    if (c.errors) {
+        // the reference aborts here: "Stack overflow with np = %d. Increase MXSTACK!" (src/ompmc.c:1937-1940)
+        h->err = "particle stack / queue overflow on the device: increase option stack_depth (or pool_size)";
+        return 7;
+    }
+    return 0;
+}
+
+int omc_gpu_get_tallies(omc_gpu_handle h, double *accum, double *accum2, double *ensrc) {
+    if (!h || !h->have_geom) return 2;
+    int rc = omc_gpu_synchronize(h);
+    if (rc) return rc;
+    const size_t n = (size_t)h->P.nreg * sizeof(double);
+    if (accum) CK(cudaMemcpy(accum, h->accum, n, cudaMemcpyDeviceToHost));
+    if (accum2) CK(cudaMemcpy(accum2, h->accum2, n, cudaMemcpyDeviceToHost));
+    if (ensrc) CK(cudaMemcpy(ensrc, h->P.ensrc, sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int omc_gpu_get_batch_grid(omc_gpu_handle h, double *endep) {
+    if (!h || !h->have_geom || !endep) return 2;
+    int rc = omc_gpu_synchronize(h);
+    if (rc) return rc;
+    CK(cudaMemcpy(endep, h->P.endep, (size_t)h->P.nreg * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int omc_gpu_reset_tallies(omc_gpu_handle h, int which) {
+    if (!h || !h->have_geom) return 2;
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->P.nreg;
+    CK(cudaMemsetAsync(h->accum, 0, n * sizeof(double), h->stream));
+    if (which == 0) {
+        CK(cudaMemsetAsync(h->accum2, 0, n * sizeof(double), h->stream));
+        CK(cudaMemsetAsync(h->P.endep, 0, n * sizeof(double), h->stream));
+        CK(cudaMemsetAsync(h->P.endep32, 0, n * sizeof(float), h->stream));
+        CK(cudaMemsetAsync(h->P.ensrc, 0, sizeof(double), h->stream));
+        CK(cudaMemsetAsync(h->P.counters, 0, sizeof(Counters), h->stream));
+        h->launches = 0;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int omc_gpu_device_ptrs(omc_gpu_handle h, void **endep, void **accum, void **accum2, long long *nreg) {
+    if (!h || !h->have_geom) return 2;
+    if (endep) *endep = h->P.endep;
+    if (accum) *accum = h->accum;
+    if (accum2) *accum2 = h->accum2;
+    if (nreg) *nreg = h->P.nreg;
+    return 0;
+}
+
+int omc_gpu_abi_sizeof(int what) {
+    switch (what) {
+        case 0: return (int)sizeof(omc_media_tables);
+        case 1: return (int)sizeof(omc_geometry);
+        case 2: return (int)sizeof(omc_source_dosxyz);
+        case 3: return (int)sizeof(omc_source_matrad);
+        case 4: return (int)sizeof(omc_history_record);
+        case 5: return (int)sizeof(omc_gpu_counters);
+        default: return -1;
+    }
+}
+
+void *omc_gpu_stream(omc_gpu_handle h) { return h ? (void *)h->stream : nullptr; }
+
+int omc_gpu_get_counters(omc_gpu_handle h, omc_gpu_counters *out) {
+    if (!h || !out) return 2;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    static_assert(sizeof(Counters) == sizeof(omc_gpu_counters), "counter layouts must match");
+    CK(cudaMemcpy(out, h->P.counters, sizeof(Counters), cudaMemcpyDeviceToHost));
+    out->kernel_launches = h->launches;
+    return 0;
+}
+
+int omc_gpu_get_history_records(omc_gpu_handle h, omc_history_record *out, long long n) {
+    if (!h || !out) return 2;
+    if (!h->records || n > h->last_nhist) return fail(h, "no history records (set option record_histories=1 before running)");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out, h->records, (size_t)n * sizeof(omc_history_record), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int omc_gpu_test_geometry(omc_gpu_handle h, int n, const double *xyzuvw, const int *ir, const double *ustep_in, int *idisc,
+                          int *irnew, double *ustep_out, double *tperp) {
+    if (!h || !h->have_geom) return 2;
+    if (n <= 0) return 0;
+    CK(cudaSetDevice(h->device));
+    double *dq = nullptr, *dus = nullptr, *duo = nullptr, *dtp = nullptr;
+    int *dir = nullptr, *did = nullptr, *dirn = nullptr;
+    CK(cudaMalloc((void **)&dq, (size_t)6 * n * sizeof(double))); CK(cudaMalloc((void **)&dus, (size_t)n * sizeof(double)));
+    CK(cudaMalloc((void **)&duo, (size_t)n * sizeof(double)));    CK(cudaMalloc((void **)&dtp, (size_t)n * sizeof(double)));
+    CK(cudaMalloc((void **)&dir, (size_t)n * sizeof(int)));       CK(cudaMalloc((void **)&did, (size_t)n * sizeof(int)));
+    CK(cudaMalloc((void **)&dirn, (size_t)n * sizeof(int)));
+    CK(cudaMemcpy(dq, xyzuvw, (size_t)6 * n * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dus, ustep_in, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dir, ir, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    launch_test_geometry(h->P, n, dq, dir, dus, did, dirn, duo, dtp, h->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(idisc, did, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(irnew, dirn, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ustep_out, duo, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(tperp, dtp, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dq); cudaFree(dus); cudaFree(duo); cudaFree(dtp); cudaFree(dir); cudaFree(did); cudaFree(dirn);
+    return 0;
+}
+
+int omc_gpu_test_rng(omc_gpu_handle h, long long hist, int n, double *out) {
+    if (!h || !out || n <= 0) return 2;
+    CK(cudaSetDevice(h->device));
+    double *d = nullptr;
+    CK(cudaMalloc((void **)&d, (size_t)n * sizeof(double)));
+    launch_test_rng(h->P.seed0, h->P.seed1, (unsigned long long)hist, n, d, h->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out, d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return 0;
+}
+
+}  // extern "C"
