@@ -101,6 +101,12 @@ class _CpuTransport:
         self._f("get_endep")(out.ctypes.data)
         return out
 
+    def set_endep(self, grid):
+        grid = np.ascontiguousarray(grid, dtype=np.float64)
+        assert grid.size == self.nreg
+        fn = self._f("set_endep"); fn.argtypes = [C.c_void_p]
+        fn(grid.ctypes.data)
+
     def get_accum(self):
         a = np.zeros(self.nreg); a2 = np.zeros(self.nreg); e = C.c_double(0.0)
         self._f("get_accum")(a.ctypes.data, a2.ctypes.data, C.byref(e))
@@ -159,6 +165,21 @@ class OracleTransport(_CpuTransport):
 
     def __init__(self):
         super().__init__(oracle_lib_path())
+        self.lib.orc_test_ranmar.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+        self.lib.orc_get_work.argtypes = [C.c_void_p]
+
+    def test_ranmar(self, ixx: int, jxx: int, n: int) -> np.ndarray:
+        out = np.zeros(n)
+        self.lib.orc_test_ranmar(ixx, jxx, n, out.ctypes.data)
+        return out
+
+    def work_per_history(self) -> dict:
+        """Per-history operation counts since reset_score() (SURVEY.md 8d's B_alg inputs)."""
+        w = np.zeros(7, dtype=np.uint64)
+        self.lib.orc_get_work(w.ctypes.data)
+        n = max(int(w[6]), 1)
+        names = ["ausgab", "howfar", "hownear", "pwlf", "mscat", "spin"]
+        return {k: float(w[i]) / n for i, k in enumerate(names)}
 
 
 def ref_lib_path(omp: bool = False) -> str:

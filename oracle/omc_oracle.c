@@ -78,6 +78,14 @@ typedef struct hist_ctx {
     double edep_sum;
 } hist_ctx;
 
+/* per-history operation counts entering SURVEY.md 8d's algorithmic-bytes formula */
+typedef struct work_counts { unsigned long long ausgab, howfar, hownear, pwlf, mscat, spin, hist; } work_counts;
+static work_counts g_work;
+#ifdef _OPENMP
+#pragma omp threadprivate(g_work)
+#endif
+static work_counts g_work_total;
+
 static int g_rng_mode = 1;
 static uint32_t g_seed0 = 97, g_seed1 = 33;
 static hist_ctx *g_ctx;            /* one per OpenMP thread */
@@ -132,12 +140,14 @@ static inline int pwlf_interval(int idx, double lvar, const double *c1, const do
     return (int)(lvar * c1[idx] + c0[idx]);
 }
 static inline double pwlf_eval(int idx, double lvar, const double *c1, const double *c0) {
+    g_work.pwlf++;
     return lvar * c1[idx] + c0[idx];
 }
 
 /* ---- a19: ausgab(), omc_dosxyz.c:683-694 ----------------------------------------------------- */
 static inline void deposit(hist_ctx *c, const part *p, double edep) {
     double en = p->wt * edep;
+    g_work.ausgab++;
     c->ndeposit++;
     c->edep_sum += en;
 #ifdef _OPENMP
@@ -150,6 +160,7 @@ static inline void deposit(hist_ctx *c, const part *p, double edep) {
 static void howfar(const part *p, int *idisc, int *irnew, double *ustep) {
     const omc_geometry *g = &PB.G;
     int irl = p->ir;
+    g_work.howfar++;
     if (irl == 0) { *idisc = 1; return; }
     int imax = g->isize, ijmax = g->isize * g->jsize;
     int irx = (irl - 1) % imax;
@@ -183,6 +194,7 @@ static void howfar(const part *p, int *idisc, int *irnew, double *ustep) {
 static double hownear(const part *p) {
     const omc_geometry *g = &PB.G;
     int irl = p->ir;
+    g_work.hownear++;
     if (irl == 0) return 0.0;
     int imax = g->isize, ijmax = g->isize * g->jsize;
     int irx = (irl - 1) % imax;
@@ -594,6 +606,7 @@ static double spin_rejection(hist_ctx *c, int imed, int qel, double elke, double
                              int *spin_index, int is_single, spin_state *sr) {
     const omc_media_tables *T = &PB.T;
     double ai, aj, ak, qq1, xi, r;
+    g_work.spin++;
     if (*spin_index) {
         *spin_index = 0;
         if (beta2 >= T->b2spin_min) {
@@ -654,6 +667,7 @@ static void mscat(hist_ctx *c, int imed, int qel, int *spin_index, int *find_ind
                   double q1, double lambda, double chia2, double *cost, double *sint, ms_state *ms, spin_state *sr) {
     const omc_media_tables *T = &PB.T;
     double xi, rejf, r;
+    g_work.mscat++;
     double explambda = exp(-lambda);
     if (lambda <= 13.8) {
         double sprob = rnd(c);
@@ -1526,7 +1540,28 @@ void orc_run_histories(long long first, long long n, omc_history_record *rec) {
         }
     }
     PB.ensrc += ensrc;
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+    {
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        {
+            g_work_total.ausgab += g_work.ausgab; g_work_total.howfar += g_work.howfar; g_work_total.hownear += g_work.hownear;
+            g_work_total.pwlf += g_work.pwlf; g_work_total.mscat += g_work.mscat; g_work_total.spin += g_work.spin;
+            memset(&g_work, 0, sizeof g_work);
+        }
+    }
+    g_work_total.hist += (unsigned long long)n;
 }
+
+/* totals since the last orc_reset_score(): {ausgab, howfar, hownear, pwlfEval, mscat, spinRejection, histories} */
+void orc_get_work(unsigned long long *out) {
+    out[0] = g_work_total.ausgab; out[1] = g_work_total.howfar; out[2] = g_work_total.hownear; out[3] = g_work_total.pwlf;
+    out[4] = g_work_total.mscat; out[5] = g_work_total.spin; out[6] = g_work_total.hist;
+}
+void orc_set_endep(const double *in) { memcpy(PB.endep, in, (size_t)PB.nreg * sizeof(double)); }
 
 /* a20: accumEndep(), omc_dosxyz.c:696-717 */
 void orc_accum_endep(void) {
@@ -1541,6 +1576,7 @@ void orc_reset_score(void) {
     size_t n = (size_t)PB.nreg * sizeof(double);
     memset(PB.endep, 0, n); memset(PB.accum, 0, n); memset(PB.accum2, 0, n);
     PB.ensrc = 0.0;
+    memset(&g_work_total, 0, sizeof g_work_total);
 }
 void orc_get_endep(double *out) { memcpy(out, PB.endep, (size_t)PB.nreg * sizeof(double)); }
 void orc_get_accum(double *a, double *a2, double *ensrc) {

@@ -31,6 +31,8 @@ void   orc_test_geometry(int n, const double *xyzuvw, const int *ir, const doubl
 void   orc_test_rng(long long hist, int n, double *out);
 void   orc_run_particle(long long hist, int iq, double e, const double *xyzuvw, int ir, double wt,
                         omc_history_record *rec);
+void   orc_get_work(unsigned long long *out7);
+void   orc_set_endep(const double *in);
 /* n RANMAR draws for seeds (ixx, jxx), src/omc_random.c:58-187 */
 void   orc_test_ranmar(int ixx, int jxx, int n, double *out);
 #endif

@@ -328,6 +328,7 @@ void ref_reset_score(void) {
     score.ensrc = 0.0;
 }
 
+void ref_set_endep(const double *in) { memcpy(score.endep, in, (size_t)ref_nreg() * sizeof(double)); }
 void ref_get_endep(double *out) { memcpy(out, score.endep, (size_t)ref_nreg() * sizeof(double)); }
 void ref_get_accum(double *a, double *a2, double *ensrc) {
     size_t n = (size_t)ref_nreg() * sizeof(double);
