@@ -23,7 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libompmc_b200.so")
 
 KERNEL_LOCKSTEP, KERNEL_WAVEFRONT = 0, 1
-DEFAULT_KERNEL = KERNEL_LOCKSTEP     # production default used by bench.py
+DEFAULT_KERNEL = KERNEL_WAVEFRONT    # production default used by bench.py (nsplit == 1)
 
 RECORD_DTYPE = np.dtype([("ndraws", "<u4"), ("ir_start", "<i4"), ("ndeposit", "<u4"), ("flags", "<u4"), ("edep", "<f8")])
 COUNTER_NAMES = ["histories", "kernel_launches", "photon_steps", "electron_steps", "deposits", "rng_draws", "errors"]

@@ -34,6 +34,15 @@ struct omc_gpu_ctx {
     omc_history_record *records = nullptr;
     long long records_cap = 0, last_nhist = 0;
     unsigned long long launches = 0;
+    // wavefront state
+    WaveQueues wq{};
+    std::vector<void *> wave_bufs;
+    WaveCtl *ctl = nullptr;        // device
+    WaveCtl *ctl_host = nullptr;   // pinned
+    unsigned pool_target = 1u << 22;
+    unsigned pool_cap = 0;
+    int electron_iters = 4, max_cross = 16, check_every = 4;
+    unsigned long long waves = 0;
 };
 
 #define CK(call)                                                                                         \
@@ -64,6 +73,75 @@ static int upload(omc_gpu_handle h, std::vector<void *> &pool, const T *host, si
 static void free_pool(std::vector<void *> &pool) {
     for (void *p : pool) cudaFree(p);
     pool.clear();
+}
+
+static int alloc_queue(omc_gpu_handle h, PartQueue &q, unsigned cap) {
+    q.cap = cap;
+    double **f[9] = {&q.x, &q.y, &q.z, &q.u, &q.v, &q.w, &q.e, &q.wt, &q.aux};
+    for (auto pp : f) {
+        CK(cudaMalloc((void **)pp, (size_t)cap * sizeof(double)));
+        h->wave_bufs.push_back(*pp);
+    }
+    CK(cudaMalloc((void **)&q.irq, (size_t)cap * sizeof(int2)));
+    h->wave_bufs.push_back(q.irq);
+    CK(cudaMalloc((void **)&q.rng, (size_t)cap * sizeof(uint4)));
+    h->wave_bufs.push_back(q.rng);
+    return 0;
+}
+
+// Drive waves until every history of [first, first+nhist) has been started and all queues drained.
+static int run_wavefront(omc_gpu_handle h, long long first, long long nhist) {
+    DevProblem &P = h->P;
+    const unsigned target = h->pool_target;
+    const unsigned cap = 2u * target + 65536u;
+    if (h->pool_cap != cap) {
+        free_pool(h->wave_bufs);
+        h->pool_cap = 0;
+        for (int i = 0; i < 2; i++) {
+            if (alloc_queue(h, h->wq.p[i], cap)) return 1;
+            if (alloc_queue(h, h->wq.e[i], cap)) return 1;
+        }
+        if (alloc_queue(h, h->wq.iq_phot, cap)) return 1;
+        if (alloc_queue(h, h->wq.iq_elec, cap)) return 1;
+        h->pool_cap = cap;
+    }
+    if (!h->ctl) {
+        CK(cudaMalloc((void **)&h->ctl, sizeof(WaveCtl)));
+        CK(cudaMallocHost((void **)&h->ctl_host, sizeof(WaveCtl)));
+    }
+    WaveCtl c;
+    memset(&c, 0, sizeof c);
+    c.target = target; c.cap_p = cap; c.cap_e = cap;
+    c.hist_next = (unsigned long long)first; c.hist_end = (unsigned long long)(first + nhist);
+    CK(cudaMemcpyAsync(h->ctl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
+    WaveLaunch L;
+    L.blocks_elec = h->max_blocks > 0 ? h->max_blocks : h->sm_count * wave_blocks_per_sm(0);
+    L.blocks_phot = h->max_blocks > 0 ? h->max_blocks : h->sm_count * wave_blocks_per_sm(1);
+    L.blocks_int = h->max_blocks > 0 ? h->max_blocks : h->sm_count * 2;
+    L.max_cross = h->max_cross; L.electron_iters = h->electron_iters;
+    int parity = 0;
+    const int every = h->check_every > 0 ? h->check_every : 1;
+    for (unsigned long long wave = 0;; wave++) {
+        launch_wave(P, h->ctl, h->wq, parity, L, h->stream);
+        parity ^= 1;
+        h->launches += 6;
+        h->waves += 1;
+        if ((wave + 1) % every == 0) {
+            CK(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            const WaveCtl &s = *h->ctl_host;
+            if (s.overflow) {
+                h->err = "particle queue overflow on the device: increase option pool_size";
+                return 7;
+            }
+            if (s.hist_next >= s.hist_end && s.live == 0) break;
+        }
+        if (wave > 50000000ull) return fail(h, "wavefront did not terminate");
+    }
+    launch_flush(P.endep32, P.endep, P.nreg, h->stream);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
 }
 
 extern "C" {
@@ -104,7 +182,9 @@ void omc_gpu_destroy(omc_gpu_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    free_pool(h->media_bufs); free_pool(h->geom_bufs); free_pool(h->source_bufs);
+    free_pool(h->media_bufs); free_pool(h->geom_bufs); free_pool(h->source_bufs); free_pool(h->wave_bufs);
+    cudaFree(h->ctl);
+    if (h->ctl_host) cudaFreeHost(h->ctl_host);
     cudaFree(h->P.endep); cudaFree(h->P.endep32); cudaFree(h->accum); cudaFree(h->accum2);
     cudaFree(h->P.counters); cudaFree(h->P.ensrc); cudaFree(h->stack); cudaFree(h->records);
     cudaStreamDestroy(h->stream);
@@ -265,6 +345,10 @@ int omc_gpu_set_option(omc_gpu_handle h, const char *key, long long value) {
     else if (k == "stack_depth") h->stack_depth = (int)value;
     else if (k == "max_blocks") h->max_blocks = (int)value;
     else if (k == "record_histories") h->record = (int)value;
+    else if (k == "pool_size") h->pool_target = (unsigned)value;
+    else if (k == "electron_iters") h->electron_iters = (int)value;
+    else if (k == "max_cross") h->max_cross = (int)value;
+    else if (k == "check_every") h->check_every = (int)value;
     else return fail(h, "unknown option");
     return 0;
 }
@@ -304,8 +388,13 @@ int omc_gpu_run_histories(omc_gpu_handle h, long long first, long long nhist, in
         launch_lockstep(P, h->stack, depth, blocks, tpb, first, nhist, h->stream);
         h->launches += 1;
         CK(cudaGetLastError());
+    } else if (h->kernel == OMC_KERNEL_WAVEFRONT) {
+        if (P.nsplit != 1) return fail(h, "wavefront kernels implement nsplit = 1; use the lock-step kernel for photon splitting");
+        if (h->record) return fail(h, "per-history records are a lock-step kernel feature");
+        int rc = run_wavefront(h, first, nhist);
+        if (rc) return rc;
     } else {
-        return fail(h, "wavefront kernels not built yet");
+        return fail(h, "unknown kernel");
     }
     return 0;
 }

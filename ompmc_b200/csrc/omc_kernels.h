@@ -13,4 +13,34 @@ void launch_test_geometry(const DevProblem &P, int n, const double *xyzuvw, cons
 void launch_test_rng(uint32_t s0, uint32_t s1, unsigned long long hist, int n, double *out, cudaStream_t stream);
 void launch_accum(double *endep, double *accum, double *accum2, long long n, cudaStream_t stream);
 
+
+// ---- omc_wavefront.cu ---------------------------------------------------------------------------
+// One particle queue in HBM, structure-of-arrays (coalesced 8-byte lanes); irq = {ir, iq | tag << 16},
+// rng = {hist_lo, hist_hi, stream, draws consumed}; aux = photon mfp left (-1: not sampled yet).
+struct PartQueue {
+    double *x, *y, *z, *u, *v, *w, *e, *wt, *aux;
+    int2 *irq;
+    uint4 *rng;
+    unsigned cap;
+};
+constexpr size_t PART_QUEUE_BYTES_PER_SLOT = 9 * sizeof(double) + sizeof(int2) + sizeof(uint4);
+
+struct WaveCtl {
+    unsigned n_p_cur, n_e_cur, n_p_next, n_e_next, n_iq_phot, n_iq_elec;
+    unsigned target, cap_p, cap_e, overflow, live, waves;
+    unsigned long long hist_next, hist_end;
+};
+
+struct WaveQueues {
+    PartQueue p[2], e[2], iq_phot, iq_elec;
+};
+
+struct WaveLaunch {
+    int blocks_phot, blocks_elec, blocks_int, max_cross, electron_iters;
+};
+
+int wave_blocks_per_sm(int which);
+void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, int parity, const WaveLaunch &L, cudaStream_t s);
+void launch_flush(float *g32, double *g64, long long n, cudaStream_t s);
+
 }  // namespace omc

@@ -55,9 +55,8 @@ __device__ void photon_ls(const DevProblem &P, HistCtx &c) {
             return;
         }
     }
-    double eig = p.e, gle = log(eig), cohfac = 0.0, gmfp = 0.0, pmax1 = 0.0, pmax0 = 0.0;
-    double gbr11 = 0, gbr10 = 0, gbr21 = 0, gbr20 = 0;
-    int imed = 0;
+    double eig = p.e, gle = log(eig), cohfac = 0.0, gmfp = 0.0;
+    int imed = 0, lgle_last = 0;
 
     for (;;) {                                                  // start_mfp_loop
         double r = g.next();
@@ -97,8 +96,7 @@ __device__ void photon_ls(const DevProblem &P, HistCtx &c) {
                     cohfac = pwl(gle, b.x, b.y);
                     gmfp *= cohfac;
                     tstep = gmfp * dpmfp;
-                    gbr11 = __ldg(&B->gbr11); gbr10 = __ldg(&B->gbr10); gbr21 = __ldg(&B->gbr21); gbr20 = __ldg(&B->gbr20);
-                    pmax1 = __ldg(&B->pmax1); pmax0 = __ldg(&B->pmax0);
+                    lgle_last = lgle;
                 } else {
                     tstep = 1.0E8;
                 }
@@ -125,11 +123,14 @@ __device__ void photon_ls(const DevProblem &P, HistCtx &c) {
 
             save.x = p.x; save.y = p.y; save.z = p.z; save.ir = p.ir;
 
+            // table values at the site: index = (medium of the CURRENT region, lgle of the last march
+            // iteration) exactly as the reference's pwlfEval(imed*MXGE + lgle, ...) calls (:1107, :2046, :2054)
+            const PhotBin *Bs = P.phot + imed * MXGE + lgle_last;
             r = g.next();                                       // Rayleigh? :2027-2040
             if (r <= 1.0 - cohfac) {
                 if (isplit != i_survive) { np -= 1; c.np = np; continue; }
                 p.wt *= nsplit;
-                rayleigh(P, g, p, pwl(gle, pmax1, pmax0), eig);
+                rayleigh(P, g, p, pwl(gle, __ldg(&Bs->pmax1), __ldg(&Bs->pmax0)), eig);
                 s[np] = p;
                 continue;
             }
@@ -137,11 +138,11 @@ __device__ void photon_ls(const DevProblem &P, HistCtx &c) {
             Part q;
             bool created = false;
             c.npold = np;
-            const double gbr1 = pwl(gle, gbr11, gbr10);
+            const double gbr1 = pwl(gle, __ldg(&Bs->gbr11), __ldg(&Bs->gbr10));
             if (r <= gbr1 && eig > 2.0 * RM) {
                 pair(P, g, p, q, imed); created = true;
             } else {
-                const double gbr2 = pwl(gle, gbr21, gbr20);
+                const double gbr2 = pwl(gle, __ldg(&Bs->gbr21), __ldg(&Bs->gbr20));
                 if (r < gbr2) { compton(g, p, q); created = true; }
                 else photo(g, p, R.ecut);
             }

@@ -1,0 +1,124 @@
+"""GPU tests of the wavefront (production) kernels through the C-ABI.
+
+The wavefront kernels use the same physics device functions as the lock-step kernel but other random
+sub-streams (one per particle) and fp32 dose atomics, so agreement is STATISTICAL: per-voxel z-scores
+from the batch method against the lock-step kernel, which itself is in lock-step with the
+reference (tests/test_gpu_lockstep.py).  Integer bookkeeping (history count) and the source sampling
+(primary particles use stream 0 of their history, like the lock-step kernel) are exact.
+"""
+import numpy as np
+import pytest
+
+from oracle.gen_fixtures import golden_problem
+from ompmc_b200 import problem as P
+from ompmc_b200.api import OmcGpuError
+
+pytestmark = pytest.mark.gpu
+
+
+def batches(gpu, kernel, nb, per, first=0):
+    gpu.set_option("kernel", kernel)
+    gpu.reset_tallies()
+    for ib in range(nb):
+        gpu.run_batch(first + ib * per, per)
+    a, a2, ensrc = gpu.get_tallies()
+    a, a2 = a[1:], a2[1:]                                        # region 0 = outside the phantom
+    mean = a / nb
+    var = np.maximum(a2 / nb - mean * mean, 0.0) / (nb - 1)      # variance of the batch mean
+    return mean, var, ensrc, gpu.counters()
+
+
+def zscore_check(m1, v1, m2, v2, frac_dmax=0.2):
+    sel = (m1 > frac_dmax * m1.max()) & (v1 + v2 > 0)
+    z = (m1[sel] - m2[sel]) / np.sqrt(v1[sel] + v2[sel])
+    return z, sel
+
+
+CASES = [
+    ("water6mv", dict(mset="media_700_water.blob", ph=lambda: P.water_phantom("H2O700ICRU", (15, 15, 20), (1.0, 1.0, 1.0)),
+                      spec="mohan6", coll=(-5, 5, -5, 5), ssd=100.0, ecut=0.7, charge=0, mono=0.0), 10, 200000),
+    ("tissue6mv", dict(mset="media_700_tissue4.blob", ph=lambda: P.tissue_phantom((24, 10, 24), (0.8, 0.8, 0.8)),
+                       spec="var_6MV", coll=(-4, 4, -3, 3), ssd=90.0, ecut=0.7, charge=0, mono=0.0), 10, 200000),
+    ("water250kV", dict(mset="media_521_water.blob", ph=lambda: P.water_phantom("H2O521ICRU", (12, 12, 12), (1.0, 1.0, 1.0)),
+                        spec="250", coll=(-3, 3, -3, 3), ssd=100.0, ecut=0.521, charge=0, mono=0.0), 10, 300000),
+    ("e-6MeV", dict(mset="media_700_water.blob", ph=lambda: P.water_phantom("H2O700ICRU", (11, 11, 16), (0.8, 0.8, 0.25)),
+                    spec=None, coll=(-2, 2, -2, 2), ssd=100.0, ecut=0.7, charge=-1, mono=6.0), 10, 20000),
+    ("e+3MeV", dict(mset="media_521_water.blob", ph=lambda: P.water_phantom("H2O521ICRU", (11, 11, 16), (0.8, 0.8, 0.25)),
+                    spec=None, coll=(-2, 2, -2, 2), ssd=100.0, ecut=0.521, charge=1, mono=3.0), 10, 20000),
+]
+
+
+def make_problem(cfg):
+    media = P.load_blob(P.golden(cfg["mset"]))
+    ph = cfg["ph"]()
+    cdf = (media["cdfinv1_" + cfg["spec"]], media["cdfinv2_" + cfg["spec"]]) if cfg["spec"] else None
+    prob = P.build_problem(media, ph, ecut=cfg["ecut"], pcut=0.01, collimator=cfg["coll"], ssd=cfg["ssd"], charge=cfg["charge"],
+                           cdfinv=cdf, mono_energy=cfg["mono"], nsplit=1)
+    return prob, ph
+
+
+@pytest.mark.parametrize("name,cfg,nb,per", CASES, ids=[c[0] for c in CASES])
+def test_wavefront_matches_lockstep_statistically(gpu, name, cfg, nb, per):
+    prob, ph = make_problem(cfg)
+    gpu.load_problem(prob)
+    m0, v0, e0, c0 = batches(gpu, 0, nb, per)
+    m1, v1, e1, c1 = batches(gpu, 1, nb, per)
+    # exact bookkeeping
+    assert c0["histories"] == c1["histories"] == nb * per
+    assert c1["errors"] == 0
+    assert abs(e0 - e1) <= 1e-9 * e0            # same primaries (stream 0 of every history)
+    # energy balance: total deposited energy agrees within its statistical error
+    tot0, tot1 = m0.sum(), m1.sum()
+    s_tot = np.sqrt(v0.sum() + v1.sum()) * 3.0 + 1e-4 * tot0     # voxel sums are positively correlated: generous
+    assert abs(tot0 - tot1) < max(s_tot, 0.004 * tot0), (tot0, tot1)
+    # per-voxel: north_star criterion "voxels with dose > 20 % of Dmax agree within 2 sigma" (95.4 % expected)
+    z, sel = zscore_check(m0, v0, m1, v1)
+    assert sel.sum() >= 20
+    within2 = (np.abs(z) < 2.0).mean()
+    assert within2 >= 0.90, f"{within2:.3f} of {sel.sum()} voxels within 2 sigma"
+    assert abs(z.mean()) < 0.35, f"systematic offset: mean z = {z.mean():.3f}"
+    assert 0.6 < z.std() < 1.5, f"z spread {z.std():.3f}"
+
+
+def test_wavefront_scheduling_independence(gpu):
+    """Per-particle Philox sub-streams: pool size / iterations per wave change only fp32 summation order."""
+    prob, ph = make_problem(CASES[1][1])
+    gpu.load_problem(prob)
+    gpu.set_option("kernel", 1)
+    res = []
+    for pool, iters, cross in ((1 << 22, 4, 16), (1 << 14, 1, 7), (1 << 16, 5, 1000)):
+        gpu.set_option("pool_size", pool); gpu.set_option("electron_iters", iters); gpu.set_option("max_cross", cross)
+        gpu.reset_tallies()
+        gpu.run_histories(0, 50000)
+        res.append((gpu.get_endep()[1:], gpu.counters()))
+    gpu.set_option("pool_size", 1 << 22); gpu.set_option("electron_iters", 4); gpu.set_option("max_cross", 16)
+    g0, c0 = res[0]
+    for g, c in res[1:]:
+        assert c["deposits"] == c0["deposits"] and c["photon_steps"] == c0["photon_steps"]
+        assert c["electron_steps"] == c0["electron_steps"]
+        np.testing.assert_allclose(g, g0, rtol=2e-4, atol=1e-4 * g0.max())
+        assert abs(g.sum() - g0.sum()) < 1e-5 * g0.sum()
+
+
+def test_wavefront_rejects_unsupported(gpu):
+    prob, _, _ = golden_problem("golden_water700_6MV_ns5")
+    gpu.load_problem(prob)
+    gpu.set_option("kernel", 1)
+    with pytest.raises(OmcGpuError):
+        gpu.run_histories(0, 100)          # nsplit = 5: lock-step kernel only
+    gpu.set_option("kernel", 0)
+
+
+def test_wavefront_queue_overflow_is_loud(gpu):
+    prob, ph = make_problem(CASES[0][1])
+    gpu.load_problem(prob)
+    gpu.set_option("kernel", 1)
+    gpu.set_option("pool_size", 64)                 # far too small for 10^5 histories in flight
+    gpu.reset_tallies()
+    with pytest.raises(OmcGpuError):
+        gpu.run_histories(0, 100000)
+        gpu.synchronize()
+    gpu.set_option("pool_size", 1 << 22)
+    gpu.reset_tallies()
+    gpu.run_histories(0, 1000)
+    gpu.synchronize()
