@@ -49,7 +49,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [path] + headers):
-            cmd = [nvcc()] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+            tune = os.environ.get("OMC_NVCC_FLAGS", "").split()     # experiments only, e.g. -DOMC_WAVE_MINBLOCKS=2
+            cmd = [nvcc()] + ARCH + COMMON + extra + tune + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if verbose or r.returncode != 0:
                 sys.stderr.write(r.stdout + r.stderr)

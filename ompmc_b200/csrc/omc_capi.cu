@@ -35,13 +35,16 @@ struct omc_gpu_ctx {
     long long records_cap = 0, last_nhist = 0;
     unsigned long long launches = 0;
     // wavefront state
+    std::vector<MedRec> med_host;
+    double cut_e[OMC_MXMED] = {0}, cut_p[OMC_MXMED] = {0};
+    bool cuts_uniform = false, med_dirty = false;
     WaveQueues wq{};
     std::vector<void *> wave_bufs;
     WaveCtl *ctl = nullptr;        // device
     WaveCtl *ctl_host = nullptr;   // pinned
     unsigned pool_target = 1u << 22;
-    unsigned pool_cap = 0;
-    int electron_iters = 4, max_cross = 16, check_every = 4;
+    unsigned pool_cap = 0, pool_cap_opt = 0;
+    int electron_iters = 1, max_cross = 16, check_every = 16;
     unsigned long long waves = 0;
 };
 
@@ -93,16 +96,16 @@ static int alloc_queue(omc_gpu_handle h, PartQueue &q, unsigned cap) {
 static int run_wavefront(omc_gpu_handle h, long long first, long long nhist) {
     DevProblem &P = h->P;
     const unsigned target = h->pool_target;
-    const unsigned cap = 2u * target + 65536u;
+    const unsigned cap = h->pool_cap_opt ? h->pool_cap_opt : 2u * target + 65536u;
     if (h->pool_cap != cap) {
         free_pool(h->wave_bufs);
         h->pool_cap = 0;
         for (int i = 0; i < 2; i++) {
             if (alloc_queue(h, h->wq.p[i], cap)) return 1;
             if (alloc_queue(h, h->wq.e[i], cap)) return 1;
+            if (alloc_queue(h, h->wq.ip[i], cap)) return 1;
+            if (alloc_queue(h, h->wq.ie[i], cap)) return 1;
         }
-        if (alloc_queue(h, h->wq.iq_phot, cap)) return 1;
-        if (alloc_queue(h, h->wq.iq_elec, cap)) return 1;
         h->pool_cap = cap;
     }
     if (!h->ctl) {
@@ -111,20 +114,17 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist) {
     }
     WaveCtl c;
     memset(&c, 0, sizeof c);
-    c.target = target; c.cap_p = cap; c.cap_e = cap;
+    c.target = target;
     c.hist_next = (unsigned long long)first; c.hist_end = (unsigned long long)(first + nhist);
+    c.n_src = (unsigned)((unsigned long long)nhist < (unsigned long long)target ? nhist : target);
     CK(cudaMemcpyAsync(h->ctl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
     WaveLaunch L;
-    L.blocks_elec = h->max_blocks > 0 ? h->max_blocks : h->sm_count * wave_blocks_per_sm(0);
-    L.blocks_phot = h->max_blocks > 0 ? h->max_blocks : h->sm_count * wave_blocks_per_sm(1);
-    L.blocks_int = h->max_blocks > 0 ? h->max_blocks : h->sm_count * 2;
+    L.blocks = h->max_blocks > 0 ? h->max_blocks : h->sm_count * wave_blocks_per_sm();
     L.max_cross = h->max_cross; L.electron_iters = h->electron_iters;
-    int parity = 0;
     const int every = h->check_every > 0 ? h->check_every : 1;
     for (unsigned long long wave = 0;; wave++) {
-        launch_wave(P, h->ctl, h->wq, parity, L, h->stream);
-        parity ^= 1;
-        h->launches += 6;
+        launch_wave(P, h->ctl, h->wq, L, h->stream);
+        h->launches += 1;
         h->waves += 1;
         if ((wave + 1) % every == 0) {
             CK(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, h->stream));
@@ -134,7 +134,7 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist) {
                 h->err = "particle queue overflow on the device: increase option pool_size";
                 return 7;
             }
-            if (s.hist_next >= s.hist_end && s.live == 0) break;
+            if (s.hist_next >= s.hist_end && s.live == 0 && s.n_src == 0) break;
         }
         if (wave > 50000000ull) return fail(h, "wavefront did not terminate");
     }
@@ -217,6 +217,8 @@ int omc_gpu_set_media(omc_gpu_handle h, const omc_media_tables *t) {
         r.sig_ismonotone[1] = t->sig_ismonotone[1 * nmed + m];
     }
     if (upload(h, h->media_bufs, med.data(), med.size(), &P.med)) return 1;
+    h->med_host = med;
+    h->med_dirty = true;
     // photon bins
     std::vector<PhotBin> pb((size_t)nmed * MXGE);
     for (size_t i = 0; i < pb.size(); i++) {
@@ -288,6 +290,28 @@ int omc_gpu_set_geometry(omc_gpu_handle h, const omc_geometry *g) {
         if (g->med[i] < -1 || g->med[i] >= OMC_MXMED) return fail(h, "region medium index out of range");
     }
     if (upload(h, h->geom_bufs, reg.data(), reg.size(), &P.reg)) return 1;
+    // compact 8-byte records for the wavefront kernels when the cut-offs depend on the medium only
+    {
+        bool uniform = true;
+        bool seen[OMC_MXMED] = {false};
+        for (int i = 1; i < P.nreg && uniform; i++) {
+            const int m = g->med[i];
+            if (m < 0) continue;
+            if (!seen[m]) { seen[m] = true; h->cut_e[m] = g->ecut[i]; h->cut_p[m] = g->pcut[i]; }
+            else if (h->cut_e[m] != g->ecut[i] || h->cut_p[m] != g->pcut[i]) uniform = false;
+        }
+        P.reg8 = nullptr;
+        h->cuts_uniform = uniform;
+        if (uniform) {
+            struct R8 { float rhof; int med; };
+            std::vector<R8> r8((size_t)P.nreg);
+            for (int i = 0; i < P.nreg; i++) { r8[i].rhof = (float)g->rhof[i]; r8[i].med = g->med[i]; }
+            const R8 *d = nullptr;
+            if (upload(h, h->geom_bufs, r8.data(), r8.size(), &d)) return 1;
+            P.reg8 = d;
+        }
+        h->med_dirty = true;
+    }
     cudaFree(P.endep); cudaFree(P.endep32); cudaFree(h->accum); cudaFree(h->accum2);
     P.endep = nullptr; P.endep32 = nullptr; h->accum = h->accum2 = nullptr;
     CK(cudaMalloc((void **)&P.endep, (size_t)P.nreg * sizeof(double)));
@@ -346,6 +370,7 @@ int omc_gpu_set_option(omc_gpu_handle h, const char *key, long long value) {
     else if (k == "max_blocks") h->max_blocks = (int)value;
     else if (k == "record_histories") h->record = (int)value;
     else if (k == "pool_size") h->pool_target = (unsigned)value;
+    else if (k == "pool_cap") h->pool_cap_opt = (unsigned)value;
     else if (k == "electron_iters") h->electron_iters = (int)value;
     else if (k == "max_cross") h->max_cross = (int)value;
     else if (k == "check_every") h->check_every = (int)value;
@@ -360,6 +385,12 @@ int omc_gpu_run_histories(omc_gpu_handle h, long long first, long long nhist, in
     if (nhist <= 0) return 0;
     CK(cudaSetDevice(h->device));
     DevProblem &P = h->P;
+    if (h->med_dirty) {                 // per-medium cut-offs (from the geometry) into the per-medium records
+        for (size_t m = 0; m < h->med_host.size(); m++) { h->med_host[m].ecut = h->cut_e[m]; h->med_host[m].pcut = h->cut_p[m]; }
+        CK(cudaMemcpyAsync((void *)P.med, h->med_host.data(), h->med_host.size() * sizeof(MedRec), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->med_dirty = false;
+    }
     if (h->record) {
         if (h->records_cap < nhist) {
             cudaFree(h->records);

@@ -25,22 +25,26 @@ struct PartQueue {
 };
 constexpr size_t PART_QUEUE_BYTES_PER_SLOT = 9 * sizeof(double) + sizeof(int2) + sizeof(uint4);
 
+constexpr int WAVE_THREADS = 128;   // threads per block == particles per chunk
+
 struct WaveCtl {
-    unsigned n_p_cur, n_e_cur, n_p_next, n_e_next, n_iq_phot, n_iq_elec;
-    unsigned target, cap_p, cap_e, overflow, live, waves;
+    unsigned n_p[2], n_e[2], n_ip[2], n_ie[2];   // queue fill counts, [parity]: cur = parity, next = parity ^ 1
+    unsigned tk[5];                              // chunk tickets per class
+    unsigned n_src;                              // histories injected by the current wave
+    unsigned done, parity, target, overflow, live, waves;
     unsigned long long hist_next, hist_end;
 };
 
 struct WaveQueues {
-    PartQueue p[2], e[2], iq_phot, iq_elec;
+    PartQueue p[2], e[2], ip[2], ie[2];
 };
 
 struct WaveLaunch {
-    int blocks_phot, blocks_elec, blocks_int, max_cross, electron_iters;
+    int blocks, max_cross, electron_iters;
 };
 
-int wave_blocks_per_sm(int which);
-void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, int parity, const WaveLaunch &L, cudaStream_t s);
+int wave_blocks_per_sm();
+void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, cudaStream_t s);
 void launch_flush(float *g32, double *g64, long long n, cudaStream_t s);
 
 }  // namespace omc

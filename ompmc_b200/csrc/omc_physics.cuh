@@ -8,6 +8,11 @@
 #pragma once
 #include "omc_types.cuh"
 
+// The transport kernels are instruction-cache bound when every sampler is inlined at every call site
+// (the fused wave kernel was ~200 KB of SASS with stall_no_instruction as its top stall reason), so the
+// samplers and the Philox refill are real functions: one copy each.
+#define OMC_FN static __device__ __noinline__
+
 namespace omc {
 
 // ---------------------------------------------------------------------------------------------
@@ -29,8 +34,11 @@ struct Rng {
         if (ndrawn & 3u) { refill(); pos = ndrawn & 3u; }
     }
     __device__ __forceinline__ uint32_t ndraws() const { return blk * 4u - (4u - pos); }
+    // drop the unread words of the current block, so that the lanes of a warp that are about to run the
+    // same sampling routine refill together (wavefront kernels only; a pure function of this stream)
+    __device__ __forceinline__ void align() { pos = 4u; }
 
-    __device__ __forceinline__ void refill() {
+    __device__ __noinline__ void refill() {
         uint32_t c0 = blk, c1 = stream, c2 = h0, c3 = h1, ka = k0, kb = k1;
 #pragma unroll
         for (int r = 0; r < 10; r++) {
@@ -68,6 +76,21 @@ __device__ __forceinline__ RegionRec load_region(const DevProblem &P, int ir) {
 }
 __device__ __forceinline__ int region_med(const DevProblem &P, int ir) { return __ldg(&P.reg[ir].med); }
 
+// Wavefront kernels: when ecut/pcut depend on the medium only (always true for regions filled by the
+// reference's initRegions(), omc_dosxyz.c:890-962) a voxel is an 8-byte {float rhof, int med} record and the
+// cut-offs come from the per-medium record; 3M voxels then take 24 MB (L2-resident) instead of 96 MB.
+__device__ __forceinline__ RegionRec load_region_w(const DevProblem &P, int ir) {
+    if (P.reg8 == nullptr) return load_region(P, ir);
+    const int2 a = __ldg(reinterpret_cast<const int2 *>(P.reg8) + ir);
+    RegionRec r;
+    r.rhof = (double)__int_as_float(a.x);
+    r.med = a.y;
+    r.pad = 0;
+    if (a.y >= 0) { r.ecut = P.med[a.y].ecut; r.pcut = P.med[a.y].pcut; }
+    else { r.ecut = 0.0; r.pcut = 0.0; }
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // geometry: howfar()/hownear(), omc_dosxyz.c:187-334.  Axis test order z, x, y; strict '<'.
 // ---------------------------------------------------------------------------------------------
@@ -77,7 +100,7 @@ __device__ __forceinline__ void decode_region(const DevProblem &P, int irl, int 
     iry = ((irl - 1 - irx) - irz * P.ijmax) / P.isize;
 }
 
-__device__ inline void howfar(const DevProblem &P, const Part &p, int &idisc, int &irnew, double &ustep) {
+OMC_FN void howfar(const DevProblem &P, const Part &p, int &idisc, int &irnew, double &ustep) {
     const int irl = p.ir;
     if (irl == 0) { idisc = 1; return; }
     int irx, iry, irz;
@@ -106,7 +129,7 @@ __device__ inline void howfar(const DevProblem &P, const Part &p, int &idisc, in
     }
 }
 
-__device__ inline double hownear(const DevProblem &P, const Part &p) {
+OMC_FN double hownear(const DevProblem &P, const Part &p) {
     const int irl = p.ir;
     if (irl == 0) return 0.0;
     int irx, iry, irz;
@@ -121,7 +144,7 @@ __device__ inline double hownear(const DevProblem &P, const Part &p) {
 // ---------------------------------------------------------------------------------------------
 // azimuth + rotations: selectAzimuthalAngle / uphi21 / uphi32, src/ompmc.c:101-199
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void azimuth(Rng &g, double &cphi, double &sphi) {
+OMC_FN void azimuth(Rng &g, double &cphi, double &sphi) {
     double x, x2, y, y2, r2;
     do {
         x = g.next(); x = 2.0 * x - 1.0; x2 = x * x;
@@ -167,7 +190,7 @@ constexpr double HC_INVERSE = 80.65506856998;
 constexpr double TWICE_HC2 = 0.000307444456;
 
 // rayleigh(), src/ompmc.c:1102-1145.  Q2: ibin == 0 always; Q3: medium-0 form factor tables.
-__device__ inline void rayleigh(const DevProblem &P, Rng &g, Part &p, double pmax, double eig) {
+OMC_FN void rayleigh(const DevProblem &P, Rng &g, Part &p, double pmax, double eig) {
     const double xmax = HC_INVERSE * eig;
     const double dwi = (double)OMC_MXRAYFF - 1.0;
     double r0, r1, xv, costhe, csqthe;
@@ -199,7 +222,7 @@ __device__ __forceinline__ double pair_rej(double zbrang, double xi, double esed
 }
 
 // pair(), src/ompmc.c:1429-1667: p (photon) -> first charged particle, q -> the lower-energy one.
-__device__ inline void pair(const DevProblem &P, Rng &g, Part &p, Part &q, int imed) {
+OMC_FN void pair(const DevProblem &P, Rng &g, Part &p, Part &q, int imed) {
     const MedRec &M = P.med[imed];
     const double eig = p.e;
     double ese1, ese2;
@@ -300,7 +323,7 @@ __device__ inline void pair(const DevProblem &P, Rng &g, Part &p, Part &q, int i
 }
 
 // compton(), src/ompmc.c:1670-1783: p -> scattered photon, q -> recoil electron
-__device__ inline void compton(Rng &g, Part &p, Part &q) {
+OMC_FN void compton(Rng &g, Part &p, Part &q) {
     const double eig = p.e, ko = p.e / RM;
     const double broi = 1.0 + 2.0 * ko, bro = 1.0 / broi;
     bool first_time = true;
@@ -355,7 +378,7 @@ __device__ inline void compton(Rng &g, Part &p, Part &q) {
 }
 
 // photo(), src/ompmc.c:1786-1846: photon becomes an electron of energy hv + RM, Sauter angle
-__device__ inline void photo(Rng &g, Part &p, double ecut) {
+OMC_FN void photo(Rng &g, Part &p, double ecut) {
     p.e += RM;
     p.iq = -1;
     const double eelec = p.e;
@@ -394,7 +417,7 @@ __device__ inline void photo(Rng &g, Part &p, double ecut) {
 struct SpinState { int i, j; };
 
 // spinRejection(), src/ompmc.c:3097-3168
-__device__ inline double spin_rejection(const DevProblem &P, Rng &g, int imed, int qel, double elke, double beta2, double q1,
+OMC_FN double spin_rejection(const DevProblem &P, Rng &g, int imed, int qel, double elke, double beta2, double q1,
                                         double cost, bool &spin_index, bool is_single, SpinState &sr) {
     if (spin_index) {
         spin_index = false;
@@ -435,7 +458,7 @@ __device__ inline double spin_rejection(const DevProblem &P, Rng &g, int imed, i
 }
 
 // sscat(), src/ompmc.c:3170-3199
-__device__ inline void sscat(const DevProblem &P, Rng &g, int imed, int qel, double chia2, double elke, double beta2,
+OMC_FN void sscat(const DevProblem &P, Rng &g, int imed, int qel, double chia2, double elke, double beta2,
                              double &cost, double &sint) {
     bool spin_index = true;
     SpinState sr;
@@ -454,7 +477,7 @@ struct MsState { int i, j; double omega2; };
 
 // mscat(), src/ompmc.c:3606-3785.  Q1: du == 0 (its draw is still consumed); Q7: lambda > 1e5 leaves
 // cost/sint untouched.
-__device__ inline void mscat(const DevProblem &P, Rng &g, int imed, int qel, bool &spin_index, bool &find_index, double elke,
+OMC_FN void mscat(const DevProblem &P, Rng &g, int imed, int qel, bool &spin_index, bool &find_index, double elke,
                              double beta2, double q1, double lambda, double chia2, double &cost, double &sint, MsState &ms,
                              SpinState &sr) {
     double xi, rejf, r;
@@ -547,7 +570,8 @@ __device__ inline void mscat(const DevProblem &P, Rng &g, int imed, int qel, boo
 }
 
 // msdist(), src/ompmc.c:3787-3976 (PRESTA-II): returns the straight-line step; (xf..wf) = end point
-__device__ inline double msdist(const DevProblem &P, Rng &g, const Part &p, int imed, int qel, double rhof, double de,
+template <bool ALIGN = false>
+__device__ __noinline__ double msdist(const DevProblem &P, Rng &g, const Part &p, int imed, int qel, double rhof, double de,
                                 double tustep, double eke, double &xf, double &yf, double &zf, double &uf, double &vf,
                                 double &wf) {
     const MedRec &M = P.med[imed];
@@ -581,9 +605,13 @@ __device__ inline double msdist(const DevProblem &P, Rng &g, const Part &p, int 
     double xi = q1 * lambda;
     bool find_index = true, spin_index = true;
     double w1 = 1.0, sint1 = 0.0, cphi1, sphi1, w2 = 1.0, sint2 = 0.0, cphi2, sphi2;
+    if (ALIGN) g.align();
     mscat(P, g, imed, qel, spin_index, find_index, elke, beta2, xi, lambda, chia2, w1, sint1, ms, sr);
+    if (ALIGN) g.align();
     azimuth(g, cphi1, sphi1);
+    if (ALIGN) g.align();
     mscat(P, g, imed, qel, spin_index, find_index, elke, beta2, xi, lambda, chia2, w2, sint2, ms, sr);
+    if (ALIGN) g.align();
     azimuth(g, cphi2, sphi2);
     const double u2 = sint2 * cphi2, v2 = sint2 * sphi2;
     double u2p = w1 * u2 + sint1 * w2;
@@ -630,7 +658,7 @@ __device__ inline double msdist(const DevProblem &P, Rng &g, const Part &p, int 
 // CSDA helpers
 // ---------------------------------------------------------------------------------------------
 // computeDrange(), src/ompmc.c:3979-4014; B = bin record of (qel, imed, lelke)
-__device__ __forceinline__ double drange(const ElecBin *B, double ekei, double ekef, double elkei, double elkef) {
+OMC_FN double drange(const ElecBin *B, double ekei, double ekef, double elkei, double elkef) {
     const double fedep = 1.0 - ekef / ekei;
     const double elktmp = 0.5 * (elkei + elkef + 0.25 * fedep * fedep * (1.0 + fedep * (1.0 + 0.875 * fedep)));
     const double d1 = __ldg(&B->dedx1);
@@ -642,7 +670,7 @@ __device__ __forceinline__ double drange(const ElecBin *B, double ekei, double e
 }
 
 // computeEloss(), src/ompmc.c:4016-4108; B0 = first bin record of (qel, imed)
-__device__ inline double eloss(const ElecBin *B0, const MedRec &M, double rhof, double tustep, double range, double eke,
+OMC_FN double eloss(const ElecBin *B0, const MedRec &M, double rhof, double tustep, double range, double eke,
                                double elke, int lelke) {
     double aux, dedxmid, de, fedep;
     double tuss = range - __ldg(&B0[lelke].range_ep) / rhof;
@@ -687,7 +715,7 @@ __device__ __forceinline__ void roulette(Rng &g, Part &ph, int nsplit) {
 }
 
 // rannih(), src/ompmc.c:4111-4167 (Q6: one unused draw): p, q = the two 511 keV photons
-__device__ inline void rannih(Rng &g, Part &p, Part &q, int nsplit) {
+OMC_FN void rannih(Rng &g, Part &p, Part &q, int nsplit) {
     double r = g.next();
     const double costhe = 2.0 * r - 1;
     const double sinthe = sqrt(fmax(0.0, (1.0 - costhe) * (1.0 + costhe)));
@@ -702,7 +730,7 @@ __device__ inline void rannih(Rng &g, Part &p, Part &q, int nsplit) {
 }
 
 // brems(), src/ompmc.c:4170-4356: p = radiating e-/e+ (keeps its direction), q = photon
-__device__ inline void brems(const DevProblem &P, Rng &g, Part &p, Part &q, int imed, int nsplit) {
+OMC_FN void brems(const DevProblem &P, Rng &g, Part &p, Part &q, int imed, int nsplit) {
     const MedRec &M = P.med[imed];
     const double eie = p.e;
     const int l = (eie < 50.0) ? 1 : 3, l1 = l + 1;
@@ -773,7 +801,7 @@ __device__ inline void brems(const DevProblem &P, Rng &g, Part &p, Part &q, int 
 }
 
 // moller(), src/ompmc.c:4359-4435: returns false (nothing happens) below the kinematic threshold
-__device__ inline bool moller(const DevProblem &P, Rng &g, Part &p, Part &q, int imed) {
+OMC_FN bool moller(const DevProblem &P, Rng &g, Part &p, Part &q, int imed) {
     const MedRec &M = P.med[imed];
     const double eie = p.e, ekin = eie - RM;
     if (ekin <= 2.0 * M.te) return false;
@@ -806,7 +834,7 @@ __device__ inline bool moller(const DevProblem &P, Rng &g, Part &p, Part &q, int
 }
 
 // bhabha(), src/ompmc.c:4438-4525: the lower-energy particle always ends up in q
-__device__ inline void bhabha(const DevProblem &P, Rng &g, Part &p, Part &q, int imed) {
+OMC_FN void bhabha(const DevProblem &P, Rng &g, Part &p, Part &q, int imed) {
     const MedRec &M = P.med[imed];
     const double eip = p.e, ekin = eip - RM, t0 = ekin / RM, e0 = t0 + 1.0;
     const double yy = 1.0 / (t0 + 2.0), beta2 = ((e0 * e0) - 1.0) / (e0 * e0);
@@ -840,7 +868,7 @@ __device__ inline void bhabha(const DevProblem &P, Rng &g, Part &p, Part &q, int
 }
 
 // annih(), src/ompmc.c:4528-4645: positron -> two photons p, q
-__device__ inline void annih(Rng &g, Part &p, Part &q, int nsplit) {
+OMC_FN void annih(Rng &g, Part &p, Part &q, int nsplit) {
     const double avip = p.e + RM, a = avip / RM, gg = a - 1.0, t = gg - 1.0, pp = sqrt(a * t);
     const double pot = pp / t, ep0 = 1.0 / (a + pp), wsamp = log((1.0 - ep0) / ep0);
     const double aa = p.u, bb = p.v, cc = p.w;
@@ -887,7 +915,7 @@ __device__ inline void annih(Rng &g, Part &p, Part &q, int nsplit) {
 // ---------------------------------------------------------------------------------------------
 // source: initHistory(), omc_dosxyz.c:964-1068.  Returns the sampled kinetic energy (score.ensrc).
 // ---------------------------------------------------------------------------------------------
-__device__ inline double init_history_dosxyz(const DevProblem &P, Rng &g, Part &p) {
+OMC_FN double init_history_dosxyz(const DevProblem &P, Rng &g, Part &p) {
     const SourceDosxyz &S = P.src;
     p.iq = S.charge;
     double ein;

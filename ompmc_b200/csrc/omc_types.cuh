@@ -59,6 +59,7 @@ struct MedRec {
     double te, thmoll, ap;
     double delcm, zbrang, bpar0, bpar1;
     double dl[6][8];         // pair_data.dl1..dl6 [8]
+    double ecut, pcut;       // region.ecut/pcut when they depend on the medium only (see DevProblem::reg8)
     int sig_ismonotone[2];   // [qel]
 };
 
@@ -87,6 +88,7 @@ struct DevProblem {
     int isize, jsize, ksize, ijmax, nreg, nmed;
     const double *xb, *yb, *zb;
     const RegionRec *reg;
+    const void *reg8;        // compact {float rhof; int med} records, or nullptr (see load_region_w)
     // media
     const MedRec *med;
     const PhotBin *phot;     // [nmed*MXGE]

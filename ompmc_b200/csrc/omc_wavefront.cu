@@ -1,31 +1,43 @@
 // omc_wavefront.cu -- production path: event-based particle queues (BASELINE.json north_star (a)).
 //
-// Particles live in HBM as structure-of-arrays queues.  One "wave" runs every live particle through
-// exactly one event of its kind, with one kernel per event class so that a warp executes one code
-// path:
+// Particles live in HBM as structure-of-arrays queues.  One launch of wave_kernel ("a wave") moves every
+// live particle through one event of its class.  The kernel is persistent (one grid that fills the
+// machine); its blocks pull typed CHUNKS of 128 particles from per-class tickets, so a block -- and
+// every warp in it -- runs a single code path at a time:
 //
-//     photon_flight   P_cur  -> P_next (flight not finished) | IQ_phot (at an interaction site)
-//     electron_step   E_cur  -> E_next (still travelling)    | IQ_elec (discrete interaction due)
-//     photon_interact IQ_phot-> P_next, E_next               (Compton / pair / photo / Rayleigh)
-//     electron_interact IQ_elec -> E_next, P_next            (brems / Moller / Bhabha / annihilation)
-//     source          tops P_next (or E_next) up with new histories while any remain
-//     advance         next -> cur bookkeeping (single thread)
+//     chunk E   electron_chunk     E[cur]  -> E[next] (still travelling) | IE[next] (interaction due)
+//     chunk P   photon_chunk       P[cur]  -> P[next] (flight unfinished)| IP[next] (at a site)
+//     chunk IE  e_interact_chunk   IE[cur] -> E[next], P[next]      brems / Moller / Bhabha / annihilation
+//     chunk IP  p_interact_chunk   IP[cur] -> P[next], E[next]      Compton / pair / photo / Rayleigh
+//     chunk S   source_chunk       initHistory() for new history ids -> P[next] or E[next]
+//
+// (interaction queues are consumed one wave after they were filled, which makes all five chunk classes
+// independent within a launch; the last block to finish swaps cur/next and sizes the next injection).
+// Inside an electron chunk the block re-sorts its electrons in shared memory after the step size is
+// known, condensed-history steps to the low thread ids and boundary-crossing (single-scattering) steps
+// to the high ones, because those two paths are long and otherwise split every warp in half.
 //
 // Physics = the same device functions as the lock-step kernel (omc_physics.cuh).  Differences that
-// are statistically neutral: every particle owns a Philox sub-stream derived from its parent's, so
-// results do not depend on scheduling; the reference's zero-length "second ustep iteration"
-// (src/ompmc.c:4787 re-initialises total_tstep) is not executed, its only effect being
-// one wasted random draw; with nsplit == 1 the unused survivor-index draw of photon() (:1916) is
-// skipped.  Dose is scored with fp32 atomics into a chunk grid that is folded into the fp64 batch grid
-// at the end of every omc_gpu_run_histories() call (north_star (d)).
+// are statistically neutral: every particle owns a Philox sub-stream derived from its parent's (results
+// do not depend on scheduling); unread words of a Philox block are dropped at a few fixed points so
+// that warps refill together; the reference's zero-length "second ustep iteration" (src/ompmc.c:4787
+// re-initialises total_tstep) is not executed, its only effect being one wasted draw;
+// with nsplit == 1 the unused survivor-index draw of photon() (:1916) is skipped.  Dose is scored with
+// fp32 atomics into a chunk grid folded into the fp64 batch grid at the end of every
+// omc_gpu_run_histories() call (north_star (d)).
 #include "omc_physics.cuh"
 #include "omc_kernels.h"
 
 #ifndef OMC_WARP_AGGREGATE_DOSE
 #define OMC_WARP_AGGREGATE_DOSE 0
 #endif
+#ifndef OMC_WAVE_MINBLOCKS
+#define OMC_WAVE_MINBLOCKS 3
+#endif
 
 namespace omc {
+
+constexpr int NT = WAVE_THREADS;   // threads per block == particles per chunk
 
 // ---- queues ----------------------------------------------------------------------------------
 __device__ __forceinline__ void q_load(const PartQueue &q, unsigned i, Part &p, Rng &g, const DevProblem &P, double &aux, int &tag) {
@@ -71,10 +83,11 @@ __device__ __forceinline__ void child_rng(const Rng &parent, Rng &c, unsigned k)
     c.blk = 0; c.pos = 4;
 }
 
-// ausgab(): fp32 chunk grid (north_star (d)); warp-aggregated when lanes hit the same voxel
 struct Tally {
-    unsigned ndep, nstep;
+    unsigned ndep, nestep, npstep;
 };
+
+// ausgab(): fp32 chunk grid (north_star (d)); optionally warp-aggregated when lanes hit the same voxel
 __device__ __forceinline__ void deposit32(const DevProblem &P, Tally &t, int ir, double en) {
     t.ndep++;
 #if OMC_WARP_AGGREGATE_DOSE
@@ -83,7 +96,6 @@ __device__ __forceinline__ void deposit32(const DevProblem &P, Tally &t, int ir,
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(peers) - 1;
     float v = (float)en;
-    // butterfly over the peer set
     for (unsigned rest = peers & ~(1u << leader); rest; rest &= rest - 1) {
         const int src = __ffs(rest) - 1;
         const float o = __shfl_sync(peers, v, src);
@@ -98,214 +110,313 @@ __device__ __forceinline__ void deposit32(const DevProblem &P, Tally &t, int ir,
 enum { TAG_NONE = 0, TAG_COMPTON = 1, TAG_PAIR = 2, TAG_PHOTO = 3, TAG_RAYLEIGH = 4, TAG_BREMS = 5, TAG_MOLLER = 6, TAG_BHABHA = 7,
        TAG_ANNIH = 8, TAG_RANNIH = 9 };
 
+struct WaveArgs {
+    WaveCtl *ctl;
+    WaveQueues Q;
+    int max_cross, electron_iters;
+};
+
 // ---------------------------------------------------------------------------------------------
-// photon free flight: photon(), src/ompmc.c:1884-2067 for nsplit == 1
+// chunk P: photon free flight, photon() src/ompmc.c:1884-2067 for nsplit == 1
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) photon_flight_kernel(const __grid_constant__ DevProblem P, WaveCtl *ctl, PartQueue cur,
-                                                            PartQueue next, PartQueue iq, int max_cross) {
-    const unsigned n = ctl->n_p_cur;
-    Tally t = {0, 0};
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        Part p; Rng g; double dpmfp; int tag;
-        q_load(cur, i, p, g, P, dpmfp, tag);
-        RegionRec R = load_region(P, p.ir);
-        if (dpmfp < 0.0) {                                     // fresh photon: cut-off test + number of mfp
-            if (p.e <= R.pcut || p.wt == 0) { deposit32(P, t, p.ir, p.wt * p.e); continue; }
-            const double r = g.next();
-            dpmfp = -log(1.0 - r);                             // eta' = 1 - r  (:1905-1932 with nsplit = 1)
-        }
-        const double gle = log(p.e);
-        int imed = R.med, medc = -2;
-        double gmfpr0 = 0.0, cohfac = 0.0, gmfp = 0.0;
-        int irl = p.ir;
-        bool at_site = false, gone = false;
-        for (int k = 0; k < max_cross; k++) {                  // voxel-to-voxel march, :1951-2019
-            double tstep;
-            if (imed != -1) {
-                if (imed != medc) {                            // (imed, gle) -> table values, reused while the medium stays
-                    const MedRec &M = P.med[imed];
-                    const int lgle = (int)(gle * M.ge1 + M.ge0) - 1;
-                    const PhotBin *B = P.phot + imed * MXGE + lgle;
-                    const double2 a = __ldg(reinterpret_cast<const double2 *>(&B->gmfp1));
-                    const double2 b = __ldg(reinterpret_cast<const double2 *>(&B->cohe1));
-                    gmfpr0 = pwl(gle, a.x, a.y);
-                    cohfac = pwl(gle, b.x, b.y);
-                    medc = imed;
-                }
-                gmfp = gmfpr0 / R.rhof;
-                gmfp *= cohfac;
-                tstep = gmfp * dpmfp;
-            } else {
-                tstep = 1.0E8;
+__device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, int par, unsigned i, unsigned n, Tally &t) {
+    if (i >= n) return;
+    WaveCtl *ctl = A.ctl;
+    Part p; Rng g; double dpmfp; int tag;
+    q_load(A.Q.p[par], i, p, g, P, dpmfp, tag);
+    RegionRec R = load_region_w(P, p.ir);
+    if (dpmfp < 0.0) {                                         // fresh photon: cut-off test + number of mfp
+        if (p.e <= R.pcut || p.wt == 0) { deposit32(P, t, p.ir, p.wt * p.e); return; }
+        g.align();
+        const double r = g.next();
+        dpmfp = -log(1.0 - r);                                 // eta' = 1 - r  (:1905-1932 with nsplit = 1)
+    }
+    const double gle = log(p.e);
+    int imed = R.med, medc = -2;
+    double gmfpr0 = 0.0, cohfac = 0.0, gmfp = 0.0;
+    int irl = p.ir;
+    bool at_site = false;
+    for (int k = 0; k < A.max_cross; k++) {                    // voxel-to-voxel march, :1951-2019
+        double tstep;
+        if (imed != -1) {
+            if (imed != medc) {                                // (imed, gle) -> table values, kept while the medium stays
+                const MedRec &M = P.med[imed];
+                const int lgle = (int)(gle * M.ge1 + M.ge0) - 1;
+                const PhotBin *B = P.phot + imed * MXGE + lgle;
+                const double2 a = __ldg(reinterpret_cast<const double2 *>(&B->gmfp1));
+                const double2 b = __ldg(reinterpret_cast<const double2 *>(&B->cohe1));
+                gmfpr0 = pwl(gle, a.x, a.y);
+                cohfac = pwl(gle, b.x, b.y);
+                medc = imed;
             }
-            int irnew = irl, idisc = 0;
-            double ustep = tstep;
-            howfar(P, p, idisc, irnew, ustep);
-            t.nstep++;
-            p.x += ustep * p.u; p.y += ustep * p.v; p.z += ustep * p.w;
-            if (idisc > 0) { gone = true; break; }
-            if (imed != -1) dpmfp = fmax(0.0, dpmfp - ustep / gmfp);
-            if (irnew != irl) {
-                p.ir = irnew; irl = irnew;
-                R = load_region(P, irl);
-                imed = R.med;
-            }
-            if (imed != -1 && dpmfp <= 1.0E-05) { at_site = true; break; }
-        }
-        if (gone) continue;
-        if (!at_site) { q_push(next, &ctl->n_p_next, ctl, p, g, dpmfp, TAG_NONE); continue; }
-        if (imed != medc) {                                    // site reached right after a medium change
-            const MedRec &M = P.med[imed];
-            const int lgle = (int)(gle * M.ge1 + M.ge0) - 1;
-            const PhotBin *B = P.phot + imed * MXGE + lgle;
-            cohfac = pwl(gle, __ldg(&B->cohe1), __ldg(&B->cohe0));
-        }
-        double r = g.next();                                   // :2027-2067
-        if (r <= 1.0 - cohfac) {
-            tag = TAG_RAYLEIGH;
+            gmfp = gmfpr0 / R.rhof;
+            gmfp *= cohfac;
+            tstep = gmfp * dpmfp;
         } else {
-            const MedRec &M = P.med[imed];
-            const int lgle = (int)(gle * M.ge1 + M.ge0) - 1;
-            const PhotBin *B = P.phot + imed * MXGE + lgle;
-            r = g.next();
-            const double gbr1 = pwl(gle, __ldg(&B->gbr11), __ldg(&B->gbr10));
-            if (r <= gbr1 && p.e > 2.0 * RM) tag = TAG_PAIR;
-            else {
-                const double gbr2 = pwl(gle, __ldg(&B->gbr21), __ldg(&B->gbr20));
-                tag = (r < gbr2) ? TAG_COMPTON : TAG_PHOTO;
-            }
+            tstep = 1.0E8;
         }
-        q_push(iq, &ctl->n_iq_phot, ctl, p, g, -1.0, tag);
+        int irnew = irl, idisc = 0;
+        double ustep = tstep;
+        howfar(P, p, idisc, irnew, ustep);
+        t.npstep++;
+        p.x += ustep * p.u; p.y += ustep * p.v; p.z += ustep * p.w;
+        if (idisc > 0) return;                                 // left the phantom
+        if (imed != -1) dpmfp = fmax(0.0, dpmfp - ustep / gmfp);
+        if (irnew != irl) {
+            p.ir = irnew; irl = irnew;
+            R = load_region_w(P, irl);
+            imed = R.med;
+        }
+        if (imed != -1 && dpmfp <= 1.0E-05) { at_site = true; break; }
     }
-    if (t.nstep) atomicAdd(&P.counters->photon_steps, (unsigned long long)t.nstep);
-    if (t.ndep) atomicAdd(&P.counters->deposits, (unsigned long long)t.ndep);
+    if (!at_site) { q_push(A.Q.p[par ^ 1], &ctl->n_p[par ^ 1], ctl, p, g, dpmfp, TAG_NONE); return; }
+    const MedRec &M = P.med[imed];
+    const int lgle = (int)(gle * M.ge1 + M.ge0) - 1;
+    const PhotBin *B = P.phot + imed * MXGE + lgle;
+    if (imed != medc) cohfac = pwl(gle, __ldg(&B->cohe1), __ldg(&B->cohe0));   // site right after a medium change
+    g.align();
+    double r = g.next();                                       // :2027-2067
+    if (r <= 1.0 - cohfac) {
+        tag = TAG_RAYLEIGH;
+    } else {
+        r = g.next();
+        const double gbr1 = pwl(gle, __ldg(&B->gbr11), __ldg(&B->gbr10));
+        if (r <= gbr1 && p.e > 2.0 * RM) tag = TAG_PAIR;
+        else {
+            const double gbr2 = pwl(gle, __ldg(&B->gbr21), __ldg(&B->gbr20));
+            tag = (r < gbr2) ? TAG_COMPTON : TAG_PHOTO;
+        }
+    }
+    q_push(A.Q.ip[par ^ 1], &ctl->n_ip[par ^ 1], ctl, p, g, -1.0, tag);
 }
 
-__global__ void __launch_bounds__(256) photon_interact_kernel(const __grid_constant__ DevProblem P, WaveCtl *ctl, PartQueue iq,
-                                                              PartQueue pnext, PartQueue enext) {
-    const unsigned n = ctl->n_iq_phot;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        Part p, q; Rng g, gq; double aux; int tag;
-        q_load(iq, i, p, g, P, aux, tag);
-        const RegionRec R = load_region(P, p.ir);
-        const int imed = R.med;
-        if (tag == TAG_COMPTON) {
-            compton(g, p, q);
-            child_rng(g, gq, 0);
-            q_push(pnext, &ctl->n_p_next, ctl, p, g, -1.0, TAG_NONE);
-            q_push(enext, &ctl->n_e_next, ctl, q, gq, 0.0, TAG_NONE);
-        } else if (tag == TAG_PAIR) {
-            pair(P, g, p, q, imed);
-            child_rng(g, gq, 0);
-            q_push(enext, &ctl->n_e_next, ctl, p, g, 0.0, TAG_NONE);
-            q_push(enext, &ctl->n_e_next, ctl, q, gq, 0.0, TAG_NONE);
-        } else if (tag == TAG_PHOTO) {
-            photo(g, p, R.ecut);
-            q_push(enext, &ctl->n_e_next, ctl, p, g, 0.0, TAG_NONE);
-        } else {                                               // Rayleigh: direction change only
-            const MedRec &M = P.med[imed];
-            const double gle = log(p.e);
-            const int lgle = (int)(gle * M.ge1 + M.ge0) - 1;
-            const PhotBin *B = P.phot + imed * MXGE + lgle;
-            rayleigh(P, g, p, pwl(gle, __ldg(&B->pmax1), __ldg(&B->pmax0)), p.e);
-            q_push(pnext, &ctl->n_p_next, ctl, p, g, -1.0, TAG_NONE);
-        }
+// chunk IP: photon interactions
+__device__ void p_interact_chunk(const DevProblem &P, const WaveArgs &A, int par, unsigned i, unsigned n) {
+    if (i >= n) return;
+    WaveCtl *ctl = A.ctl;
+    const PartQueue &pn = A.Q.p[par ^ 1], &en = A.Q.e[par ^ 1];
+    Part p, q; Rng g, gq; double aux; int tag;
+    q_load(A.Q.ip[par], i, p, g, P, aux, tag);
+    g.align();
+    const RegionRec R = load_region_w(P, p.ir);
+    const int imed = R.med;
+    if (tag == TAG_COMPTON) {
+        compton(g, p, q);
+        child_rng(g, gq, 0);
+        q_push(pn, &ctl->n_p[par ^ 1], ctl, p, g, -1.0, TAG_NONE);
+        q_push(en, &ctl->n_e[par ^ 1], ctl, q, gq, 0.0, TAG_NONE);
+    } else if (tag == TAG_PAIR) {
+        pair(P, g, p, q, imed);
+        child_rng(g, gq, 0);
+        q_push(en, &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
+        q_push(en, &ctl->n_e[par ^ 1], ctl, q, gq, 0.0, TAG_NONE);
+    } else if (tag == TAG_PHOTO) {
+        photo(g, p, R.ecut);
+        q_push(en, &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
+    } else {                                                   // Rayleigh: direction change only
+        const MedRec &M = P.med[imed];
+        const double gle = log(p.e);
+        const int lgle = (int)(gle * M.ge1 + M.ge0) - 1;
+        const PhotBin *B = P.phot + imed * MXGE + lgle;
+        rayleigh(P, g, p, pwl(gle, __ldg(&B->pmax1), __ldg(&B->pmax0)), p.e);
+        q_push(pn, &ctl->n_p[par ^ 1], ctl, p, g, -1.0, TAG_NONE);
     }
+}
+
+// chunk IE: discrete electron / positron interactions
+__device__ void e_interact_chunk(const DevProblem &P, const WaveArgs &A, int par, unsigned i, unsigned n) {
+    if (i >= n) return;
+    WaveCtl *ctl = A.ctl;
+    const PartQueue &pn = A.Q.p[par ^ 1], &en = A.Q.e[par ^ 1];
+    Part p, q; Rng g, gq; double aux; int tag;
+    q_load(A.Q.ie[par], i, p, g, P, aux, tag);
+    g.align();
+    const int imed = load_region_w(P, p.ir).med;
+    if (tag == TAG_MOLLER) {
+        const bool created = moller(P, g, p, q, imed);
+        q_push(en, &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
+        if (created) {
+            child_rng(g, gq, 0);
+            q_push(en, &ctl->n_e[par ^ 1], ctl, q, gq, 0.0, TAG_NONE);
+        }
+    } else if (tag == TAG_BREMS) {
+        brems(P, g, p, q, imed, 1);
+        child_rng(g, gq, 0);
+        q_push(en, &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
+        q_push(pn, &ctl->n_p[par ^ 1], ctl, q, gq, -1.0, TAG_NONE);
+    } else if (tag == TAG_BHABHA) {
+        bhabha(P, g, p, q, imed);
+        child_rng(g, gq, 0);
+        q_push(en, &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
+        q_push(en, &ctl->n_e[par ^ 1], ctl, q, gq, 0.0, TAG_NONE);
+    } else {                                                   // annihilation in flight / at rest
+        if (tag == TAG_ANNIH) annih(g, p, q, 1);
+        else rannih(g, p, q, 1);
+        child_rng(g, gq, 0);
+        q_push(pn, &ctl->n_p[par ^ 1], ctl, p, g, -1.0, TAG_NONE);
+        q_push(pn, &ctl->n_p[par ^ 1], ctl, q, gq, -1.0, TAG_NONE);
+    }
+}
+
+// chunk S: initHistory() for history ids hist_next + [i0, i0 + NT)
+__device__ void source_chunk(const DevProblem &P, const WaveArgs &A, int par, unsigned i, unsigned n, double &ensrc) {
+    if (i >= n) return;
+    WaveCtl *ctl = A.ctl;
+    Rng g;
+    g.seed(P.seed0, P.seed1, ctl->hist_next + i, 0u);
+    Part p;
+    ensrc += init_history_dosxyz(P, g, p);
+    if (p.iq == 0) q_push(A.Q.p[par ^ 1], &ctl->n_p[par ^ 1], ctl, p, g, -1.0, TAG_NONE);
+    else q_push(A.Q.e[par ^ 1], &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
 }
 
 // ---------------------------------------------------------------------------------------------
-// one condensed-history / boundary-crossing electron step: the tstep/ustep loops of electron(),
-// src/ompmc.c:4694-5372, one real step per call.  Returns a TAG_* (interaction due), 0 = keep
-// travelling, -1 = particle finished.
+// chunk E: condensed-history / boundary-crossing electron steps, the tstep/ustep loops of electron()
+// src/ompmc.c:4694-5372, `iters` real steps per chunk.
 // ---------------------------------------------------------------------------------------------
-__device__ int electron_iter(const DevProblem &P, Rng &g, Part &p, Tally &t) {
-    RegionRec R = load_region(P, p.ir);
-    int imed = R.med;
-    const int iq = p.iq, qel = (1 + iq) / 2;
-    double eie = p.e;
-    t.nstep++;
+enum { CLS_NONE = 0, CLS_CH = 1, CLS_BCA = 2 };
+
+// state handed from the "step size" phase to the "do the step" phase through shared memory
+struct EStep {
+    double eke, elke, demfp, sig0, total_tstep, range, tustep, tperp, rhof, ecut, dedx, blccl, ssmfp;
+    int lelke, imed;
+};
+constexpr int ES_ND = 8 + 13;   // doubles per exchanged electron (Part + EStep)
+constexpr int ES_NI = 8;        // 32-bit words per exchanged electron (ir, iq, rng x4, lelke, imed)
+
+struct ESmem {
+    double d[ES_ND][NT];
+    unsigned w[ES_NI][NT];
+    unsigned wsum[2][NT / 32];
+};
+
+__device__ __forceinline__ void es_put(ESmem &S, int s, const Part &p, const Rng &g, const EStep &e) {
+    S.d[0][s] = p.x; S.d[1][s] = p.y; S.d[2][s] = p.z; S.d[3][s] = p.u; S.d[4][s] = p.v; S.d[5][s] = p.w; S.d[6][s] = p.e; S.d[7][s] = p.wt;
+    S.d[8][s] = e.eke; S.d[9][s] = e.elke; S.d[10][s] = e.demfp; S.d[11][s] = e.sig0; S.d[12][s] = e.total_tstep; S.d[13][s] = e.range;
+    S.d[14][s] = e.tustep; S.d[15][s] = e.tperp; S.d[16][s] = e.rhof; S.d[17][s] = e.ecut; S.d[18][s] = e.dedx; S.d[19][s] = e.blccl;
+    S.d[20][s] = e.ssmfp;
+    S.w[0][s] = (unsigned)p.ir; S.w[1][s] = (unsigned)p.iq; S.w[2][s] = g.h0; S.w[3][s] = g.h1; S.w[4][s] = g.stream;
+    S.w[5][s] = g.ndraws(); S.w[6][s] = (unsigned)e.lelke; S.w[7][s] = (unsigned)e.imed;
+}
+__device__ __forceinline__ void es_get(const ESmem &S, int s, Part &p, Rng &g, EStep &e, const DevProblem &P) {
+    p.x = S.d[0][s]; p.y = S.d[1][s]; p.z = S.d[2][s]; p.u = S.d[3][s]; p.v = S.d[4][s]; p.w = S.d[5][s]; p.e = S.d[6][s]; p.wt = S.d[7][s];
+    e.eke = S.d[8][s]; e.elke = S.d[9][s]; e.demfp = S.d[10][s]; e.sig0 = S.d[11][s]; e.total_tstep = S.d[12][s]; e.range = S.d[13][s];
+    e.tustep = S.d[14][s]; e.tperp = S.d[15][s]; e.rhof = S.d[16][s]; e.ecut = S.d[17][s]; e.dedx = S.d[18][s]; e.blccl = S.d[19][s];
+    e.ssmfp = S.d[20][s];
+    p.ir = (int)S.w[0][s]; p.iq = (int)S.w[1][s];
+    g.seed(P.seed0, P.seed1, ((unsigned long long)S.w[3][s] << 32) | S.w[2][s], S.w[4][s], S.w[5][s]);
+    e.lelke = (int)S.w[6][s]; e.imed = (int)S.w[7][s];
+}
+
+// Phase A: cut-off test, distance to the next discrete interaction, step-size restrictions.
+// Returns the step class, or CLS_NONE with `st` = -1 (finished) / TAG_RANNIH.
+__device__ __forceinline__ int estep_size(const DevProblem &P, Rng &g, Part &p, EStep &e, Tally &t, int &st) {
+    const RegionRec R = load_region_w(P, p.ir);
+    const int imed = R.med, iq = p.iq, qel = (1 + iq) / 2;
+    const double eie = p.e;
+    t.nestep++;
+    st = 0;
     if (eie <= R.ecut) {                                       // :4665-4687
         deposit32(P, t, p.ir, p.wt * (eie - RM));
-        return (iq > 0) ? TAG_RANNIH : -1;
+        st = (iq > 0) ? TAG_RANNIH : -1;
+        return CLS_NONE;
     }
-    double ustep, tustep = 0.0, tvstep, de = 0.0, range = 0.0, sig0 = 0.0, demfp = 0.0, total_tstep = 0.0, rhof = R.rhof;
-    double eke = eie - RM, elke = 0.0;
-    int lelke = 0;
-    bool call_howfar, do_single = false, called_msdist = false;
-    double xf = 0, yf = 0, zf = 0, uf = 0, vf = 0, wf = 0;
-    const ElecBin *B0 = nullptr;
-    if (imed == -1) {                                          // vacuum (region 0 = outside): :4815-4821
-        ustep = 10.0E8; tustep = ustep; call_howfar = true;
+    e.imed = imed; e.rhof = R.rhof; e.ecut = R.ecut;
+    e.eke = eie - RM;
+    if (imed == -1) {                                          // vacuum / outside: handled by the BCA group
+        e.tustep = 10.0E8; e.tperp = 0.0; e.demfp = 0.0; e.sig0 = 0.0; e.total_tstep = 0.0; e.range = 0.0; e.elke = 0.0; e.lelke = 0;
+        e.dedx = 0.0; e.blccl = 0.0; e.ssmfp = 0.0;
+        return CLS_BCA;
+    }
+    const MedRec &M = P.med[imed];
+    const ElecBin *B0 = P.ebin + (size_t)qel * P.nmed * MXEKE + imed * MXEKE;
+    const double rhof = R.rhof, eke = e.eke;
+    g.align();
+    double r = g.next();
+    if (r == 0.0) r = 1.0E-30;
+    e.demfp = fmax(-log(r), 1.0E-5);
+    const double elke = log(eke);
+    const int lelke = elec_interval(M, elke);
+    e.elke = elke; e.lelke = lelke;
+    const ElecBin *B = B0 + lelke;
+    const double dedx0 = pwl(elke, __ldg(&B->dedx1), __ldg(&B->dedx0));
+    double sig0;
+    if (M.sig_ismonotone[qel]) sig0 = pwl(elke, __ldg(&B->sig1), __ldg(&B->sig0)) / dedx0;
+    else sig0 = (iq < 0) ? M.esig_e : M.psig_e;
+    double tstep;
+    e.total_tstep = 0.0;
+    if (sig0 <= 0.0) {
+        tstep = 10.0E8; sig0 = 1.0E-15;
     } else {
-        const MedRec &M = P.med[imed];
-        B0 = P.ebin + (size_t)qel * P.nmed * MXEKE + imed * MXEKE;
-        double r = g.next();
-        if (r == 0.0) r = 1.0E-30;
-        demfp = fmax(-log(r), 1.0E-5);
-        elke = log(eke);
-        lelke = elec_interval(M, elke);
-        const ElecBin *B = B0 + lelke;
-        const double dedx0 = pwl(elke, __ldg(&B->dedx1), __ldg(&B->dedx0));
-        if (M.sig_ismonotone[qel]) sig0 = pwl(elke, __ldg(&B->sig1), __ldg(&B->sig0)) / dedx0;
-        else sig0 = (iq < 0) ? M.esig_e : M.psig_e;
-        double tstep;
-        if (sig0 <= 0.0) {
-            tstep = 10.0E8; sig0 = 1.0E-15;
+        const double ekef = eke - e.demfp / sig0;
+        if (ekef <= __ldg(&B0[0].e_array)) {
+            tstep = 10.0E8;
         } else {
-            const double ekef = eke - demfp / sig0;
-            if (ekef <= __ldg(&B0[0].e_array)) {
-                tstep = 10.0E8;
+            const double elkef = log(ekef);
+            const int lelkef = elec_interval(M, elkef);
+            if (lelkef == lelke) {
+                tstep = drange(B, eke, ekef, elke, elkef);
             } else {
-                const double elkef = log(ekef);
-                const int lelkef = elec_interval(M, elkef);
-                if (lelkef == lelke) {
-                    tstep = drange(B, eke, ekef, elke, elkef);
-                } else {
-                    double ekei = __ldg(&B->e_array), elkei = (lelke + 1 - M.eke0) / M.eke1;
-                    const double tuss = drange(B, eke, ekei, elke, elkei);
-                    ekei = __ldg(&B0[lelkef + 1].e_array);
-                    elkei = ((lelkef + 2) - M.eke0) / M.eke1;
-                    tstep = drange(B0 + lelkef, ekei, ekef, elkei, elkef);
-                    tstep += tuss + __ldg(&B->range_ep) - __ldg(&B0[lelkef + 1].range_ep);
-                }
+                double ekei = __ldg(&B->e_array), elkei = (lelke + 1 - M.eke0) / M.eke1;
+                const double tuss = drange(B, eke, ekei, elke, elkei);
+                ekei = __ldg(&B0[lelkef + 1].e_array);
+                elkei = ((lelkef + 2) - M.eke0) / M.eke1;
+                tstep = drange(B0 + lelkef, ekei, ekef, elkei, elkef);
+                tstep += tuss + __ldg(&B->range_ep) - __ldg(&B0[lelkef + 1].range_ep);
             }
-            total_tstep = tstep;
-            tstep = total_tstep / rhof;
         }
-        const double dedx = rhof * dedx0;
-        const double tmxs = pwl(elke, __ldg(&B->tmxs1), __ldg(&B->tmxs0)) / rhof;
-        {
-            const double ekei = __ldg(&B->e_array), elkei = (lelke + 1 - M.eke0) / M.eke1;
-            range = (drange(B, eke, ekei, elke, elkei) + __ldg(&B->range_ep)) / rhof;
-        }
-        tustep = fmin(fmin(tstep, tmxs), range);
-        const double tperp = hownear(P, p);
-        double blccl = rhof * M.blcc;
-        const double xccl = rhof * M.xcc;
-        const double p2 = eke * (eke + 2.0 * RM);
-        const double beta2 = p2 / (p2 + (RM * RM));
-        const double etap = pwl(elke, __ldg(&B->eta1), __ldg(&B->eta0));
-        const double ms_corr = pwl(elke, __ldg(&B->blcce1), __ldg(&B->blcce0));
-        blccl = blccl / etap / (1.0 + 0.25 * etap * xccl / blccl / p2) * ms_corr;
-        const double ssmfp = beta2 / blccl;
-        const double skindepth = 3 * ssmfp;
-        tustep = fmin(tustep, fmax(tperp, skindepth));
-        if ((tustep <= tperp) && (tustep > skindepth)) {       // condensed-history step, :4973-4996
-            call_howfar = false; called_msdist = true;
-            de = eloss(B0, M, rhof, tustep, range, eke, elke, lelke);
-            ustep = msdist(P, g, p, imed, qel, rhof, de, tustep, eke, xf, yf, zf, uf, vf, wf);
-        } else {                                               // exact boundary crossing, :4997-5057
-            r = g.next();
-            if (r < 1.0E-30) r = 1.0E-30;
-            const double lambda = (-1.0) * log(1.0 - r);
-            double lambda_max = 0.5 * blccl * RM / dedx;
-            lambda_max *= (eke / RM + 1.0) * (eke / RM + 1.0) * (eke / RM + 1.0);
-            if (!(lambda >= 0.0 && lambda_max > 0.0)) return -1;   // Q8: dropped without deposit
-            const double tuss = (lambda < lambda_max) ? lambda * ssmfp * (1.0 - 0.5 * lambda / lambda_max) : 0.5 * lambda * ssmfp;
-            if (tuss < tustep) { tustep = tuss; do_single = true; }
-            ustep = tustep;
-            call_howfar = !(ustep < tperp);
-        }
+        e.total_tstep = tstep;
+        tstep = tstep / rhof;
+    }
+    e.sig0 = sig0;
+    e.dedx = rhof * dedx0;
+    const double tmxs = pwl(elke, __ldg(&B->tmxs1), __ldg(&B->tmxs0)) / rhof;
+    {
+        const double ekei = __ldg(&B->e_array), elkei = (lelke + 1 - M.eke0) / M.eke1;
+        e.range = (drange(B, eke, ekei, elke, elkei) + __ldg(&B->range_ep)) / rhof;
+    }
+    double tustep = fmin(fmin(tstep, tmxs), e.range);
+    const double tperp = hownear(P, p);
+    double blccl = rhof * M.blcc;
+    const double xccl = rhof * M.xcc;
+    const double p2 = eke * (eke + 2.0 * RM);
+    const double beta2 = p2 / (p2 + (RM * RM));
+    const double etap = pwl(elke, __ldg(&B->eta1), __ldg(&B->eta0));
+    const double ms_corr = pwl(elke, __ldg(&B->blcce1), __ldg(&B->blcce0));
+    blccl = blccl / etap / (1.0 + 0.25 * etap * xccl / blccl / p2) * ms_corr;
+    const double ssmfp = beta2 / blccl;
+    const double skindepth = 3 * ssmfp;
+    tustep = fmin(tustep, fmax(tperp, skindepth));
+    e.tustep = tustep; e.tperp = tperp; e.blccl = blccl; e.ssmfp = ssmfp;
+    return ((tustep <= tperp) && (tustep > skindepth)) ? CLS_CH : CLS_BCA;
+}
+
+// Phase B: take the step.  Returns 0 = keep travelling, -1 = finished, TAG_* = interaction due.
+__device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, const EStep &e, int cls, Tally &t) {
+    const int iq = p.iq, qel = (1 + iq) / 2, imed = e.imed;
+    double eie = p.e, ustep, tustep = e.tustep, tvstep, de = 0.0;
+    const double rhof = e.rhof, eke0 = e.eke;
+    bool call_howfar, do_single = false;
+    double xf = 0, yf = 0, zf = 0, uf = 0, vf = 0, wf = 0;
+    const ElecBin *B0 = (imed >= 0) ? P.ebin + (size_t)qel * P.nmed * MXEKE + imed * MXEKE : nullptr;
+    if (cls == CLS_CH) {                                       // condensed-history step, :4973-4996
+        call_howfar = false;
+        de = eloss(B0, P.med[imed], rhof, tustep, e.range, eke0, e.elke, e.lelke);
+        ustep = msdist<true>(P, g, p, imed, qel, rhof, de, tustep, eke0, xf, yf, zf, uf, vf, wf);
+    } else if (imed == -1) {                                   // :4815-4821
+        ustep = tustep; call_howfar = true;
+    } else {                                                   // exact boundary crossing, :4997-5057
+        g.align();
+        double r = g.next();
+        if (r < 1.0E-30) r = 1.0E-30;
+        const double lambda = (-1.0) * log(1.0 - r);
+        double lambda_max = 0.5 * e.blccl * RM / e.dedx;
+        lambda_max *= (eke0 / RM + 1.0) * (eke0 / RM + 1.0) * (eke0 / RM + 1.0);
+        if (!(lambda >= 0.0 && lambda_max > 0.0)) return -1;   // Q8: dropped without deposit
+        const double tuss = (lambda < lambda_max) ? lambda * e.ssmfp * (1.0 - 0.5 * lambda / lambda_max) : 0.5 * lambda * e.ssmfp;
+        if (tuss < tustep) { tustep = tuss; do_single = true; }
+        ustep = tustep;
+        call_howfar = !(ustep < e.tperp);
     }
     const int irl = p.ir;
     int irnew = irl, idisc = 0;
@@ -315,31 +426,27 @@ __device__ int electron_iter(const DevProblem &P, Rng &g, Part &p, Tally &t) {
         return -1;
     }
     if (ustep < 0) ustep = 0.0;
+    double ecut = e.ecut;
     if (ustep == 0.0 || imed == -1) {                          // :5097-5146
         if (ustep != 0.0) { p.x += p.u * ustep; p.y += p.v * ustep; p.z += p.w * ustep; }
         if (irnew != irl) {
             p.ir = irnew;
-            R = load_region(P, irnew);
+            ecut = load_region_w(P, irnew).ecut;
         }
-        if (eie <= R.ecut) {
+        if (eie <= ecut) {
             deposit32(P, t, p.ir, p.wt * (eie - RM));
             return (iq > 0) ? TAG_RANNIH : -1;
         }
         return 0;
     }
     const MedRec &M = P.med[imed];
-    if (call_howfar) {
-        tvstep = ustep;
-        if (tvstep != tustep) do_single = false;
-        de = eloss(B0, M, rhof, tvstep, range, eke, elke, lelke);
-    } else {
-        tvstep = tustep;
-        if (!called_msdist) de = eloss(B0, M, rhof, tvstep, range, eke, elke, lelke);
-    }
-    if (!called_msdist) {
+    if (cls != CLS_CH) {
+        tvstep = call_howfar ? ustep : tustep;
+        if (call_howfar && tvstep != tustep) do_single = false;
+        de = eloss(B0, M, rhof, tvstep, e.range, eke0, e.elke, e.lelke);
         xf = p.x + p.u * ustep; yf = p.y + p.v * ustep; zf = p.z + p.w * ustep;
         if (do_single) {                                       // :5180-5207
-            const double ekems = fmax(eke - de, R.ecut - RM);
+            const double ekems = fmax(eke0 - de, ecut - RM);
             const double p2 = ekems * (ekems + 2.0 * RM);
             const double beta2 = p2 / (p2 + (RM * RM));
             double chia2 = M.xcc / (4.0 * M.blcc * p2);
@@ -347,43 +454,46 @@ __device__ int electron_iter(const DevProblem &P, Rng &g, Part &p, Tally &t) {
             const int lelkems = elec_interval(M, elkems);
             chia2 *= pwl(elkems, __ldg(&B0[lelkems].eta1), __ldg(&B0[lelkems].eta0));
             double costhe, sinthe;
+            g.align();
             sscat(P, g, imed, qel, chia2, elkems, beta2, costhe, sinthe);
+            g.align();
             Frame fr;
             uphi21(g, fr, costhe, sinthe, p);
         }
         uf = p.u; vf = p.v; wf = p.w;
+    } else {
+        tvstep = tustep;
     }
     deposit32(P, t, p.ir, p.wt * de);                          // :5245
     p.x = xf; p.y = yf; p.z = zf; p.u = uf; p.v = vf; p.w = wf;
     eie -= de;
     p.e = eie;
-    if (irnew == irl && eie <= R.ecut) {
+    if (irnew == irl && eie <= ecut) {
         deposit32(P, t, p.ir, p.wt * (eie - RM));
         return (iq > 0) ? TAG_RANNIH : -1;
     }
-    eke = eie - RM;
-    elke = log(eke);
-    lelke = elec_interval(M, elke);
+    const double eke = eie - RM, elke = log(eke);
+    const int lelke = elec_interval(M, elke);
     int imed_new = imed;
     if (irnew != irl) {
         p.ir = irnew;
-        R = load_region(P, irnew);
-        imed_new = R.med;
+        const RegionRec R = load_region_w(P, irnew);
+        imed_new = R.med; ecut = R.ecut;
     }
-    if (eie <= R.ecut) {
+    if (eie <= ecut) {
         deposit32(P, t, p.ir, p.wt * (eie - RM));
         return (iq > 0) ? TAG_RANNIH : -1;
     }
     if (imed_new != imed) return 0;                            // new medium: resample from the top
-    demfp -= de * sig0;
-    total_tstep -= tvstep * rhof;
-    if (total_tstep < 1.0E-9) demfp = 0.0;
-    if (demfp >= 1.0E-5) return 0;   // interaction point not reached (the reference then burns a zero step and resamples)
+    double demfp = e.demfp - de * e.sig0;
+    if (e.total_tstep - tvstep * rhof < 1.0E-9) demfp = 0.0;
+    if (demfp >= 1.0E-5) return 0;   // interaction point not reached (the reference burns a zero step, then resamples)
     // fictitious cross-section rejection, :5354-5372
     const ElecBin *B = B0 + lelke;
     const double sigf = pwl(elke, __ldg(&B->sig1), __ldg(&B->sig0)) / pwl(elke, __ldg(&B->dedx1), __ldg(&B->dedx0));
+    g.align();
     const double rfict = g.next();
-    if (rfict >= sigf / sig0) return 0;
+    if (rfict >= sigf / e.sig0) return 0;
     const double br1 = pwl(elke, __ldg(&B->bra1), __ldg(&B->bra0));   // :5375-5429
     const double r = g.next();
     if (iq < 0) {
@@ -396,98 +506,143 @@ __device__ int electron_iter(const DevProblem &P, Rng &g, Part &p, Tally &t) {
     return (r < pbr2) ? TAG_BHABHA : TAG_ANNIH;
 }
 
-__global__ void __launch_bounds__(128) electron_step_kernel(const __grid_constant__ DevProblem P, WaveCtl *ctl, PartQueue cur,
-                                                            PartQueue next, PartQueue iq, int iters) {
-    const unsigned n = ctl->n_e_cur;
-    Tally t = {0, 0};
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        Part p; Rng g; double aux; int tag;
-        q_load(cur, i, p, g, P, aux, tag);
-        int st = 0;
-        for (int k = 0; k < iters && st == 0; k++) st = electron_iter(P, g, p, t);
-        if (st == 0) q_push(next, &ctl->n_e_next, ctl, p, g, 0.0, TAG_NONE);
-        else if (st > 0) q_push(iq, &ctl->n_iq_elec, ctl, p, g, 0.0, st);
+__device__ void electron_chunk(const DevProblem &P, const WaveArgs &A, int par, unsigned i, unsigned n, ESmem &S, Tally &t) {
+    WaveCtl *ctl = A.ctl;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    Part p; Rng g; EStep e;
+    bool have = false;
+    if (i < n) {
+        double aux; int tag;
+        q_load(A.Q.e[par], i, p, g, P, aux, tag);
+        have = true;
     }
-    if (t.nstep) atomicAdd(&P.counters->electron_steps, (unsigned long long)t.nstep);
-    if (t.ndep) atomicAdd(&P.counters->deposits, (unsigned long long)t.ndep);
+    for (int it = 0; it < A.electron_iters; it++) {
+        int cls = CLS_NONE, st = 0;
+        if (have) {
+            cls = estep_size(P, g, p, e, t, st);
+            if (cls == CLS_NONE) {                             // finished at the cut-off
+                if (st > 0) q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st);
+                have = false;
+            }
+        }
+        // block-wide re-sort: CH steps -> threads [0, nch), BCA steps -> [nch, nch + nbca)
+        const unsigned mch = __ballot_sync(0xffffffffu, cls == CLS_CH), mbc = __ballot_sync(0xffffffffu, cls == CLS_BCA);
+        if (lane == 0) { S.wsum[0][wid] = __popc(mch); S.wsum[1][wid] = __popc(mbc); }
+        __syncthreads();
+        unsigned nch = 0, nbc = 0, och = 0, obc = 0;
+#pragma unroll
+        for (int k = 0; k < NT / 32; k++) {
+            const unsigned a = S.wsum[0][k], b = S.wsum[1][k];
+            if (k < wid) { och += a; obc += b; }
+            nch += a; nbc += b;
+        }
+        if (nch + nbc == 0) break;                             // block-uniform
+        const unsigned below = (1u << lane) - 1u;
+        if (cls == CLS_CH) es_put(S, och + __popc(mch & below), p, g, e);
+        else if (cls == CLS_BCA) es_put(S, nch + obc + __popc(mbc & below), p, g, e);
+        __syncthreads();
+        have = (unsigned)tid < nch + nbc;
+        if (have) {
+            es_get(S, tid, p, g, e, P);
+            st = estep_do(P, g, p, e, (unsigned)tid < nch ? CLS_CH : CLS_BCA, t);
+            if (st != 0) {
+                if (st > 0) q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st);
+                have = false;
+            }
+        }
+        __syncthreads();                                       // S is reused by the next iteration
+    }
+    if (have) q_push(A.Q.e[par ^ 1], &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
 }
 
-__global__ void __launch_bounds__(256) electron_interact_kernel(const __grid_constant__ DevProblem P, WaveCtl *ctl, PartQueue iq,
-                                                                PartQueue enext, PartQueue pnext) {
-    const unsigned n = ctl->n_iq_elec;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        Part p, q; Rng g, gq; double aux; int tag;
-        q_load(iq, i, p, g, P, aux, tag);
-        const int imed = region_med(P, p.ir);
-        if (tag == TAG_MOLLER) {
-            const bool created = moller(P, g, p, q, imed);
-            q_push(enext, &ctl->n_e_next, ctl, p, g, 0.0, TAG_NONE);
-            if (created) {
-                child_rng(g, gq, 0);
-                q_push(enext, &ctl->n_e_next, ctl, q, gq, 0.0, TAG_NONE);
+// ---------------------------------------------------------------------------------------------
+// the wave kernel
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned vload(const unsigned *p) { return *reinterpret_cast<const volatile unsigned *>(p); }
+
+// swap cur/next and size the next injection; executed by the last block to finish a wave
+__device__ void advance(const DevProblem &P, WaveCtl *c) {
+    const int par = (int)c->parity, nxt = par ^ 1;
+    c->hist_next += c->n_src;
+    P.counters->histories += c->n_src;
+    c->n_p[par] = 0; c->n_e[par] = 0; c->n_ip[par] = 0; c->n_ie[par] = 0;
+    const unsigned live = vload(&c->n_p[nxt]) + vload(&c->n_e[nxt]) + vload(&c->n_ip[nxt]) + vload(&c->n_ie[nxt]);
+    const unsigned long long left = c->hist_end - c->hist_next;
+    const unsigned room = (live < c->target) ? c->target - live : 0u;
+    c->n_src = (unsigned)(left < (unsigned long long)room ? left : (unsigned long long)room);
+    c->live = live;
+    c->tk[0] = c->tk[1] = c->tk[2] = c->tk[3] = c->tk[4] = 0;
+    c->done = 0;
+    c->parity = (unsigned)nxt;
+    c->waves += 1;
+    const unsigned ov = vload(&c->overflow);
+    if (ov) P.counters->errors = ov;
+}
+
+__global__ void __launch_bounds__(NT, OMC_WAVE_MINBLOCKS) wave_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ WaveArgs A) {
+    __shared__ ESmem S;
+    __shared__ unsigned s_type, s_chunk, s_cnt[5];
+    WaveCtl *ctl = A.ctl;
+    const int par = (int)ctl->parity;
+    if (threadIdx.x == 0) {
+        // chunk classes: 0 electron interactions, 1 photon interactions, 2 source, 3 photon flights, 4 electron steps
+        // (counts are clamped to the queue capacity: after an overflow the counters run past it)
+        const unsigned cap = A.Q.p[0].cap;
+        s_cnt[0] = min(ctl->n_ie[par], cap); s_cnt[1] = min(ctl->n_ip[par], cap); s_cnt[2] = ctl->n_src;
+        s_cnt[3] = min(ctl->n_p[par], cap); s_cnt[4] = min(ctl->n_e[par], cap);
+    }
+    __syncthreads();
+    Tally t = {0, 0, 0};
+    double ensrc = 0.0;
+    unsigned open = 0x1f, rr = blockIdx.x;                     // (thread 0) classes that may still have chunks; pull phase
+    for (;;) {
+        if (threadIdx.x == 0) {
+            // pull pattern IE, IP, S, P, E, E, E, E: electrons dominate the work, the latency-bound photon chunks
+            // are interleaved with them.  8 consecutive phases visit every class, so type 5 == nothing left.
+            unsigned type = 5, chunk = 0;
+            for (int tries = 0; tries < 8 && open; tries++) {
+                const unsigned k = rr & 7u;
+                rr++;
+                const unsigned c = k < 4u ? k : 4u;
+                if (!(open & (1u << c))) continue;
+                const unsigned tk = atomicAdd(&ctl->tk[c], 1u);
+                if ((unsigned long long)tk * NT < s_cnt[c]) { type = c; chunk = tk; break; }
+                open &= ~(1u << c);
             }
-        } else if (tag == TAG_BREMS) {
-            brems(P, g, p, q, imed, 1);
-            child_rng(g, gq, 0);
-            q_push(enext, &ctl->n_e_next, ctl, p, g, 0.0, TAG_NONE);
-            q_push(pnext, &ctl->n_p_next, ctl, q, gq, -1.0, TAG_NONE);
-        } else if (tag == TAG_BHABHA) {
-            bhabha(P, g, p, q, imed);
-            child_rng(g, gq, 0);
-            q_push(enext, &ctl->n_e_next, ctl, p, g, 0.0, TAG_NONE);
-            q_push(enext, &ctl->n_e_next, ctl, q, gq, 0.0, TAG_NONE);
-        } else {                                               // annihilation in flight / at rest
-            if (tag == TAG_ANNIH) annih(g, p, q, 1);
-            else rannih(g, p, q, 1);
-            child_rng(g, gq, 0);
-            q_push(pnext, &ctl->n_p_next, ctl, p, g, -1.0, TAG_NONE);
-            q_push(pnext, &ctl->n_p_next, ctl, q, gq, -1.0, TAG_NONE);
+            s_type = type; s_chunk = chunk;
+        }
+        __syncthreads();
+        const unsigned type = s_type, i = s_chunk * NT + threadIdx.x;
+        if (type == 5) break;
+        if (type == 4) electron_chunk(P, A, par, i, s_cnt[4], S, t);
+        else if (type == 3) photon_chunk(P, A, par, i, s_cnt[3], t);
+        else if (type == 2) source_chunk(P, A, par, i, s_cnt[2], ensrc);
+        else if (type == 1) p_interact_chunk(P, A, par, i, s_cnt[1]);
+        else e_interact_chunk(P, A, par, i, s_cnt[0]);
+        __syncthreads();
+    }
+    // per-block tallies
+    for (int o = 16; o > 0; o >>= 1) {
+        ensrc += __shfl_xor_sync(0xffffffffu, ensrc, o);
+        t.ndep += __shfl_xor_sync(0xffffffffu, t.ndep, o);
+        t.nestep += __shfl_xor_sync(0xffffffffu, t.nestep, o);
+        t.npstep += __shfl_xor_sync(0xffffffffu, t.npstep, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (ensrc != 0.0) atomicAdd(P.ensrc, ensrc);
+        if (t.ndep) atomicAdd(&P.counters->deposits, (unsigned long long)t.ndep);
+        if (t.nestep) atomicAdd(&P.counters->electron_steps, (unsigned long long)t.nestep);
+        if (t.npstep) atomicAdd(&P.counters->photon_steps, (unsigned long long)t.npstep);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned d = atomicAdd(&ctl->done, 1u);
+        if (d == gridDim.x - 1) {
+            __threadfence();
+            advance(P, ctl);
         }
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// source + bookkeeping
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned n_inject(const WaveCtl *c) {
-    const unsigned live = c->n_p_next + c->n_e_next;
-    const unsigned long long left = c->hist_end - c->hist_next;
-    unsigned room = (live < c->target) ? c->target - live : 0u;
-    return (unsigned)(left < (unsigned long long)room ? left : (unsigned long long)room);
-}
-
-// initHistory() for the next n_inject(ctl) history ids, appended to the photon or electron queue
-__global__ void __launch_bounds__(256) source_kernel(const __grid_constant__ DevProblem P, const WaveCtl *ctl, PartQueue pnext,
-                                                     PartQueue enext) {
-    const unsigned n = n_inject(ctl);
-    const bool photons = (P.src.charge == 0);
-    const PartQueue &q = photons ? pnext : enext;
-    const unsigned base = photons ? ctl->n_p_next : ctl->n_e_next;
-    double ensrc = 0.0;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        Rng g;
-        g.seed(P.seed0, P.seed1, ctl->hist_next + i, 0u);
-        Part p;
-        ensrc += init_history_dosxyz(P, g, p);
-        if (base + i < q.cap) q_store(q, base + i, p, g, -1.0, TAG_NONE);
-    }
-    for (int o = 16; o > 0; o >>= 1) ensrc += __shfl_xor_sync(0xffffffffu, ensrc, o);
-    if ((threadIdx.x & 31) == 0 && ensrc != 0.0) atomicAdd(P.ensrc, ensrc);
-}
-
-__global__ void advance_kernel(const __grid_constant__ DevProblem P, WaveCtl *ctl) {
-    if (blockIdx.x || threadIdx.x) return;
-    const unsigned n = n_inject(ctl);
-    unsigned np = ctl->n_p_next, ne = ctl->n_e_next;
-    if (P.src.charge == 0) np += n; else ne += n;
-    if (np > ctl->cap_p || ne > ctl->cap_e) { ctl->overflow += 1; np = min(np, ctl->cap_p); ne = min(ne, ctl->cap_e); }
-    ctl->hist_next += n;
-    P.counters->histories += n;
-    ctl->n_p_cur = np; ctl->n_e_cur = ne;
-    ctl->n_p_next = 0; ctl->n_e_next = 0; ctl->n_iq_phot = 0; ctl->n_iq_elec = 0;
-    ctl->waves += 1;
-    ctl->live = np + ne;
-    if (P.counters && ctl->overflow) P.counters->errors = ctl->overflow;
 }
 
 // fold the fp32 chunk grid into the fp64 batch grid
@@ -499,23 +654,16 @@ __global__ void flush_kernel(float *__restrict__ g32, double *__restrict__ g64, 
 }
 
 // ---- host-side launchers ----------------------------------------------------------------------
-int wave_blocks_per_sm(int which) {
+int wave_blocks_per_sm() {
     int n = 0;
-    cudaError_t e;
-    if (which == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, electron_step_kernel, 128, 0);
-    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photon_flight_kernel, 256, 0);
-    return (e == cudaSuccess && n > 0) ? n : 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wave_kernel, NT, 0) != cudaSuccess || n < 1) n = 1;
+    return n;
 }
 
-// One wave.  `parity` selects which half of the double-buffered queues is "cur".
-void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, int parity, const WaveLaunch &L, cudaStream_t s) {
-    const PartQueue &pc = Q.p[parity], &pn = Q.p[parity ^ 1], &ec = Q.e[parity], &en = Q.e[parity ^ 1];
-    photon_flight_kernel<<<L.blocks_phot, 256, 0, s>>>(P, ctl, pc, pn, Q.iq_phot, L.max_cross);
-    electron_step_kernel<<<L.blocks_elec, 128, 0, s>>>(P, ctl, ec, en, Q.iq_elec, L.electron_iters);
-    photon_interact_kernel<<<L.blocks_int, 256, 0, s>>>(P, ctl, Q.iq_phot, pn, en);
-    electron_interact_kernel<<<L.blocks_int, 256, 0, s>>>(P, ctl, Q.iq_elec, en, pn);
-    source_kernel<<<L.blocks_int, 256, 0, s>>>(P, ctl, pn, en);
-    advance_kernel<<<1, 32, 0, s>>>(P, ctl);
+void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, cudaStream_t s) {
+    WaveArgs A;
+    A.ctl = ctl; A.Q = Q; A.max_cross = L.max_cross; A.electron_iters = L.electron_iters;
+    wave_kernel<<<L.blocks, NT, 0, s>>>(P, A);
 }
 
 void launch_flush(float *g32, double *g64, long long n, cudaStream_t s) {

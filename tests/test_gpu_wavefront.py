@@ -113,12 +113,12 @@ def test_wavefront_queue_overflow_is_loud(gpu):
     prob, ph = make_problem(CASES[0][1])
     gpu.load_problem(prob)
     gpu.set_option("kernel", 1)
-    gpu.set_option("pool_size", 64)                 # far too small for 10^5 histories in flight
+    gpu.set_option("pool_cap", 1000)                # queues far too small for the 4M-particle target
     gpu.reset_tallies()
     with pytest.raises(OmcGpuError):
         gpu.run_histories(0, 100000)
         gpu.synchronize()
-    gpu.set_option("pool_size", 1 << 22)
+    gpu.set_option("pool_cap", 0)
     gpu.reset_tallies()
     gpu.run_histories(0, 1000)
     gpu.synchronize()
