@@ -265,6 +265,17 @@ int omc_gpu_set_media(omc_gpu_handle h, const omc_media_tables *t) {
         ms[i].ums = t->ums[i]; ms[i].fms = t->fms[i]; ms[i].wms = t->wms[i]; ms[i].ims = t->ims[i]; ms[i].pad = 0;
     }
     if (upload(h, h->media_bufs, ms.data(), nms, &P.ms)) return 1;
+    {   // fp32 copies used by the wavefront kernels' single-precision angle samplers
+        std::vector<MsEntryF> msf(nms);
+        for (size_t i = 0; i < nms; i++) {
+            msf[i].ums = (float)t->ums[i]; msf[i].wms = (float)t->wms[i]; msf[i].ims = t->ims[i]; msf[i].fms = (float)t->fms[i];
+        }
+        if (upload(h, h->media_bufs, msf.data(), nms, &P.ms_f)) return 1;
+        const size_t nsp = (size_t)nmed * 2 * OMC_SPIN_NE * OMC_SPIN_NQ * OMC_SPIN_NU;
+        std::vector<float> spf(nsp);
+        for (size_t i = 0; i < nsp; i++) spf[i] = (float)t->spin_rej[i];
+        if (upload(h, h->media_bufs, spf.data(), nsp, &P.spin_rej_f)) return 1;
+    }
     P.dllambi = t->dllambi; P.dqmsi = t->dqmsi;
     h->have_media = true;
     return 0;

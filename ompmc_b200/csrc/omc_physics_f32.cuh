@@ -1,0 +1,285 @@
+// omc_physics_f32.cuh -- single-precision elastic-scattering samplers for the wavefront kernels.
+//
+// The condensed-history step spends most of its instructions in msdist()/mscat()/spinRejection()
+// (src/ompmc.c:3097-3199, 3606-3976): angle sampling, not bookkeeping.  Angles do not need 53-bit
+// arithmetic (the reference's own tables are 16-bit (spin) / text (msnew.data) precision), whereas fp64
+// logs/exps/divisions/square roots are software sequences on the GPU and double every register.  These
+// versions compute the SAME algorithm in fp32 with the hardware MUFU approximations; positions, energies,
+// path lengths and all CSDA bookkeeping stay fp64 in the callers.  Cancellation-prone forms are avoided:
+// samplers work with xi = 1 - cos(theta) instead of cos(theta).
+// The lock-step kernel never uses this header (it stays bit-faithful fp64).
+#pragma once
+#include "omc_physics.cuh"
+
+namespace omc {
+
+constexpr float RMf = (float)OMC_RM;
+
+__device__ __forceinline__ float nextf(Rng &g) {           // 24-bit lattice in [0,1), like RANMAR's
+    if (g.pos >= 4u) g.refill();
+    const uint32_t w = g.pos == 0u ? g.b0 : (g.pos == 1u ? g.b1 : (g.pos == 2u ? g.b2 : g.b3));
+    g.pos += 1;
+    return (float)(w >> 8) * (1.0f / 16777216.0f);
+}
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float frcp(float a) { return __frcp_rn(a); }
+
+// selectAzimuthalAngle(), src/ompmc.c:101-122
+static __device__ __noinline__ void azimuth_f(Rng &g, float &cphi, float &sphi) {
+    float x, x2, y, y2, r2;
+    do {
+        x = nextf(g); x = 2.0f * x - 1.0f; x2 = x * x;
+        y = nextf(g); y2 = y * y;
+        r2 = x2 + y2;
+    } while (r2 > 1.0f || r2 == 0.0f);
+    r2 = frcp(r2);
+    cphi = (x2 - y2) * r2;
+    sphi = 2.0f * x * y * r2;
+}
+
+// spinRejection(), src/ompmc.c:3097-3168, argument omc = 1 - cos(theta)
+static __device__ __noinline__ float spin_rejection_f(const DevProblem &P, Rng &g, int imed, int qel, float elke, float beta2, float q1,
+                                                      float omc_, bool &spin_index, bool is_single, SpinState &sr) {
+    if (spin_index) {
+        spin_index = false;
+        float ai;
+        const float b2min = (float)P.b2spin_min, espml = (float)P.espml;
+        if (beta2 >= b2min) {
+            ai = (beta2 - b2min) * (float)P.dbeta2i;
+            sr.i = (int)ai; ai -= (float)sr.i; sr.i += 16;
+            if (sr.i > 30) { sr.i = 30; ai = 1.0f; }               // beta2 -> 1 in fp32
+        } else if (elke > espml) {
+            ai = (elke - espml) * (float)P.dleneri;
+            sr.i = (int)ai; ai -= (float)sr.i;
+        } else {
+            sr.i = 0; ai = -1.0f;
+        }
+        float r = nextf(g);
+        if (r < ai) sr.i += 1;
+        if (is_single) {
+            sr.j = 0;
+        } else {
+            float qq1 = 2.0f * q1;
+            qq1 = fdiv(qq1, 1.0f + qq1);
+            float aj = qq1 * (float)P.dqq1i;
+            sr.j = (int)aj;
+            if (sr.j >= 15) {
+                sr.j = 15;
+            } else {
+                aj -= (float)sr.j;
+                r = nextf(g);
+                if (r < aj) sr.j += 1;
+            }
+        }
+    }
+    const float xi = sqrtf(0.5f * omc_);
+    float ak = xi * 31.0f;
+    int k = (int)ak;
+    if (k > 30) k = 30;
+    ak -= (float)k;
+    const float *row = P.spin_rej_f + (((size_t)(imed * 2 + qel) * OMC_SPIN_NE + sr.i) * OMC_SPIN_NQ + sr.j) * OMC_SPIN_NU;
+    return (1.0f - ak) * __ldg(row + k) + ak * __ldg(row + k + 1);
+}
+
+// sscat(), src/ompmc.c:3170-3199
+static __device__ __noinline__ void sscat_f(const DevProblem &P, Rng &g, int imed, int qel, float chia2, float elke, float beta2,
+                                            float &cost, float &sint) {
+    bool spin_index = true;
+    SpinState sr;
+    float xi, rejf, r;
+    do {
+        xi = nextf(g);
+        xi = fdiv(2.0f * chia2 * xi, 1.0f - xi + chia2);
+        rejf = spin_rejection_f(P, g, imed, qel, elke, beta2, 0.0f, xi, spin_index, true, sr);
+        r = nextf(g);
+    } while (r > rejf);
+    cost = 1.0f - xi;
+    sint = sqrtf(xi * (2.0f - xi));
+}
+
+// mscat(), src/ompmc.c:3606-3785 (Q1: u takes tabulated values only, its interpolation draw is still made)
+static __device__ __noinline__ void mscat_f(const DevProblem &P, Rng &g, int imed, int qel, bool &spin_index, bool &find_index,
+                                            float elke, float beta2, float q1, float lambda, float chia2, float &cost, float &sint,
+                                            MsState &ms, SpinState &sr) {
+    float xi, rejf, r;
+    const float explambda = __expf(-lambda);
+    if (lambda <= 13.8f) {
+        const float sprob = nextf(g);
+        if (sprob < explambda) { cost = 1.0f; sint = 0.0f; return; }
+        float wsum = (1.0f + lambda) * explambda;
+        if (sprob < wsum) {
+            do {
+                xi = nextf(g);
+                xi = fdiv(2.0f * chia2 * xi, 1.0f - xi + chia2);
+                rejf = spin_rejection_f(P, g, imed, qel, elke, beta2, q1, xi, spin_index, false, sr);
+                r = nextf(g);
+            } while (r > rejf);
+            cost = 1.0f - xi;
+            sint = sqrtf(xi * (2.0f - xi));
+            return;
+        }
+        if (lambda <= 1.0f) {
+            int icount = 0;
+            float wprob = explambda, sinz, cosz, phi;
+            wsum = explambda;
+            cost = 1.0f; sint = 0.0f;
+            do {
+                icount += 1;
+                if (icount > 20) break;
+                wprob = wprob * lambda / (float)icount;
+                wsum = wsum + wprob;
+                do {
+                    xi = nextf(g);
+                    xi = fdiv(2.0f * chia2 * xi, 1.0f - xi + chia2);
+                    rejf = spin_rejection_f(P, g, imed, qel, elke, beta2, q1, xi, spin_index, false, sr);
+                    r = nextf(g);
+                } while (r > rejf);
+                cosz = 1.0f - xi;
+                sinz = xi * (2.0f - xi);
+                if (sinz > 1.0E-20f) {
+                    sinz = sqrtf(sinz);
+                    xi = nextf(g);
+                    phi = xi * 6.2831853f;
+                    cost = cost * cosz - sint * sinz * __cosf(phi);
+                    sint = sqrtf(fmaxf(0.0f, (1.0f - cost) * (1.0f + cost)));
+                }
+            } while (wsum <= sprob);
+            return;
+        }
+    }
+    if (lambda <= 1.0E5f) {
+        const float llmbda = __logf(lambda);
+        if (find_index) {
+            float ai = llmbda * (float)P.dllambi;
+            ms.i = (int)ai; ai -= (float)ms.i;
+            xi = nextf(g);
+            if (xi < ai) ms.i += 1;
+            if (ms.i > 63) ms.i = 63;
+            if (q1 < 1.0E-3f) {
+                ms.j = 0;
+            } else if (q1 < 0.5f) {
+                float aj = q1 * (float)P.dqmsi;
+                ms.j = (int)aj; aj -= (float)ms.j;
+                xi = nextf(g);
+                if (xi < aj) ms.j += 1;
+            } else {
+                ms.j = 7;
+            }
+            float om;
+            if (llmbda < 2.2299f)
+                om = chia2 * (lambda + 4.0f) * (1.347006f + llmbda * (0.209364f - llmbda * (0.45525f - llmbda * (0.50142f - 0.081234f * llmbda))));
+            else
+                om = chia2 * (lambda + 4.0f) * (-2.77164f + llmbda * (2.94874f - llmbda * (0.1535754f - llmbda * 0.00552888f)));
+            ms.omega2 = (double)om;
+            find_index = false;
+        }
+        const float omega2 = (float)ms.omega2;
+        const MsEntryF *tab = P.ms_f + (ms.i * OMC_MS_NQ + ms.j) * OMC_MS_NU;
+        do {
+            xi = nextf(g);
+            float ak = xi * 31.0f;
+            int k = (int)ak;
+            ak -= (float)k;
+            const float4 t0 = __ldg(reinterpret_cast<const float4 *>(tab + k));   // {ums, wms, ims, fms}
+            if (ak > t0.y) k = __float_as_int(t0.z);
+            const float u = __ldg(&tab[k].ums);
+            xi = nextf(g);                                     // Q1: dead interpolation draw
+            xi = fdiv(omega2 * u, 1.0f + 0.5f * omega2 - u);
+            if (xi > 1.99999f) xi = 1.99999f;
+            rejf = spin_rejection_f(P, g, imed, qel, elke, beta2, q1, xi, spin_index, false, sr);
+            r = nextf(g);
+        } while (r > rejf);
+        cost = 1.0f - xi;
+        sint = sqrtf(xi * (2.0f - xi));
+    }
+}
+
+// msdist(), src/ompmc.c:3787-3976 (PRESTA-II) in fp32; end point and direction are returned in fp64
+static __device__ __noinline__ double msdist_f(const DevProblem &P, Rng &g, const Part &p, int imed, int qel, double rhof_d, double de_d,
+                                               double tustep_d, double eke_d, double &xf, double &yf, double &zf, double &uf,
+                                               double &vf, double &wf) {
+    const MedRec &M = P.med[imed];
+    MsState ms;
+    SpinState sr;
+    const float rhof = (float)rhof_d, de = (float)de_d, tustep = (float)tustep_d, eke = (float)eke_d;
+    const float xcc = (float)M.xcc, blcc = (float)M.blcc;
+    float e = eke - 0.5f * de;
+    const float tau = e * (1.0f / RMf), tau2 = tau * tau;
+    const float epsilon = fdiv(de, eke), epsilonp = fdiv(de, e);
+    e *= (1.0f - (epsilonp * epsilonp) * fdiv(6.0f + 10.0f * tau + 5.0f * tau2, 24.0f * tau2 + 72.0f * tau + 48.0f));
+    const float p2 = e * (e + 2.0f * RMf);
+    const float beta2 = fdiv(p2, p2 + (RMf * RMf));
+    float chia2 = fdiv(xcc, 4.0f * p2 * blcc);
+    float lambda = fdiv(0.5f * tustep * rhof * blcc, beta2);
+    const float t12 = fdiv(epsilonp, (tau + 1.0f) * (tau + 2.0f));
+    const float temp2 = 0.166666f * (4.0f + tau * (6.0f + tau * (7.0f + tau * (4.0f + tau)))) * t12 * t12;
+    lambda *= (1.0f - temp2);
+    float elke = __logf(e);
+    int lelke = (int)(elke * (float)M.eke1 + (float)M.eke0) - 1;
+    if (lelke < 0) { lelke = 0; elke = (float)((1.0 - M.eke0) / M.eke1); }
+    const ElecBin *B = P.ebin + (size_t)qel * P.nmed * MXEKE + imed * MXEKE + lelke;
+    const float etap = elke * (float)__ldg(&B->eta1) + (float)__ldg(&B->eta0);
+    const float xi_corr = elke * (float)__ldg(&B->q1c1) + (float)__ldg(&B->q1c0);
+    float gamma = elke * (float)__ldg(&B->q2c1) + (float)__ldg(&B->q2c0);
+    const float ms_corr = elke * (float)__ldg(&B->blcce1) + (float)__ldg(&B->blcce0);
+    chia2 *= etap;
+    lambda = fdiv(lambda, etap * (1.0f + chia2));
+    lambda *= ms_corr;
+    const float chilog = __logf(1.0f + frcp(chia2));
+    const float q1 = 2.0f * chia2 * (chilog * (1.0f + chia2) - 1.0f);
+    gamma = fdiv(6.0f * chia2 * (1.0f + chia2) * (chilog * (1.0f + 2.0f * chia2) - 2.0f), q1) * gamma;
+    float xi = q1 * lambda;
+    bool find_index = true, spin_index = true;
+    float w1 = 1.0f, sint1 = 0.0f, cphi1, sphi1, w2 = 1.0f, sint2 = 0.0f, cphi2, sphi2;
+    g.align();
+    mscat_f(P, g, imed, qel, spin_index, find_index, elke, beta2, xi, lambda, chia2, w1, sint1, ms, sr);
+    g.align();
+    azimuth_f(g, cphi1, sphi1);
+    g.align();
+    mscat_f(P, g, imed, qel, spin_index, find_index, elke, beta2, xi, lambda, chia2, w2, sint2, ms, sr);
+    g.align();
+    azimuth_f(g, cphi2, sphi2);
+    const float u2 = sint2 * cphi2, v2 = sint2 * sphi2;
+    float u2p = w1 * u2 + sint1 * w2;
+    float us = u2p * cphi1 - v2 * sphi1, vs = u2p * sphi1 + v2 * cphi1, ws = w1 * w2 - sint1 * u2;
+    xi *= 2.0f * xi_corr;
+    const float eta = nextf(g);
+    const float eta1 = 0.5f * (1.0f - eta);
+    float delta = 0.9082483f - (0.1020621f - 0.0263747f * gamma) * xi;
+    float temp1 = 2.0f + tau;
+    float temp = fdiv(2.0f + tau * temp1, (tau + 1.0f) * temp1);
+    const float c1 = chilog * (1.0f + chia2) - 1.0f, c2 = chilog * (1.0f + 2.0f * chia2) - 2.0f;
+    temp -= fdiv(tau + 1.0f, (tau + 2.0f) * c1);
+    temp *= epsilonp;
+    temp1 = 1.0f - temp;
+    delta += 0.40824829f * (fdiv(epsilon * (tau + 1.0f), (tau + 2.0f) * c1 * c2) - 0.25f * (temp * temp));
+    const float b = eta * delta, cc = eta * (1.0f - delta);
+    const float w1v2 = w1 * v2;
+    float ut = b * sint1 * cphi1 + cc * (cphi1 * u2 - sphi1 * w1v2) + eta1 * us * temp1;
+    float vt = b * sint1 * sphi1 + cc * (sphi1 * u2 + cphi1 * w1v2) + eta1 * vs * temp1;
+    float wt = eta1 * (1.0f + temp) + b * w1 + cc * w2 + eta1 * ws * temp1;
+    const float ustep = tustep * sqrtf(ut * ut + vt * vt + wt * wt);
+    const float u0 = (float)p.u, v0 = (float)p.v, w0 = (float)p.w;
+    const float sint02 = u0 * u0 + v0 * v0;
+    if (sint02 > 1.0E-20f) {
+        const float sint0i = rsqrtf(sint02), sint0 = sint02 * sint0i;
+        const float cphi0 = sint0i * u0, sphi0 = sint0i * v0;
+        u2p = w0 * us + sint0 * ws;
+        ws = w0 * ws - sint0 * us;
+        us = u2p * cphi0 - vs * sphi0;
+        vs = u2p * sphi0 + vs * cphi0;
+        u2p = w0 * ut + sint0 * wt;
+        wt = w0 * wt - sint0 * ut;
+        ut = u2p * cphi0 - vt * sphi0;
+        vt = u2p * sphi0 + vt * cphi0;
+    } else {
+        wt = w0 * wt; ws = w0 * ws;
+    }
+    // keep the direction a unit vector in fp32 (the fp64 path relies on 1e-16 rounding instead)
+    const float nrm = rsqrtf(us * us + vs * vs + ws * ws);
+    xf = p.x + tustep_d * (double)ut; yf = p.y + tustep_d * (double)vt; zf = p.z + tustep_d * (double)wt;
+    uf = (double)(us * nrm); vf = (double)(vs * nrm); wf = (double)(ws * nrm);
+    return (double)ustep;
+}
+
+}  // namespace omc

@@ -69,6 +69,13 @@ struct __align__(32) MsEntry {
     int ims, pad;
 };
 
+// fp32 copy of MsEntry for the single-precision samplers (omc_physics_f32.cuh): one 16-byte load
+struct __align__(16) MsEntryF {
+    float ums, wms;
+    int ims;
+    float fms;
+};
+
 struct SourceDosxyz {       // struct Source, omc_dosxyz.c:342-366
     int spectrum, charge;
     double energy, deltak;
@@ -98,6 +105,8 @@ struct DevProblem {
     double b2spin_min, dbeta2i, espml, dleneri, dqq1i;    // spin_data
     const double *spin_rej;  // [nmed][2][32][16][32]
     const MsEntry *ms;       // [64][8][32]
+    const float *spin_rej_f; // fp32 copies for the wavefront kernels
+    const MsEntryF *ms_f;
     double dllambi, dqmsi;
     SourceDosxyz src;
     int nsplit;

@@ -26,7 +26,12 @@
 // fp32 atomics into a chunk grid folded into the fp64 batch grid at the end of every
 // omc_gpu_run_histories() call (north_star (d)).
 #include "omc_physics.cuh"
+#include "omc_physics_f32.cuh"
 #include "omc_kernels.h"
+
+#ifndef OMC_WAVE_F32
+#define OMC_WAVE_F32 1     // 1: fp32 angle samplers (omc_physics_f32.cuh); 0: the fp64 ones of the lock-step kernel
+#endif
 
 #ifndef OMC_WARP_AGGREGATE_DOSE
 #define OMC_WARP_AGGREGATE_DOSE 0
@@ -402,7 +407,11 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
     if (cls == CLS_CH) {                                       // condensed-history step, :4973-4996
         call_howfar = false;
         de = eloss(B0, P.med[imed], rhof, tustep, e.range, eke0, e.elke, e.lelke);
+#if OMC_WAVE_F32
+        ustep = msdist_f(P, g, p, imed, qel, rhof, de, tustep, eke0, xf, yf, zf, uf, vf, wf);
+#else
         ustep = msdist<true>(P, g, p, imed, qel, rhof, de, tustep, eke0, xf, yf, zf, uf, vf, wf);
+#endif
     } else if (imed == -1) {                                   // :4815-4821
         ustep = tustep; call_howfar = true;
     } else {                                                   // exact boundary crossing, :4997-5057
@@ -455,7 +464,13 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
             chia2 *= pwl(elkems, __ldg(&B0[lelkems].eta1), __ldg(&B0[lelkems].eta0));
             double costhe, sinthe;
             g.align();
+#if OMC_WAVE_F32
+            float cf, sf;
+            sscat_f(P, g, imed, qel, (float)chia2, (float)elkems, (float)beta2, cf, sf);
+            costhe = (double)cf; sinthe = (double)sf;
+#else
             sscat(P, g, imed, qel, chia2, elkems, beta2, costhe, sinthe);
+#endif
             g.align();
             Frame fr;
             uphi21(g, fr, costhe, sinthe, p);
