@@ -46,6 +46,7 @@ struct omc_gpu_ctx {
     unsigned pool_cap = 0, pool_cap_opt = 0;
     int electron_iters = 1, max_cross = 16, check_every = 16;
     unsigned long long waves = 0;
+    int trace = 0;
 };
 
 #define CK(call)                                                                                         \
@@ -92,6 +93,19 @@ static int alloc_queue(omc_gpu_handle h, PartQueue &q, unsigned cap) {
     return 0;
 }
 
+static int alloc_estep_queue(omc_gpu_handle h, EStepQueue &q, unsigned cap) {
+    q.cap = cap;
+    for (int i = 0; i < 21; i++) {
+        CK(cudaMalloc((void **)&q.d[i], (size_t)cap * sizeof(double)));
+        h->wave_bufs.push_back(q.d[i]);
+    }
+    for (int i = 0; i < 2; i++) {
+        CK(cudaMalloc((void **)&q.w[i], (size_t)cap * sizeof(uint4)));
+        h->wave_bufs.push_back(q.w[i]);
+    }
+    return 0;
+}
+
 // Drive waves until every history of [first, first+nhist) has been started and all queues drained.
 static int run_wavefront(omc_gpu_handle h, long long first, long long nhist) {
     DevProblem &P = h->P;
@@ -106,6 +120,8 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist) {
             if (alloc_queue(h, h->wq.ip[i], cap)) return 1;
             if (alloc_queue(h, h->wq.ie[i], cap)) return 1;
         }
+        if (alloc_estep_queue(h, h->wq.ch, cap)) return 1;
+        if (alloc_estep_queue(h, h->wq.bca, cap)) return 1;
         h->pool_cap = cap;
     }
     if (!h->ctl) {
@@ -119,17 +135,22 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist) {
     c.n_src = (unsigned)((unsigned long long)nhist < (unsigned long long)target ? nhist : target);
     CK(cudaMemcpyAsync(h->ctl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
     WaveLaunch L;
-    L.blocks = h->max_blocks > 0 ? h->max_blocks : h->sm_count * wave_blocks_per_sm();
+    int occ[4];
+    wave_blocks_per_sm(occ);
+    for (int i = 0; i < 4; i++) L.blocks[i] = h->max_blocks > 0 ? h->max_blocks : h->sm_count * occ[i];
     L.max_cross = h->max_cross; L.electron_iters = h->electron_iters;
     const int every = h->check_every > 0 ? h->check_every : 1;
     for (unsigned long long wave = 0;; wave++) {
         launch_wave(P, h->ctl, h->wq, L, h->stream);
-        h->launches += 1;
+        h->launches += 5;
         h->waves += 1;
         if ((wave + 1) % every == 0) {
             CK(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
             const WaveCtl &s = *h->ctl_host;
+            if (h->trace)
+                fprintf(stderr, "wave %llu live %u n_src %u P %u E %u IP %u IE %u hist_next %llu\n", wave, s.live, s.n_src, s.n_p[s.parity],
+                        s.n_e[s.parity], s.n_ip[s.parity], s.n_ie[s.parity], s.hist_next);
             if (s.overflow) {
                 h->err = "particle queue overflow on the device: increase option pool_size";
                 return 7;
@@ -381,6 +402,7 @@ int omc_gpu_set_option(omc_gpu_handle h, const char *key, long long value) {
     else if (k == "max_blocks") h->max_blocks = (int)value;
     else if (k == "record_histories") h->record = (int)value;
     else if (k == "pool_size") h->pool_target = (unsigned)value;
+    else if (k == "trace") h->trace = (int)value;
     else if (k == "pool_cap") h->pool_cap_opt = (unsigned)value;
     else if (k == "electron_iters") h->electron_iters = (int)value;
     else if (k == "max_cross") h->max_cross = (int)value;

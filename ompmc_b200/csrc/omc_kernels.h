@@ -29,21 +29,30 @@ constexpr int WAVE_THREADS = 128;   // threads per block == particles per chunk
 
 struct WaveCtl {
     unsigned n_p[2], n_e[2], n_ip[2], n_ie[2];   // queue fill counts, [parity]: cur = parity, next = parity ^ 1
-    unsigned tk[5];                              // chunk tickets per class
+    unsigned n_ch, n_bca;                        // step-class queues, filled and drained inside one wave
+    unsigned tk[5];                              // chunk tickets per class (misc_kernel)
     unsigned n_src;                              // histories injected by the current wave
-    unsigned done, parity, target, overflow, live, waves;
+    unsigned parity, target, overflow, live, waves;
     unsigned long long hist_next, hist_end;
+};
+
+// electrons between "step size known" and "step taken": Part + EStep (21 doubles) + {ir, iq, lelke, imed} + rng
+struct EStepQueue {
+    double *d[21];
+    uint4 *w[2];
+    unsigned cap;
 };
 
 struct WaveQueues {
     PartQueue p[2], e[2], ip[2], ie[2];
+    EStepQueue ch, bca;
 };
 
 struct WaveLaunch {
-    int blocks, max_cross, electron_iters;
+    int blocks[4], max_cross, electron_iters;
 };
 
-int wave_blocks_per_sm();
+void wave_blocks_per_sm(int out[4]);
 void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, cudaStream_t s);
 void launch_flush(float *g32, double *g64, long long n, cudaStream_t s);
 

@@ -1,30 +1,33 @@
 // omc_wavefront.cu -- production path: event-based particle queues (BASELINE.json north_star (a)).
 //
-// Particles live in HBM as structure-of-arrays queues.  One launch of wave_kernel ("a wave") moves every
-// live particle through one event of its class.  The kernel is persistent (one grid that fills the
-// machine); its blocks pull typed CHUNKS of 128 particles from per-class tickets, so a block -- and
-// every warp in it -- runs a single code path at a time:
+// Particles live in HBM as structure-of-arrays queues.  One "wave" moves every live particle through one
+// event of its class, with one kernel per event class so that ALL warps on the machine run the same,
+// instruction-cache-sized code at the same time:
 //
-//     chunk E   electron_chunk     E[cur]  -> E[next] (still travelling) | IE[next] (interaction due)
-//     chunk P   photon_chunk       P[cur]  -> P[next] (flight unfinished)| IP[next] (at a site)
-//     chunk IE  e_interact_chunk   IE[cur] -> E[next], P[next]      brems / Moller / Bhabha / annihilation
-//     chunk IP  p_interact_chunk   IP[cur] -> P[next], E[next]      Compton / pair / photo / Rayleigh
-//     chunk S   source_chunk       initHistory() for new history ids -> P[next] or E[next]
+//   misc_kernel     persistent, typed 128-particle chunks pulled from tickets:
+//        P   photon flight       P[cur]  -> P[next] (flight unfinished) | IP[next] (at an interaction site)
+//        IP  photon interaction  IP[cur] -> P[next], E[next]            Compton / pair / photo / Rayleigh
+//        IE  e+- interaction     IE[cur] -> E[next], P[next]            brems / Moller / Bhabha / annihilation
+//        S   source              initHistory() for new history ids -> P[next] or E[next]
+//   esize_kernel    E[cur] -> CH | BCA      cut-off test, distance to the next interaction, step-size limits
+//   ech_kernel      CH  -> E[next] | IE[next]   condensed-history step (PRESTA-II msdist)
+//   ebca_kernel     BCA -> E[next] | IE[next]   boundary-crossing / single-scattering step
+//   advance_kernel  swaps cur/next, sizes the next injection so that `pool_size` particles stay in flight
 //
-// (interaction queues are consumed one wave after they were filled, which makes all five chunk classes
-// independent within a launch; the last block to finish swaps cur/next and sizes the next injection).
-// Inside an electron chunk the block re-sorts its electrons in shared memory after the step size is
-// known, condensed-history steps to the low thread ids and boundary-crossing (single-scattering) steps
-// to the high ones, because those two paths are long and otherwise split every warp in half.
+// (interaction queues are consumed one wave after they were filled).  Sorting electrons into the CH and
+// BCA queues after the step size is known matters because those two long paths otherwise split every warp.
+// An earlier version fused everything into one persistent kernel with an in-block shared-memory re-sort;
+// ncu showed it stalled on instruction fetch (stall_no_instruction on top, ~100 KB hot path, every block at
+// a different pc) and on the re-sort barriers, see profiles/r01_wave_kernel_summary.md.
 //
-// Physics = the same device functions as the lock-step kernel (omc_physics.cuh).  Differences that
-// are statistically neutral: every particle owns a Philox sub-stream derived from its parent's (results
-// do not depend on scheduling); unread words of a Philox block are dropped at a few fixed points so
-// that warps refill together; the reference's zero-length "second ustep iteration" (src/ompmc.c:4787
-// re-initialises total_tstep) is not executed, its only effect being one wasted draw;
-// with nsplit == 1 the unused survivor-index draw of photon() (:1916) is skipped.  Dose is scored with
-// fp32 atomics into a chunk grid folded into the fp64 batch grid at the end of every
-// omc_gpu_run_histories() call (north_star (d)).
+// Physics = the same device functions as the lock-step kernel (omc_physics.cuh) except that the elastic
+// scattering angles are sampled in fp32 (omc_physics_f32.cuh).  Differences that are statistically neutral:
+// every particle owns a Philox sub-stream derived from its parent's (results do not depend on scheduling);
+// unread words of a Philox block are dropped at fixed physics points so that warps refill together; the
+// reference's zero-length "second ustep iteration" (src/ompmc.c:4787 re-initialises total_tstep, see
+// DESIGN.md) is not executed, its only effect being one wasted draw; with nsplit == 1 the unused
+// survivor-index draw of photon() (:1916) is skipped.  Dose is scored with fp32 atomics into a chunk grid
+// folded into the fp64 batch grid at the end of every omc_gpu_run_histories() call (north_star (d)).
 #include "omc_physics.cuh"
 #include "omc_physics_f32.cuh"
 #include "omc_kernels.h"
@@ -63,7 +66,7 @@ __device__ __forceinline__ void q_store(const PartQueue &q, unsigned i, const Pa
 
 // warp-aggregated slot reservation: one atomic per (warp, queue) instead of one per lane
 __device__ __forceinline__ unsigned q_reserve(unsigned *count) {
-    const unsigned m = __activemask();
+    const unsigned m = __match_any_sync(__activemask(), (unsigned long long)count);
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(m) - 1;
     unsigned base = 0;
@@ -286,31 +289,23 @@ struct EStep {
     double eke, elke, demfp, sig0, total_tstep, range, tustep, tperp, rhof, ecut, dedx, blccl, ssmfp;
     int lelke, imed;
 };
-constexpr int ES_ND = 8 + 13;   // doubles per exchanged electron (Part + EStep)
-constexpr int ES_NI = 8;        // 32-bit words per exchanged electron (ir, iq, rng x4, lelke, imed)
-
-struct ESmem {
-    double d[ES_ND][NT];
-    unsigned w[ES_NI][NT];
-    unsigned wsum[2][NT / 32];
-};
-
-__device__ __forceinline__ void es_put(ESmem &S, int s, const Part &p, const Rng &g, const EStep &e) {
+// (EStepQueue in omc_kernels.h carries Part + Rng + EStep between esize_kernel and ech/ebca_kernel)
+__device__ __forceinline__ void es_put(const EStepQueue &S, unsigned s, const Part &p, const Rng &g, const EStep &e) {
     S.d[0][s] = p.x; S.d[1][s] = p.y; S.d[2][s] = p.z; S.d[3][s] = p.u; S.d[4][s] = p.v; S.d[5][s] = p.w; S.d[6][s] = p.e; S.d[7][s] = p.wt;
     S.d[8][s] = e.eke; S.d[9][s] = e.elke; S.d[10][s] = e.demfp; S.d[11][s] = e.sig0; S.d[12][s] = e.total_tstep; S.d[13][s] = e.range;
     S.d[14][s] = e.tustep; S.d[15][s] = e.tperp; S.d[16][s] = e.rhof; S.d[17][s] = e.ecut; S.d[18][s] = e.dedx; S.d[19][s] = e.blccl;
     S.d[20][s] = e.ssmfp;
-    S.w[0][s] = (unsigned)p.ir; S.w[1][s] = (unsigned)p.iq; S.w[2][s] = g.h0; S.w[3][s] = g.h1; S.w[4][s] = g.stream;
-    S.w[5][s] = g.ndraws(); S.w[6][s] = (unsigned)e.lelke; S.w[7][s] = (unsigned)e.imed;
+    S.w[0][s] = make_uint4((unsigned)p.ir, (unsigned)p.iq, (unsigned)e.lelke, (unsigned)e.imed);
+    S.w[1][s] = make_uint4(g.h0, g.h1, g.stream, g.ndraws());
 }
-__device__ __forceinline__ void es_get(const ESmem &S, int s, Part &p, Rng &g, EStep &e, const DevProblem &P) {
+__device__ __forceinline__ void es_get(const EStepQueue &S, unsigned s, Part &p, Rng &g, EStep &e, const DevProblem &P) {
     p.x = S.d[0][s]; p.y = S.d[1][s]; p.z = S.d[2][s]; p.u = S.d[3][s]; p.v = S.d[4][s]; p.w = S.d[5][s]; p.e = S.d[6][s]; p.wt = S.d[7][s];
     e.eke = S.d[8][s]; e.elke = S.d[9][s]; e.demfp = S.d[10][s]; e.sig0 = S.d[11][s]; e.total_tstep = S.d[12][s]; e.range = S.d[13][s];
     e.tustep = S.d[14][s]; e.tperp = S.d[15][s]; e.rhof = S.d[16][s]; e.ecut = S.d[17][s]; e.dedx = S.d[18][s]; e.blccl = S.d[19][s];
     e.ssmfp = S.d[20][s];
-    p.ir = (int)S.w[0][s]; p.iq = (int)S.w[1][s];
-    g.seed(P.seed0, P.seed1, ((unsigned long long)S.w[3][s] << 32) | S.w[2][s], S.w[4][s], S.w[5][s]);
-    e.lelke = (int)S.w[6][s]; e.imed = (int)S.w[7][s];
+    const uint4 a = S.w[0][s], r = S.w[1][s];
+    p.ir = (int)a.x; p.iq = (int)a.y; e.lelke = (int)a.z; e.imed = (int)a.w;
+    g.seed(P.seed0, P.seed1, ((unsigned long long)r.y << 32) | r.x, r.z, r.w);
 }
 
 // Phase A: cut-off test, distance to the next discrete interaction, step-size restrictions.
@@ -521,122 +516,7 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
     return (r < pbr2) ? TAG_BHABHA : TAG_ANNIH;
 }
 
-__device__ void electron_chunk(const DevProblem &P, const WaveArgs &A, int par, unsigned i, unsigned n, ESmem &S, Tally &t) {
-    WaveCtl *ctl = A.ctl;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    Part p; Rng g; EStep e;
-    bool have = false;
-    if (i < n) {
-        double aux; int tag;
-        q_load(A.Q.e[par], i, p, g, P, aux, tag);
-        have = true;
-    }
-    for (int it = 0; it < A.electron_iters; it++) {
-        int cls = CLS_NONE, st = 0;
-        if (have) {
-            cls = estep_size(P, g, p, e, t, st);
-            if (cls == CLS_NONE) {                             // finished at the cut-off
-                if (st > 0) q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st);
-                have = false;
-            }
-        }
-        // block-wide re-sort: CH steps -> threads [0, nch), BCA steps -> [nch, nch + nbca)
-        const unsigned mch = __ballot_sync(0xffffffffu, cls == CLS_CH), mbc = __ballot_sync(0xffffffffu, cls == CLS_BCA);
-        if (lane == 0) { S.wsum[0][wid] = __popc(mch); S.wsum[1][wid] = __popc(mbc); }
-        __syncthreads();
-        unsigned nch = 0, nbc = 0, och = 0, obc = 0;
-#pragma unroll
-        for (int k = 0; k < NT / 32; k++) {
-            const unsigned a = S.wsum[0][k], b = S.wsum[1][k];
-            if (k < wid) { och += a; obc += b; }
-            nch += a; nbc += b;
-        }
-        if (nch + nbc == 0) break;                             // block-uniform
-        const unsigned below = (1u << lane) - 1u;
-        if (cls == CLS_CH) es_put(S, och + __popc(mch & below), p, g, e);
-        else if (cls == CLS_BCA) es_put(S, nch + obc + __popc(mbc & below), p, g, e);
-        __syncthreads();
-        have = (unsigned)tid < nch + nbc;
-        if (have) {
-            es_get(S, tid, p, g, e, P);
-            st = estep_do(P, g, p, e, (unsigned)tid < nch ? CLS_CH : CLS_BCA, t);
-            if (st != 0) {
-                if (st > 0) q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st);
-                have = false;
-            }
-        }
-        __syncthreads();                                       // S is reused by the next iteration
-    }
-    if (have) q_push(A.Q.e[par ^ 1], &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
-}
-
-// ---------------------------------------------------------------------------------------------
-// the wave kernel
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned vload(const unsigned *p) { return *reinterpret_cast<const volatile unsigned *>(p); }
-
-// swap cur/next and size the next injection; executed by the last block to finish a wave
-__device__ void advance(const DevProblem &P, WaveCtl *c) {
-    const int par = (int)c->parity, nxt = par ^ 1;
-    c->hist_next += c->n_src;
-    P.counters->histories += c->n_src;
-    c->n_p[par] = 0; c->n_e[par] = 0; c->n_ip[par] = 0; c->n_ie[par] = 0;
-    const unsigned live = vload(&c->n_p[nxt]) + vload(&c->n_e[nxt]) + vload(&c->n_ip[nxt]) + vload(&c->n_ie[nxt]);
-    const unsigned long long left = c->hist_end - c->hist_next;
-    const unsigned room = (live < c->target) ? c->target - live : 0u;
-    c->n_src = (unsigned)(left < (unsigned long long)room ? left : (unsigned long long)room);
-    c->live = live;
-    c->tk[0] = c->tk[1] = c->tk[2] = c->tk[3] = c->tk[4] = 0;
-    c->done = 0;
-    c->parity = (unsigned)nxt;
-    c->waves += 1;
-    const unsigned ov = vload(&c->overflow);
-    if (ov) P.counters->errors = ov;
-}
-
-__global__ void __launch_bounds__(NT, OMC_WAVE_MINBLOCKS) wave_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ WaveArgs A) {
-    __shared__ ESmem S;
-    __shared__ unsigned s_type, s_chunk, s_cnt[5];
-    WaveCtl *ctl = A.ctl;
-    const int par = (int)ctl->parity;
-    if (threadIdx.x == 0) {
-        // chunk classes: 0 electron interactions, 1 photon interactions, 2 source, 3 photon flights, 4 electron steps
-        // (counts are clamped to the queue capacity: after an overflow the counters run past it)
-        const unsigned cap = A.Q.p[0].cap;
-        s_cnt[0] = min(ctl->n_ie[par], cap); s_cnt[1] = min(ctl->n_ip[par], cap); s_cnt[2] = ctl->n_src;
-        s_cnt[3] = min(ctl->n_p[par], cap); s_cnt[4] = min(ctl->n_e[par], cap);
-    }
-    __syncthreads();
-    Tally t = {0, 0, 0};
-    double ensrc = 0.0;
-    unsigned open = 0x1f, rr = blockIdx.x;                     // (thread 0) classes that may still have chunks; pull phase
-    for (;;) {
-        if (threadIdx.x == 0) {
-            // pull pattern IE, IP, S, P, E, E, E, E: electrons dominate the work, the latency-bound photon chunks
-            // are interleaved with them.  8 consecutive phases visit every class, so type 5 == nothing left.
-            unsigned type = 5, chunk = 0;
-            for (int tries = 0; tries < 8 && open; tries++) {
-                const unsigned k = rr & 7u;
-                rr++;
-                const unsigned c = k < 4u ? k : 4u;
-                if (!(open & (1u << c))) continue;
-                const unsigned tk = atomicAdd(&ctl->tk[c], 1u);
-                if ((unsigned long long)tk * NT < s_cnt[c]) { type = c; chunk = tk; break; }
-                open &= ~(1u << c);
-            }
-            s_type = type; s_chunk = chunk;
-        }
-        __syncthreads();
-        const unsigned type = s_type, i = s_chunk * NT + threadIdx.x;
-        if (type == 5) break;
-        if (type == 4) electron_chunk(P, A, par, i, s_cnt[4], S, t);
-        else if (type == 3) photon_chunk(P, A, par, i, s_cnt[3], t);
-        else if (type == 2) source_chunk(P, A, par, i, s_cnt[2], ensrc);
-        else if (type == 1) p_interact_chunk(P, A, par, i, s_cnt[1]);
-        else e_interact_chunk(P, A, par, i, s_cnt[0]);
-        __syncthreads();
-    }
-    // per-block tallies
+__device__ __forceinline__ void flush_tally(const DevProblem &P, Tally &t, double ensrc) {
     for (int o = 16; o > 0; o >>= 1) {
         ensrc += __shfl_xor_sync(0xffffffffu, ensrc, o);
         t.ndep += __shfl_xor_sync(0xffffffffu, t.ndep, o);
@@ -649,15 +529,116 @@ __global__ void __launch_bounds__(NT, OMC_WAVE_MINBLOCKS) wave_kernel(const __gr
         if (t.nestep) atomicAdd(&P.counters->electron_steps, (unsigned long long)t.nestep);
         if (t.npstep) atomicAdd(&P.counters->photon_steps, (unsigned long long)t.npstep);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned d = atomicAdd(&ctl->done, 1u);
-        if (d == gridDim.x - 1) {
-            __threadfence();
-            advance(P, ctl);
+}
+
+// ---------------------------------------------------------------------------------------------
+// electron kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) esize_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ WaveArgs A) {
+    WaveCtl *ctl = A.ctl;
+    const int par = (int)ctl->parity;
+    const unsigned n = min(ctl->n_e[par], A.Q.e[0].cap);
+    Tally t = {0, 0, 0};
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Part p; Rng g; EStep e; double aux; int tag, st;
+        q_load(A.Q.e[par], i, p, g, P, aux, tag);
+        const int cls = estep_size(P, g, p, e, t, st);
+        if (cls == CLS_NONE) {
+            if (st > 0) q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st);
+            continue;
+        }
+        // (two branches on purpose: q_reserve() aggregates over the lanes that are active TOGETHER)
+        if (cls == CLS_CH) {
+            const unsigned slot = q_reserve(&ctl->n_ch);
+            if (slot < A.Q.ch.cap) es_put(A.Q.ch, slot, p, g, e);
+            else atomicAdd(&ctl->overflow, 1u);
+        } else {
+            const unsigned slot = q_reserve(&ctl->n_bca);
+            if (slot < A.Q.bca.cap) es_put(A.Q.bca, slot, p, g, e);
+            else atomicAdd(&ctl->overflow, 1u);
         }
     }
+    flush_tally(P, t, 0.0);
+}
+
+template <int CLS>
+__global__ void __launch_bounds__(NT) edo_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ WaveArgs A) {
+    WaveCtl *ctl = A.ctl;
+    const int par = (int)ctl->parity;
+    const EStepQueue &S = (CLS == CLS_CH) ? A.Q.ch : A.Q.bca;
+    const unsigned n = min(CLS == CLS_CH ? ctl->n_ch : ctl->n_bca, S.cap);
+    Tally t = {0, 0, 0};
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Part p; Rng g; EStep e;
+        es_get(S, i, p, g, e, P);
+        const int st = estep_do(P, g, p, e, CLS, t);
+        if (st == 0) q_push(A.Q.e[par ^ 1], &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
+        else if (st > 0) q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st);
+    }
+    flush_tally(P, t, 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// photons, interactions, source: persistent kernel, typed chunks
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned vload(const unsigned *p) { return *reinterpret_cast<const volatile unsigned *>(p); }
+
+__global__ void __launch_bounds__(NT) misc_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ WaveArgs A) {
+    __shared__ unsigned s_type, s_chunk, s_cnt[4];
+    WaveCtl *ctl = A.ctl;
+    const int par = (int)ctl->parity;
+    if (threadIdx.x == 0) {
+        // chunk classes: 0 electron interactions, 1 photon interactions, 2 source, 3 photon flights
+        // (counts are clamped to the queue capacity: after an overflow the counters run past it)
+        const unsigned cap = A.Q.p[0].cap;
+        s_cnt[0] = min(ctl->n_ie[par], cap); s_cnt[1] = min(ctl->n_ip[par], cap); s_cnt[2] = ctl->n_src;
+        s_cnt[3] = min(ctl->n_p[par], cap);
+    }
+    __syncthreads();
+    Tally t = {0, 0, 0};
+    double ensrc = 0.0;
+    unsigned open = 0xf, rr = blockIdx.x;                      // (thread 0) classes that may still have chunks; pull phase
+    for (;;) {
+        if (threadIdx.x == 0) {
+            unsigned type = 4, chunk = 0;
+            for (int tries = 0; tries < 4 && open; tries++) {
+                const unsigned c = rr & 3u;
+                rr++;
+                if (!(open & (1u << c))) continue;
+                const unsigned tk = atomicAdd(&ctl->tk[c], 1u);
+                if ((unsigned long long)tk * NT < s_cnt[c]) { type = c; chunk = tk; break; }
+                open &= ~(1u << c);
+            }
+            s_type = type; s_chunk = chunk;
+        }
+        __syncthreads();
+        const unsigned type = s_type, i = s_chunk * NT + threadIdx.x;
+        if (type == 4) break;
+        if (type == 3) photon_chunk(P, A, par, i, s_cnt[3], t);
+        else if (type == 2) source_chunk(P, A, par, i, s_cnt[2], ensrc);
+        else if (type == 1) p_interact_chunk(P, A, par, i, s_cnt[1]);
+        else e_interact_chunk(P, A, par, i, s_cnt[0]);
+        __syncthreads();
+    }
+    flush_tally(P, t, ensrc);
+}
+
+// swap cur/next and size the next injection (one thread, after all kernels of the wave)
+__global__ void advance_kernel(const __grid_constant__ DevProblem P, WaveCtl *c) {
+    if (blockIdx.x || threadIdx.x) return;
+    const int par = (int)c->parity, nxt = par ^ 1;
+    c->hist_next += c->n_src;
+    P.counters->histories += c->n_src;
+    c->n_p[par] = 0; c->n_e[par] = 0; c->n_ip[par] = 0; c->n_ie[par] = 0; c->n_ch = 0; c->n_bca = 0;
+    const unsigned live = c->n_p[nxt] + c->n_e[nxt] + c->n_ip[nxt] + c->n_ie[nxt];
+    const unsigned long long left = c->hist_end - c->hist_next;
+    const unsigned room = (live < c->target) ? c->target - live : 0u;
+    c->n_src = (unsigned)(left < (unsigned long long)room ? left : (unsigned long long)room);
+    c->live = live;
+    c->tk[0] = c->tk[1] = c->tk[2] = c->tk[3] = c->tk[4] = 0;
+    c->parity = (unsigned)nxt;
+    c->waves += 1;
+    if (c->overflow) P.counters->errors = c->overflow;
 }
 
 // fold the fp32 chunk grid into the fp64 batch grid
@@ -669,16 +650,24 @@ __global__ void flush_kernel(float *__restrict__ g32, double *__restrict__ g64, 
 }
 
 // ---- host-side launchers ----------------------------------------------------------------------
-int wave_blocks_per_sm() {
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wave_kernel, NT, 0) != cudaSuccess || n < 1) n = 1;
-    return n;
+void wave_blocks_per_sm(int out[4]) {
+    const void *k[4] = {(const void *)misc_kernel, (const void *)esize_kernel, (const void *)edo_kernel<CLS_CH>,
+                        (const void *)edo_kernel<CLS_BCA>};
+    for (int i = 0; i < 4; i++) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k[i], NT, 0) != cudaSuccess || n < 1) n = 1;
+        out[i] = n;
+    }
 }
 
 void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, cudaStream_t s) {
     WaveArgs A;
     A.ctl = ctl; A.Q = Q; A.max_cross = L.max_cross; A.electron_iters = L.electron_iters;
-    wave_kernel<<<L.blocks, NT, 0, s>>>(P, A);
+    misc_kernel<<<L.blocks[0], NT, 0, s>>>(P, A);
+    esize_kernel<<<L.blocks[1], NT, 0, s>>>(P, A);
+    edo_kernel<CLS_CH><<<L.blocks[2], NT, 0, s>>>(P, A);
+    edo_kernel<CLS_BCA><<<L.blocks[3], NT, 0, s>>>(P, A);
+    advance_kernel<<<1, 32, 0, s>>>(P, ctl);
 }
 
 void launch_flush(float *g32, double *g64, long long n, cudaStream_t s) {
