@@ -243,7 +243,10 @@ class GpuTransport:
     def counters(self) -> dict:
         c = Counters()
         self._ck(self.lib.omc_gpu_get_counters(self.h, C.byref(c)), "omc_gpu_get_counters")
-        return {n: int(getattr(c, n)) for n in COUNTER_NAMES}
+        out = {n: int(getattr(c, n)) for n in COUNTER_NAMES}
+        if any(c.reserved):
+            out["reserved"] = [int(v) for v in c.reserved[:4]]
+        return out
 
     def stream_ptr(self) -> int:
         return int(self.lib.omc_gpu_stream(self.h) or 0)

@@ -46,7 +46,8 @@ struct omc_gpu_ctx {
     unsigned pool_cap = 0, pool_cap_opt = 0;
     int electron_iters = 1, max_cross = 16, check_every = 16;
     unsigned long long waves = 0;
-    int trace = 0;
+    int trace = 0, use_graph = 1;
+    unsigned drain_threshold = 32768;
 };
 
 #define CK(call)                                                                                         \
@@ -140,24 +141,63 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist) {
     for (int i = 0; i < 4; i++) L.blocks[i] = h->max_blocks > 0 ? h->max_blocks : h->sm_count * occ[i];
     L.max_cross = h->max_cross; L.electron_iters = h->electron_iters;
     const int every = h->check_every > 0 ? h->check_every : 1;
-    for (unsigned long long wave = 0;; wave++) {
-        launch_wave(P, h->ctl, h->wq, L, h->stream);
-        h->launches += 5;
-        h->waves += 1;
-        if ((wave + 1) % every == 0) {
-            CK(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
-            const WaveCtl &s = *h->ctl_host;
-            if (h->trace)
-                fprintf(stderr, "wave %llu live %u n_src %u P %u E %u IP %u IE %u hist_next %llu\n", wave, s.live, s.n_src, s.n_p[s.parity],
-                        s.n_e[s.parity], s.n_ip[s.parity], s.n_ie[s.parity], s.hist_next);
-            if (s.overflow) {
-                h->err = "particle queue overflow on the device: increase option pool_size";
-                return 7;
-            }
-            if (s.hist_next >= s.hist_end && s.live == 0 && s.n_src == 0) break;
+    // `every` waves are captured once into a CUDA graph (all launch parameters are wave-invariant: cur/next
+    // parity lives in WaveCtl on the device), so the host issues one graph launch per `every` waves
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    if (h->use_graph) {
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        for (int k = 0; k < every; k++) launch_wave(P, h->ctl, h->wq, L, h->stream);
+        CK(cudaStreamEndCapture(h->stream, &graph));
+        CK(cudaGraphInstantiate(&gexec, graph, 0));
+    }
+    int rc = 0;
+    bool drained = false;
+    for (unsigned long long wave = 0;; wave += every) {
+        if (gexec) {
+            CK(cudaGraphLaunch(gexec, h->stream));
+        } else {
+            for (int k = 0; k < every; k++) launch_wave(P, h->ctl, h->wq, L, h->stream);
         }
-        if (wave > 50000000ull) return fail(h, "wavefront did not terminate");
+        h->launches += 5ull * every;
+        h->waves += every;
+        CK(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        const WaveCtl &s = *h->ctl_host;
+        if (h->trace)
+            fprintf(stderr, "wave %llu live %u n_src %u P %u E %u IP %u IE %u hist_next %llu\n", wave + every, s.live, s.n_src,
+                    s.n_p[s.parity], s.n_e[s.parity], s.n_ip[s.parity], s.n_ie[s.parity], s.hist_next);
+        if (s.overflow) {
+            h->err = "particle queue overflow on the device: increase option pool_size";
+            rc = 7;
+            break;
+        }
+        const bool exhausted = s.hist_next >= s.hist_end && s.n_src == 0;
+        if (exhausted && s.live == 0) break;
+        if (exhausted && s.live <= h->drain_threshold) { drained = true; break; }
+        if (wave > 50000000ull) { rc = fail(h, "wavefront did not terminate"); break; }
+    }
+    if (gexec) { cudaGraphExecDestroy(gexec); cudaGraphDestroy(graph); }
+    if (rc) return rc;
+    if (drained) {
+        // few particles left: one thread follows each to the end (omc_lockstep.cu: drain_kernel)
+        const int par = (int)h->ctl_host->parity;
+        const int tpb = 128;
+        const int blocks = h->sm_count * lockstep_blocks_per_sm(tpb);
+        const int depth = 48;
+        const size_t need = (size_t)depth * blocks * tpb * sizeof(Part);
+        if (need > h->stack_bytes) {
+            cudaFree(h->stack);
+            h->stack = nullptr; h->stack_bytes = 0;
+            CK(cudaMalloc((void **)&h->stack, need));
+            h->stack_bytes = need;
+        }
+        DrainArgs D;
+        D.q[0] = h->wq.p[par]; D.q[1] = h->wq.e[par]; D.q[2] = h->wq.ip[par]; D.q[3] = h->wq.ie[par];
+        D.count[0] = &h->ctl->n_p[par]; D.count[1] = &h->ctl->n_e[par]; D.count[2] = &h->ctl->n_ip[par]; D.count[3] = &h->ctl->n_ie[par];
+        D.ticket = &h->ctl->drain_ticket;
+        launch_drain(P, D, h->stack, depth, blocks, h->stream);
+        h->launches += 1;
     }
     launch_flush(P.endep32, P.endep, P.nreg, h->stream);
     h->launches += 1;
@@ -403,6 +443,8 @@ int omc_gpu_set_option(omc_gpu_handle h, const char *key, long long value) {
     else if (k == "record_histories") h->record = (int)value;
     else if (k == "pool_size") h->pool_target = (unsigned)value;
     else if (k == "trace") h->trace = (int)value;
+    else if (k == "use_graph") h->use_graph = (int)value;
+    else if (k == "drain_threshold") h->drain_threshold = (unsigned)value;
     else if (k == "pool_cap") h->pool_cap_opt = (unsigned)value;
     else if (k == "electron_iters") h->electron_iters = (int)value;
     else if (k == "max_cross") h->max_cross = (int)value;

@@ -32,7 +32,7 @@ struct WaveCtl {
     unsigned n_ch, n_bca;                        // step-class queues, filled and drained inside one wave
     unsigned tk[5];                              // chunk tickets per class (misc_kernel)
     unsigned n_src;                              // histories injected by the current wave
-    unsigned parity, target, overflow, live, waves;
+    unsigned parity, target, overflow, live, waves, drain_ticket;
     unsigned long long hist_next, hist_end;
 };
 
@@ -53,6 +53,15 @@ struct WaveLaunch {
 };
 
 void wave_blocks_per_sm(int out[4]);
+
+// omc_lockstep.cu: finish the last particles of a wavefront run one per thread (see drain_kernel);
+// queues = {P, E, IP, IE} of the current wave, tags as in omc_wavefront.cu (TAG_*)
+struct DrainArgs {
+    PartQueue q[4];
+    const unsigned *count[4];
+    unsigned *ticket;
+};
+void launch_drain(const DevProblem &P, const DrainArgs &D, Part *stack, int depth, int blocks, cudaStream_t stream);
 void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, cudaStream_t s);
 void launch_flush(float *g32, double *g64, long long n, cudaStream_t s);
 

@@ -500,6 +500,85 @@ __global__ void __launch_bounds__(128) lockstep_kernel(const __grid_constant__ D
     if (nerr) atomicAdd(&P.counters->errors, nerr);
 }
 
+// Drain kernel for the wavefront path.  When only a few thousand particles are left in flight a wave costs
+// its latency, not its work, and the stragglers (e.g. electrons crossing hundreds of air voxels) need
+// thousands more waves.  Each thread instead takes one queued particle -- from the photon, electron or
+// pending-interaction queues of the current wave -- and follows it and everything it creates to the end
+// with the per-thread LIFO shower above, continuing the particle's own Philox stream.
+__global__ void __launch_bounds__(128) drain_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ DrainArgs D,
+                                                    Part *stack, int depth) {
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned n[4], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { n[k] = min(*D.count[k], D.q[k].cap); tot += n[k]; }
+    HistCtx c;
+    c.s.base = stack + tid;
+    c.s.stride = nthreads;
+    c.depth = depth;
+    c.nphot_steps = c.nelec_steps = 0;
+    unsigned long long ndep = 0, nerr = 0;
+    for (;;) {
+        unsigned j = atomicAdd(D.ticket, 1u);
+        if (j >= tot) break;
+        int k = 0;
+        while (j >= n[k]) { j -= n[k]; k++; }
+        const PartQueue &q = D.q[k];
+        Part p, s2;
+        p.x = q.x[j]; p.y = q.y[j]; p.z = q.z[j]; p.u = q.u[j]; p.v = q.v[j]; p.w = q.w[j]; p.e = q.e[j]; p.wt = q.wt[j];
+        const int2 a = q.irq[j];
+        p.ir = a.x; p.iq = (int)(short)(a.y & 0xffff);
+        const int tag = a.y >> 16;
+        const uint4 r = q.rng[j];
+        c.g.seed(P.seed0, P.seed1, ((unsigned long long)r.y << 32) | r.x, r.z, r.w);
+        c.ndeposit = 0; c.flags = 0; c.edep_sum = 0.0;
+        bool two = false;
+        if (tag != 0) {                                       // interaction that was due in the next wave
+            const RegionRec R = load_region(P, p.ir);
+            const int imed = R.med;
+            switch (tag) {
+                case 1: compton(c.g, p, s2); two = true; break;
+                case 2: pair(P, c.g, p, s2, imed); two = true; break;
+                case 3: photo(c.g, p, R.ecut); break;
+                case 4: {
+                    const MedRec &M = P.med[imed];
+                    const double gle = log(p.e);
+                    const PhotBin *B = P.phot + imed * MXGE + ((int)(gle * M.ge1 + M.ge0) - 1);
+                    rayleigh(P, c.g, p, pwl(gle, __ldg(&B->pmax1), __ldg(&B->pmax0)), p.e);
+                } break;
+                case 5: brems(P, c.g, p, s2, imed, 1); two = true; break;
+                case 6: two = moller(P, c.g, p, s2, imed); break;
+                case 7: bhabha(P, c.g, p, s2, imed); two = true; break;
+                case 8: annih(c.g, p, s2, 1); two = true; break;
+                default: rannih(c.g, p, s2, 1); two = true; break;
+            }
+        }
+        c.np = 0;
+        c.s[0] = p;
+        if (two) { c.s[1] = s2; c.np = 1; }
+        const unsigned steps0 = c.nelec_steps;
+        while (c.np >= 0) {
+            if (c.s[c.np].iq == 0) photon_ls(P, c);          // a photon caught in mid flight resamples its path (memoryless)
+            else electron_ls(P, c);
+        }
+        ndep += c.ndeposit; nerr += (c.flags & 1u);
+        atomicMax(&P.counters->reserved[0], (unsigned long long)(c.nelec_steps - steps0));   // longest drained chain
+        if (c.nelec_steps - steps0 > 20000u) {
+            atomicAdd(&P.counters->reserved[1], 1ull);
+            P.counters->reserved[2] = (unsigned long long)__double_as_longlong(p.e);
+            P.counters->reserved[3] = (unsigned long long)(unsigned)p.ir | ((unsigned long long)(unsigned)(p.iq + 2) << 32);
+        }
+    }
+    atomicAdd(&P.counters->photon_steps, (unsigned long long)c.nphot_steps);
+    atomicAdd(&P.counters->electron_steps, (unsigned long long)c.nelec_steps);
+    atomicAdd(&P.counters->deposits, ndep);
+    if (nerr) atomicAdd(&P.counters->errors, nerr);
+}
+
+void launch_drain(const DevProblem &P, const DrainArgs &D, Part *stack, int depth, int blocks, cudaStream_t stream) {
+    drain_kernel<<<blocks, 128, 0, stream>>>(P, D, stack, depth);
+}
+
 int lockstep_blocks_per_sm(int threads) {
     int n = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lockstep_kernel, threads, 0) != cudaSuccess) n = 1;

@@ -81,23 +81,40 @@ def test_wavefront_matches_lockstep_statistically(gpu, name, cfg, nb, per):
 
 
 def test_wavefront_scheduling_independence(gpu):
-    """Per-particle Philox sub-streams: pool size / iterations per wave change only fp32 summation order."""
+    """Per-particle Philox sub-streams: pool size / crossings per wave / launch batching change only the fp32
+    summation order.  (The drain kernel continues a particle's stream sequentially through its descendants,
+    so WHERE the drain starts changes the draws: it is switched off for the exact comparison and checked
+    statistically afterwards.)"""
     prob, ph = make_problem(CASES[1][1])
     gpu.load_problem(prob)
     gpu.set_option("kernel", 1)
+    gpu.set_option("drain_threshold", 0)
     res = []
-    for pool, iters, cross in ((1 << 22, 4, 16), (1 << 14, 1, 7), (1 << 16, 5, 1000)):
-        gpu.set_option("pool_size", pool); gpu.set_option("electron_iters", iters); gpu.set_option("max_cross", cross)
+    for pool, cross, every, graph in ((1 << 22, 16, 16, 1), (1 << 14, 7, 3, 0), (1 << 16, 1000, 5, 1)):
+        gpu.set_option("pool_size", pool); gpu.set_option("max_cross", cross); gpu.set_option("check_every", every)
+        gpu.set_option("use_graph", graph)
         gpu.reset_tallies()
         gpu.run_histories(0, 50000)
         res.append((gpu.get_endep()[1:], gpu.counters()))
-    gpu.set_option("pool_size", 1 << 22); gpu.set_option("electron_iters", 4); gpu.set_option("max_cross", 16)
+    gpu.set_option("pool_size", 1 << 22); gpu.set_option("max_cross", 16); gpu.set_option("check_every", 16); gpu.set_option("use_graph", 1)
     g0, c0 = res[0]
     for g, c in res[1:]:
         assert c["deposits"] == c0["deposits"] and c["photon_steps"] == c0["photon_steps"]
         assert c["electron_steps"] == c0["electron_steps"]
         np.testing.assert_allclose(g, g0, rtol=2e-4, atol=1e-4 * g0.max())
         assert abs(g.sum() - g0.sum()) < 1e-5 * g0.sum()
+    # with the drain: same configuration twice -> same bookkeeping; vs no drain -> statistically the same
+    gpu.set_option("drain_threshold", 20000)
+    runs = []
+    for _ in range(2):
+        gpu.reset_tallies()
+        gpu.run_histories(0, 50000)
+        runs.append((gpu.get_endep()[1:], gpu.counters()))
+    gpu.set_option("drain_threshold", 32768)
+    assert runs[0][1] == runs[1][1]
+    np.testing.assert_allclose(runs[0][0], runs[1][0], rtol=2e-4, atol=1e-4 * g0.max())
+    assert abs(runs[0][0].sum() - g0.sum()) < 0.01 * g0.sum()
+    assert runs[0][1]["histories"] == c0["histories"]
 
 
 def test_wavefront_rejects_unsupported(gpu):
