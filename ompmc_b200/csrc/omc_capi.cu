@@ -46,7 +46,9 @@ struct omc_gpu_ctx {
     unsigned pool_cap = 0, pool_cap_opt = 0;
     int electron_iters = 1, max_cross = 16, check_every = 16;
     unsigned long long waves = 0;
-    int trace = 0, use_graph = 1;
+    int trace = 0, use_graph = 1, overlap = 1;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned drain_threshold = 32768;
 };
 
@@ -125,6 +127,11 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist) {
         if (alloc_estep_queue(h, h->wq.bca, cap)) return 1;
         h->pool_cap = cap;
     }
+    if (!h->stream2) {
+        CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
     if (!h->ctl) {
         CK(cudaMalloc((void **)&h->ctl, sizeof(WaveCtl)));
         CK(cudaMallocHost((void **)&h->ctl_host, sizeof(WaveCtl)));
@@ -147,7 +154,7 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist) {
     cudaGraphExec_t gexec = nullptr;
     if (h->use_graph) {
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        for (int k = 0; k < every; k++) launch_wave(P, h->ctl, h->wq, L, h->stream);
+        for (int k = 0; k < every; k++) launch_wave(P, h->ctl, h->wq, L, h->stream, h->overlap ? h->stream2 : nullptr, h->ev_fork, h->ev_join);
         CK(cudaStreamEndCapture(h->stream, &graph));
         CK(cudaGraphInstantiate(&gexec, graph, 0));
     }
@@ -157,7 +164,7 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist) {
         if (gexec) {
             CK(cudaGraphLaunch(gexec, h->stream));
         } else {
-            for (int k = 0; k < every; k++) launch_wave(P, h->ctl, h->wq, L, h->stream);
+            for (int k = 0; k < every; k++) launch_wave(P, h->ctl, h->wq, L, h->stream, h->overlap ? h->stream2 : nullptr, h->ev_fork, h->ev_join);
         }
         h->launches += 5ull * every;
         h->waves += every;
@@ -248,6 +255,7 @@ void omc_gpu_destroy(omc_gpu_handle h) {
     if (h->ctl_host) cudaFreeHost(h->ctl_host);
     cudaFree(h->P.endep); cudaFree(h->P.endep32); cudaFree(h->accum); cudaFree(h->accum2);
     cudaFree(h->P.counters); cudaFree(h->P.ensrc); cudaFree(h->stack); cudaFree(h->records);
+    if (h->stream2) { cudaStreamDestroy(h->stream2); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -444,6 +452,7 @@ int omc_gpu_set_option(omc_gpu_handle h, const char *key, long long value) {
     else if (k == "pool_size") h->pool_target = (unsigned)value;
     else if (k == "trace") h->trace = (int)value;
     else if (k == "use_graph") h->use_graph = (int)value;
+    else if (k == "overlap") h->overlap = (int)value;
     else if (k == "drain_threshold") h->drain_threshold = (unsigned)value;
     else if (k == "pool_cap") h->pool_cap_opt = (unsigned)value;
     else if (k == "electron_iters") h->electron_iters = (int)value;

@@ -62,7 +62,8 @@ struct DrainArgs {
     unsigned *ticket;
 };
 void launch_drain(const DevProblem &P, const DrainArgs &D, Part *stack, int depth, int blocks, cudaStream_t stream);
-void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, cudaStream_t s);
+void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, cudaStream_t s, cudaStream_t s2,
+                 cudaEvent_t fork, cudaEvent_t join);
 void launch_flush(float *g32, double *g64, long long n, cudaStream_t s);
 
 }  // namespace omc

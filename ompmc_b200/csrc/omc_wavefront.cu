@@ -140,12 +140,21 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, int par, un
         dpmfp = -log(1.0 - r);                                 // eta' = 1 - r  (:1905-1932 with nsplit = 1)
     }
     const double gle = log(p.e);
+    if (p.ir == 0) return;                                     // outside the phantom: howfar() discards (idisc)
+    // Voxel march, :1951-2019 + howfar() omc_dosxyz.c:187-297, restated for speed (statistically neutral):
+    // voxel indices are tracked incrementally instead of being decoded from the region number at every
+    // crossing (three integer divisions), plane distances use the reciprocal direction cosines (three fp64
+    // divisions per FLIGHT instead of per crossing), and the axis tests are selects, not branches.  Axis order
+    // z, x, y with strict '<' as in the reference.
+    int ix, iy, iz;
+    decode_region(P, p.ir, ix, iy, iz);
+    const double iu = (p.u != 0.0) ? 1.0 / p.u : 0.0, iv = (p.v != 0.0) ? 1.0 / p.v : 0.0, iw = (p.w != 0.0) ? 1.0 / p.w : 0.0;
+    const int sx = p.u > 0.0, sy = p.v > 0.0, sz = p.w > 0.0;
     int imed = R.med, medc = -2;
-    double gmfpr0 = 0.0, cohfac = 0.0, gmfp = 0.0;
-    int irl = p.ir;
+    double sig0 = 0.0, cohfac = 0.0, sig = 0.0;                // sig = 1 / gmfp
     bool at_site = false;
-    for (int k = 0; k < A.max_cross; k++) {                    // voxel-to-voxel march, :1951-2019
-        double tstep;
+    for (int k = 0; k < A.max_cross; k++) {
+        double tstep = 1.0E8;
         if (imed != -1) {
             if (imed != medc) {                                // (imed, gle) -> table values, kept while the medium stays
                 const MedRec &M = P.med[imed];
@@ -153,26 +162,33 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, int par, un
                 const PhotBin *B = P.phot + imed * MXGE + lgle;
                 const double2 a = __ldg(reinterpret_cast<const double2 *>(&B->gmfp1));
                 const double2 b = __ldg(reinterpret_cast<const double2 *>(&B->cohe1));
-                gmfpr0 = pwl(gle, a.x, a.y);
                 cohfac = pwl(gle, b.x, b.y);
+                sig0 = 1.0 / (pwl(gle, a.x, a.y) * cohfac);
                 medc = imed;
             }
-            gmfp = gmfpr0 / R.rhof;
-            gmfp *= cohfac;
-            tstep = gmfp * dpmfp;
-        } else {
-            tstep = 1.0E8;
+            sig = sig0 * R.rhof;
+            tstep = dpmfp * (double)__frcp_rn((float)sig);
         }
-        int irnew = irl, idisc = 0;
+        const double dz = (p.w != 0.0) ? (__ldg(P.zb + iz + sz) - p.z) * iw : 1.0E30;
+        const double dx = (p.u != 0.0) ? (__ldg(P.xb + ix + sx) - p.x) * iu : 1.0E30;
+        const double dy = (p.v != 0.0) ? (__ldg(P.yb + iy + sy) - p.y) * iv : 1.0E30;
         double ustep = tstep;
-        howfar(P, p, idisc, irnew, ustep);
+        int axis = -1;
+        if (dz < ustep) { ustep = dz; axis = 2; }
+        if (dx < ustep) { ustep = dx; axis = 0; }
+        if (dy < ustep) { ustep = dy; axis = 1; }
         t.npstep++;
         p.x += ustep * p.u; p.y += ustep * p.v; p.z += ustep * p.w;
-        if (idisc > 0) return;                                 // left the phantom
-        if (imed != -1) dpmfp = fmax(0.0, dpmfp - ustep / gmfp);
-        if (irnew != irl) {
-            p.ir = irnew; irl = irnew;
-            R = load_region_w(P, irl);
+        if (imed != -1) dpmfp = fmax(0.0, dpmfp - ustep * sig);
+        if (axis >= 0) {
+            int ir = p.ir;
+            bool out;
+            if (axis == 2) { iz += sz ? 1 : -1; ir += sz ? P.ijmax : -P.ijmax; out = (iz < 0) | (iz >= P.ksize); }
+            else if (axis == 0) { ix += sx ? 1 : -1; ir += sx ? 1 : -1; out = (ix < 0) | (ix >= P.isize); }
+            else { iy += sy ? 1 : -1; ir += sy ? P.isize : -P.isize; out = (iy < 0) | (iy >= P.jsize); }
+            if (out) return;                                   // left the phantom
+            p.ir = ir;
+            R = load_region_w(P, ir);
             imed = R.med;
         }
         if (imed != -1 && dpmfp <= 1.0E-05) { at_site = true; break; }
@@ -660,13 +676,22 @@ void wave_blocks_per_sm(int out[4]) {
     }
 }
 
-void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, cudaStream_t s) {
+// One wave.  misc_kernel (photons / interactions / source) and the electron chain touch disjoint inputs and
+// append to the same output queues through atomic counters, so they run as two parallel branches (second
+// stream `s2` forked and joined with events; under stream capture this becomes a fork/join in the graph).
+void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, cudaStream_t s, cudaStream_t s2,
+                 cudaEvent_t fork, cudaEvent_t join) {
     WaveArgs A;
     A.ctl = ctl; A.Q = Q; A.max_cross = L.max_cross; A.electron_iters = L.electron_iters;
-    misc_kernel<<<L.blocks[0], NT, 0, s>>>(P, A);
+    const bool par = (s2 != nullptr);
+    cudaStream_t sm = par ? s2 : s;
+    if (par) { cudaEventRecord(fork, s); cudaStreamWaitEvent(s2, fork, 0); }
+    misc_kernel<<<L.blocks[0], NT, 0, sm>>>(P, A);
+    if (par) cudaEventRecord(join, s2);
     esize_kernel<<<L.blocks[1], NT, 0, s>>>(P, A);
     edo_kernel<CLS_CH><<<L.blocks[2], NT, 0, s>>>(P, A);
     edo_kernel<CLS_BCA><<<L.blocks[3], NT, 0, s>>>(P, A);
+    if (par) cudaStreamWaitEvent(s, join, 0);
     advance_kernel<<<1, 32, 0, s>>>(P, ctl);
 }
 
