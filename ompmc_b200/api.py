@@ -74,6 +74,13 @@ class SourceDosxyz(C.Structure):
                 ("ixinl", C.c_int), ("ixinu", C.c_int), ("iyinl", C.c_int), ("iyinu", C.c_int)]
 
 
+class SourceMatrad(C.Structure):
+    _fields_ = ([("spectrum", C.c_int), ("charge", C.c_int), ("energy", C.c_double), ("deltak", C.c_double),
+                 ("cdfinv1", PD), ("cdfinv2", PD), ("nbeams", C.c_int), ("nbixels", C.c_int), ("ibeam", PI)]
+                + [(n, PD) for n in ["xsource", "ysource", "zsource", "xcorner", "ycorner", "zcorner",
+                                     "xside1", "yside1", "zside1", "xside2", "yside2", "zside2"]])
+
+
 class Counters(C.Structure):
     _fields_ = [(n, C.c_ulonglong) for n in COUNTER_NAMES] + [("reserved", C.c_ulonglong * 9)]
 
@@ -96,6 +103,7 @@ def load_library() -> C.CDLL:
     lib.omc_gpu_set_media.argtypes = [H, C.POINTER(MediaTables)]
     lib.omc_gpu_set_geometry.argtypes = [H, C.POINTER(Geometry)]
     lib.omc_gpu_set_source_dosxyz.argtypes = [H, C.POINTER(SourceDosxyz)]
+    lib.omc_gpu_set_source_matrad.argtypes = [H, C.POINTER(SourceMatrad)]
     lib.omc_gpu_set_vrt.argtypes = [H, C.c_int]
     lib.omc_gpu_set_seed.argtypes = [H, C.c_int, C.c_int]
     lib.omc_gpu_set_option.argtypes = [H, C.c_char_p, C.c_longlong]
@@ -183,15 +191,27 @@ class GpuTransport:
         g.med, g.rhof, g.pcut, g.ecut = pi("region_med"), pd("region_rhof"), pd("region_pcut"), pd("region_ecut")
         self._ck(self.lib.omc_gpu_set_geometry(self.h, C.byref(g)), "omc_gpu_set_geometry")
         self.nreg = g.isize * g.jsize * g.ksize + 1
-        s = SourceDosxyz()
-        s.spectrum, s.charge = int(prob["src_spectrum"][0]), int(prob["src_charge"][0])
-        s.energy, s.deltak = float(prob["src_energy"][0]), float(prob["src_deltak"][0])
-        s.cdfinv1, s.cdfinv2 = pd("src_cdfinv1"), pd("src_cdfinv2")
-        for k in ["ssd", "xinl", "xinu", "yinl", "yinu", "xsize", "ysize"]:
-            setattr(s, k, float(prob["src_" + k][0]))
-        for k in ["ixinl", "ixinu", "iyinl", "iyinu"]:
-            setattr(s, k, int(prob["src_" + k][0]))
-        self._ck(self.lib.omc_gpu_set_source_dosxyz(self.h, C.byref(s)), "omc_gpu_set_source_dosxyz")
+        if "mr_nbeamlets" in prob:                     # matRad beamlet source (omc_matrad.c)
+            m = SourceMatrad()
+            m.spectrum, m.charge = int(prob["src_spectrum"][0]), int(prob["src_charge"][0])
+            m.energy, m.deltak = float(prob["src_energy"][0]), float(prob["src_deltak"][0])
+            m.cdfinv1, m.cdfinv2 = pd("src_cdfinv1"), pd("src_cdfinv2")
+            m.nbixels, m.nbeams = int(prob["mr_nbeamlets"][0]), len(prob["mr_xsource"])
+            m.ibeam = pi("mr_ibeam")
+            for k in ["xsource", "ysource", "zsource", "xcorner", "ycorner", "zcorner", "xside1", "yside1", "zside1",
+                      "xside2", "yside2", "zside2"]:
+                setattr(m, k, pd("mr_" + k))
+            self._ck(self.lib.omc_gpu_set_source_matrad(self.h, C.byref(m)), "omc_gpu_set_source_matrad")
+        else:
+            s = SourceDosxyz()
+            s.spectrum, s.charge = int(prob["src_spectrum"][0]), int(prob["src_charge"][0])
+            s.energy, s.deltak = float(prob["src_energy"][0]), float(prob["src_deltak"][0])
+            s.cdfinv1, s.cdfinv2 = pd("src_cdfinv1"), pd("src_cdfinv2")
+            for k in ["ssd", "xinl", "xinu", "yinl", "yinu", "xsize", "ysize"]:
+                setattr(s, k, float(prob["src_" + k][0]))
+            for k in ["ixinl", "ixinu", "iyinl", "iyinu"]:
+                setattr(s, k, int(prob["src_" + k][0]))
+            self._ck(self.lib.omc_gpu_set_source_dosxyz(self.h, C.byref(s)), "omc_gpu_set_source_dosxyz")
         self._ck(self.lib.omc_gpu_set_vrt(self.h, int(prob["nsplit"][0])), "omc_gpu_set_vrt")
         self._ck(self.lib.omc_gpu_set_seed(self.h, int(seeds[0]), int(seeds[1])), "omc_gpu_set_seed")
         del keep   # arrays were copied to the device by the set_* calls

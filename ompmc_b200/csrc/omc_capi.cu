@@ -46,7 +46,7 @@ struct omc_gpu_ctx {
     unsigned pool_cap = 0, pool_cap_opt = 0;
     int electron_iters = 1, max_cross = 16, check_every = 16;
     unsigned long long waves = 0;
-    int trace = 0, use_graph = 1, overlap = 1;
+    int trace = 0, use_graph = 1, overlap = 1, source_kind = 0;
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned drain_threshold = 32768;
@@ -110,7 +110,7 @@ static int alloc_estep_queue(omc_gpu_handle h, EStepQueue &q, unsigned cap) {
 }
 
 // Drive waves until every history of [first, first+nhist) has been started and all queues drained.
-static int run_wavefront(omc_gpu_handle h, long long first, long long nhist) {
+static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int ibeamlet) {
     DevProblem &P = h->P;
     const unsigned target = h->pool_target;
     const unsigned cap = h->pool_cap_opt ? h->pool_cap_opt : 2u * target + 65536u;
@@ -146,7 +146,7 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist) {
     int occ[4];
     wave_blocks_per_sm(occ);
     for (int i = 0; i < 4; i++) L.blocks[i] = h->max_blocks > 0 ? h->max_blocks : h->sm_count * occ[i];
-    L.max_cross = h->max_cross; L.electron_iters = h->electron_iters;
+    L.max_cross = h->max_cross; L.electron_iters = h->electron_iters; L.ibeamlet = ibeamlet;
     const int every = h->check_every > 0 ? h->check_every : 1;
     // `every` waves are captured once into a CUDA graph (all launch parameters are wave-invariant: cur/next
     // parity lives in WaveCtl on the device), so the host issues one graph launch per `every` waves
@@ -420,12 +420,42 @@ int omc_gpu_set_source_dosxyz(omc_gpu_handle h, const omc_source_dosxyz *s) {
         if (upload(h, h->source_bufs, s->cdfinv2, n, &S.cdfinv2)) return 1;
     }
     h->have_source = true;
+    h->source_kind = 0;
     return 0;
 }
 
 int omc_gpu_set_source_matrad(omc_gpu_handle h, const omc_source_matrad *s) {
-    (void)s;
-    return fail(h, "omc_gpu_set_source_matrad: beamlet source not implemented in this build");
+    if (!h || !s) return 2;
+    if (s->charge < -1 || s->charge > 1) return fail(h, "Particle kind not recognized.");
+    if (s->nbixels < 1 || s->nbeams < 1) return fail(h, "beamlet source without beamlets");
+    CK(cudaSetDevice(h->device));
+    free_pool(h->source_bufs);
+    SourceDosxyz &S = h->P.src;
+    memset(&S, 0, sizeof S);
+    S.spectrum = s->spectrum; S.charge = s->charge; S.energy = s->energy; S.deltak = s->deltak;
+    if (s->spectrum) {
+        const size_t n = (size_t)s->deltak;
+        if (n < 1 || !s->cdfinv1 || !s->cdfinv2) return fail(h, "spectrum source without inverse-CDF tables");
+        if (upload(h, h->source_bufs, s->cdfinv1, n, &S.cdfinv1)) return 1;
+        if (upload(h, h->source_bufs, s->cdfinv2, n, &S.cdfinv2)) return 1;
+    }
+    SourceMatrad &M = h->P.msrc;
+    M.nbixels = s->nbixels; M.nbeams = s->nbeams;
+    for (int i = 0; i < s->nbixels; i++)
+        if (s->ibeam[i] < 0 || s->ibeam[i] >= s->nbeams) return fail(h, "beamlet refers to a beam that does not exist");
+    const size_t nb = (size_t)s->nbixels, nm = (size_t)s->nbeams;
+    if (upload(h, h->source_bufs, s->ibeam, nb, &M.ibeam)) return 1;
+    if (upload(h, h->source_bufs, s->xsource, nm, &M.xsource) || upload(h, h->source_bufs, s->ysource, nm, &M.ysource) ||
+        upload(h, h->source_bufs, s->zsource, nm, &M.zsource)) return 1;
+    if (upload(h, h->source_bufs, s->xcorner, nb, &M.xcorner) || upload(h, h->source_bufs, s->ycorner, nb, &M.ycorner) ||
+        upload(h, h->source_bufs, s->zcorner, nb, &M.zcorner)) return 1;
+    if (upload(h, h->source_bufs, s->xside1, nb, &M.xside1) || upload(h, h->source_bufs, s->yside1, nb, &M.yside1) ||
+        upload(h, h->source_bufs, s->zside1, nb, &M.zside1)) return 1;
+    if (upload(h, h->source_bufs, s->xside2, nb, &M.xside2) || upload(h, h->source_bufs, s->yside2, nb, &M.yside2) ||
+        upload(h, h->source_bufs, s->zside2, nb, &M.zside2)) return 1;
+    h->have_source = true;
+    h->source_kind = 1;
+    return 0;
 }
 
 int omc_gpu_set_vrt(omc_gpu_handle h, int nsplit) {
@@ -465,7 +495,11 @@ int omc_gpu_set_option(omc_gpu_handle h, const char *key, long long value) {
 int omc_gpu_run_histories(omc_gpu_handle h, long long first, long long nhist, int ibeamlet) {
     if (!h) return 2;
     if (!h->have_media || !h->have_geom || !h->have_source) return fail(h, "media, geometry and source must be set first");
-    if (ibeamlet >= 0) return fail(h, "beamlet sources not implemented in this build");
+    if (h->source_kind == 1) {
+        if (ibeamlet < 0 || ibeamlet >= h->P.msrc.nbixels) return fail(h, "beamlet index out of range for the matRad source");
+    } else {
+        ibeamlet = -1;                  // omc_dosxyz source: the argument is ignored, as the reference has none
+    }
     if (nhist <= 0) return 0;
     CK(cudaSetDevice(h->device));
     DevProblem &P = h->P;
@@ -500,13 +534,13 @@ int omc_gpu_run_histories(omc_gpu_handle h, long long first, long long nhist, in
             CK(cudaMalloc((void **)&h->stack, need));
             h->stack_bytes = need;
         }
-        launch_lockstep(P, h->stack, depth, blocks, tpb, first, nhist, h->stream);
+        launch_lockstep(P, h->stack, depth, blocks, tpb, first, nhist, ibeamlet, h->stream);
         h->launches += 1;
         CK(cudaGetLastError());
     } else if (h->kernel == OMC_KERNEL_WAVEFRONT) {
         if (P.nsplit != 1) return fail(h, "wavefront kernels implement nsplit = 1; use the lock-step kernel for photon splitting");
         if (h->record) return fail(h, "per-history records are a lock-step kernel feature");
-        int rc = run_wavefront(h, first, nhist);
+        int rc = run_wavefront(h, first, nhist, ibeamlet);
         if (rc) return rc;
     } else {
         return fail(h, "unknown kernel");

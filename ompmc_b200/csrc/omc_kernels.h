@@ -6,7 +6,7 @@ namespace omc {
 
 // omc_lockstep.cu
 void launch_lockstep(const DevProblem &P, Part *stack, int depth, int blocks, int threads, long long first, long long nhist,
-                     cudaStream_t stream);
+                     int ibeamlet, cudaStream_t stream);
 int lockstep_blocks_per_sm(int threads);
 void launch_test_geometry(const DevProblem &P, int n, const double *xyzuvw, const int *ir, const double *ustep_in, int *idisc,
                           int *irnew, double *ustep_out, double *tperp, cudaStream_t stream);
@@ -49,7 +49,7 @@ struct WaveQueues {
 };
 
 struct WaveLaunch {
-    int blocks[4], max_cross, electron_iters;
+    int blocks[4], max_cross, electron_iters, ibeamlet;
 };
 
 void wave_blocks_per_sm(int out[4]);

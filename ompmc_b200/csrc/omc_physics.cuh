@@ -955,4 +955,59 @@ OMC_FN double init_history_dosxyz(const DevProblem &P, Rng &g, Part &p) {
     return ein;
 }
 
+// initHistory(ibeamlet), omc_matrad.c:1084-1254 (Q13: the z clamp uses ybounds[0]; the 2*DBL_MIN nudges are
+// no-ops for non-zero bounds).  Returns the sampled kinetic energy.
+OMC_FN double init_history_matrad(const DevProblem &P, Rng &g, Part &p, int ib) {
+    const SourceDosxyz &S = P.src;
+    const SourceMatrad &M = P.msrc;
+    p.iq = S.charge;
+    double ein;
+    if (S.spectrum) {
+        double r1 = g.next(), r2 = g.next();
+        int k = (int)fmin(S.deltak * r1, S.deltak - 1.0);
+        ein = __ldg(S.cdfinv1 + k) + r2 * __ldg(S.cdfinv2 + k);
+    } else {
+        ein = S.energy;
+    }
+    p.e = (p.iq != 0) ? ein + RM : ein;
+    const double r1 = g.next(), r2 = g.next();
+    const double xiso = r1 * __ldg(M.xside1 + ib) + r2 * __ldg(M.xside2 + ib) + __ldg(M.xcorner + ib);
+    const double yiso = r1 * __ldg(M.yside1 + ib) + r2 * __ldg(M.yside2 + ib) + __ldg(M.ycorner + ib);
+    const double ziso = r1 * __ldg(M.zside1 + ib) + r2 * __ldg(M.zside2 + ib) + __ldg(M.zcorner + ib);
+    const int ibeam = __ldg(M.ibeam + ib);
+    const double dx = xiso - __ldg(M.xsource + ibeam), dy = yiso - __ldg(M.ysource + ibeam), dz = ziso - __ldg(M.zsource + ibeam);
+    const double vnorm = sqrt((dx * dx) + (dy * dy) + (dz * dz));
+    const double u = -dx / vnorm, v = -dy / vnorm, w = -dz / vnorm;
+    const double xlo = __ldg(P.xb), xhi = __ldg(P.xb + P.isize), ylo = __ldg(P.yb), yhi = __ldg(P.yb + P.jsize);
+    const double zlo = __ldg(P.zb), zhi = __ldg(P.zb + P.ksize);
+    double ustep = 1.0E5, dist;
+    if (u > 0.0) { dist = (xhi - xiso) / u; if (dist < ustep) ustep = dist; }
+    if (u < 0.0) { dist = -(xiso - xlo) / u; if (dist < ustep) ustep = dist; }
+    if (v > 0.0) { dist = (yhi - yiso) / v; if (dist < ustep) ustep = dist; }
+    if (v < 0.0) { dist = -(yiso - ylo) / v; if (dist < ustep) ustep = dist; }
+    if (w > 0.0) { dist = (zhi - ziso) / w; if (dist < ustep) ustep = dist; }
+    if (w < 0.0) { dist = -(ziso - zlo) / w; if (dist < ustep) ustep = dist; }
+    p.x = xiso + ustep * u; p.y = yiso + ustep * v; p.z = ziso + ustep * w;
+    p.u = -u; p.v = -v; p.w = -w;
+    const double tiny = 2.0 * 2.2250738585072014e-308;
+    if (p.x < xlo) p.x = xlo + tiny;
+    if (p.x > xhi) p.x = xhi - tiny;
+    if (p.y < ylo) p.y = ylo + tiny;
+    if (p.y > yhi) p.y = yhi - tiny;
+    if (p.z < zlo) p.z = ylo + tiny;                               // Q13
+    if (p.z > zhi) p.z = zhi - tiny;
+    int ix = 0, iy = 0, iz = 0;
+    while (__ldg(P.xb + ix + 1) < p.x) ix++;
+    while (__ldg(P.yb + iy + 1) < p.y) iy++;
+    while (__ldg(P.zb + iz + 1) < p.z) iz++;
+    p.ir = 1 + ix + iy * P.isize + iz * P.ijmax;
+    p.wt = 1.0;
+    return ein;
+}
+
+// source dispatch: ibeamlet < 0 -> omc_dosxyz point source, else the matRad beamlet `ibeamlet`
+__device__ __forceinline__ double init_history(const DevProblem &P, Rng &g, Part &p, int ibeamlet) {
+    return (ibeamlet < 0) ? init_history_dosxyz(P, g, p) : init_history_matrad(P, g, p, ibeamlet);
+}
+
 }  // namespace omc

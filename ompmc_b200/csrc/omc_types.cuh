@@ -84,6 +84,13 @@ struct SourceDosxyz {       // struct Source, omc_dosxyz.c:342-366
     int ixinl, iyinl;
 };
 
+struct SourceMatrad {       // struct Source of omc_matrad.c:507-541 (bixel arrays), device pointers
+    int nbixels, nbeams;
+    const int *ibeam;
+    const double *xsource, *ysource, *zsource;
+    const double *xcorner, *ycorner, *zcorner, *xside1, *yside1, *zside1, *xside2, *yside2, *zside2;
+};
+
 struct Counters {            // mirrors omc_gpu_counters (include/ompmc_b200.h)
     unsigned long long histories, kernel_launches, photon_steps, electron_steps, deposits, rng_draws, errors;
     unsigned long long reserved[9];
@@ -108,7 +115,8 @@ struct DevProblem {
     const float *spin_rej_f; // fp32 copies for the wavefront kernels
     const MsEntryF *ms_f;
     double dllambi, dqmsi;
-    SourceDosxyz src;
+    SourceDosxyz src;        // spectrum / charge / energy are shared by both source kinds
+    SourceMatrad msrc;
     int nsplit;
     uint32_t seed0, seed1;
     // scoring

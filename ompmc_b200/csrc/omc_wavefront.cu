@@ -121,7 +121,7 @@ enum { TAG_NONE = 0, TAG_COMPTON = 1, TAG_PAIR = 2, TAG_PHOTO = 3, TAG_RAYLEIGH 
 struct WaveArgs {
     WaveCtl *ctl;
     WaveQueues Q;
-    int max_cross, electron_iters;
+    int max_cross, electron_iters, ibeamlet;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -289,7 +289,7 @@ __device__ void source_chunk(const DevProblem &P, const WaveArgs &A, int par, un
     Rng g;
     g.seed(P.seed0, P.seed1, ctl->hist_next + i, 0u);
     Part p;
-    ensrc += init_history_dosxyz(P, g, p);
+    ensrc += init_history(P, g, p, A.ibeamlet);
     if (p.iq == 0) q_push(A.Q.p[par ^ 1], &ctl->n_p[par ^ 1], ctl, p, g, -1.0, TAG_NONE);
     else q_push(A.Q.e[par ^ 1], &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
 }
@@ -682,7 +682,7 @@ void wave_blocks_per_sm(int out[4]) {
 void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, cudaStream_t s, cudaStream_t s2,
                  cudaEvent_t fork, cudaEvent_t join) {
     WaveArgs A;
-    A.ctl = ctl; A.Q = Q; A.max_cross = L.max_cross; A.electron_iters = L.electron_iters;
+    A.ctl = ctl; A.Q = Q; A.max_cross = L.max_cross; A.electron_iters = L.electron_iters; A.ibeamlet = L.ibeamlet;
     const bool par = (s2 != nullptr);
     cudaStream_t sm = par ? s2 : s;
     if (par) { cudaEventRecord(fork, s); cudaStreamWaitEvent(s2, fork, 0); }

@@ -388,3 +388,54 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file
 
 def golden(name: str) -> str:
     return os.path.join(GOLDEN_DIR, name)
+
+
+# --------------------------------------------------------------------------------------------
+# matRad beamlet source (ucodes/omc_matrad/omc_matrad.c): struct Source :507-541, filled from the matRad
+# `mcSrc` struct (:702-748).  A bixel is a parallelogram corner + r1*side1 + r2*side2 on the isocentre plane.
+# --------------------------------------------------------------------------------------------
+
+def matrad_beamlets(ph: Phantom, gantry_deg=(0.0,), nbix=(3, 3), bixel_cm: float = 0.5, sad_cm: float = 100.0,
+                    isocentre=None) -> dict[str, np.ndarray]:
+    """Synthetic stand-in for matRad's beamlet export: for every gantry angle (rotation about the y axis,
+    0 deg = beam travelling along +z) an nbix[0] x nbix[1] grid of square bixels centred on the isocentre."""
+    if isocentre is None:
+        isocentre = (0.5 * (ph.xbounds[0] + ph.xbounds[-1]), 0.5 * (ph.ybounds[0] + ph.ybounds[-1]),
+                     0.5 * (ph.zbounds[0] + ph.zbounds[-1]))
+    c = np.asarray(isocentre, dtype=np.float64)
+    src, ib, corner, s1, s2 = [], [], [], [], []
+    for b, ang in enumerate(gantry_deg):
+        t = math.radians(ang)
+        d = np.array([math.sin(t), 0.0, math.cos(t)])            # beam direction
+        e1 = np.array([math.cos(t), 0.0, -math.sin(t)])          # in-plane axes of the isocentre plane
+        e2 = np.array([0.0, 1.0, 0.0])
+        src.append(c - sad_cm * d)
+        for j in range(nbix[1]):
+            for i in range(nbix[0]):
+                corner.append(c + (i - 0.5 * nbix[0]) * bixel_cm * e1 + (j - 0.5 * nbix[1]) * bixel_cm * e2)
+                s1.append(bixel_cm * e1); s2.append(bixel_cm * e2); ib.append(b)
+    src, corner, s1, s2 = (np.asarray(a, dtype=np.float64) for a in (src, corner, s1, s2))
+    out = {"mr_nbeamlets": np.array([len(ib)], dtype=np.int32), "mr_ibeam": np.asarray(ib, dtype=np.int32)}
+    for k, a in (("source", src), ("corner", corner), ("side1", s1), ("side2", s2)):
+        for ax, name in enumerate("xyz"):
+            out[f"mr_{name}{k}"] = np.ascontiguousarray(a[:, ax])
+    return out
+
+
+def build_problem_matrad(media, ph: Phantom, beamlets: dict, *, ecut: float, pcut: float, charge: int = 0, cdfinv=None,
+                         mono_energy: float = 0.0, nsplit: int = 1) -> dict[str, np.ndarray]:
+    """Problem dict for the matRad user code: same media/geometry/regions, beamlet source instead of the
+    dosxyz collimated point source."""
+    prob = dict(media_only(media))
+    prob.update(geometry_arrays(ph))
+    prob.update(init_regions(ph, media, ecut, pcut))
+    spectrum = 1 if cdfinv is not None else 0
+    f = lambda v: np.array([v], dtype=np.float64)
+    i = lambda v: np.array([v], dtype=np.int32)
+    prob.update({"src_spectrum": i(spectrum), "src_charge": i(charge), "src_energy": f(0.0 if spectrum else mono_energy),
+                 "src_deltak": f(float(len(cdfinv[0])) if spectrum else 0.0),
+                 "src_cdfinv1": np.asarray(cdfinv[0], dtype=np.float64) if spectrum else np.zeros(1),
+                 "src_cdfinv2": np.asarray(cdfinv[1], dtype=np.float64) if spectrum else np.zeros(1)})
+    prob.update(beamlets)
+    prob["nsplit"] = i(nsplit)
+    return prob

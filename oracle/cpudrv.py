@@ -84,6 +84,10 @@ class _CpuTransport:
     def set_nsplit(self, n: int):
         self._f("set_nsplit")(int(n))
 
+    def set_beamlet(self, ibeamlet: int):
+        fn = self._f("set_beamlet"); fn.argtypes = [C.c_int]
+        fn(int(ibeamlet))
+
     # -- hot path --------------------------------------------------------------------------
     def run_histories(self, first: int, n: int, records: bool = False):
         rec = np.zeros(n, dtype=RECORD_DTYPE) if records else None
@@ -146,10 +150,11 @@ class _CpuTransport:
 class RefTransport(_CpuTransport):
     prefix = "ref_"
 
-    def __init__(self, omp: bool = False):
-        super().__init__(ref_lib_path(omp))
-        self.lib.ref_init_from_inp.argtypes = [C.c_char_p]
-        self.lib.ref_dump_problem.argtypes = [C.c_char_p]
+    def __init__(self, omp: bool = False, matrad: bool = False):
+        super().__init__(os.path.join(HERE, "_ref", "libompmc_ref_matrad.so") if matrad else ref_lib_path(omp))
+        if not matrad:
+            self.lib.ref_init_from_inp.argtypes = [C.c_char_p]
+            self.lib.ref_dump_problem.argtypes = [C.c_char_p]
 
     def init_from_inp(self, stem: str):
         self.lib.ref_init_from_inp(stem.encode())
@@ -190,5 +195,7 @@ def oracle_lib_path() -> str:
     return os.path.join(HERE, "libomc_oracle.so")
 
 
-def have_ref(omp: bool = False) -> bool:
+def have_ref(omp: bool = False, matrad: bool = False) -> bool:
+    if matrad:
+        return os.path.exists(os.path.join(HERE, "_ref", "libompmc_ref_matrad.so"))
     return os.path.exists(ref_lib_path(omp))

@@ -48,6 +48,8 @@ typedef struct problem {
     omc_media_tables T;
     omc_geometry G;
     omc_source_dosxyz S;
+    omc_source_matrad M;      /* used instead of S when is_matrad */
+    int is_matrad, ibeamlet;
     int nsplit;
     int nreg;
     double *endep, *accum, *accum2;   /* struct Score, omc_dosxyz.c:636-645 */
@@ -1425,6 +1427,57 @@ static double init_history(hist_ctx *c) {
     return ein;
 }
 
+/* ---- a22: initHistory(ibeamlet), omc_matrad.c:1084-1254 (Q13: z clamp uses ybounds[0]; the 2*DBL_MIN
+ * nudges are no-ops for non-zero bounds) ------------------------------------------------------------ */
+static double init_history_matrad(hist_ctx *c, int ib) {
+    const omc_source_matrad *S = &PB.M;
+    const omc_geometry *G = &PB.G;
+    part *p = &c->stk[0];
+    const int imax = G->isize, ijmax = G->isize * G->jsize;
+    c->np = 0;
+    p->iq = S->charge;
+    double ein;
+    if (S->spectrum) {
+        double r1 = rnd(c), r2 = rnd(c);
+        int k = (int)fmin(S->deltak * r1, S->deltak - 1.0);
+        ein = S->cdfinv1[k] + r2 * S->cdfinv2[k];
+    } else {
+        ein = S->energy;
+    }
+    p->e = (p->iq != 0) ? ein + RM : ein;
+    double r1 = rnd(c), r2 = rnd(c);
+    double xiso = r1 * S->xside1[ib] + r2 * S->xside2[ib] + S->xcorner[ib];
+    double yiso = r1 * S->yside1[ib] + r2 * S->yside2[ib] + S->ycorner[ib];
+    double ziso = r1 * S->zside1[ib] + r2 * S->zside2[ib] + S->zcorner[ib];
+    int ibeam = S->ibeam[ib];
+    double dx = xiso - S->xsource[ibeam], dy = yiso - S->ysource[ibeam], dz = ziso - S->zsource[ibeam];
+    double vnorm = sqrt((dx * dx) + (dy * dy) + (dz * dz));
+    double u = -(xiso - S->xsource[ibeam]) / vnorm, v = -(yiso - S->ysource[ibeam]) / vnorm, w = -(ziso - S->zsource[ibeam]) / vnorm;
+    double ustep = 1.0E5, dist;
+    if (u > 0.0) { dist = (G->xbounds[G->isize] - xiso) / u; if (dist < ustep) ustep = dist; }
+    if (u < 0.0) { dist = -(xiso - G->xbounds[0]) / u; if (dist < ustep) ustep = dist; }
+    if (v > 0.0) { dist = (G->ybounds[G->jsize] - yiso) / v; if (dist < ustep) ustep = dist; }
+    if (v < 0.0) { dist = -(yiso - G->ybounds[0]) / v; if (dist < ustep) ustep = dist; }
+    if (w > 0.0) { dist = (G->zbounds[G->ksize] - ziso) / w; if (dist < ustep) ustep = dist; }
+    if (w < 0.0) { dist = -(ziso - G->zbounds[0]) / w; if (dist < ustep) ustep = dist; }
+    p->x = xiso + ustep * u; p->y = yiso + ustep * v; p->z = ziso + ustep * w;
+    p->u = -u; p->v = -v; p->w = -w;
+    const double tiny = 2.0 * 2.2250738585072014e-308;
+    if (p->x < G->xbounds[0]) p->x = G->xbounds[0] + tiny;
+    if (p->x > G->xbounds[G->isize]) p->x = G->xbounds[G->isize] - tiny;
+    if (p->y < G->ybounds[0]) p->y = G->ybounds[0] + tiny;
+    if (p->y > G->ybounds[G->jsize]) p->y = G->ybounds[G->jsize] - tiny;
+    if (p->z < G->zbounds[0]) p->z = G->ybounds[0] + tiny;                       /* Q13 */
+    if (p->z > G->zbounds[G->ksize]) p->z = G->zbounds[G->ksize] - tiny;
+    int ix = 0, iy = 0, iz = 0;
+    while (G->xbounds[ix + 1] < p->x) ix++;
+    while (G->ybounds[iy + 1] < p->y) iy++;
+    while (G->zbounds[iz + 1] < p->z) iz++;
+    p->ir = 1 + ix + iy * imax + iz * ijmax;
+    p->wt = 1.0;
+    return ein;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* API                                                                                         */
 /* ------------------------------------------------------------------------------------------ */
@@ -1475,12 +1528,28 @@ int orc_load_problem(const char *path) {
     S->spectrum = omc_blob_i32(b, "src_spectrum")[0]; S->charge = omc_blob_i32(b, "src_charge")[0];
     S->energy = omc_blob_f64(b, "src_energy")[0];     S->deltak = omc_blob_f64(b, "src_deltak")[0];
     S->cdfinv1 = omc_blob_f64(b, "src_cdfinv1");      S->cdfinv2 = omc_blob_f64(b, "src_cdfinv2");
+    PB.is_matrad = 0; PB.ibeamlet = 0;
+    for (int i = 0; i < b->n; i++) if (!strncmp(b->e[i].name, "mr_nbeamlets", 32)) PB.is_matrad = 1;
+    if (PB.is_matrad) {
+        omc_source_matrad *Mr = &PB.M;
+        Mr->spectrum = S->spectrum; Mr->charge = S->charge; Mr->energy = S->energy; Mr->deltak = S->deltak;
+        Mr->cdfinv1 = S->cdfinv1; Mr->cdfinv2 = S->cdfinv2;
+        Mr->nbixels = omc_blob_i32(b, "mr_nbeamlets")[0];
+        Mr->nbeams = (int)omc_blob_find(b, "mr_xsource")->count;
+        Mr->ibeam = omc_blob_i32(b, "mr_ibeam");
+        Mr->xsource = omc_blob_f64(b, "mr_xsource"); Mr->ysource = omc_blob_f64(b, "mr_ysource"); Mr->zsource = omc_blob_f64(b, "mr_zsource");
+        Mr->xcorner = omc_blob_f64(b, "mr_xcorner"); Mr->ycorner = omc_blob_f64(b, "mr_ycorner"); Mr->zcorner = omc_blob_f64(b, "mr_zcorner");
+        Mr->xside1 = omc_blob_f64(b, "mr_xside1"); Mr->yside1 = omc_blob_f64(b, "mr_yside1"); Mr->zside1 = omc_blob_f64(b, "mr_zside1");
+        Mr->xside2 = omc_blob_f64(b, "mr_xside2"); Mr->yside2 = omc_blob_f64(b, "mr_yside2"); Mr->zside2 = omc_blob_f64(b, "mr_zside2");
+    }
+    if (!PB.is_matrad) {
     S->ssd = omc_blob_f64(b, "src_ssd")[0];
     S->xinl = omc_blob_f64(b, "src_xinl")[0]; S->xinu = omc_blob_f64(b, "src_xinu")[0];
     S->yinl = omc_blob_f64(b, "src_yinl")[0]; S->yinu = omc_blob_f64(b, "src_yinu")[0];
     S->xsize = omc_blob_f64(b, "src_xsize")[0]; S->ysize = omc_blob_f64(b, "src_ysize")[0];
     S->ixinl = omc_blob_i32(b, "src_ixinl")[0]; S->ixinu = omc_blob_i32(b, "src_ixinu")[0];
     S->iyinl = omc_blob_i32(b, "src_iyinl")[0]; S->iyinu = omc_blob_i32(b, "src_iyinu")[0];
+    }
     PB.nsplit = omc_blob_i32(b, "nsplit")[0];
     PB.nreg = G->isize * G->jsize * G->ksize + 1;
     free(PB.endep); free(PB.accum); free(PB.accum2);
@@ -1495,6 +1564,7 @@ int orc_load_problem(const char *path) {
 
 void orc_set_rng(int mode, int seed0, int seed1) { g_rng_mode = mode; g_seed0 = (uint32_t)seed0; g_seed1 = (uint32_t)seed1; }
 void orc_set_nsplit(int nsplit) { PB.nsplit = nsplit; }
+void orc_set_beamlet(int ibeamlet) { PB.ibeamlet = ibeamlet; }
 int orc_nreg(void) { return PB.nreg; }
 int orc_num_threads(void) {
 #ifdef _OPENMP
@@ -1531,7 +1601,7 @@ void orc_run_histories(long long first, long long n, omc_history_record *rec) {
 #endif
         hist_ctx *c = &g_ctx[tid];
         begin_history(c, first + i);
-        ensrc += init_history(c);
+        ensrc += PB.is_matrad ? init_history_matrad(c, PB.ibeamlet) : init_history(c);
         int ir0 = c->stk[0].ir;
         shower(c);
         if (rec) {
@@ -1578,6 +1648,7 @@ void orc_reset_score(void) {
     PB.ensrc = 0.0;
     memset(&g_work_total, 0, sizeof g_work_total);
 }
+void orc_zero_accum(void) { memset(PB.accum, 0, (size_t)PB.nreg * sizeof(double)); }   /* omc_matrad.c:1482 */
 void orc_get_endep(double *out) { memcpy(out, PB.endep, (size_t)PB.nreg * sizeof(double)); }
 void orc_get_accum(double *a, double *a2, double *ensrc) {
     size_t n = (size_t)PB.nreg * sizeof(double);

@@ -17,10 +17,12 @@
 int    orc_load_problem(const char *blob_path);
 void   orc_set_rng(int mode /*0 RANMAR, 1 Philox*/, int seed0, int seed1);
 void   orc_set_nsplit(int nsplit);
+void   orc_set_beamlet(int ibeamlet);   /* matRad source: beamlet of the following run_histories() calls */
 int    orc_nreg(void);
 void   orc_run_histories(long long first, long long n, omc_history_record *rec);
 void   orc_accum_endep(void);
 void   orc_reset_score(void);
+void   orc_zero_accum(void);
 void   orc_get_endep(double *out);
 void   orc_get_accum(double *a, double *a2, double *ensrc);
 double orc_time_batches(long long first, long long nperbatch, int nbatch);

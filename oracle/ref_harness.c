@@ -20,11 +20,23 @@
  */
 #define _GNU_SOURCE
 #include <time.h>
+#ifdef OMC_REF_MATRAD
+/* matRad user code: compiled against oracle/mexshim/mex.h (no MATLAB here); only its initHistory(ibeamlet),
+ * callbacks and scoring are used, mexFunction()/parseInput() are never called. */
+#define ausgab omc_dosxyz_reference_ausgab
+#include "ucodes/omc_matrad/omc_matrad.c"
+#undef ausgab
+#undef exit
+static int g_ibeamlet_shared = 0;      /* beamlet of the running batch (the reference's outer loop variable) */
+#define INIT_HISTORY() initHistory(g_ibeamlet_shared)
+#else
 #define main omc_dosxyz_reference_main
 #define ausgab omc_dosxyz_reference_ausgab
 #include "ucodes/omc_dosxyz/omc_dosxyz.c"
 #undef main
 #undef ausgab
+#define INIT_HISTORY() initHistory()
+#endif
 
 #include <stdint.h>
 #include "omc_philox.h"
@@ -36,9 +48,14 @@ extern void ranmar_initRandom(void);
 extern double ranmar_setRandom(void);
 extern void ranmar_cleanRandom(void);
 
-/* main() of omc_dosxyz.c (renamed, never called) still references these two */
+/* main() / mexFunction() of the user code (never called) still reference these two */
 void initRandom(void) { ranmar_initRandom(); }
 void cleanRandom(void) { ranmar_cleanRandom(); }
+#ifdef OMC_REF_MATRAD
+void ref_set_beamlet(int ibeamlet) { g_ibeamlet_shared = ibeamlet; }
+#else
+void ref_set_beamlet(int ibeamlet) { (void)ibeamlet; }
+#endif
 
 /* ---- (1) RNG dispatch -------------------------------------------------------------------- */
 static int g_rng_mode = 0;              /* 0 = RANMAR (reference), 1 = Philox per history */
@@ -91,6 +108,7 @@ void ref_set_num_threads(int n) {
 #endif
 }
 
+#ifndef OMC_REF_MATRAD
 /* init chain of main(), omc_dosxyz.c:1155-1191 */
 int ref_init_from_inp(const char *inp_stem) {
     char *stem = strdup(inp_stem);
@@ -107,6 +125,8 @@ int ref_init_from_inp(const char *inp_stem) {
     g_ready = 1;
     return 0;
 }
+
+#endif
 
 void ref_set_rng(int mode, int seed0, int seed1) {
     g_rng_mode = mode;
@@ -126,6 +146,7 @@ int ref_nreg(void) { return geometry.isize * geometry.jsize * geometry.ksize + 1
     X(etae_ms1) X(etap_ms0) X(etap_ms1) X(q1ce_ms0) X(q1ce_ms1) X(q1cp_ms0) X(q1cp_ms1)            \
     X(q2ce_ms0) X(q2ce_ms1) X(q2cp_ms0) X(q2cp_ms1)
 
+#ifndef OMC_REF_MATRAD
 int ref_dump_problem(const char *path) {
     static omc_blob b;
     b.n = 0;
@@ -209,6 +230,8 @@ int ref_dump_problem(const char *path) {
     return rc;
 }
 
+#endif
+
 static double *dup_f64(const omc_blob *b, const char *name) {
     const omc_blob_entry *e = omc_blob_find(b, name);
     double *p = malloc((e->count ? e->count : 1) * sizeof(double));
@@ -272,12 +295,21 @@ int ref_load_problem(const char *path) {
     source.spectrum = isc(&b, "src_spectrum"); source.charge = isc(&b, "src_charge");
     source.energy = sc(&b, "src_energy");      source.deltak = sc(&b, "src_deltak");
     source.cdfinv1 = dup_f64(&b, "src_cdfinv1"); source.cdfinv2 = dup_f64(&b, "src_cdfinv2");
+#ifdef OMC_REF_MATRAD
+    source.nbeamlets = isc(&b, "mr_nbeamlets");
+    source.ibeam = dup_i32(&b, "mr_ibeam");
+    source.xsource = dup_f64(&b, "mr_xsource"); source.ysource = dup_f64(&b, "mr_ysource"); source.zsource = dup_f64(&b, "mr_zsource");
+    source.xcorner = dup_f64(&b, "mr_xcorner"); source.ycorner = dup_f64(&b, "mr_ycorner"); source.zcorner = dup_f64(&b, "mr_zcorner");
+    source.xside1 = dup_f64(&b, "mr_xside1"); source.yside1 = dup_f64(&b, "mr_yside1"); source.zside1 = dup_f64(&b, "mr_zside1");
+    source.xside2 = dup_f64(&b, "mr_xside2"); source.yside2 = dup_f64(&b, "mr_yside2"); source.zside2 = dup_f64(&b, "mr_zside2");
+#else
     source.ssd = sc(&b, "src_ssd");
     source.xinl = sc(&b, "src_xinl"); source.xinu = sc(&b, "src_xinu");
     source.yinl = sc(&b, "src_yinl"); source.yinu = sc(&b, "src_yinu");
     source.xsize = sc(&b, "src_xsize"); source.ysize = sc(&b, "src_ysize");
     source.ixinl = isc(&b, "src_ixinl"); source.ixinu = isc(&b, "src_ixinu");
     source.iyinl = isc(&b, "src_iyinl"); source.iyinu = isc(&b, "src_iyinu");
+#endif
     vrt.nsplit = isc(&b, "nsplit");
     omc_blob_free(&b);
     initScore();
@@ -307,7 +339,7 @@ void ref_run_histories(long long first, long long n, omc_history_record *rec) {
         if (g_rng_mode == 1) omc_philox_seed(&g_philox, g_seed0, g_seed1, (uint64_t)(first + i), 0);
         g_ndeposit = 0;
         g_edep_sum = 0.0;
-        initHistory();
+        INIT_HISTORY();
         int ir0 = stack.ir[0];
         shower();
         if (rec) {
@@ -338,6 +370,7 @@ void ref_get_accum(double *a, double *a2, double *ensrc) {
 }
 /* accumulateResults() in place (omc_dosxyz.c:719-799): accum -> dose or energy, accum2 -> rel. sigma */
 void ref_accumulate_results(int iout, int nhist, int nbatch) { accumulateResults(iout, nhist, nbatch); }
+#ifndef OMC_REF_MATRAD
 int ref_write_3ddose(const char *stem, int nperbatch, int nbatch) {
     /* outputResults() (omc_dosxyz.c:801-886) needs "output folder"; stem is taken relative to cwd */
     strcpy(input_items[1].key, "output folder ");
@@ -348,6 +381,8 @@ int ref_write_3ddose(const char *stem, int nperbatch, int nbatch) {
     free(s);
     return 0;
 }
+
+#endif
 
 /* timing helper: the whole batch loop, returns wall seconds */
 double ref_time_batches(long long first, long long nperbatch, int nbatch) {

@@ -35,6 +35,7 @@ def test_struct_layouts(lib):
     assert lib.omc_gpu_abi_sizeof(0) == C.sizeof(api.MediaTables)
     assert lib.omc_gpu_abi_sizeof(1) == C.sizeof(api.Geometry)
     assert lib.omc_gpu_abi_sizeof(2) == C.sizeof(api.SourceDosxyz)
+    assert lib.omc_gpu_abi_sizeof(3) == C.sizeof(api.SourceMatrad)
     assert lib.omc_gpu_abi_sizeof(4) == api.RECORD_DTYPE.itemsize
     assert lib.omc_gpu_abi_sizeof(5) == C.sizeof(api.Counters)
 

@@ -1,0 +1,172 @@
+"""matRad path (BASELINE config 4): beamlet source initHistory(ibeamlet) + dose-influence column assembly.
+
+CPU part: the oracle restatement against the reference's own omc_matrad.c, compiled here with a mex.h stand-in
+(oracle/mexshim) -- bit-exact with the per-history Philox stream; the CSC assembly against a direct numpy
+restatement of omc_matrad.c:1416-1477; beamlet sharding over 2 gloo ranks.
+GPU part: lock-step kernel vs oracle (lock-step), wavefront kernels statistically.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from ompmc_b200 import matrad, problem as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def matrad_problem(nbix=(2, 2), angles=(0.0, 70.0, 200.0)):
+    media = P.load_blob(P.golden("media_700_tissue4.blob"))
+    ph = P.tissue_phantom((24, 10, 24), (0.8, 0.8, 0.8))
+    bl = P.matrad_beamlets(ph, gantry_deg=angles, nbix=nbix, bixel_cm=0.5)
+    prob = P.build_problem_matrad(media, ph, bl, ecut=0.7, pcut=0.01, cdfinv=(media["cdfinv1_var_6MV"], media["cdfinv2_var_6MV"]))
+    return prob, ph, int(bl["mr_nbeamlets"][0])
+
+
+def test_oracle_matches_reference_matrad_source(oracle_lib):
+    from oracle import cpudrv
+    if not cpudrv.have_ref(matrad=True):
+        pytest.skip("oracle/_ref/libompmc_ref_matrad.so not built (no /root/reference here)")
+    prob, ph, nb = matrad_problem()
+    ref = cpudrv.RefTransport(matrad=True)
+    ref.load_problem(prob); ref.set_rng("philox")
+    oracle_lib.set_num_threads(1)
+    oracle_lib.load_problem(prob); oracle_lib.set_rng("philox")
+    for b in (0, 3, 6, nb - 1):
+        ref.reset_score(); oracle_lib.reset_score()
+        ref.set_beamlet(b); oracle_lib.set_beamlet(b)
+        r1 = ref.run_histories(5000 * b, 700, records=True)
+        r2 = oracle_lib.run_histories(5000 * b, 700, records=True)
+        assert np.array_equal(r1, r2)
+        assert np.array_equal(ref.get_endep(), oracle_lib.get_endep())
+
+
+class _OracleAsTransport:
+    """Adapter giving the CPU oracle the run_batch/get_tallies/reset_tallies surface of GpuTransport."""
+
+    def __init__(self, orc):
+        self.o = orc
+
+    def run_batch(self, first, n, ibeamlet=-1):
+        self.o.set_beamlet(max(ibeamlet, 0))
+        self.o.run_histories(first, n)
+        self.o.accum_endep()
+
+    def get_tallies(self):
+        return self.o.get_accum()
+
+    def reset_tallies(self, which=0):
+        if which == 0:
+            self.o.reset_score()
+        else:                                    # accum_endep only (omc_matrad.c:1482)
+            a, a2, _ = self.o.get_accum()
+            lib = self.o.lib
+            import ctypes as C
+            lib.orc_zero_accum.argtypes = []
+            lib.orc_zero_accum()
+
+
+def test_dose_influence_matrix_assembly(oracle_lib):
+    prob, ph, nb = matrad_problem(nbix=(2, 1), angles=(0.0, 90.0))
+    oracle_lib.set_num_threads(2)
+    oracle_lib.load_problem(prob); oracle_lib.set_rng("philox")
+    tr = _OracleAsTransport(oracle_lib)
+    jc, ir, val = matrad.dose_influence_matrix(tr, ph, nb, "2000", "4", 0.01)
+    assert jc[0] == 0 and jc[-1] == len(ir) == len(val) and len(jc) == nb + 1
+    assert (np.diff(jc) > 0).all()
+    # direct restatement of the column loop for beamlet 1
+    oracle_lib.reset_score()
+    oracle_lib.set_beamlet(1)
+    for ib in range(4):
+        oracle_lib.run_histories(1 * 2000 + ib * 500, 500)
+        oracle_lib.accum_endep()
+    a, a2, _ = oracle_lib.get_accum()
+    dose, _ = P.accumulate_results(ph, a, a2, 2000, 4)           # nhist, not nperbatch (Q11)
+    keep = np.nonzero(dose > dose.max() * 0.01)[0]
+    np.testing.assert_array_equal(ir[jc[1]:jc[2]], keep)
+    np.testing.assert_allclose(val[jc[1]:jc[2]], dose[keep], rtol=1e-12)
+    assert (np.diff(ir[jc[1]:jc[2]]) > 0).all()                   # rows ascending, like mxCreateSparse wants
+    oracle_lib.set_num_threads(1)
+
+
+WORKER = r"""
+import sys
+import numpy as np
+sys.path.insert(0, %(root)r)
+import torch.distributed as dist
+from oracle.cpudrv import OracleTransport
+from ompmc_b200 import matrad
+from tests.test_matrad import matrad_problem, _OracleAsTransport
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+prob, ph, nb = matrad_problem(nbix=(2, 1), angles=(0.0, 90.0, 180.0))
+orc = OracleTransport(); orc.set_num_threads(1); orc.load_problem(prob); orc.set_rng("philox")
+jc, ir, val = matrad.dose_influence_matrix(_OracleAsTransport(orc), ph, nb, "600", "3", 0.02, rank, world, matrad.gather_columns_torch)
+np.savez(%(out)r + f".{rank}.npz", jc=jc, ir=ir, val=val)
+dist.destroy_process_group()
+"""
+
+
+def test_beamlets_sharded_over_two_ranks(tmp_path, oracle_lib):
+    out = str(tmp_path / "dij")
+    script = tmp_path / "w.py"
+    script.write_text(WORKER % dict(root=ROOT, out=out))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29633", str(script)], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    prob, ph, nb = matrad_problem(nbix=(2, 1), angles=(0.0, 90.0, 180.0))
+    oracle_lib.set_num_threads(1)
+    oracle_lib.load_problem(prob); oracle_lib.set_rng("philox")
+    jc, ir, val = matrad.dose_influence_matrix(_OracleAsTransport(oracle_lib), ph, nb, "600", "3", 0.02)
+    for rank in (0, 1):
+        z = np.load(out + f".{rank}.npz")
+        np.testing.assert_array_equal(z["jc"], jc)
+        np.testing.assert_array_equal(z["ir"], ir)
+        np.testing.assert_allclose(z["val"], val, rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_gpu_matrad_lockstep_vs_oracle(gpu, oracle_lib):
+    prob, ph, nb = matrad_problem()
+    gpu.load_problem(prob)
+    gpu.set_option("kernel", 0)
+    oracle_lib.set_num_threads(1)
+    oracle_lib.load_problem(prob); oracle_lib.set_rng("philox")
+    for b in (0, 5, nb - 1):
+        gpu.reset_tallies(); oracle_lib.reset_score()
+        oracle_lib.set_beamlet(b)
+        ro = oracle_lib.run_histories(9000 * b, 1500, records=True)
+        rg = gpu.run_histories(9000 * b, 1500, records=True, ibeamlet=b)
+        assert np.array_equal(rg["ir_start"], ro["ir_start"])
+        same = (rg["ndraws"] == ro["ndraws"]) & (rg["ndeposit"] == ro["ndeposit"])
+        assert same.mean() >= 0.998
+        rel = np.abs(rg["edep"][same] - ro["edep"][same]) / np.maximum(ro["edep"][same], 1e-30)
+        assert rel.max() < 1e-9
+    from ompmc_b200.api import OmcGpuError
+    with pytest.raises(OmcGpuError):
+        gpu.run_histories(0, 10, ibeamlet=nb)          # beamlet index out of range
+
+
+@pytest.mark.gpu
+def test_gpu_matrad_dij_wavefront_vs_lockstep(gpu):
+    prob, ph, nb = matrad_problem(nbix=(2, 1), angles=(0.0, 120.0))
+    gpu.load_problem(prob)
+    cols = {}
+    for kernel in (0, 1):
+        gpu.set_option("kernel", kernel)
+        cols[kernel] = matrad.dose_influence_matrix(gpu, ph, nb, "200000", "10", 0.05)
+    gpu.set_option("kernel", 1)
+    jc0, ir0, v0 = cols[0]
+    jc1, ir1, v1 = cols[1]
+    assert len(jc0) == len(jc1) == nb + 1
+    for b in range(nb):
+        d0 = np.zeros(ph.nvox); d1 = np.zeros(ph.nvox)
+        d0[ir0[jc0[b]:jc0[b + 1]]] = v0[jc0[b]:jc0[b + 1]]
+        d1[ir1[jc1[b]:jc1[b + 1]]] = v1[jc1[b]:jc1[b + 1]]
+        assert abs(d0.sum() - d1.sum()) < 0.02 * d0.sum()
+        hot = d0 > 0.5 * d0.max()
+        assert hot.sum() >= 3
+        assert np.abs(d1[hot] / d0[hot] - 1.0).mean() < 0.05
