@@ -163,11 +163,11 @@ def run_reference_arm(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="prostate6mv", choices=list(WORKLOADS))
-    ap.add_argument("--hist-per-step", type=int, default=1 << 21, help="histories per step PER GPU")
+    ap.add_argument("--hist-per-step", type=int, default=1 << 23, help="histories per step PER GPU")
     ap.add_argument("--kernel", type=int, default=-1, help="-1 production default, 0 lock-step, 1 wavefront")
     ap.add_argument("--nsplit", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -254,6 +254,8 @@ def main() -> None:
         kb.record(stream)
         tr.synchronize()
         kms += ka.elapsed_time(kb)
+        if world > 1:
+            allreduce(tr)             # keep these batches comparable with the reduced ones in the sigma estimate
         tr.accum_batch()
     kernel_ms = kms / nk
     launches_per_step = cnt["kernel_launches"] / max(args.steps, 1)
