@@ -13,15 +13,29 @@
 
 using namespace omc;
 
+// Device buffers of one set_*() call are kept in a pool and REUSED by the next call when the sizes repeat
+// (a user code that re-uploads the same-shaped problem pays no cudaMalloc/cudaFree, only the copies).
+struct BufPool {
+    std::vector<void *> ptr;
+    std::vector<size_t> bytes;
+    size_t next = 0;
+    void begin() { next = 0; }
+    void clear() {
+        for (void *p : ptr) cudaFree(p);
+        ptr.clear(); bytes.clear(); next = 0;
+    }
+};
+
 struct omc_gpu_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     std::string err;
     DevProblem P{};
-    std::vector<void *> media_bufs, geom_bufs, source_bufs;
+    BufPool media_bufs, geom_bufs, source_bufs;
     bool have_media = false, have_geom = false, have_source = false;
     double *accum = nullptr, *accum2 = nullptr;
+    int tally_nreg = -1;
     // options
     int kernel = OMC_KERNEL_LOCKSTEP;
     int threads_per_block = 128;
@@ -67,10 +81,20 @@ static int fail(omc_gpu_handle h, const char *msg) {
 }
 
 template <typename T>
-static int upload(omc_gpu_handle h, std::vector<void *> &pool, const T *host, size_t n, const T **dev) {
+static int upload(omc_gpu_handle h, BufPool &pool, const T *host, size_t n, const T **dev) {
+    const size_t nb = (n ? n : 1) * sizeof(T);
     void *d = nullptr;
-    CK(cudaMalloc(&d, (n ? n : 1) * sizeof(T)));
-    pool.push_back(d);
+    if (pool.next < pool.ptr.size() && pool.bytes[pool.next] == nb) {
+        d = pool.ptr[pool.next];
+    } else {
+        if (pool.next < pool.ptr.size()) {          // shape changed: drop this and all later buffers
+            for (size_t i = pool.next; i < pool.ptr.size(); i++) cudaFree(pool.ptr[i]);
+            pool.ptr.resize(pool.next); pool.bytes.resize(pool.next);
+        }
+        CK(cudaMalloc(&d, nb));
+        pool.ptr.push_back(d); pool.bytes.push_back(nb);
+    }
+    pool.next++;
     if (n) CK(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     *dev = static_cast<const T *>(d);
@@ -250,7 +274,7 @@ void omc_gpu_destroy(omc_gpu_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    free_pool(h->media_bufs); free_pool(h->geom_bufs); free_pool(h->source_bufs); free_pool(h->wave_bufs);
+    h->media_bufs.clear(); h->geom_bufs.clear(); h->source_bufs.clear(); free_pool(h->wave_bufs);
     cudaFree(h->ctl);
     if (h->ctl_host) cudaFreeHost(h->ctl_host);
     cudaFree(h->P.endep); cudaFree(h->P.endep32); cudaFree(h->accum); cudaFree(h->accum2);
@@ -266,7 +290,7 @@ int omc_gpu_set_media(omc_gpu_handle h, const omc_media_tables *t) {
     if (!h || !t) return 2;
     if (t->nmed < 1 || t->nmed > OMC_MXMED) return fail(h, "nmed out of range (MXMED = 9, src/ompmc.h:356)");
     CK(cudaSetDevice(h->device));
-    free_pool(h->media_bufs);
+    h->media_bufs.begin();
     const int nmed = t->nmed;
     DevProblem &P = h->P;
     P.nmed = nmed;
@@ -356,7 +380,7 @@ int omc_gpu_set_geometry(omc_gpu_handle h, const omc_geometry *g) {
     const long long nvox = (long long)g->isize * g->jsize * g->ksize;
     if (nvox + 1 > 2147483647LL) return fail(h, "region index must fit the reference's 32-bit int");
     CK(cudaSetDevice(h->device));
-    free_pool(h->geom_bufs);
+    h->geom_bufs.begin();
     DevProblem &P = h->P;
     P.isize = g->isize; P.jsize = g->jsize; P.ksize = g->ksize;
     P.ijmax = g->isize * g->jsize;
@@ -392,12 +416,15 @@ int omc_gpu_set_geometry(omc_gpu_handle h, const omc_geometry *g) {
         }
         h->med_dirty = true;
     }
-    cudaFree(P.endep); cudaFree(P.endep32); cudaFree(h->accum); cudaFree(h->accum2);
-    P.endep = nullptr; P.endep32 = nullptr; h->accum = h->accum2 = nullptr;
-    CK(cudaMalloc((void **)&P.endep, (size_t)P.nreg * sizeof(double)));
-    CK(cudaMalloc((void **)&P.endep32, (size_t)P.nreg * sizeof(float)));
-    CK(cudaMalloc((void **)&h->accum, (size_t)P.nreg * sizeof(double)));
-    CK(cudaMalloc((void **)&h->accum2, (size_t)P.nreg * sizeof(double)));
+    if (h->tally_nreg != P.nreg) {
+        cudaFree(P.endep); cudaFree(P.endep32); cudaFree(h->accum); cudaFree(h->accum2);
+        P.endep = nullptr; P.endep32 = nullptr; h->accum = h->accum2 = nullptr;
+        CK(cudaMalloc((void **)&P.endep, (size_t)P.nreg * sizeof(double)));
+        CK(cudaMalloc((void **)&P.endep32, (size_t)P.nreg * sizeof(float)));
+        CK(cudaMalloc((void **)&h->accum, (size_t)P.nreg * sizeof(double)));
+        CK(cudaMalloc((void **)&h->accum2, (size_t)P.nreg * sizeof(double)));
+        h->tally_nreg = P.nreg;
+    }
     h->have_geom = true;
     return omc_gpu_reset_tallies(h, 0);
 }
@@ -407,7 +434,7 @@ int omc_gpu_set_source_dosxyz(omc_gpu_handle h, const omc_source_dosxyz *s) {
     if (s->charge < -1 || s->charge > 1) return fail(h, "Particle kind not recognized.");          // omc_dosxyz.c:602-605
     if (s->ssd < 0) return fail(h, "SSD must be greater than zero.");                              // omc_dosxyz.c:614-617
     CK(cudaSetDevice(h->device));
-    free_pool(h->source_bufs);
+    h->source_bufs.begin();
     SourceDosxyz &S = h->P.src;
     S.spectrum = s->spectrum; S.charge = s->charge; S.energy = s->energy; S.deltak = s->deltak;
     S.ssd = s->ssd; S.xinl = s->xinl; S.yinl = s->yinl; S.xsize = s->xsize; S.ysize = s->ysize;
@@ -429,7 +456,7 @@ int omc_gpu_set_source_matrad(omc_gpu_handle h, const omc_source_matrad *s) {
     if (s->charge < -1 || s->charge > 1) return fail(h, "Particle kind not recognized.");
     if (s->nbixels < 1 || s->nbeams < 1) return fail(h, "beamlet source without beamlets");
     CK(cudaSetDevice(h->device));
-    free_pool(h->source_bufs);
+    h->source_bufs.begin();
     SourceDosxyz &S = h->P.src;
     memset(&S, 0, sizeof S);
     S.spectrum = s->spectrum; S.charge = s->charge; S.energy = s->energy; S.deltak = s->deltak;

@@ -282,4 +282,57 @@ static __device__ __noinline__ double msdist_f(const DevProblem &P, Rng &g, cons
     return (double)ustep;
 }
 
+// ---------------------------------------------------------------------------------------------
+// CSDA helpers in mixed precision: energies and path lengths are fp64 quantities, but the series below only
+// needs RATIOS to ~1e-7, so the logs / divisions (software sequences in fp64) are done in fp32.  Differences of
+// nearly equal energies are taken in fp64 BEFORE the conversion (no cancellation in fp32).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double flog(double x) { return (double)__logf((float)x); }
+
+// computeDrange(), src/ompmc.c:3979-4014
+static __device__ __forceinline__ double drange_m(const ElecBin *B, double ekei, double ekef, double elkei, double elkef) {
+    const float fedep = fdiv((float)(ekei - ekef), (float)ekei);
+    const float elktmp = 0.5f * ((float)elkei + (float)elkef + 0.25f * fedep * fedep * (1.0f + fedep * (1.0f + 0.875f * fedep)));
+    const float d1 = (float)__ldg(&B->dedx1);
+    const float dedxmid = frcp(elktmp * d1 + (float)__ldg(&B->dedx0));
+    float aux = d1 * dedxmid;
+    const float tf = 2.0f - fedep;
+    aux = fdiv(aux * (1.0f + 2.0f * aux) * fedep * fedep, 6.0f * tf * tf);
+    return (double)(fedep * dedxmid * (1.0f + aux)) * ekei;
+}
+
+// computeEloss(), src/ompmc.c:4016-4108; rinv = 1 / rhof
+static __device__ __noinline__ double eloss_m(const ElecBin *B0, const MedRec &M, double rhof, double rinv, double tustep, double range,
+                                              double eke, double elke, int lelke) {
+    double de;
+    double tuss = range - __ldg(&B0[lelke].range_ep) * rinv;
+    if (tuss >= tustep) {
+        const float d1 = (float)__ldg(&B0[lelke].dedx1);
+        const float dedxmid = (float)elke * d1 + (float)__ldg(&B0[lelke].dedx0);
+        const float aux = fdiv(d1, dedxmid);
+        const float def = dedxmid * (float)(tustep * rhof);
+        const float fedep = fdiv(def, (float)eke);
+        de = (double)(def * (1.0f - 0.5f * fedep * aux * (1.0f - 0.333333f * fedep * (aux - 1.0f - 0.25f * fedep * (2.0f - aux * (4.0f - aux))))));
+    } else {
+        int lt = lelke;
+        tuss = (range - tustep) * rhof;
+        if (tuss <= 0) {
+            de = eke - M.te * 0.99;
+        } else {
+            while (tuss < __ldg(&B0[lt].range_ep)) lt -= 1;
+            const float elktmp = fdiv((float)(lt + 2) - (float)M.eke0, (float)M.eke1);
+            const double eketmp = __ldg(&B0[lt + 1].e_array);
+            tuss = (__ldg(&B0[lt + 1].range_ep) - tuss) * rinv;
+            const float d1 = (float)__ldg(&B0[lt].dedx1);
+            const float dedxmid = elktmp * d1 + (float)__ldg(&B0[lt].dedx0);
+            const float aux = fdiv(d1, dedxmid);
+            const float def = dedxmid * (float)(tuss * rhof);
+            const float fedep = fdiv(def, (float)eketmp);
+            de = (double)(def * (1.0f - 0.5f * fedep * aux * (1.0f - 0.333333f * fedep * (aux - 1.0f - 0.25f * fedep * (2.0f - aux * (4.0f - aux))))));
+            de += eke - eketmp;
+        }
+    }
+    return de;
+}
+
 }  // namespace omc

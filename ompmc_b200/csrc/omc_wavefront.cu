@@ -347,7 +347,66 @@ __device__ __forceinline__ int estep_size(const DevProblem &P, Rng &g, Part &p, 
     const MedRec &M = P.med[imed];
     const ElecBin *B0 = P.ebin + (size_t)qel * P.nmed * MXEKE + imed * MXEKE;
     const double rhof = R.rhof, eke = e.eke;
+    const double rinv = 1.0 / rhof;
     g.align();
+#if OMC_WAVE_F32
+    // mixed precision (see omc_physics_f32.cuh): logs and ratios in fp32, energy / length sums in fp64
+    float rf = nextf(g);
+    if (rf == 0.0f) rf = 1.0E-30f;
+    e.demfp = fmax((double)(-__logf(rf)), 1.0E-5);
+    const double elke = flog(eke);
+    const int lelke = elec_interval(M, elke);
+    e.elke = elke; e.lelke = lelke;
+    const ElecBin *B = B0 + lelke;
+    const double dedx0 = pwl(elke, __ldg(&B->dedx1), __ldg(&B->dedx0));
+    double sig0;
+    if (M.sig_ismonotone[qel]) sig0 = (double)fdiv((float)pwl(elke, __ldg(&B->sig1), __ldg(&B->sig0)), (float)dedx0);
+    else sig0 = (iq < 0) ? M.esig_e : M.psig_e;
+    double tstep;
+    e.total_tstep = 0.0;
+    if (sig0 <= 0.0) {
+        tstep = 10.0E8; sig0 = 1.0E-15;
+    } else {
+        const double ekef = eke - (double)fdiv((float)e.demfp, (float)sig0);
+        if (ekef <= __ldg(&B0[0].e_array)) {
+            tstep = 10.0E8;
+        } else {
+            const double elkef = flog(ekef);
+            const int lelkef = elec_interval(M, elkef);
+            if (lelkef == lelke) {
+                tstep = drange_m(B, eke, ekef, elke, elkef);
+            } else {
+                const float ieke1 = frcp((float)M.eke1);
+                double ekei = __ldg(&B->e_array), elkei = (double)(((float)(lelke + 1) - (float)M.eke0) * ieke1);
+                const double tuss = drange_m(B, eke, ekei, elke, elkei);
+                ekei = __ldg(&B0[lelkef + 1].e_array);
+                elkei = (double)(((float)(lelkef + 2) - (float)M.eke0) * ieke1);
+                tstep = drange_m(B0 + lelkef, ekei, ekef, elkei, elkef);
+                tstep += tuss + __ldg(&B->range_ep) - __ldg(&B0[lelkef + 1].range_ep);
+            }
+        }
+        e.total_tstep = tstep;
+        tstep = tstep * rinv;
+    }
+    e.sig0 = sig0;
+    e.dedx = rhof * dedx0;
+    const double tmxs = pwl(elke, __ldg(&B->tmxs1), __ldg(&B->tmxs0)) * rinv;
+    {
+        const double ekei = __ldg(&B->e_array), elkei = (double)fdiv((float)(lelke + 1) - (float)M.eke0, (float)M.eke1);
+        e.range = (drange_m(B, eke, ekei, elke, elkei) + __ldg(&B->range_ep)) * rinv;
+    }
+    double tustep = fmin(fmin(tstep, tmxs), e.range);
+    const double tperp = hownear(P, p);
+    const float xccl = (float)(rhof * M.xcc);
+    const float p2 = (float)(eke * (eke + 2.0 * RM));
+    const float beta2 = fdiv(p2, p2 + RMf * RMf);
+    const float etap = (float)pwl(elke, __ldg(&B->eta1), __ldg(&B->eta0));
+    const float ms_corr = (float)pwl(elke, __ldg(&B->blcce1), __ldg(&B->blcce0));
+    float blcclf = (float)(rhof * M.blcc);
+    blcclf = fdiv(fdiv(blcclf, etap), 1.0f + fdiv(0.25f * etap * xccl, blcclf * p2)) * ms_corr;
+    const double blccl = (double)blcclf;
+    const double ssmfp = (double)fdiv(beta2, blcclf);
+#else
     double r = g.next();
     if (r == 0.0) r = 1.0E-30;
     e.demfp = fmax(-log(r), 1.0E-5);
@@ -382,14 +441,14 @@ __device__ __forceinline__ int estep_size(const DevProblem &P, Rng &g, Part &p, 
             }
         }
         e.total_tstep = tstep;
-        tstep = tstep / rhof;
+        tstep = tstep * rinv;
     }
     e.sig0 = sig0;
     e.dedx = rhof * dedx0;
-    const double tmxs = pwl(elke, __ldg(&B->tmxs1), __ldg(&B->tmxs0)) / rhof;
+    const double tmxs = pwl(elke, __ldg(&B->tmxs1), __ldg(&B->tmxs0)) * rinv;
     {
         const double ekei = __ldg(&B->e_array), elkei = (lelke + 1 - M.eke0) / M.eke1;
-        e.range = (drange(B, eke, ekei, elke, elkei) + __ldg(&B->range_ep)) / rhof;
+        e.range = (drange(B, eke, ekei, elke, elkei) + __ldg(&B->range_ep)) * rinv;
     }
     double tustep = fmin(fmin(tstep, tmxs), e.range);
     const double tperp = hownear(P, p);
@@ -401,6 +460,7 @@ __device__ __forceinline__ int estep_size(const DevProblem &P, Rng &g, Part &p, 
     const double ms_corr = pwl(elke, __ldg(&B->blcce1), __ldg(&B->blcce0));
     blccl = blccl / etap / (1.0 + 0.25 * etap * xccl / blccl / p2) * ms_corr;
     const double ssmfp = beta2 / blccl;
+#endif
     const double skindepth = 3 * ssmfp;
     tustep = fmin(tustep, fmax(tperp, skindepth));
     e.tustep = tustep; e.tperp = tperp; e.blccl = blccl; e.ssmfp = ssmfp;
@@ -417,10 +477,11 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
     const ElecBin *B0 = (imed >= 0) ? P.ebin + (size_t)qel * P.nmed * MXEKE + imed * MXEKE : nullptr;
     if (cls == CLS_CH) {                                       // condensed-history step, :4973-4996
         call_howfar = false;
-        de = eloss(B0, P.med[imed], rhof, tustep, e.range, eke0, e.elke, e.lelke);
 #if OMC_WAVE_F32
+        de = eloss_m(B0, P.med[imed], rhof, 1.0 / rhof, tustep, e.range, eke0, e.elke, e.lelke);
         ustep = msdist_f(P, g, p, imed, qel, rhof, de, tustep, eke0, xf, yf, zf, uf, vf, wf);
 #else
+        de = eloss(B0, P.med[imed], rhof, tustep, e.range, eke0, e.elke, e.lelke);
         ustep = msdist<true>(P, g, p, imed, qel, rhof, de, tustep, eke0, xf, yf, zf, uf, vf, wf);
 #endif
     } else if (imed == -1) {                                   // :4815-4821
@@ -463,7 +524,11 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
     if (cls != CLS_CH) {
         tvstep = call_howfar ? ustep : tustep;
         if (call_howfar && tvstep != tustep) do_single = false;
+#if OMC_WAVE_F32
+        de = eloss_m(B0, M, rhof, 1.0 / rhof, tvstep, e.range, eke0, e.elke, e.lelke);
+#else
         de = eloss(B0, M, rhof, tvstep, e.range, eke0, e.elke, e.lelke);
+#endif
         xf = p.x + p.u * ustep; yf = p.y + p.v * ustep; zf = p.z + p.w * ustep;
         if (do_single) {                                       // :5180-5207
             const double ekems = fmax(eke0 - de, ecut - RM);
@@ -498,7 +563,11 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
         deposit32(P, t, p.ir, p.wt * (eie - RM));
         return (iq > 0) ? TAG_RANNIH : -1;
     }
+#if OMC_WAVE_F32
+    const double eke = eie - RM, elke = flog(eke);
+#else
     const double eke = eie - RM, elke = log(eke);
+#endif
     const int lelke = elec_interval(M, elke);
     int imed_new = imed;
     if (irnew != irl) {
