@@ -39,8 +39,19 @@
 #ifndef OMC_WARP_AGGREGATE_DOSE
 #define OMC_WARP_AGGREGATE_DOSE 0
 #endif
-#ifndef OMC_WAVE_MINBLOCKS
-#define OMC_WAVE_MINBLOCKS 3
+// minimum resident blocks per SM asked of ptxas for each kernel (register cap 65536 / (128 * n)); measured on
+// B200: (5,6,6,6) 4.93e7 hist/s, (4,4,3,4) 4.30e7, (8,6,5,8) 4.90e7 -- latency hiding needs >= 20 warps/SM
+#ifndef OMC_MB_MISC
+#define OMC_MB_MISC 5
+#endif
+#ifndef OMC_MB_ESIZE
+#define OMC_MB_ESIZE 6
+#endif
+#ifndef OMC_MB_ECH
+#define OMC_MB_ECH 6
+#endif
+#ifndef OMC_MB_EBCA
+#define OMC_MB_EBCA 6
 #endif
 
 namespace omc {
@@ -619,7 +630,7 @@ __device__ __forceinline__ void flush_tally(const DevProblem &P, Tally &t, doubl
 // ---------------------------------------------------------------------------------------------
 // electron kernels
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) esize_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ WaveArgs A) {
+__global__ void __launch_bounds__(NT, OMC_MB_ESIZE) esize_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ WaveArgs A) {
     WaveCtl *ctl = A.ctl;
     const int par = (int)ctl->parity;
     const unsigned n = min(ctl->n_e[par], A.Q.e[0].cap);
@@ -647,7 +658,7 @@ __global__ void __launch_bounds__(NT) esize_kernel(const __grid_constant__ DevPr
 }
 
 template <int CLS>
-__global__ void __launch_bounds__(NT) edo_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ WaveArgs A) {
+__global__ void __launch_bounds__(NT, (CLS == 1 ? OMC_MB_ECH : OMC_MB_EBCA)) edo_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ WaveArgs A) {
     WaveCtl *ctl = A.ctl;
     const int par = (int)ctl->parity;
     const EStepQueue &S = (CLS == CLS_CH) ? A.Q.ch : A.Q.bca;
@@ -668,7 +679,7 @@ __global__ void __launch_bounds__(NT) edo_kernel(const __grid_constant__ DevProb
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned vload(const unsigned *p) { return *reinterpret_cast<const volatile unsigned *>(p); }
 
-__global__ void __launch_bounds__(NT) misc_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ WaveArgs A) {
+__global__ void __launch_bounds__(NT, OMC_MB_MISC) misc_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ WaveArgs A) {
     __shared__ unsigned s_type, s_chunk, s_cnt[4];
     WaveCtl *ctl = A.ctl;
     const int par = (int)ctl->parity;
