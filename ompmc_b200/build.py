@@ -62,7 +62,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link of libompmc_b200.so failed")
+    build_host()
     return LIB
+
+
+HOST_SRC = os.path.join(HERE, "host", "omc_dosxyz_b200.c")
+HOST_EXE = os.path.join(HERE, "host", "omc_dosxyz_b200")
+
+
+def build_host(force: bool = False) -> str:
+    """The plain-C host driver (batch loop + statistics + .3ddose writer) linked against the C-ABI library."""
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    if force or _stale(HOST_EXE, [HOST_SRC, LIB, os.path.join(inc, "ompmc_b200.h")]):
+        cmd = ["gcc", "-O2", "-Wall", "-o", HOST_EXE, HOST_SRC, "-I", inc, "-L", HERE, "-lompmc_b200", "-lm", "-Wl,-rpath,$ORIGIN/.."]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("gcc failed for host/omc_dosxyz_b200.c")
+    return HOST_EXE
 
 
 if __name__ == "__main__":

@@ -1,0 +1,226 @@
+/*
+ * omc_dosxyz_b200.c -- plain-C host driver of the B200 hot path: the part of ompMC's omc_dosxyz user code that
+ * sits around the batch loop, talking to the GPU only through the C-ABI of include/ompmc_b200.h.
+ *
+ *   main() batch bookkeeping + batch loop      ucodes/omc_dosxyz/omc_dosxyz.c:1207-1263   (atoi/int semantics kept)
+ *   accumulateResults()                        omc_dosxyz.c:719-799
+ *   outputResults() -> <stem>.3ddose           omc_dosxyz.c:801-886   (same printf formats, byte-compatible)
+ *
+ * What it does NOT contain: the reference's table builders (initMediaData & co).  Their output -- plus phantom,
+ * regions and source, i.e. everything a reference user code holds in its globals just before the batch loop --
+ * is read from a problem blob (format: "OMCBLOB1", see ompmc_b200/problem.py save_blob/load_blob).  A maintainer
+ * who links the reference's own init code instead follows INTEGRATION.md; the calls below are the same.
+ *
+ * usage: omc_dosxyz_b200 -p problem.blob -n ncase -b nbatch -o out_stem [-k 0|1] [-d device] [-s "ixx jxx"]
+ * There is no CPU transport here: without a CUDA device the program exits with the library's error.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "ompmc_b200.h"
+
+/* ---- problem blob ------------------------------------------------------------------------- */
+typedef struct { char name[33]; uint32_t dtype; uint64_t count; void *data; } blob_entry;
+typedef struct { int n; blob_entry *e; } blob;
+
+static int blob_read(blob *b, const char *path) {
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return -1;
+    char magic[8];
+    uint32_t n = 0;
+    if (fread(magic, 1, 8, fp) != 8 || memcmp(magic, "OMCBLOB1", 8) || fread(&n, 4, 1, fp) != 1) { fclose(fp); return -2; }
+    b->n = (int)n;
+    b->e = calloc(n, sizeof(blob_entry));
+    for (uint32_t i = 0; i < n; i++) {
+        blob_entry *e = &b->e[i];
+        uint32_t pad;
+        if (fread(e->name, 1, 32, fp) != 32 || fread(&e->dtype, 4, 1, fp) != 1 || fread(&pad, 4, 1, fp) != 1 ||
+            fread(&e->count, 8, 1, fp) != 1) { fclose(fp); return -3; }
+        size_t sz = (size_t)e->count * (e->dtype == 0 ? 8 : 4), psz = (sz + 7) & ~(size_t)7;
+        e->data = malloc(psz ? psz : 8);
+        if (fread(e->data, 1, psz, fp) != psz) { fclose(fp); return -4; }
+    }
+    fclose(fp);
+    return 0;
+}
+static const blob_entry *blob_find(const blob *b, const char *name) {
+    for (int i = 0; i < b->n; i++) if (!strcmp(b->e[i].name, name)) return &b->e[i];
+    printf("Can not find '%s' in the problem file.\n", name);
+    exit(EXIT_FAILURE);
+}
+static const double *F(const blob *b, const char *n) { return (const double *)blob_find(b, n)->data; }
+static const int *I(const blob *b, const char *n) { return (const int *)blob_find(b, n)->data; }
+
+/* ---- accumulateResults(), omc_dosxyz.c:719-799 ---------------------------------------------- */
+static void accumulate_results(const omc_geometry *g, const double *dens, double *accum, double *accum2, int iout, int nhist, int nbatch) {
+    const int imax = g->isize, ijmax = g->isize * g->jsize;
+    const double inc_fluence = (double)nhist;
+    for (int iz = 0; iz < g->ksize; iz++)
+        for (int iy = 0; iy < g->jsize; iy++)
+            for (int ix = 0; ix < g->isize; ix++) {
+                const int irl = 1 + ix + iy * imax + iz * ijmax;
+                double endep = accum[irl] / (double)nbatch, endep2 = accum2[irl] / (double)nbatch, unc;
+                if (endep != 0.0) {
+                    unc = endep2 - endep * endep;
+                    unc /= (double)(nbatch - 1);
+                    unc = sqrt(unc) / endep;
+                } else {
+                    endep = 0.0; unc = 0.9999999;
+                }
+                if (iout) {
+                    double mass = (g->xbounds[ix + 1] - g->xbounds[ix]) * (g->ybounds[iy + 1] - g->ybounds[iy]) *
+                                  (g->zbounds[iz + 1] - g->zbounds[iz]);
+                    mass *= dens[irl - 1];
+                    endep *= 1.602E-10 / (mass * inc_fluence);
+                } else {
+                    endep /= inc_fluence;
+                }
+                if (dens[irl - 1] < 0.044) { endep = 0.0; unc = 0.9999999; }     /* "zero dose in air" */
+                accum[irl] = endep;
+                accum2[irl] = unc;
+            }
+}
+
+/* ---- outputResults(), omc_dosxyz.c:841-879 -------------------------------------------------- */
+static int write_3ddose(const char *stem, const omc_geometry *g, const double *dose, const double *unc) {
+    char *fn = malloc(strlen(stem) + 16);
+    sprintf(fn, "%s.3ddose", stem);
+    FILE *fp = fopen(fn, "w");
+    if (!fp) { printf("Unable to open file: %s\n", fn); free(fn); return 1; }
+    const int imax = g->isize, ijmax = g->isize * g->jsize;
+    fprintf(fp, "%5d%5d%5d\n", g->isize, g->jsize, g->ksize);
+    for (int i = 0; i <= g->isize; i++) fprintf(fp, "%f ", g->xbounds[i]);
+    fprintf(fp, "\n");
+    for (int i = 0; i <= g->jsize; i++) fprintf(fp, "%f ", g->ybounds[i]);
+    fprintf(fp, "\n");
+    for (int i = 0; i <= g->ksize; i++) fprintf(fp, "%f ", g->zbounds[i]);
+    fprintf(fp, "\n");
+    for (int iz = 0; iz < g->ksize; iz++)
+        for (int iy = 0; iy < g->jsize; iy++)
+            for (int ix = 0; ix < g->isize; ix++) fprintf(fp, "%e ", dose[1 + ix + iy * imax + iz * ijmax]);
+    fprintf(fp, "\n");
+    for (int iz = 0; iz < g->ksize; iz++)
+        for (int iy = 0; iy < g->jsize; iy++)
+            for (int ix = 0; ix < g->isize; ix++) fprintf(fp, "%f ", unc[1 + ix + iy * imax + iz * ijmax]);
+    fprintf(fp, "\n");
+    fclose(fp);
+    free(fn);
+    return 0;
+}
+
+static double now_s(void) {
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
+static omc_gpu_handle gpu;
+static void die(const char *what) {
+    printf("%s: %s\n", what, omc_gpu_last_error(gpu));
+    exit(EXIT_FAILURE);
+}
+
+int main(int argc, char **argv) {
+    const char *pfile = NULL, *ncase = "100000", *nbatch_s = "10", *stem = "omc_b200", *seeds = "97 33";
+    int kernel = -1, device = 0;
+    for (int i = 1; i < argc; i++) {
+        if (!strcmp(argv[i], "-p") && i + 1 < argc) pfile = argv[++i];
+        else if (!strcmp(argv[i], "-n") && i + 1 < argc) ncase = argv[++i];
+        else if (!strcmp(argv[i], "-b") && i + 1 < argc) nbatch_s = argv[++i];
+        else if (!strcmp(argv[i], "-o") && i + 1 < argc) stem = argv[++i];
+        else if (!strcmp(argv[i], "-k") && i + 1 < argc) kernel = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-d") && i + 1 < argc) device = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-s") && i + 1 < argc) seeds = argv[++i];
+        else {
+            printf("usage: %s -p problem.blob -n ncase -b nbatch -o out_stem [-k 0|1] [-d device] [-s \"ixx jxx\"]\n", argv[0]);
+            return 2;
+        }
+    }
+    if (!pfile) { printf("Can not find the problem file (-p).\n"); return 2; }
+    const double tbegin = now_s();
+    blob b;
+    if (blob_read(&b, pfile) != 0) { printf("Unable to open file: %s\n", pfile); return EXIT_FAILURE; }
+
+    omc_media_tables t;
+    memset(&t, 0, sizeof t);
+    t.nmed = I(&b, "nmed")[0];
+#define TF(f) t.f = F(&b, #f);
+#define TI(f) t.f = I(&b, #f);
+    TF(ge0) TF(ge1) TF(gmfp0) TF(gmfp1) TF(gbr10) TF(gbr11) TF(gbr20) TF(gbr21) TF(cohe0) TF(cohe1)
+    TF(ray_xgrid) TF(ray_fcum) TF(ray_b_array) TF(ray_c_array) TI(ray_i_array) TF(ray_pmax0) TF(ray_pmax1)
+    TF(dl1) TF(dl2) TF(dl3) TF(dl4) TF(dl5) TF(dl6) TF(bpar0) TF(bpar1) TF(delcm) TF(zbrang)
+    TF(esig0) TF(esig1) TF(psig0) TF(psig1) TF(ededx0) TF(ededx1) TF(pdedx0) TF(pdedx1) TF(ebr10) TF(ebr11) TF(pbr10) TF(pbr11)
+    TF(pbr20) TF(pbr21) TF(tmxs0) TF(tmxs1) TF(blcce0) TF(blcce1) TF(etae_ms0) TF(etae_ms1) TF(etap_ms0) TF(etap_ms1)
+    TF(q1ce_ms0) TF(q1ce_ms1) TF(q1cp_ms0) TF(q1cp_ms1) TF(q2ce_ms0) TF(q2ce_ms1) TF(q2cp_ms0) TF(q2cp_ms1)
+    TF(range_ep) TF(e_array) TF(eke0) TF(eke1) TI(sig_ismonotone) TF(esig_e) TF(psig_e) TF(xcc) TF(blcc)
+    TF(spin_rej) TF(ums) TF(fms) TF(wms) TI(ims) TF(pegs_ap) TF(pegs_ae) TF(pegs_te) TF(pegs_thmoll) TF(pegs_rho) TI(pegs_meke)
+#undef TF
+#undef TI
+    t.b2spin_min = F(&b, "b2spin_min")[0]; t.dbeta2i = F(&b, "dbeta2i")[0]; t.espml = F(&b, "espml")[0];
+    t.dleneri = F(&b, "dleneri")[0]; t.dqq1i = F(&b, "dqq1i")[0]; t.dllambi = F(&b, "dllambi")[0]; t.dqmsi = F(&b, "dqmsi")[0];
+
+    omc_geometry g;
+    g.isize = I(&b, "isize")[0]; g.jsize = I(&b, "jsize")[0]; g.ksize = I(&b, "ksize")[0];
+    g.xbounds = F(&b, "xbounds"); g.ybounds = F(&b, "ybounds"); g.zbounds = F(&b, "zbounds");
+    g.med = I(&b, "region_med"); g.rhof = F(&b, "region_rhof"); g.pcut = F(&b, "region_pcut"); g.ecut = F(&b, "region_ecut");
+    const double *dens = F(&b, "med_densities");
+    const int gridsize = g.isize * g.jsize * g.ksize;
+
+    omc_source_dosxyz s;
+    memset(&s, 0, sizeof s);
+    s.spectrum = I(&b, "src_spectrum")[0]; s.charge = I(&b, "src_charge")[0]; s.energy = F(&b, "src_energy")[0];
+    s.deltak = F(&b, "src_deltak")[0]; s.cdfinv1 = F(&b, "src_cdfinv1"); s.cdfinv2 = F(&b, "src_cdfinv2"); s.ssd = F(&b, "src_ssd")[0];
+    s.xinl = F(&b, "src_xinl")[0]; s.xinu = F(&b, "src_xinu")[0]; s.yinl = F(&b, "src_yinl")[0]; s.yinu = F(&b, "src_yinu")[0];
+    s.xsize = F(&b, "src_xsize")[0]; s.ysize = F(&b, "src_ysize")[0];
+    s.ixinl = I(&b, "src_ixinl")[0]; s.ixinu = I(&b, "src_ixinu")[0]; s.iyinl = I(&b, "src_iyinl")[0]; s.iyinu = I(&b, "src_iyinu")[0];
+    const int nsplit = I(&b, "nsplit")[0];
+
+    printf("Number of media in phantom : %d\n", t.nmed);
+    printf("Number of voxels on each direction (X,Y,Z) : (%d, %d, %d)\n", g.isize, g.jsize, g.ksize);
+    if (omc_gpu_create(&gpu, device)) { printf("No CUDA device: this program has no CPU transport path.\n"); return EXIT_FAILURE; }
+    if (omc_gpu_set_media(gpu, &t)) die("omc_gpu_set_media");
+    if (omc_gpu_set_geometry(gpu, &g)) die("omc_gpu_set_geometry");
+    if (omc_gpu_set_source_dosxyz(gpu, &s)) die("omc_gpu_set_source_dosxyz");
+    if (omc_gpu_set_vrt(gpu, nsplit)) die("omc_gpu_set_vrt");
+    int ixx = 97, jxx = 33;
+    sscanf(seeds, "%d %d", &ixx, &jxx);
+    omc_gpu_set_seed(gpu, ixx, jxx);
+    if (kernel < 0) kernel = nsplit > 1 ? OMC_KERNEL_LOCKSTEP : OMC_KERNEL_WAVEFRONT;
+    if (omc_gpu_set_option(gpu, "kernel", kernel)) die("omc_gpu_set_option");
+
+    /* batch bookkeeping exactly as omc_dosxyz.c:1207-1225 */
+    int nhist = atoi(ncase), nbatch = atoi(nbatch_s);
+    if (nbatch <= 0) { printf("Can not find 'nbatch' key on input file.\n"); return EXIT_FAILURE; }
+    if (nhist / nbatch == 0) nhist = nbatch;
+    const int nperbatch = nhist / nbatch;
+    nhist = nperbatch * nbatch;
+    printf("Total number of particle histories: %d\n", nhist);
+    printf("Number of statistical batches: %d\n", nbatch);
+    printf("Histories per batch: %d\n", nperbatch);
+    printf("Execution time up to this point : %8.2f seconds\n", now_s() - tbegin);
+
+    const double t0 = now_s();
+    for (int ibatch = 0; ibatch < nbatch; ibatch++) {
+        if (ibatch == 0) printf("%-10s\t%-15s\n", "Batch #", "Elapsed time");
+        printf("%-10d\t%-15.2f\n", ibatch, now_s() - tbegin);
+        if (omc_gpu_run_batch(gpu, (long long)ibatch * nperbatch, nperbatch, -1)) die("omc_gpu_run_batch");
+    }
+    double *accum = malloc(((size_t)gridsize + 1) * sizeof(double)), *accum2 = malloc(((size_t)gridsize + 1) * sizeof(double)), ensrc = 0.0;
+    if (omc_gpu_get_tallies(gpu, accum, accum2, &ensrc)) die("omc_gpu_get_tallies");
+    const double t1 = now_s();
+    printf("Simulation finished\n");
+    printf("Execution time up to this point : %8.2f seconds\n", t1 - tbegin);
+    printf("Histories per second (batch loop): %.4g\n", (double)nhist / (t1 - t0));
+    double etot = 0.0;
+    for (int irl = 1; irl < gridsize + 1; irl++) etot += accum[irl];
+    printf("Fraction of incident energy deposited in the phantom: %5.4f\n", etot / ensrc);
+    accumulate_results(&g, dens, accum, accum2, 1, nperbatch, nbatch);          /* iout = 1, nperbatch: omc_dosxyz.c:1281-1282 */
+    if (write_3ddose(stem, &g, accum, accum2)) return EXIT_FAILURE;
+    omc_gpu_destroy(gpu);
+    printf("Total execution time : %8.5f seconds\n", now_s() - tbegin);
+    return EXIT_SUCCESS;
+}

@@ -101,3 +101,35 @@ def test_accumulate_results_without_reference():
     np.testing.assert_allclose(unc[ok], s[ok], rtol=1e-12)
     assert dose[2] == 0.0 and unc[2] == 0.9999999
     np.testing.assert_allclose(dose[ok], e[ok] * 1.602e-10 / (1.0 * 100), rtol=1e-14)
+
+
+def test_resample_phantom_keeps_material_map():
+    ph = P.tissue_phantom((6, 4, 5), (0.3, 0.3, 0.3))
+    q = P.resample_phantom(ph, (3, 3, 3))
+    assert (q.isize, q.jsize, q.ksize) == (18, 12, 15)
+    np.testing.assert_allclose(np.diff(q.xbounds), 0.1, rtol=1e-9)
+    m = q.med_indices.reshape(q.ksize, q.jsize, q.isize)[::3, ::3, ::3]
+    assert np.array_equal(m.reshape(-1), ph.med_indices)
+    # mass is conserved
+    vol = lambda p: (np.diff(p.zbounds)[:, None, None] * np.diff(p.ybounds)[None, :, None] * np.diff(p.xbounds)[None, None, :]).reshape(-1)
+    assert abs((vol(q) * q.med_densities).sum() - (vol(ph) * ph.med_densities).sum()) < 1e-9
+
+
+def test_c_host_driver_builds_and_fails_loudly_without_gpu(tmp_path):
+    """ompmc_b200/host/omc_dosxyz_b200.c: the plain-C batch loop + statistics + .3ddose writer on the C-ABI."""
+    import subprocess
+    import torch
+    from ompmc_b200 import build
+    from oracle.gen_fixtures import golden_problem
+    build.build()
+    assert os.path.exists(build.HOST_EXE)
+    r = subprocess.run([build.HOST_EXE, "--help"], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stdout
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by tests/test_gpu_host.py")
+    prob, ph, cfg = golden_problem("golden_water700_6MV")
+    blob = str(tmp_path / "p.blob")
+    P.save_blob(blob, prob)
+    r = subprocess.run([build.HOST_EXE, "-p", blob, "-n", "1000", "-b", "4", "-o", str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU transport" in r.stdout
+    assert not os.path.exists(str(tmp_path / "o.3ddose"))
