@@ -145,7 +145,7 @@ typedef struct omc_gpu_ctx *omc_gpu_handle;
 
 /* kernel selection for omc_gpu_set_option("kernel", ...) */
 #define OMC_KERNEL_LOCKSTEP  0   /* one history per thread, reference draw order (parity anchor) */
-#define OMC_KERNEL_WAVEFRONT 1   /* particle-queue production kernels                            */
+#define OMC_KERNEL_WAVEFRONT 1   /* particle-queue production kernels (nsplit <= 255)            */
 
 /* ---- life cycle ------------------------------------------------------------------------- */
 /* replaces initStack()/initRandom() per thread (omc_dosxyz.c:1184-1191) */

@@ -108,7 +108,7 @@ static void free_pool(std::vector<void *> &pool) {
 
 static int alloc_queue(omc_gpu_handle h, PartQueue &q, unsigned cap) {
     q.cap = cap;
-    double **f[9] = {&q.x, &q.y, &q.z, &q.u, &q.v, &q.w, &q.e, &q.wt, &q.aux};
+    double **f[10] = {&q.x, &q.y, &q.z, &q.u, &q.v, &q.w, &q.e, &q.wt, &q.aux, &q.aux2};
     for (auto pp : f) {
         CK(cudaMalloc((void **)pp, (size_t)cap * sizeof(double)));
         h->wave_bufs.push_back(*pp);
@@ -205,7 +205,7 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
         }
         const bool exhausted = s.hist_next >= s.hist_end && s.n_src == 0;
         if (exhausted && s.live == 0) break;
-        if (exhausted && s.live <= h->drain_threshold) { drained = true; break; }
+        if (exhausted && s.live <= h->drain_threshold && P.nsplit == 1) { drained = true; break; }   // (split photons in flight cannot be handed over)
         if (wave > 50000000ull) { rc = fail(h, "wavefront did not terminate"); break; }
     }
     if (gexec) { cudaGraphExecDestroy(gexec); cudaGraphDestroy(graph); }
@@ -565,7 +565,7 @@ int omc_gpu_run_histories(omc_gpu_handle h, long long first, long long nhist, in
         h->launches += 1;
         CK(cudaGetLastError());
     } else if (h->kernel == OMC_KERNEL_WAVEFRONT) {
-        if (P.nsplit != 1) return fail(h, "wavefront kernels implement nsplit = 1; use the lock-step kernel for photon splitting");
+        if (P.nsplit > 255) return fail(h, "wavefront kernels support nsplit <= 255; use the lock-step kernel beyond");
         if (h->record) return fail(h, "per-history records are a lock-step kernel feature");
         int rc = run_wavefront(h, first, nhist, ibeamlet);
         if (rc) return rc;

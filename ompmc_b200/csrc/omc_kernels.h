@@ -16,14 +16,15 @@ void launch_accum(double *endep, double *accum, double *accum2, long long n, cud
 
 // ---- omc_wavefront.cu ---------------------------------------------------------------------------
 // One particle queue in HBM, structure-of-arrays (coalesced 8-byte lanes); irq = {ir, iq | tag << 16},
-// rng = {hist_lo, hist_hi, stream, draws consumed}; aux = photon mfp left (-1: not sampled yet).
+// rng = {hist_lo, hist_hi, stream, draws consumed}; aux = photon mfp left (-1: not sampled yet), aux2 = eta' of the
+// running split copy (photon splitting); for photons in flight tag = isplit | i_survive << 8.
 struct PartQueue {
-    double *x, *y, *z, *u, *v, *w, *e, *wt, *aux;
+    double *x, *y, *z, *u, *v, *w, *e, *wt, *aux, *aux2;
     int2 *irq;
     uint4 *rng;
     unsigned cap;
 };
-constexpr size_t PART_QUEUE_BYTES_PER_SLOT = 9 * sizeof(double) + sizeof(int2) + sizeof(uint4);
+constexpr size_t PART_QUEUE_BYTES_PER_SLOT = 10 * sizeof(double) + sizeof(int2) + sizeof(uint4);
 
 constexpr int WAVE_THREADS = 128;   // threads per block == particles per chunk
 

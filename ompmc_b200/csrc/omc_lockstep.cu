@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(128) drain_kernel(const __grid_constant__ DevP
         if (tag != 0) {                                       // interaction that was due in the next wave
             const RegionRec R = load_region(P, p.ir);
             const int imed = R.med;
-            switch (tag) {
+            switch (tag & 15) {                               // (bit 4 = survivor flag of photon splitting, always set here)
                 case 1: compton(c.g, p, s2); two = true; break;
                 case 2: pair(P, c.g, p, s2, imed); two = true; break;
                 case 3: photo(c.g, p, R.ecut); break;

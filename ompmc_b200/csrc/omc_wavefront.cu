@@ -68,9 +68,10 @@ __device__ __forceinline__ void q_load(const PartQueue &q, unsigned i, Part &p, 
     g.seed(P.seed0, P.seed1, ((unsigned long long)r.y << 32) | r.x, r.z, r.w);
 }
 
-__device__ __forceinline__ void q_store(const PartQueue &q, unsigned i, const Part &p, const Rng &g, double aux, int tag) {
+__device__ __forceinline__ void q_store(const PartQueue &q, unsigned i, const Part &p, const Rng &g, double aux, int tag,
+                                        double aux2 = 0.0) {
     q.x[i] = p.x; q.y[i] = p.y; q.z[i] = p.z; q.u[i] = p.u; q.v[i] = p.v; q.w[i] = p.w;
-    q.e[i] = p.e; q.wt[i] = p.wt; q.aux[i] = aux;
+    q.e[i] = p.e; q.wt[i] = p.wt; q.aux[i] = aux; q.aux2[i] = aux2;
     q.irq[i] = make_int2(p.ir, (p.iq & 0xffff) | (tag << 16));
     q.rng[i] = make_uint4(g.h0, g.h1, g.stream, g.ndraws());
 }
@@ -87,10 +88,10 @@ __device__ __forceinline__ unsigned q_reserve(unsigned *count) {
 }
 
 __device__ __forceinline__ void q_push(const PartQueue &q, unsigned *count, WaveCtl *ctl, const Part &p, const Rng &g, double aux,
-                                       int tag) {
+                                       int tag, double aux2 = 0.0) {
     const unsigned slot = q_reserve(count);
     if (slot >= q.cap) { atomicAdd(&ctl->overflow, 1u); return; }
-    q_store(q, slot, p, g, aux, tag);
+    q_store(q, slot, p, g, aux, tag, aux2);
 }
 
 // sub-stream of a particle created by `parent` (a function of the parent's stream position only)
@@ -144,11 +145,23 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, int par, un
     Part p; Rng g; double dpmfp; int tag;
     q_load(A.Q.p[par], i, p, g, P, dpmfp, tag);
     RegionRec R = load_region_w(P, p.ir);
+    // uniform photon splitting, :1903-1945: the record is the ray of nsplit copies of weight wt/nsplit whose
+    // interaction depths are stratified (eta'_k = eta'_0 - k/nsplit); copy `isplit` is the one in flight.
+    const int nsplit = P.nsplit;
+    const double d_eta = 1.0 / (double)nsplit;
+    int isplit = tag & 0xff, isurv = (tag >> 8) & 0xff;
+    double eta = A.Q.p[par].aux2[i];
     if (dpmfp < 0.0) {                                         // fresh photon: cut-off test + number of mfp
         if (p.e <= R.pcut || p.wt == 0) { deposit32(P, t, p.ir, p.wt * p.e); return; }
         g.align();
         const double r = g.next();
-        dpmfp = -log(1.0 - r);                                 // eta' = 1 - r  (:1905-1932 with nsplit = 1)
+        eta = 1.0 - r / (double)nsplit;                        // eta' of the first copy
+        isplit = 0; isurv = 0;
+        if (nsplit > 1) {                                      // (with nsplit == 1 the survivor draw :1916 is unused)
+            p.wt /= (double)nsplit;
+            isurv = (int)(g.next() * nsplit);
+        }
+        dpmfp = -log(eta);
     }
     const double gle = log(p.e);
     if (p.ir == 0) return;                                     // outside the phantom: howfar() discards (idisc)
@@ -163,7 +176,6 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, int par, un
     const int sx = p.u > 0.0, sy = p.v > 0.0, sz = p.w > 0.0;
     int imed = R.med, medc = -2;
     double sig0 = 0.0, cohfac = 0.0, sig = 0.0;                // sig = 1 / gmfp
-    bool at_site = false;
     for (int k = 0; k < A.max_cross; k++) {
         double tstep = 1.0E8;
         if (imed != -1) {
@@ -202,27 +214,39 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, int par, un
             R = load_region_w(P, ir);
             imed = R.med;
         }
-        if (imed != -1 && dpmfp <= 1.0E-05) { at_site = true; break; }
-    }
-    if (!at_site) { q_push(A.Q.p[par ^ 1], &ctl->n_p[par ^ 1], ctl, p, g, dpmfp, TAG_NONE); return; }
-    const MedRec &M = P.med[imed];
-    const int lgle = (int)(gle * M.ge1 + M.ge0) - 1;
-    const PhotBin *B = P.phot + imed * MXGE + lgle;
-    if (imed != medc) cohfac = pwl(gle, __ldg(&B->cohe1), __ldg(&B->cohe0));   // site right after a medium change
-    g.align();
-    double r = g.next();                                       // :2027-2067
-    if (r <= 1.0 - cohfac) {
-        tag = TAG_RAYLEIGH;
-    } else {
-        r = g.next();
-        const double gbr1 = pwl(gle, __ldg(&B->gbr11), __ldg(&B->gbr10));
-        if (r <= gbr1 && p.e > 2.0 * RM) tag = TAG_PAIR;
-        else {
-            const double gbr2 = pwl(gle, __ldg(&B->gbr21), __ldg(&B->gbr20));
-            tag = (r < gbr2) ? TAG_COMPTON : TAG_PHOTO;
+        if (imed != -1 && dpmfp <= 1.0E-05) {                  // interaction site of copy `isplit`, :2027-2067
+            const MedRec &M = P.med[imed];
+            const int lgle = (int)(gle * M.ge1 + M.ge0) - 1;
+            const PhotBin *B = P.phot + imed * MXGE + lgle;
+            const double coh = (imed != medc) ? pwl(gle, __ldg(&B->cohe1), __ldg(&B->cohe0)) : cohfac;   // site right after a medium change
+            const bool surv = (isplit == isurv);
+            int type;
+            g.align();
+            double r = g.next();
+            if (r <= 1.0 - coh) {
+                type = TAG_RAYLEIGH;
+            } else {
+                r = g.next();
+                const double gbr1 = pwl(gle, __ldg(&B->gbr11), __ldg(&B->gbr10));
+                if (r <= gbr1 && p.e > 2.0 * RM) type = TAG_PAIR;
+                else {
+                    const double gbr2 = pwl(gle, __ldg(&B->gbr21), __ldg(&B->gbr20));
+                    type = (r < gbr2) ? TAG_COMPTON : TAG_PHOTO;
+                }
+            }
+            if (surv || type != TAG_RAYLEIGH) {                // a Rayleigh-scattered non-survivor is simply dropped, :2030-2034
+                Rng gq;
+                child_rng(g, gq, (unsigned)isplit);
+                q_push(A.Q.ip[par ^ 1], &ctl->n_ip[par ^ 1], ctl, p, gq, -1.0, type | (surv ? 16 : 0));
+            }
+            isplit += 1;
+            const double eta_new = eta - d_eta;
+            if (isplit >= nsplit || eta_new <= 0.0) return;    // all copies done
+            dpmfp = log(eta / eta_new);                        // = -log(eta'_k) - sum of the previous copies' mfp
+            eta = eta_new;
         }
     }
-    q_push(A.Q.ip[par ^ 1], &ctl->n_ip[par ^ 1], ctl, p, g, -1.0, tag);
+    q_push(A.Q.p[par ^ 1], &ctl->n_p[par ^ 1], ctl, p, g, dpmfp, isplit | (isurv << 8), eta);
 }
 
 // chunk IP: photon interactions
@@ -235,24 +259,30 @@ __device__ void p_interact_chunk(const DevProblem &P, const WaveArgs &A, int par
     g.align();
     const RegionRec R = load_region_w(P, p.ir);
     const int imed = R.med;
-    if (tag == TAG_COMPTON) {
+    // photon splitting: scattered photons are kept for the surviving copy only and get the full weight back;
+    // charged secondaries of every copy are kept with the copy's weight wt/nsplit (:2072-2093)
+    const bool surv = (tag & 16) != 0;
+    const int type = tag & 15;
+    const double back = (double)P.nsplit;
+    if (type == TAG_COMPTON) {
         compton(g, p, q);
         child_rng(g, gq, 0);
-        q_push(pn, &ctl->n_p[par ^ 1], ctl, p, g, -1.0, TAG_NONE);
+        if (surv) { p.wt *= back; q_push(pn, &ctl->n_p[par ^ 1], ctl, p, g, -1.0, TAG_NONE); }
         q_push(en, &ctl->n_e[par ^ 1], ctl, q, gq, 0.0, TAG_NONE);
-    } else if (tag == TAG_PAIR) {
+    } else if (type == TAG_PAIR) {
         pair(P, g, p, q, imed);
         child_rng(g, gq, 0);
         q_push(en, &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
         q_push(en, &ctl->n_e[par ^ 1], ctl, q, gq, 0.0, TAG_NONE);
-    } else if (tag == TAG_PHOTO) {
+    } else if (type == TAG_PHOTO) {
         photo(g, p, R.ecut);
         q_push(en, &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
-    } else {                                                   // Rayleigh: direction change only
+    } else {                                                   // Rayleigh (surviving copy only): direction change
         const MedRec &M = P.med[imed];
         const double gle = log(p.e);
         const int lgle = (int)(gle * M.ge1 + M.ge0) - 1;
         const PhotBin *B = P.phot + imed * MXGE + lgle;
+        p.wt *= back;
         rayleigh(P, g, p, pwl(gle, __ldg(&B->pmax1), __ldg(&B->pmax0)), p.e);
         q_push(pn, &ctl->n_p[par ^ 1], ctl, p, g, -1.0, TAG_NONE);
     }
@@ -275,21 +305,21 @@ __device__ void e_interact_chunk(const DevProblem &P, const WaveArgs &A, int par
             q_push(en, &ctl->n_e[par ^ 1], ctl, q, gq, 0.0, TAG_NONE);
         }
     } else if (tag == TAG_BREMS) {
-        brems(P, g, p, q, imed, 1);
+        brems(P, g, p, q, imed, P.nsplit);                     // incl. Russian roulette of the photon when nsplit > 1
         child_rng(g, gq, 0);
         q_push(en, &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
-        q_push(pn, &ctl->n_p[par ^ 1], ctl, q, gq, -1.0, TAG_NONE);
+        if (q.wt != 0.0) q_push(pn, &ctl->n_p[par ^ 1], ctl, q, gq, -1.0, TAG_NONE);
     } else if (tag == TAG_BHABHA) {
         bhabha(P, g, p, q, imed);
         child_rng(g, gq, 0);
         q_push(en, &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
         q_push(en, &ctl->n_e[par ^ 1], ctl, q, gq, 0.0, TAG_NONE);
     } else {                                                   // annihilation in flight / at rest
-        if (tag == TAG_ANNIH) annih(g, p, q, 1);
-        else rannih(g, p, q, 1);
+        if (tag == TAG_ANNIH) annih(g, p, q, P.nsplit);
+        else rannih(g, p, q, P.nsplit);
         child_rng(g, gq, 0);
-        q_push(pn, &ctl->n_p[par ^ 1], ctl, p, g, -1.0, TAG_NONE);
-        q_push(pn, &ctl->n_p[par ^ 1], ctl, q, gq, -1.0, TAG_NONE);
+        if (p.wt != 0.0) q_push(pn, &ctl->n_p[par ^ 1], ctl, p, g, -1.0, TAG_NONE);
+        if (q.wt != 0.0) q_push(pn, &ctl->n_p[par ^ 1], ctl, q, gq, -1.0, TAG_NONE);
     }
 }
 

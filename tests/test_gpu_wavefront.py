@@ -45,6 +45,11 @@ CASES = [
                     spec=None, coll=(-2, 2, -2, 2), ssd=100.0, ecut=0.7, charge=-1, mono=6.0), 10, 20000),
     ("e+3MeV", dict(mset="media_521_water.blob", ph=lambda: P.water_phantom("H2O521ICRU", (11, 11, 16), (0.8, 0.8, 0.25)),
                     spec=None, coll=(-2, 2, -2, 2), ssd=100.0, ecut=0.521, charge=1, mono=3.0), 10, 20000),
+    # uniform photon splitting + Russian roulette of secondary photons (the reference's shipped input uses nsplit = 20)
+    ("water6mv-nsplit5", dict(mset="media_700_water.blob", ph=lambda: P.water_phantom("H2O700ICRU", (15, 15, 20), (1.0, 1.0, 1.0)),
+                              spec="mohan6", coll=(-5, 5, -5, 5), ssd=100.0, ecut=0.7, charge=0, mono=0.0, nsplit=5), 10, 40000),
+    ("tissue18mv-nsplit20", dict(mset="media_700_tissue4.blob", ph=lambda: P.tissue_phantom((24, 10, 24), (0.8, 0.8, 0.8)),
+                                 spec=None, coll=(-4, 4, -3, 3), ssd=90.0, ecut=0.7, charge=0, mono=18.0, nsplit=20), 10, 5000),
 ]
 
 
@@ -53,7 +58,7 @@ def make_problem(cfg):
     ph = cfg["ph"]()
     cdf = (media["cdfinv1_" + cfg["spec"]], media["cdfinv2_" + cfg["spec"]]) if cfg["spec"] else None
     prob = P.build_problem(media, ph, ecut=cfg["ecut"], pcut=0.01, collimator=cfg["coll"], ssd=cfg["ssd"], charge=cfg["charge"],
-                           cdfinv=cdf, mono_energy=cfg["mono"], nsplit=1)
+                           cdfinv=cdf, mono_energy=cfg["mono"], nsplit=cfg.get("nsplit", 1))
     return prob, ph
 
 
@@ -118,11 +123,13 @@ def test_wavefront_scheduling_independence(gpu):
 
 
 def test_wavefront_rejects_unsupported(gpu):
-    prob, _, _ = golden_problem("golden_water700_6MV_ns5")
+    prob, ph = make_problem(dict(CASES[0][1], nsplit=300))
     gpu.load_problem(prob)
     gpu.set_option("kernel", 1)
     with pytest.raises(OmcGpuError):
-        gpu.run_histories(0, 100)          # nsplit = 5: lock-step kernel only
+        gpu.run_histories(0, 100)          # nsplit > 255: lock-step kernel only
+    with pytest.raises(OmcGpuError):
+        gpu.run_histories(0, 100, records=True)   # per-history records are a lock-step feature
     gpu.set_option("kernel", 0)
 
 
