@@ -189,7 +189,7 @@ int main(int argc, char **argv) {
     int ixx = 97, jxx = 33;
     sscanf(seeds, "%d %d", &ixx, &jxx);
     omc_gpu_set_seed(gpu, ixx, jxx);
-    if (kernel < 0) kernel = nsplit > 1 ? OMC_KERNEL_LOCKSTEP : OMC_KERNEL_WAVEFRONT;
+    if (kernel < 0) kernel = nsplit > 255 ? OMC_KERNEL_LOCKSTEP : OMC_KERNEL_WAVEFRONT;
     if (omc_gpu_set_option(gpu, "kernel", kernel)) die("omc_gpu_set_option");
 
     /* batch bookkeeping exactly as omc_dosxyz.c:1207-1225 */
