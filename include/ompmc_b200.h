@@ -205,6 +205,13 @@ int omc_gpu_abi_sizeof(int what);
 int omc_gpu_test_geometry(omc_gpu_handle h, int n, const double *xyzuvw /* [6*n] */, const int *ir,
                           const double *ustep_in, int *idisc, int *irnew, double *ustep_out,
                           double *tperp);
+/*
+ * shower() (src/ompmc.c:5436-5447) for n explicit top-of-stack particles -- charge, TOTAL energy, position,
+ * direction, region, weight -- particle i using the Philox stream of history first_history + i, through the
+ * lock-step kernel.  Deposits go to the batch grid; one record per particle.  Sampler-level parity tests.
+ */
+int omc_gpu_test_particles(omc_gpu_handle h, int n, const int *iq, const double *e, const double *xyzuvw, const int *ir,
+                           const double *wt, long long first_history, omc_history_record *records);
 /* n raw Philox draws of history `hist` as the transport sees them (double in [0,1)) */
 int omc_gpu_test_rng(omc_gpu_handle h, long long hist, int n, double *out);
 

@@ -89,7 +89,8 @@ EXPORTS = ["omc_gpu_create", "omc_gpu_destroy", "omc_gpu_last_error", "omc_gpu_s
            "omc_gpu_set_source_dosxyz", "omc_gpu_set_source_matrad", "omc_gpu_set_vrt", "omc_gpu_set_seed", "omc_gpu_set_option",
            "omc_gpu_run_histories", "omc_gpu_accum_batch", "omc_gpu_run_batch", "omc_gpu_synchronize", "omc_gpu_get_tallies",
            "omc_gpu_get_batch_grid", "omc_gpu_reset_tallies", "omc_gpu_device_ptrs", "omc_gpu_stream", "omc_gpu_get_counters",
-           "omc_gpu_get_history_records", "omc_gpu_test_geometry", "omc_gpu_test_rng", "omc_gpu_abi_sizeof"]
+           "omc_gpu_get_history_records", "omc_gpu_test_geometry", "omc_gpu_test_rng", "omc_gpu_test_particles",
+           "omc_gpu_abi_sizeof"]
 
 
 def load_library() -> C.CDLL:
@@ -121,6 +122,7 @@ def load_library() -> C.CDLL:
     lib.omc_gpu_test_geometry.argtypes = [H, C.c_int] + [C.c_void_p] * 7
     lib.omc_gpu_test_rng.argtypes = [H, C.c_longlong, C.c_int, C.c_void_p]
     lib.omc_gpu_abi_sizeof.argtypes = [C.c_int]
+    lib.omc_gpu_test_particles.argtypes = [H, C.c_int] + [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]
     return lib
 
 
@@ -285,6 +287,15 @@ class GpuTransport:
                                                 idisc.ctypes.data, irnew.ctypes.data, us.ctypes.data, tp.ctypes.data),
                  "omc_gpu_test_geometry")
         return idisc, irnew, us, tp
+
+    def test_particles(self, iq, e, xyzuvw, ir, wt=None, first_history: int = 0):
+        iq = _i32(iq); e = _f64(e); xyzuvw = _f64(xyzuvw); ir = _i32(ir)
+        n = len(iq)
+        wt = _f64(np.ones(n) if wt is None else wt)
+        rec = np.zeros(n, dtype=RECORD_DTYPE)
+        self._ck(self.lib.omc_gpu_test_particles(self.h, n, iq.ctypes.data, e.ctypes.data, xyzuvw.ctypes.data, ir.ctypes.data,
+                                                 wt.ctypes.data, first_history, rec.ctypes.data), "omc_gpu_test_particles")
+        return rec
 
     def test_rng(self, hist: int, n: int) -> np.ndarray:
         out = np.zeros(n)

@@ -36,6 +36,7 @@ struct omc_gpu_ctx {
     bool have_media = false, have_geom = false, have_source = false;
     double *accum = nullptr, *accum2 = nullptr;
     int tally_nreg = -1;
+    const Part *inject = nullptr;   // unit-test hook (omc_gpu_test_particles)
     // options
     int kernel = OMC_KERNEL_LOCKSTEP;
     int threads_per_block = 128;
@@ -561,7 +562,7 @@ int omc_gpu_run_histories(omc_gpu_handle h, long long first, long long nhist, in
             CK(cudaMalloc((void **)&h->stack, need));
             h->stack_bytes = need;
         }
-        launch_lockstep(P, h->stack, depth, blocks, tpb, first, nhist, ibeamlet, h->stream);
+        launch_lockstep(P, h->stack, depth, blocks, tpb, first, nhist, ibeamlet, h->inject, h->stream);
         h->launches += 1;
         CK(cudaGetLastError());
     } else if (h->kernel == OMC_KERNEL_WAVEFRONT) {
@@ -705,6 +706,31 @@ int omc_gpu_test_geometry(omc_gpu_handle h, int n, const double *xyzuvw, const i
     CK(cudaMemcpy(tperp, dtp, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
     cudaFree(dq); cudaFree(dus); cudaFree(duo); cudaFree(dtp); cudaFree(dir); cudaFree(did); cudaFree(dirn);
     return 0;
+}
+
+int omc_gpu_test_particles(omc_gpu_handle h, int n, const int *iq, const double *e, const double *xyzuvw, const int *ir,
+                           const double *wt, long long first_history, omc_history_record *records) {
+    if (!h || n <= 0 || !records) return 2;
+    if (!h->have_media || !h->have_geom || !h->have_source) return fail(h, "media, geometry and source must be set first");
+    CK(cudaSetDevice(h->device));
+    std::vector<Part> host((size_t)n);
+    for (int i = 0; i < n; i++) {
+        Part &p = host[i];
+        p.x = xyzuvw[6 * i]; p.y = xyzuvw[6 * i + 1]; p.z = xyzuvw[6 * i + 2];
+        p.u = xyzuvw[6 * i + 3]; p.v = xyzuvw[6 * i + 4]; p.w = xyzuvw[6 * i + 5];
+        p.e = e[i]; p.wt = wt[i]; p.ir = ir[i]; p.iq = iq[i];
+        if (ir[i] < 0 || ir[i] >= h->P.nreg) return fail(h, "region index out of range");
+    }
+    Part *dev = nullptr;
+    CK(cudaMalloc((void **)&dev, (size_t)n * sizeof(Part)));
+    CK(cudaMemcpy(dev, host.data(), (size_t)n * sizeof(Part), cudaMemcpyHostToDevice));
+    const int kernel = h->kernel, record = h->record;
+    h->kernel = OMC_KERNEL_LOCKSTEP; h->record = 1; h->inject = dev;
+    int rc = omc_gpu_run_histories(h, first_history, n, -1);
+    if (!rc) rc = omc_gpu_get_history_records(h, records, n);
+    h->kernel = kernel; h->record = record; h->inject = nullptr;
+    cudaFree(dev);
+    return rc;
 }
 
 int omc_gpu_test_rng(omc_gpu_handle h, long long hist, int n, double *out) {

@@ -6,7 +6,7 @@ namespace omc {
 
 // omc_lockstep.cu
 void launch_lockstep(const DevProblem &P, Part *stack, int depth, int blocks, int threads, long long first, long long nhist,
-                     int ibeamlet, cudaStream_t stream);
+                     int ibeamlet, const Part *inject, cudaStream_t stream);
 int lockstep_blocks_per_sm(int threads);
 void launch_test_geometry(const DevProblem &P, int n, const double *xyzuvw, const int *ir, const double *ustep_in, int *idisc,
                           int *irnew, double *ustep_out, double *tperp, cudaStream_t stream);

@@ -460,7 +460,7 @@ __device__ void electron_ls(const DevProblem &P, HistCtx &c) {
 }
 
 __global__ void __launch_bounds__(128) lockstep_kernel(const __grid_constant__ DevProblem P, Part *stack, int depth,
-                                                       long long first, long long nhist, int ibeamlet) {
+                                                       long long first, long long nhist, int ibeamlet, const Part *inject) {
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     HistCtx c;
@@ -475,7 +475,8 @@ __global__ void __launch_bounds__(128) lockstep_kernel(const __grid_constant__ D
         c.g.seed(P.seed0, P.seed1, hist, 0u);
         c.ndeposit = 0; c.flags = 0; c.edep_sum = 0.0;
         Part p;
-        ensrc += init_history(P, c.g, p, ibeamlet);             // omc_dosxyz.c:1254 / omc_matrad.c:1396
+        if (inject) p = inject[i];                              // unit-test hook: explicit top-of-stack particle
+        else ensrc += init_history(P, c.g, p, ibeamlet);        // omc_dosxyz.c:1254 / omc_matrad.c:1396
         const int ir0 = p.ir;
         c.np = 0;
         c.s[0] = p;
@@ -586,8 +587,8 @@ int lockstep_blocks_per_sm(int threads) {
 }
 
 void launch_lockstep(const DevProblem &P, Part *stack, int depth, int blocks, int threads, long long first, long long nhist,
-                     int ibeamlet, cudaStream_t stream) {
-    lockstep_kernel<<<blocks, threads, 0, stream>>>(P, stack, depth, first, nhist, ibeamlet);
+                     int ibeamlet, const Part *inject, cudaStream_t stream) {
+    lockstep_kernel<<<blocks, threads, 0, stream>>>(P, stack, depth, first, nhist, ibeamlet, inject);
 }
 
 // ---- unit-test kernels ------------------------------------------------------------------------
