@@ -331,8 +331,10 @@ def main() -> None:
         achieved = balg * H / (kernel_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(f"{args.workload}:{line['config']['kernel']}")
+        if os.path.exists(tp):       # measured DRAM bytes per history (ncu --set full) x histories of one launch group
+            rec = json.load(open(tp)).get(f"{args.workload}:{line['config']['kernel']}")
+            if rec:
+                traffic = rec["dram_bytes_per_history"] * H
         line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": traffic, "peak_kind": peak_kind, "alg_bytes_per_history": balg, "work_per_history": work,
                             "kernel_ms_per_launch_group": kernel_ms, "histories_per_launch_group": H,

@@ -7,16 +7,21 @@ import csv, io, re, subprocess, sys
 from collections import defaultdict
 
 rep, kre, cubin = sys.argv[1:4]
+# "ncu-name-regex|||mangled-symbol-regex" when the two differ (templates)
+kre, sre = kre.split("|||") if "|||" in kre else (kre, kre)
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "--kernel-name", f"regex:{kre}"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-# first launch only
 hdr_idx = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
-H = rows[hdr_idx[0]]
 end = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
-stop = end[1] if len(end) > 1 else len(rows)
-body = [r for r in rows[hdr_idx[0] + 1:stop] if len(r) == len(H)]
+# which launch of the matching kernels (env NCU_LAUNCH, default the first one)
+import os
+which = int(os.environ.get("NCU_LAUNCH", "0"))
+print("kernel:", rows[end[which]][1])
+H = rows[hdr_idx[which]]
+stop = end[which + 1] if len(end) > which + 1 else len(rows)
+body = [r for r in rows[hdr_idx[which] + 1:stop] if len(r) == len(H)]
 col = {h: i for i, h in enumerate(H)}
 base = int(body[0][col["Address"]], 16)
 # nvdisasm with line info
@@ -28,7 +33,7 @@ lines = {}
 for ln in dis:
     m = fn_re.match(ln)
     if m:
-        infunc = re.search(kre, m.group(1)) is not None
+        infunc = re.search(sre, m.group(1)) is not None
         continue
     if not infunc:
         continue
