@@ -3,6 +3,7 @@
 // Host side only: packs the reference-layout tables into the device records of omc_types.cuh,
 // owns device memory / the stream, launches the kernels.  There is NO CPU transport path in this
 // library: every entry point that does physics launches a CUDA kernel or fails.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -51,7 +52,7 @@ struct omc_gpu_ctx {
     unsigned long long launches = 0;
     // wavefront state
     std::vector<MedRec> med_host;
-    double cut_e[OMC_MXMED] = {0}, cut_p[OMC_MXMED] = {0};
+    double cut_e[OMC_MXMED] = {0}, cut_p[OMC_MXMED] = {0}, rho_max[OMC_MXMED] = {0};
     bool cuts_uniform = false, med_dirty = false;
     WaveQueues wq{};
     std::vector<void *> wave_bufs;
@@ -60,6 +61,8 @@ struct omc_gpu_ctx {
     unsigned pool_target = 1u << 22;
     unsigned pool_cap = 0, pool_cap_opt = 0;
     int electron_iters = 1, max_cross = 16, check_every = 16;
+    int photon_tracking = 1;      // 0: voxel-to-voxel march as in photon(); 1: Woodcock flight when nsplit == 1
+    int max_virtual = 8;          // Woodcock: tentative collisions per photon per wave
     unsigned long long waves = 0;
     int trace = 0, use_graph = 1, overlap = 1, source_kind = 0;
     cudaStream_t stream2 = nullptr;
@@ -148,8 +151,10 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
             if (alloc_queue(h, h->wq.ip[i], cap)) return 1;
             if (alloc_queue(h, h->wq.ie[i], cap)) return 1;
         }
-        if (alloc_estep_queue(h, h->wq.ch, cap)) return 1;
-        if (alloc_estep_queue(h, h->wq.bca, cap)) return 1;
+        for (int i = 0; i < 2; i++) {
+            if (alloc_estep_queue(h, h->wq.ch[i], cap)) return 1;
+            if (alloc_estep_queue(h, h->wq.bca[i], cap)) return 1;
+        }
         h->pool_cap = cap;
     }
     if (!h->stream2) {
@@ -172,6 +177,8 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
     wave_blocks_per_sm(occ);
     for (int i = 0; i < 4; i++) L.blocks[i] = h->max_blocks > 0 ? h->max_blocks : h->sm_count * occ[i];
     L.max_cross = h->max_cross; L.electron_iters = h->electron_iters; L.ibeamlet = ibeamlet;
+    L.woodcock = (h->photon_tracking == 1 && P.nsplit == 1) ? 1 : 0;
+    L.max_virtual = h->max_virtual > 0 ? ((h->max_virtual + 1) & ~1) : 8;   // even: whole Philox blocks, so results do not depend on it
     const int every = h->check_every > 0 ? h->check_every : 1;
     // `every` waves are captured once into a CUDA graph (all launch parameters are wave-invariant: cur/next
     // parity lives in WaveCtl on the device), so the host issues one graph launch per `every` waves
@@ -197,8 +204,8 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
         CK(cudaStreamSynchronize(h->stream));
         const WaveCtl &s = *h->ctl_host;
         if (h->trace)
-            fprintf(stderr, "wave %llu live %u n_src %u P %u E %u IP %u IE %u hist_next %llu\n", wave + every, s.live, s.n_src,
-                    s.n_p[s.parity], s.n_e[s.parity], s.n_ip[s.parity], s.n_ie[s.parity], s.hist_next);
+            fprintf(stderr, "wave %llu live %u n_src %u P %u E %u IP %u IE %u CH %u BCA %u hist_next %llu\n", wave + every, s.live, s.n_src,
+                    s.n_p[s.parity], s.n_e[s.parity], s.n_ip[s.parity], s.n_ie[s.parity], s.n_ch[s.parity], s.n_bca[s.parity], s.hist_next);
         if (s.overflow) {
             h->err = "particle queue overflow on the device: increase option pool_size";
             rc = 7;
@@ -227,6 +234,8 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
         DrainArgs D;
         D.q[0] = h->wq.p[par]; D.q[1] = h->wq.e[par]; D.q[2] = h->wq.ip[par]; D.q[3] = h->wq.ie[par];
         D.count[0] = &h->ctl->n_p[par]; D.count[1] = &h->ctl->n_e[par]; D.count[2] = &h->ctl->n_ip[par]; D.count[3] = &h->ctl->n_ie[par];
+        D.sq[0] = h->wq.ch[par]; D.sq[1] = h->wq.bca[par];
+        D.scount[0] = &h->ctl->n_ch[par]; D.scount[1] = &h->ctl->n_bca[par];
         D.ticket = &h->ctl->drain_ticket;
         launch_drain(P, D, h->stack, depth, blocks, h->stream);
         h->launches += 1;
@@ -405,6 +414,30 @@ int omc_gpu_set_geometry(omc_gpu_handle h, const omc_geometry *g) {
             if (!seen[m]) { seen[m] = true; h->cut_e[m] = g->ecut[i]; h->cut_p[m] = g->pcut[i]; }
             else if (h->cut_e[m] != g->ecut[i] || h->cut_p[m] != g->pcut[i]) uniform = false;
         }
+        // largest density ratio per medium (as the kernels will read it): majorant of the Woodcock photon flight
+        for (int m = 0; m < OMC_MXMED; m++) h->rho_max[m] = 0.0;
+        for (int i = 1; i < P.nreg; i++) {
+            const int m = g->med[i];
+            if (m < 0) continue;
+            const double r = g->rhof[i], rf = (double)(float)g->rhof[i];
+            if (r > h->rho_max[m]) h->rho_max[m] = r;
+            if (rf > h->rho_max[m]) h->rho_max[m] = rf;
+        }
+        // uniformly spaced axes: voxel lookup by division (find_bin)
+        {
+            const double *b[3] = {g->xbounds, g->ybounds, g->zbounds};
+            const int nb[3] = {g->isize, g->jsize, g->ksize};
+            double inv[3]; int uni[3];
+            for (int a = 0; a < 3; a++) {
+                const double d = (b[a][nb[a]] - b[a][0]) / nb[a];
+                uni[a] = d > 0.0;
+                for (int i = 0; i < nb[a] && uni[a]; i++)
+                    if (fabs((b[a][i + 1] - b[a][i]) - d) > 1.0e-9 * d) uni[a] = 0;
+                inv[a] = d > 0.0 ? 1.0 / d : 0.0;
+            }
+            P.inv_dx = inv[0]; P.inv_dy = inv[1]; P.inv_dz = inv[2];
+            P.uniform_x = uni[0]; P.uniform_y = uni[1]; P.uniform_z = uni[2];
+        }
         P.reg8 = nullptr;
         h->cuts_uniform = uniform;
         if (uniform) {
@@ -515,6 +548,8 @@ int omc_gpu_set_option(omc_gpu_handle h, const char *key, long long value) {
     else if (k == "pool_cap") h->pool_cap_opt = (unsigned)value;
     else if (k == "electron_iters") h->electron_iters = (int)value;
     else if (k == "max_cross") h->max_cross = (int)value;
+    else if (k == "photon_tracking") h->photon_tracking = (int)value;
+    else if (k == "max_virtual") h->max_virtual = (int)value;
     else if (k == "check_every") h->check_every = (int)value;
     else return fail(h, "unknown option");
     return 0;
@@ -532,7 +567,9 @@ int omc_gpu_run_histories(omc_gpu_handle h, long long first, long long nhist, in
     CK(cudaSetDevice(h->device));
     DevProblem &P = h->P;
     if (h->med_dirty) {                 // per-medium cut-offs (from the geometry) into the per-medium records
-        for (size_t m = 0; m < h->med_host.size(); m++) { h->med_host[m].ecut = h->cut_e[m]; h->med_host[m].pcut = h->cut_p[m]; }
+        for (size_t m = 0; m < h->med_host.size(); m++) {
+            h->med_host[m].ecut = h->cut_e[m]; h->med_host[m].pcut = h->cut_p[m]; h->med_host[m].rhomax = h->rho_max[m];
+        }
         CK(cudaMemcpyAsync((void *)P.med, h->med_host.data(), h->med_host.size() * sizeof(MedRec), cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         h->med_dirty = false;

@@ -30,7 +30,7 @@ constexpr int WAVE_THREADS = 128;   // threads per block == particles per chunk
 
 struct WaveCtl {
     unsigned n_p[2], n_e[2], n_ip[2], n_ie[2];   // queue fill counts, [parity]: cur = parity, next = parity ^ 1
-    unsigned n_ch, n_bca;                        // step-class queues, filled and drained inside one wave
+    unsigned n_ch[2], n_bca[2];                  // step-class queues, [parity]: filled by esize_kernel (cur) and the edo kernels (next)
     unsigned tk[5];                              // chunk tickets per class (misc_kernel)
     unsigned n_src;                              // histories injected by the current wave
     unsigned parity, target, overflow, live, waves, drain_ticket;
@@ -46,11 +46,11 @@ struct EStepQueue {
 
 struct WaveQueues {
     PartQueue p[2], e[2], ip[2], ie[2];
-    EStepQueue ch, bca;
+    EStepQueue ch[2], bca[2];
 };
 
 struct WaveLaunch {
-    int blocks[4], max_cross, electron_iters, ibeamlet;
+    int blocks[4], max_cross, electron_iters, ibeamlet, woodcock, max_virtual;
 };
 
 void wave_blocks_per_sm(int out[4]);
@@ -60,6 +60,8 @@ void wave_blocks_per_sm(int out[4]);
 struct DrainArgs {
     PartQueue q[4];
     const unsigned *count[4];
+    EStepQueue sq[2];               // electrons waiting in the step-class queues (their step state is dropped: resampled)
+    const unsigned *scount[2];
     unsigned *ticket;
 };
 void launch_drain(const DevProblem &P, const DrainArgs &D, Part *stack, int depth, int blocks, cudaStream_t stream);

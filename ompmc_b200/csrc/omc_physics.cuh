@@ -50,6 +50,29 @@ struct Rng {
         b0 = c0; b1 = c1; b2 = c2; b3 = c3;
         blk += 1; pos = 0;
     }
+    // One whole Philox block as a pure function of the counter: register-only, no buffered words.  The wavefront
+    // kernels' photon path consumes its streams in whole blocks at fixed program points (block()), so the state
+    // never has to live in local memory and the lanes of a warp always generate together.
+    static __device__ __forceinline__ uint4 philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t ka, uint32_t kb) {
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            c0 = hi1 ^ c1 ^ ka; c1 = lo1; c2 = hi0 ^ c3 ^ kb; c3 = lo0;
+            ka += 0x9E3779B9u; kb += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+    __device__ __forceinline__ uint4 block() {
+        const uint4 r = philox(blk, stream, h0, h1, k0, k1);
+        blk += 1u; pos = 4u;
+        return r;
+    }
+    // seed at the first block boundary at or after draw `ndrawn` (block-wise consumers)
+    __device__ __forceinline__ void seed_blocks(uint32_t s0, uint32_t s1, uint32_t hlo, uint32_t hhi, uint32_t strm, uint32_t ndrawn) {
+        k0 = s0; k1 = s1; stream = strm; h0 = hlo; h1 = hhi;
+        blk = (ndrawn + 3u) >> 2; pos = 4u;
+    }
     __device__ __forceinline__ double next() {
         if (pos >= 4u) refill();
         uint32_t w = pos == 0u ? b0 : (pos == 1u ? b1 : (pos == 2u ? b2 : b3));
@@ -89,6 +112,64 @@ __device__ __forceinline__ RegionRec load_region_w(const DevProblem &P, int ir) 
     if (a.y >= 0) { r.ecut = P.med[a.y].ecut; r.pcut = P.med[a.y].pcut; }
     else { r.ecut = 0.0; r.pcut = 0.0; }
     return r;
+}
+
+// region record without the cut-offs: {rhof, med} only
+__device__ __forceinline__ void load_region_rm(const DevProblem &P, int ir, double &rhof, int &med) {
+    if (P.reg8 == nullptr) {
+        const RegionRec r = load_region(P, ir);
+        rhof = r.rhof; med = r.med;
+        return;
+    }
+    const int2 a = __ldg(reinterpret_cast<const int2 *>(P.reg8) + ir);
+    rhof = (double)__int_as_float(a.x);
+    med = a.y;
+}
+
+// total photon cross section per unit density ratio, 1 / (gmfp * cohfac) of photon() src/ompmc.c:1954-1966
+__device__ __forceinline__ double phot_sig0(const DevProblem &P, int imed, double gle) {
+    const MedRec &M = P.med[imed];
+    const int lgle = (int)(gle * M.ge1 + M.ge0) - 1;
+    const PhotBin *B = P.phot + imed * MXGE + lgle;
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(&B->gmfp1));
+    const double2 b = __ldg(reinterpret_cast<const double2 *>(&B->cohe1));
+    return 1.0 / (pwl(gle, a.x, a.y) * pwl(gle, b.x, b.y));
+}
+
+// interaction choice at a photon interaction site, photon() src/ompmc.c:2027-2067: 1 Compton, 2 pair, 3 photo, 4 Rayleigh
+__device__ __forceinline__ int photon_interaction_type(const DevProblem &P, Rng &g, int imed, double gle, double eig) {
+    const MedRec &M = P.med[imed];
+    const int lgle = (int)(gle * M.ge1 + M.ge0) - 1;
+    const PhotBin *B = P.phot + imed * MXGE + lgle;
+    const double coh = pwl(gle, __ldg(&B->cohe1), __ldg(&B->cohe0));
+    double r = g.next();
+    if (r <= 1.0 - coh) return 4;
+    r = g.next();
+    const double gbr1 = pwl(gle, __ldg(&B->gbr11), __ldg(&B->gbr10));
+    if (r <= gbr1 && eig > 2.0 * RM) return 2;
+    const double gbr2 = pwl(gle, __ldg(&B->gbr21), __ldg(&B->gbr20));
+    return (r < gbr2) ? 1 : 3;
+}
+
+// index i with b[i] <= x < b[i+1], clamped to the first / last bin for points outside [b[0], b[n]); uniform grids
+// by division (corrected against the tabulated planes, so the answer is the same as a search), others by bisection
+__device__ __forceinline__ int find_bin(const double *b, int n, double x, double inv, bool uniform) {
+    int i;
+    if (uniform) {
+        i = (int)((x - __ldg(b)) * inv);
+        i = max(0, min(i, n - 1));
+        if (x < __ldg(b + i)) i -= 1;
+        else if (x >= __ldg(b + i + 1)) i += 1;
+        i = max(0, min(i, n - 1));
+    } else {
+        int lo = 0, hi = n;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (x >= __ldg(b + mid)) lo = mid; else hi = mid;
+        }
+        i = lo;
+    }
+    return i;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -60,6 +60,7 @@ struct MedRec {
     double delcm, zbrang, bpar0, bpar1;
     double dl[6][8];         // pair_data.dl1..dl6 [8]
     double ecut, pcut;       // region.ecut/pcut when they depend on the medium only (see DevProblem::reg8)
+    double rhomax;           // largest region.rhof of the voxels filled with this medium (0: medium absent); Woodcock majorant
     int sig_ismonotone[2];   // [qel]
 };
 
@@ -103,6 +104,8 @@ struct DevProblem {
     const double *xb, *yb, *zb;
     const RegionRec *reg;
     const void *reg8;        // compact {float rhof; int med} records, or nullptr (see load_region_w)
+    double inv_dx, inv_dy, inv_dz;   // 1 / voxel size per axis when that axis is uniformly spaced (find_bin)
+    int uniform_x, uniform_y, uniform_z;
     // media
     const MedRec *med;
     const PhotBin *phot;     // [nmed*MXGE]

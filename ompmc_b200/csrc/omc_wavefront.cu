@@ -36,6 +36,9 @@
 #define OMC_WAVE_F32 1     // 1: fp32 angle samplers (omc_physics_f32.cuh); 0: the fp64 ones of the lock-step kernel
 #endif
 
+#ifndef OMC_FUSE_ESIZE
+#define OMC_FUSE_ESIZE 0
+#endif
 #ifndef OMC_WARP_AGGREGATE_DOSE
 #define OMC_WARP_AGGREGATE_DOSE 0
 #endif
@@ -133,7 +136,7 @@ enum { TAG_NONE = 0, TAG_COMPTON = 1, TAG_PAIR = 2, TAG_PHOTO = 3, TAG_RAYLEIGH 
 struct WaveArgs {
     WaveCtl *ctl;
     WaveQueues Q;
-    int max_cross, electron_iters, ibeamlet;
+    int max_cross, electron_iters, ibeamlet, woodcock, max_virtual;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -175,18 +178,13 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, int par, un
     const double iu = (p.u != 0.0) ? 1.0 / p.u : 0.0, iv = (p.v != 0.0) ? 1.0 / p.v : 0.0, iw = (p.w != 0.0) ? 1.0 / p.w : 0.0;
     const int sx = p.u > 0.0, sy = p.v > 0.0, sz = p.w > 0.0;
     int imed = R.med, medc = -2;
-    double sig0 = 0.0, cohfac = 0.0, sig = 0.0;                // sig = 1 / gmfp
+    double sig0 = 0.0, sig = 0.0;                              // sig = 1 / gmfp
+    bool hit = false;
     for (int k = 0; k < A.max_cross; k++) {
         double tstep = 1.0E8;
         if (imed != -1) {
             if (imed != medc) {                                // (imed, gle) -> table values, kept while the medium stays
-                const MedRec &M = P.med[imed];
-                const int lgle = (int)(gle * M.ge1 + M.ge0) - 1;
-                const PhotBin *B = P.phot + imed * MXGE + lgle;
-                const double2 a = __ldg(reinterpret_cast<const double2 *>(&B->gmfp1));
-                const double2 b = __ldg(reinterpret_cast<const double2 *>(&B->cohe1));
-                cohfac = pwl(gle, b.x, b.y);
-                sig0 = 1.0 / (pwl(gle, a.x, a.y) * cohfac);
+                sig0 = phot_sig0(P, imed, gle);
                 medc = imed;
             }
             sig = sig0 * R.rhof;
@@ -215,29 +213,14 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, int par, un
             imed = R.med;
         }
         if (imed != -1 && dpmfp <= 1.0E-05) {                  // interaction site of copy `isplit`, :2027-2067
-            const MedRec &M = P.med[imed];
-            const int lgle = (int)(gle * M.ge1 + M.ge0) - 1;
-            const PhotBin *B = P.phot + imed * MXGE + lgle;
-            const double coh = (imed != medc) ? pwl(gle, __ldg(&B->cohe1), __ldg(&B->cohe0)) : cohfac;   // site right after a medium change
+            // The interaction type is sampled by the interaction chunk of the next wave (p_interact_chunk), where
+            // all lanes of a warp do it together, from the copy's own sub-stream.
             const bool surv = (isplit == isurv);
-            int type;
-            g.align();
-            double r = g.next();
-            if (r <= 1.0 - coh) {
-                type = TAG_RAYLEIGH;
-            } else {
-                r = g.next();
-                const double gbr1 = pwl(gle, __ldg(&B->gbr11), __ldg(&B->gbr10));
-                if (r <= gbr1 && p.e > 2.0 * RM) type = TAG_PAIR;
-                else {
-                    const double gbr2 = pwl(gle, __ldg(&B->gbr21), __ldg(&B->gbr20));
-                    type = (r < gbr2) ? TAG_COMPTON : TAG_PHOTO;
-                }
-            }
-            if (surv || type != TAG_RAYLEIGH) {                // a Rayleigh-scattered non-survivor is simply dropped, :2030-2034
+            if (nsplit == 1) { hit = true; break; }            // the photon itself goes on, pushed below
+            {
                 Rng gq;
                 child_rng(g, gq, (unsigned)isplit);
-                q_push(A.Q.ip[par ^ 1], &ctl->n_ip[par ^ 1], ctl, p, gq, -1.0, type | (surv ? 16 : 0));
+                q_push(A.Q.ip[par ^ 1], &ctl->n_ip[par ^ 1], ctl, p, gq, -1.0, TAG_NONE | (surv ? 16 : 0));
             }
             isplit += 1;
             const double eta_new = eta - d_eta;
@@ -246,7 +229,80 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, int par, un
             eta = eta_new;
         }
     }
-    q_push(A.Q.p[par ^ 1], &ctl->n_p[par ^ 1], ctl, p, g, dpmfp, isplit | (isurv << 8), eta);
+    if (hit) q_push(A.Q.ip[par ^ 1], &ctl->n_ip[par ^ 1], ctl, p, g, -1.0, TAG_NONE | 16);
+    else q_push(A.Q.p[par ^ 1], &ctl->n_p[par ^ 1], ctl, p, g, dpmfp, isplit | (isurv << 8), eta);
+}
+
+// chunk P, Woodcock flight (nsplit == 1): the distance to the next TENTATIVE collision is sampled with the
+// majorant cross section of the whole phantom, max over media of sigma_m(E) * rhomax_m; the collision is real
+// with probability sigma(voxel) / majorant.  Interaction sites have exactly the distribution of the reference's
+// voxel-to-voxel march (photon() src/ompmc.c:1951-2019: mean free paths accumulated over the voxels crossed),
+// but a flight costs a few voxel look-ups instead of one per voxel crossed, and there is no dependent chain of
+// voxel-record loads.  Draws are consumed in whole Philox blocks: {distance, accept} x 2 per block.
+__device__ void photon_chunk_wc(const DevProblem &P, const WaveArgs &A, int par, unsigned i, unsigned n, Tally &t) {
+    if (i >= n) return;
+    WaveCtl *ctl = A.ctl;
+    const PartQueue &q = A.Q.p[par];
+    Part p; Rng g;
+    p.x = q.x[i]; p.y = q.y[i]; p.z = q.z[i]; p.u = q.u[i]; p.v = q.v[i]; p.w = q.w[i]; p.e = q.e[i]; p.wt = q.wt[i];
+    bool entered = q.aux[i] <= -2.0;                           // has been seen inside the phantom box (see below)
+    {
+        const int2 a = q.irq[i];
+        p.ir = a.x; p.iq = 0;
+        const uint4 r = q.rng[i];
+        g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
+    }
+    if (p.ir == 0) return;                                     // outside the phantom: howfar() discards (idisc)
+    {   // cut-off test of photon() :1884 (a flight that spans several waves repeats it, harmlessly)
+        double rhof; int med;
+        load_region_rm(P, p.ir, rhof, med);
+        const double pcut = (P.reg8 != nullptr) ? (med >= 0 ? P.med[med].pcut : 0.0) : load_region(P, p.ir).pcut;
+        if (p.e <= pcut || p.wt == 0) { deposit32(P, t, p.ir, p.wt * p.e); return; }
+    }
+    const double gle = log(p.e);
+    double smaj = 0.0;
+    for (int m = 0; m < P.nmed; m++) {
+        const double rmax = P.med[m].rhomax;
+        if (rmax > 0.0) smaj = fmax(smaj, rmax * phot_sig0(P, m, gle));
+    }
+    if (!(smaj > 0.0)) return;                                 // vacuum everywhere: the photon leaves
+    const double imaj = 1.0 / smaj;
+    const double x0 = __ldg(P.xb), x1 = __ldg(P.xb + P.isize), y0 = __ldg(P.yb), y1 = __ldg(P.yb + P.jsize),
+                 z0 = __ldg(P.zb), z1 = __ldg(P.zb + P.ksize);
+    int medc = -2;
+    double sigc = 0.0;
+    bool hit = false;
+    uint4 b = make_uint4(0u, 0u, 0u, 0u);
+    for (int k = 0; k < A.max_virtual; k++) {
+        if (!(k & 1)) b = g.block();
+        const uint32_t w0 = (k & 1) ? b.z : b.x, w1 = (k & 1) ? b.w : b.y;
+        const float r = ((float)(w0 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const double s = (double)(-__logf(r)) * imaj;
+        p.x += s * p.u; p.y += s * p.v; p.z += s * p.w;
+        t.npstep++;
+        if (p.x >= x0 && p.x < x1 && p.y >= y0 && p.y < y1 && p.z >= z0 && p.z < z1) {
+            entered = true;
+        } else {
+            if (entered) return;                               // left the phantom
+            // Not inside yet: a source particle sitting exactly on a max face, or one that the matRad source
+            // clamped with the wrong bound (omc_matrad.c:1225, SURVEY Q13: p.z = ybounds[0]).  The reference keeps
+            // such a particle in the voxel layer it was assigned to until it crosses a plane; the clamped
+            // look-up below does the same.  It is discarded if it moves away from the box.
+            if ((p.x < x0 && p.u <= 0.0) || (p.x >= x1 && p.u >= 0.0) || (p.y < y0 && p.v <= 0.0) || (p.y >= y1 && p.v >= 0.0) ||
+                (p.z < z0 && p.w <= 0.0) || (p.z >= z1 && p.w >= 0.0)) return;
+        }
+        const int ix = find_bin(P.xb, P.isize, p.x, P.inv_dx, P.uniform_x != 0);
+        const int iy = find_bin(P.yb, P.jsize, p.y, P.inv_dy, P.uniform_y != 0);
+        const int iz = find_bin(P.zb, P.ksize, p.z, P.inv_dz, P.uniform_z != 0);
+        p.ir = 1 + ix + iy * P.isize + iz * P.ijmax;
+        double rhof; int med;
+        load_region_rm(P, p.ir, rhof, med);
+        if (med < 0) continue;
+        if (med != medc) { sigc = phot_sig0(P, med, gle); medc = med; }
+        if ((double)w1 * (1.0 / 4294967296.0) * smaj < sigc * rhof) { hit = true; break; }
+    }
+    if (hit) q_push(A.Q.ip[par ^ 1], &ctl->n_ip[par ^ 1], ctl, p, g, -1.0, TAG_NONE | 16);
+    else q_push(A.Q.p[par ^ 1], &ctl->n_p[par ^ 1], ctl, p, g, entered ? -2.0 : -1.0, TAG_NONE);
 }
 
 // chunk IP: photon interactions
@@ -262,8 +318,13 @@ __device__ void p_interact_chunk(const DevProblem &P, const WaveArgs &A, int par
     // photon splitting: scattered photons are kept for the surviving copy only and get the full weight back;
     // charged secondaries of every copy are kept with the copy's weight wt/nsplit (:2072-2093)
     const bool surv = (tag & 16) != 0;
-    const int type = tag & 15;
+    int type = tag & 15;
     const double back = (double)P.nsplit;
+    if (type == TAG_NONE) {                                    // interaction choice, photon() :2027-2067
+        type = photon_interaction_type(P, g, imed, log(p.e), p.e);
+        if (!surv && type == TAG_RAYLEIGH) return;             // a Rayleigh-scattered non-survivor is simply dropped, :2030-2034
+        g.align();
+    }
     if (type == TAG_COMPTON) {
         compton(g, p, q);
         child_rng(g, gq, 0);
@@ -657,8 +718,28 @@ __device__ __forceinline__ void flush_tally(const DevProblem &P, Tally &t, doubl
     }
 }
 
+// append to the step-class queue `cls` of parity `par`
+// (two branches on purpose: q_reserve() aggregates over the lanes that are active TOGETHER)
+__device__ __forceinline__ void es_push(const WaveArgs &A, WaveCtl *ctl, int par, int cls, const Part &p, const Rng &g, const EStep &e) {
+    if (cls == CLS_CH) {
+        const unsigned slot = q_reserve(&ctl->n_ch[par]);
+        if (slot < A.Q.ch[par].cap) es_put(A.Q.ch[par], slot, p, g, e);
+        else atomicAdd(&ctl->overflow, 1u);
+    } else {
+        const unsigned slot = q_reserve(&ctl->n_bca[par]);
+        if (slot < A.Q.bca[par].cap) es_put(A.Q.bca[par], slot, p, g, e);
+        else atomicAdd(&ctl->overflow, 1u);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
-// electron kernels
+// electron kernels.  esize_kernel sizes the next step of every electron in E[cur] and sorts it into the CH or BCA
+// queue of this wave; the step kernels push survivors back to E[next].
+// OMC_FUSE_ESIZE=1 (experiment, measured SLOWER on B200: 5.28e7 vs 5.67e7 histories/s): the step kernels size the
+// next step of a surviving electron in registers and push it straight into the step-class queue of the next
+// wave (one 200-byte record per step instead of a particle record plus a step record).  It removes a third of
+// the queue traffic, but the kernels are latency bound, not bandwidth bound, and the longer per-thread
+// dependent chain plus the extra divergence (finished lanes idle through the sizing code) cost more.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT, OMC_MB_ESIZE) esize_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ WaveArgs A) {
     WaveCtl *ctl = A.ctl;
@@ -674,15 +755,7 @@ __global__ void __launch_bounds__(NT, OMC_MB_ESIZE) esize_kernel(const __grid_co
             continue;
         }
         // (two branches on purpose: q_reserve() aggregates over the lanes that are active TOGETHER)
-        if (cls == CLS_CH) {
-            const unsigned slot = q_reserve(&ctl->n_ch);
-            if (slot < A.Q.ch.cap) es_put(A.Q.ch, slot, p, g, e);
-            else atomicAdd(&ctl->overflow, 1u);
-        } else {
-            const unsigned slot = q_reserve(&ctl->n_bca);
-            if (slot < A.Q.bca.cap) es_put(A.Q.bca, slot, p, g, e);
-            else atomicAdd(&ctl->overflow, 1u);
-        }
+        es_push(A, ctl, par, cls, p, g, e);                    // into the step-class queues of THIS wave
     }
     flush_tally(P, t, 0.0);
 }
@@ -691,15 +764,25 @@ template <int CLS>
 __global__ void __launch_bounds__(NT, (CLS == 1 ? OMC_MB_ECH : OMC_MB_EBCA)) edo_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ WaveArgs A) {
     WaveCtl *ctl = A.ctl;
     const int par = (int)ctl->parity;
-    const EStepQueue &S = (CLS == CLS_CH) ? A.Q.ch : A.Q.bca;
-    const unsigned n = min(CLS == CLS_CH ? ctl->n_ch : ctl->n_bca, S.cap);
+    const EStepQueue &S = (CLS == CLS_CH) ? A.Q.ch[par] : A.Q.bca[par];
+    const unsigned n = min(CLS == CLS_CH ? ctl->n_ch[par] : ctl->n_bca[par], S.cap);
     Tally t = {0, 0, 0};
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Part p; Rng g; EStep e;
         es_get(S, i, p, g, e, P);
         const int st = estep_do(P, g, p, e, CLS, t);
+#if OMC_FUSE_ESIZE
+        if (st == 0) {                                         // keeps travelling: size the next step right here
+            int st2;
+            const int cls = estep_size(P, g, p, e, t, st2);    // (st2: -1 finished / TAG_RANNIH when below the cut-off)
+            if (cls != CLS_NONE) es_push(A, ctl, par ^ 1, cls, p, g, e);
+            else if (st2 > 0) q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st2);
+            continue;
+        }
+#else
         if (st == 0) q_push(A.Q.e[par ^ 1], &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
-        else if (st > 0) q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st);
+#endif
+        if (st > 0) q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st);
     }
     flush_tally(P, t, 0.0);
 }
@@ -707,44 +790,44 @@ __global__ void __launch_bounds__(NT, (CLS == 1 ? OMC_MB_ECH : OMC_MB_EBCA)) edo
 // ---------------------------------------------------------------------------------------------
 // photons, interactions, source: persistent kernel, typed chunks
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned vload(const unsigned *p) { return *reinterpret_cast<const volatile unsigned *>(p); }
-
 __global__ void __launch_bounds__(NT, OMC_MB_MISC) misc_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ WaveArgs A) {
-    __shared__ unsigned s_type, s_chunk, s_cnt[4];
+    // Every WARP pulls its own typed 32-particle chunks (no block-level barrier: an earlier block-granular version
+    // spent 14 % of its stall samples on the per-chunk __syncthreads(), waiting for the slowest warp).
+    constexpr unsigned CH = 32u;
     WaveCtl *ctl = A.ctl;
     const int par = (int)ctl->parity;
-    if (threadIdx.x == 0) {
-        // chunk classes: 0 electron interactions, 1 photon interactions, 2 source, 3 photon flights
-        // (counts are clamped to the queue capacity: after an overflow the counters run past it)
-        const unsigned cap = A.Q.p[0].cap;
-        s_cnt[0] = min(ctl->n_ie[par], cap); s_cnt[1] = min(ctl->n_ip[par], cap); s_cnt[2] = ctl->n_src;
-        s_cnt[3] = min(ctl->n_p[par], cap);
-    }
-    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    // chunk classes: 0 electron interactions, 1 photon interactions, 2 source, 3 photon flights
+    // (counts are clamped to the queue capacity: after an overflow the counters run past it)
+    const unsigned cap = A.Q.p[0].cap;
+    const unsigned cnt0 = min(ctl->n_ie[par], cap), cnt1 = min(ctl->n_ip[par], cap), cnt2 = ctl->n_src, cnt3 = min(ctl->n_p[par], cap);
     Tally t = {0, 0, 0};
     double ensrc = 0.0;
-    unsigned open = 0xf, rr = blockIdx.x;                      // (thread 0) classes that may still have chunks; pull phase
+    unsigned open = 0xf, rr = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);   // (lane 0) classes that may still have chunks; pull phase
     for (;;) {
-        if (threadIdx.x == 0) {
-            unsigned type = 4, chunk = 0;
+        unsigned type = 4, chunk = 0;
+        if (lane == 0) {
             for (int tries = 0; tries < 4 && open; tries++) {
                 const unsigned c = rr & 3u;
                 rr++;
                 if (!(open & (1u << c))) continue;
+                const unsigned cnt = c == 0 ? cnt0 : (c == 1 ? cnt1 : (c == 2 ? cnt2 : cnt3));
                 const unsigned tk = atomicAdd(&ctl->tk[c], 1u);
-                if ((unsigned long long)tk * NT < s_cnt[c]) { type = c; chunk = tk; break; }
+                if ((unsigned long long)tk * CH < cnt) { type = c; chunk = tk; break; }
                 open &= ~(1u << c);
             }
-            s_type = type; s_chunk = chunk;
         }
-        __syncthreads();
-        const unsigned type = s_type, i = s_chunk * NT + threadIdx.x;
+        type = __shfl_sync(0xffffffffu, type, 0);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
         if (type == 4) break;
-        if (type == 3) photon_chunk(P, A, par, i, s_cnt[3], t);
-        else if (type == 2) source_chunk(P, A, par, i, s_cnt[2], ensrc);
-        else if (type == 1) p_interact_chunk(P, A, par, i, s_cnt[1]);
-        else e_interact_chunk(P, A, par, i, s_cnt[0]);
-        __syncthreads();
+        const unsigned i = chunk * CH + lane;
+        if (type == 3) {
+            if (A.woodcock) photon_chunk_wc(P, A, par, i, cnt3, t);
+            else photon_chunk(P, A, par, i, cnt3, t);
+        } else if (type == 2) source_chunk(P, A, par, i, cnt2, ensrc);
+        else if (type == 1) p_interact_chunk(P, A, par, i, cnt1);
+        else e_interact_chunk(P, A, par, i, cnt0);
+        __syncwarp();
     }
     flush_tally(P, t, ensrc);
 }
@@ -755,8 +838,8 @@ __global__ void advance_kernel(const __grid_constant__ DevProblem P, WaveCtl *c)
     const int par = (int)c->parity, nxt = par ^ 1;
     c->hist_next += c->n_src;
     P.counters->histories += c->n_src;
-    c->n_p[par] = 0; c->n_e[par] = 0; c->n_ip[par] = 0; c->n_ie[par] = 0; c->n_ch = 0; c->n_bca = 0;
-    const unsigned live = c->n_p[nxt] + c->n_e[nxt] + c->n_ip[nxt] + c->n_ie[nxt];
+    c->n_p[par] = 0; c->n_e[par] = 0; c->n_ip[par] = 0; c->n_ie[par] = 0; c->n_ch[par] = 0; c->n_bca[par] = 0;
+    const unsigned live = c->n_p[nxt] + c->n_e[nxt] + c->n_ip[nxt] + c->n_ie[nxt] + c->n_ch[nxt] + c->n_bca[nxt];
     const unsigned long long left = c->hist_end - c->hist_next;
     const unsigned room = (live < c->target) ? c->target - live : 0u;
     c->n_src = (unsigned)(left < (unsigned long long)room ? left : (unsigned long long)room);
@@ -793,6 +876,7 @@ void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const W
                  cudaEvent_t fork, cudaEvent_t join) {
     WaveArgs A;
     A.ctl = ctl; A.Q = Q; A.max_cross = L.max_cross; A.electron_iters = L.electron_iters; A.ibeamlet = L.ibeamlet;
+    A.woodcock = L.woodcock; A.max_virtual = L.max_virtual;
     const bool par = (s2 != nullptr);
     cudaStream_t sm = par ? s2 : s;
     if (par) { cudaEventRecord(fork, s); cudaStreamWaitEvent(s2, fork, 0); }

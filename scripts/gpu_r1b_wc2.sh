@@ -1,0 +1,3 @@
+set -x
+python -m pytest tests -m gpu -q 2>&1 | tail -8
+bash scripts/gpu_diag_psteps.sh

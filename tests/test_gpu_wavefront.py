@@ -85,6 +85,55 @@ def test_wavefront_matches_lockstep_statistically(gpu, name, cfg, nb, per):
     assert 0.6 < z.std() < 1.5, f"z spread {z.std():.3f}"
 
 
+@pytest.mark.parametrize("idx", [0, 1], ids=["water6mv", "tissue6mv"])
+def test_wavefront_voxel_march_matches_lockstep_statistically(gpu, idx):
+    """photon_tracking = 0: the reference's voxel-to-voxel photon march instead of the default Woodcock flight
+    (the parametrised test above runs the default, i.e. Woodcock for nsplit == 1 and the march for nsplit > 1)."""
+    name, cfg, nb, per = CASES[idx]
+    prob, ph = make_problem(cfg)
+    gpu.load_problem(prob)
+    m0, v0, e0, c0 = batches(gpu, 0, nb, per)
+    gpu.set_option("photon_tracking", 0)
+    try:
+        m1, v1, e1, c1 = batches(gpu, 1, nb, per)
+    finally:
+        gpu.set_option("photon_tracking", 1)
+    assert c0["histories"] == c1["histories"] == nb * per and c1["errors"] == 0
+    assert abs(e0 - e1) <= 1e-9 * e0
+    # The march crosses the same voxels as the lock-step kernel.  The reference (and the lock-step kernel) discover
+    # that a photon has left on the NEXT howfar() call (irl == 0 -> idisc), one extra counted step per escaping
+    # photon (~1 per history here; measured 0.566 = the escape probability for an uncollided 6 MeV primary);
+    # the march discards at the crossing itself.
+    extra = c0["photon_steps"] - c1["photon_steps"]
+    assert 0 < extra < 2 * nb * per and extra < 0.06 * c0["photon_steps"]
+    z, sel = zscore_check(m0, v0, m1, v1)
+    assert (np.abs(z) < 2.0).mean() >= 0.90
+    assert abs(z.mean()) < 0.35 and 0.6 < z.std() < 1.5
+
+
+def test_woodcock_flight_on_nonuniform_grid(gpu):
+    """Voxel look-up of the Woodcock flight by bisection when the planes are not equally spaced: same dose as
+    the voxel march on a phantom whose z planes are graded."""
+    name, cfg, nb, per = CASES[0]
+    media = P.load_blob(P.golden(cfg["mset"]))
+    ph = cfg["ph"]()
+    z = np.asarray(ph.zbounds, dtype=np.float64)
+    ph.zbounds = z[0] + (z - z[0]) * (0.6 + 0.4 * (z - z[0]) / (z[-1] - z[0]))      # graded, monotone
+    prob = P.build_problem(media, ph, ecut=cfg["ecut"], pcut=0.01, collimator=cfg["coll"], ssd=cfg["ssd"], charge=0,
+                           cdfinv=(media["cdfinv1_" + cfg["spec"]], media["cdfinv2_" + cfg["spec"]]), mono_energy=0.0)
+    gpu.load_problem(prob)
+    gpu.set_option("photon_tracking", 0)
+    try:
+        m0, v0, e0, c0 = batches(gpu, 1, nb, per)
+    finally:
+        gpu.set_option("photon_tracking", 1)
+    m1, v1, e1, c1 = batches(gpu, 1, nb, per)
+    assert c1["errors"] == 0 and c1["photon_steps"] < 0.5 * c0["photon_steps"]
+    zs, sel = zscore_check(m0, v0, m1, v1)
+    assert sel.sum() >= 20 and (np.abs(zs) < 2.0).mean() >= 0.90
+    assert abs(zs.mean()) < 0.35 and 0.6 < zs.std() < 1.5
+
+
 def test_wavefront_scheduling_independence(gpu):
     """Per-particle Philox sub-streams: pool size / crossings per wave / launch batching change only the fp32
     summation order.  (The drain kernel continues a particle's stream sequentially through its descendants,
@@ -97,11 +146,13 @@ def test_wavefront_scheduling_independence(gpu):
     res = []
     for pool, cross, every, graph in ((1 << 22, 16, 16, 1), (1 << 14, 7, 3, 0), (1 << 16, 1000, 5, 1)):
         gpu.set_option("pool_size", pool); gpu.set_option("max_cross", cross); gpu.set_option("check_every", every)
+        gpu.set_option("max_virtual", {16: 8, 7: 3, 1000: 64}[cross])      # Woodcock flight: tentative collisions per wave
         gpu.set_option("use_graph", graph)
         gpu.reset_tallies()
         gpu.run_histories(0, 50000)
         res.append((gpu.get_endep()[1:], gpu.counters()))
     gpu.set_option("pool_size", 1 << 22); gpu.set_option("max_cross", 16); gpu.set_option("check_every", 16); gpu.set_option("use_graph", 1)
+    gpu.set_option("max_virtual", 8)
     g0, c0 = res[0]
     for g, c in res[1:]:
         assert c["deposits"] == c0["deposits"] and c["photon_steps"] == c0["photon_steps"]
