@@ -110,12 +110,17 @@ static void free_pool(std::vector<void *> &pool) {
     pool.clear();
 }
 
-static int alloc_queue(omc_gpu_handle h, PartQueue &q, unsigned cap) {
+static int alloc_queue(omc_gpu_handle h, PartQueue &q, unsigned cap, bool photons) {
     q.cap = cap;
-    double **f[10] = {&q.x, &q.y, &q.z, &q.u, &q.v, &q.w, &q.e, &q.wt, &q.aux, &q.aux2};
+    double2 **f[4] = {&q.xy, &q.zu, &q.vw, &q.ew};
     for (auto pp : f) {
-        CK(cudaMalloc((void **)pp, (size_t)cap * sizeof(double)));
+        CK(cudaMalloc((void **)pp, (size_t)cap * sizeof(double2)));
         h->wave_bufs.push_back(*pp);
+    }
+    q.aux = nullptr;
+    if (photons) {
+        CK(cudaMalloc((void **)&q.aux, (size_t)cap * sizeof(double2)));
+        h->wave_bufs.push_back(q.aux);
     }
     CK(cudaMalloc((void **)&q.irq, (size_t)cap * sizeof(int2)));
     h->wave_bufs.push_back(q.irq);
@@ -125,15 +130,17 @@ static int alloc_queue(omc_gpu_handle h, PartQueue &q, unsigned cap) {
 }
 
 static int alloc_estep_queue(omc_gpu_handle h, EStepQueue &q, unsigned cap) {
-    q.cap = cap;
-    for (int i = 0; i < 21; i++) {
-        CK(cudaMalloc((void **)&q.d[i], (size_t)cap * sizeof(double)));
-        h->wave_bufs.push_back(q.d[i]);
+    q.cap = cap;                                  // per step class; both classes share arrays of 2 * cap slots
+    for (int i = 0; i < 6; i++) {
+        CK(cudaMalloc((void **)&q.v[i], (size_t)2 * cap * sizeof(double2)));
+        h->wave_bufs.push_back(q.v[i]);
     }
-    for (int i = 0; i < 2; i++) {
-        CK(cudaMalloc((void **)&q.w[i], (size_t)cap * sizeof(uint4)));
-        h->wave_bufs.push_back(q.w[i]);
-    }
+    CK(cudaMalloc((void **)&q.f, (size_t)2 * cap * sizeof(float4)));
+    h->wave_bufs.push_back(q.f);
+    CK(cudaMalloc((void **)&q.m, (size_t)2 * cap * sizeof(uint4)));
+    h->wave_bufs.push_back(q.m);
+    CK(cudaMalloc((void **)&q.rng, (size_t)2 * cap * sizeof(uint4)));
+    h->wave_bufs.push_back(q.rng);
     return 0;
 }
 
@@ -146,15 +153,12 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
         free_pool(h->wave_bufs);
         h->pool_cap = 0;
         for (int i = 0; i < 2; i++) {
-            if (alloc_queue(h, h->wq.p[i], cap)) return 1;
-            if (alloc_queue(h, h->wq.e[i], cap)) return 1;
-            if (alloc_queue(h, h->wq.ip[i], cap)) return 1;
-            if (alloc_queue(h, h->wq.ie[i], cap)) return 1;
+            if (alloc_queue(h, h->wq.p[i], cap, true)) return 1;
+            if (alloc_queue(h, h->wq.e[i], cap, false)) return 1;
+            if (alloc_queue(h, h->wq.ip[i], cap, false)) return 1;
+            if (alloc_queue(h, h->wq.ie[i], cap, false)) return 1;
         }
-        for (int i = 0; i < 2; i++) {
-            if (alloc_estep_queue(h, h->wq.ch[i], cap)) return 1;
-            if (alloc_estep_queue(h, h->wq.bca[i], cap)) return 1;
-        }
+        if (alloc_estep_queue(h, h->wq.es, cap)) return 1;
         h->pool_cap = cap;
     }
     if (!h->stream2) {
@@ -204,8 +208,8 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
         CK(cudaStreamSynchronize(h->stream));
         const WaveCtl &s = *h->ctl_host;
         if (h->trace)
-            fprintf(stderr, "wave %llu live %u n_src %u P %u E %u IP %u IE %u CH %u BCA %u hist_next %llu\n", wave + every, s.live, s.n_src,
-                    s.n_p[s.parity], s.n_e[s.parity], s.n_ip[s.parity], s.n_ie[s.parity], s.n_ch[s.parity], s.n_bca[s.parity], s.hist_next);
+            fprintf(stderr, "wave %llu live %u n_src %u P %u E %u IP %u IE %u hist_next %llu\n", wave + every, s.live, s.n_src,
+                    s.n_p[s.parity], s.n_e[s.parity], s.n_ip[s.parity], s.n_ie[s.parity], s.hist_next);
         if (s.overflow) {
             h->err = "particle queue overflow on the device: increase option pool_size";
             rc = 7;
@@ -234,8 +238,6 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
         DrainArgs D;
         D.q[0] = h->wq.p[par]; D.q[1] = h->wq.e[par]; D.q[2] = h->wq.ip[par]; D.q[3] = h->wq.ie[par];
         D.count[0] = &h->ctl->n_p[par]; D.count[1] = &h->ctl->n_e[par]; D.count[2] = &h->ctl->n_ip[par]; D.count[3] = &h->ctl->n_ie[par];
-        D.sq[0] = h->wq.ch[par]; D.sq[1] = h->wq.bca[par];
-        D.scount[0] = &h->ctl->n_ch[par]; D.scount[1] = &h->ctl->n_bca[par];
         D.ticket = &h->ctl->drain_ticket;
         launch_drain(P, D, h->stack, depth, blocks, h->stream);
         h->launches += 1;

@@ -15,38 +15,47 @@ void launch_accum(double *endep, double *accum, double *accum2, long long n, cud
 
 
 // ---- omc_wavefront.cu ---------------------------------------------------------------------------
-// One particle queue in HBM, structure-of-arrays (coalesced 8-byte lanes); irq = {ir, iq | tag << 16},
-// rng = {hist_lo, hist_hi, stream, draws consumed}; aux = photon mfp left (-1: not sampled yet), aux2 = eta' of the
-// running split copy (photon splitting); for photons in flight tag = isplit | i_survive << 8.
+// One particle queue in HBM, structure-of-arrays with 16-byte lanes (one 128-bit access per warp and field pair):
+// {x,y} {z,u} {v,w} {e,wt}; irq = {ir, iq | tag << 16}; rng = {hist_lo, hist_hi, stream, draws consumed}.
+// Photon queues only (aux != nullptr): aux = {mfp left (-1: not sampled yet; Woodcock flight: -1 / -2 = not yet / already
+// inside the phantom box), eta' of the running split copy}; for photons in flight tag = isplit | i_survive << 8.
 struct PartQueue {
-    double *x, *y, *z, *u, *v, *w, *e, *wt, *aux, *aux2;
+    double2 *xy, *zu, *vw, *ew;
+    double2 *aux;
     int2 *irq;
     uint4 *rng;
     unsigned cap;
 };
-constexpr size_t PART_QUEUE_BYTES_PER_SLOT = 10 * sizeof(double) + sizeof(int2) + sizeof(uint4);
+constexpr size_t PART_QUEUE_BYTES_PER_SLOT = 4 * sizeof(double2) + sizeof(int2) + sizeof(uint4);   // + 16 for photon queues
 
 constexpr int WAVE_THREADS = 128;   // threads per block == particles per chunk
 
 struct WaveCtl {
     unsigned n_p[2], n_e[2], n_ip[2], n_ie[2];   // queue fill counts, [parity]: cur = parity, next = parity ^ 1
-    unsigned n_ch[2], n_bca[2];                  // step-class queues, [parity]: filled by esize_kernel (cur) and the edo kernels (next)
+    unsigned n_ch, n_bca;                        // step-class queues, filled and drained inside one wave
     unsigned tk[5];                              // chunk tickets per class (misc_kernel)
     unsigned n_src;                              // histories injected by the current wave
     unsigned parity, target, overflow, live, waves, drain_ticket;
     unsigned long long hist_next, hist_end;
 };
 
-// electrons between "step size known" and "step taken": Part + EStep (21 doubles) + {ir, iq, lelke, imed} + rng
+// electrons between "step size known" and "step taken", 144 bytes in nine 16-byte lanes:
+//   v[0..5] = {x,y} {z,u} {v,w} {e,total_tstep} {range,tustep} {tperp, (float wt, float elke)}
+//   f = {demfp, sig0, rhof, dedx} (fp32: these are fp32-born or only enter ratios)
+//   m = {float blccl, float ssmfp, ir, iq+1 | (imed+1) << 2 | lelke << 16};  rng as in PartQueue
+// ONE set of arrays of 2*cap slots holds both step classes: condensed-history steps fill slots 0, 1, 2, ... and
+// boundary-crossing steps 2*cap-1, 2*cap-2, ..., so esize_kernel stores with a single converged code path.
 struct EStepQueue {
-    double *d[21];
-    uint4 *w[2];
-    unsigned cap;
+    double2 *v[6];
+    float4 *f;
+    uint4 *m;
+    uint4 *rng;
+    unsigned cap;                                // per class
 };
 
 struct WaveQueues {
     PartQueue p[2], e[2], ip[2], ie[2];
-    EStepQueue ch[2], bca[2];
+    EStepQueue es;
 };
 
 struct WaveLaunch {
@@ -60,8 +69,6 @@ void wave_blocks_per_sm(int out[4]);
 struct DrainArgs {
     PartQueue q[4];
     const unsigned *count[4];
-    EStepQueue sq[2];               // electrons waiting in the step-class queues (their step state is dropped: resampled)
-    const unsigned *scount[2];
     unsigned *ticket;
 };
 void launch_drain(const DevProblem &P, const DrainArgs &D, Part *stack, int depth, int blocks, cudaStream_t stream);

@@ -510,11 +510,9 @@ __global__ void __launch_bounds__(128) drain_kernel(const __grid_constant__ DevP
                                                     Part *stack, int depth) {
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned n[6], tot = 0;
+    unsigned n[4], tot = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) { n[k] = min(*D.count[k], D.q[k].cap); tot += n[k]; }
-#pragma unroll
-    for (int k = 0; k < 2; k++) { n[4 + k] = min(*D.scount[k], D.sq[k].cap); tot += n[4 + k]; }
     HistCtx c;
     c.s.base = stack + tid;
     c.s.stride = nthreads;
@@ -526,24 +524,16 @@ __global__ void __launch_bounds__(128) drain_kernel(const __grid_constant__ DevP
         if (j >= tot) break;
         int k = 0;
         while (j >= n[k]) { j -= n[k]; k++; }
+        const PartQueue &q = D.q[k];
         Part p, s2;
-        int tag = 0;
-        uint4 r;
-        if (k < 4) {
-            const PartQueue &q = D.q[k];
-            p.x = q.x[j]; p.y = q.y[j]; p.z = q.z[j]; p.u = q.u[j]; p.v = q.v[j]; p.w = q.w[j]; p.e = q.e[j]; p.wt = q.wt[j];
-            const int2 a = q.irq[j];
-            p.ir = a.x; p.iq = (int)(short)(a.y & 0xffff);
-            tag = a.y >> 16;
-            r = q.rng[j];
-        } else {                                              // electron with a sized step pending: the step is resampled
-            const EStepQueue &q = D.sq[k - 4];
-            p.x = q.d[0][j]; p.y = q.d[1][j]; p.z = q.d[2][j]; p.u = q.d[3][j]; p.v = q.d[4][j]; p.w = q.d[5][j];
-            p.e = q.d[6][j]; p.wt = q.d[7][j];
-            const uint4 a = q.w[0][j];
-            p.ir = (int)a.x; p.iq = (int)a.y;
-            r = q.w[1][j];
+        {
+            const double2 xy = q.xy[j], zu = q.zu[j], vw = q.vw[j], ew = q.ew[j];
+            p.x = xy.x; p.y = xy.y; p.z = zu.x; p.u = zu.y; p.v = vw.x; p.w = vw.y; p.e = ew.x; p.wt = ew.y;
         }
+        const int2 a = q.irq[j];
+        p.ir = a.x; p.iq = (int)(short)(a.y & 0xffff);
+        const int tag = a.y >> 16;
+        const uint4 r = q.rng[j];
         c.g.seed(P.seed0, P.seed1, ((unsigned long long)r.y << 32) | r.x, r.z, r.w);
         c.ndeposit = 0; c.flags = 0; c.edep_sum = 0.0;
         bool two = false;

@@ -210,7 +210,7 @@ OMC_FN void howfar(const DevProblem &P, const Part &p, int &idisc, int &irnew, d
     }
 }
 
-OMC_FN double hownear(const DevProblem &P, const Part &p) {
+__device__ __forceinline__ double hownear_i(const DevProblem &P, const Part &p) {
     const int irl = p.ir;
     if (irl == 0) return 0.0;
     int irx, iry, irz;
@@ -221,6 +221,7 @@ OMC_FN double hownear(const DevProblem &P, const Part &p) {
     t = fmin(t, __ldg(P.zb + irz + 1) - p.z); t = fmin(t, p.z - __ldg(P.zb + irz));
     return t;
 }
+OMC_FN double hownear(const DevProblem &P, const Part &p) { return hownear_i(P, p); }
 
 // ---------------------------------------------------------------------------------------------
 // azimuth + rotations: selectAzimuthalAngle / uphi21 / uphi32, src/ompmc.c:101-199

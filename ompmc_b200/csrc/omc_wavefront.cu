@@ -36,9 +36,6 @@
 #define OMC_WAVE_F32 1     // 1: fp32 angle samplers (omc_physics_f32.cuh); 0: the fp64 ones of the lock-step kernel
 #endif
 
-#ifndef OMC_FUSE_ESIZE
-#define OMC_FUSE_ESIZE 0
-#endif
 #ifndef OMC_WARP_AGGREGATE_DOSE
 #define OMC_WARP_AGGREGATE_DOSE 0
 #endif
@@ -48,7 +45,7 @@
 #define OMC_MB_MISC 5
 #endif
 #ifndef OMC_MB_ESIZE
-#define OMC_MB_ESIZE 6
+#define OMC_MB_ESIZE 5
 #endif
 #ifndef OMC_MB_ECH
 #define OMC_MB_ECH 6
@@ -62,19 +59,25 @@ namespace omc {
 constexpr int NT = WAVE_THREADS;   // threads per block == particles per chunk
 
 // ---- queues ----------------------------------------------------------------------------------
-__device__ __forceinline__ void q_load(const PartQueue &q, unsigned i, Part &p, Rng &g, const DevProblem &P, double &aux, int &tag) {
-    p.x = q.x[i]; p.y = q.y[i]; p.z = q.z[i]; p.u = q.u[i]; p.v = q.v[i]; p.w = q.w[i];
-    p.e = q.e[i]; p.wt = q.wt[i]; aux = q.aux[i];
-    const int2 a = q.irq[i];
+__device__ __forceinline__ void q_load_part(const PartQueue &q, unsigned i, Part &p, int &tag) {
+    const int2 a = q.irq[i];                                   // first: a voxel-record load usually depends on it
+    const double2 xy = q.xy[i], zu = q.zu[i], vw = q.vw[i], ew = q.ew[i];
     p.ir = a.x; p.iq = (int)(short)(a.y & 0xffff); tag = a.y >> 16;
+    p.x = xy.x; p.y = xy.y; p.z = zu.x; p.u = zu.y; p.v = vw.x; p.w = vw.y; p.e = ew.x; p.wt = ew.y;
+}
+
+__device__ __forceinline__ void q_load(const PartQueue &q, unsigned i, Part &p, Rng &g, const DevProblem &P, double &aux, int &tag) {
+    q_load_part(q, i, p, tag);
+    aux = q.aux ? q.aux[i].x : 0.0;
     const uint4 r = q.rng[i];
     g.seed(P.seed0, P.seed1, ((unsigned long long)r.y << 32) | r.x, r.z, r.w);
 }
 
 __device__ __forceinline__ void q_store(const PartQueue &q, unsigned i, const Part &p, const Rng &g, double aux, int tag,
                                         double aux2 = 0.0) {
-    q.x[i] = p.x; q.y[i] = p.y; q.z[i] = p.z; q.u[i] = p.u; q.v[i] = p.v; q.w[i] = p.w;
-    q.e[i] = p.e; q.wt[i] = p.wt; q.aux[i] = aux; q.aux2[i] = aux2;
+    q.xy[i] = make_double2(p.x, p.y); q.zu[i] = make_double2(p.z, p.u); q.vw[i] = make_double2(p.v, p.w);
+    q.ew[i] = make_double2(p.e, p.wt);
+    if (q.aux) q.aux[i] = make_double2(aux, aux2);             // photon queues only
     q.irq[i] = make_int2(p.ir, (p.iq & 0xffff) | (tag << 16));
     q.rng[i] = make_uint4(g.h0, g.h1, g.stream, g.ndraws());
 }
@@ -153,7 +156,7 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, int par, un
     const int nsplit = P.nsplit;
     const double d_eta = 1.0 / (double)nsplit;
     int isplit = tag & 0xff, isurv = (tag >> 8) & 0xff;
-    double eta = A.Q.p[par].aux2[i];
+    double eta = A.Q.p[par].aux[i].y;
     if (dpmfp < 0.0) {                                         // fresh photon: cut-off test + number of mfp
         if (p.e <= R.pcut || p.wt == 0) { deposit32(P, t, p.ir, p.wt * p.e); return; }
         g.align();
@@ -244,11 +247,11 @@ __device__ void photon_chunk_wc(const DevProblem &P, const WaveArgs &A, int par,
     WaveCtl *ctl = A.ctl;
     const PartQueue &q = A.Q.p[par];
     Part p; Rng g;
-    p.x = q.x[i]; p.y = q.y[i]; p.z = q.z[i]; p.u = q.u[i]; p.v = q.v[i]; p.w = q.w[i]; p.e = q.e[i]; p.wt = q.wt[i];
-    bool entered = q.aux[i] <= -2.0;                           // has been seen inside the phantom box (see below)
+    bool entered;                                              // has been seen inside the phantom box (see below)
     {
-        const int2 a = q.irq[i];
-        p.ir = a.x; p.iq = 0;
+        int tag;
+        q_load_part(q, i, p, tag);
+        entered = q.aux[i].x <= -2.0;
         const uint4 r = q.rng[i];
         g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
     }
@@ -407,22 +410,34 @@ struct EStep {
     double eke, elke, demfp, sig0, total_tstep, range, tustep, tperp, rhof, ecut, dedx, blccl, ssmfp;
     int lelke, imed;
 };
-// (EStepQueue in omc_kernels.h carries Part + Rng + EStep between esize_kernel and ech/ebca_kernel)
+// (EStepQueue in omc_kernels.h carries Part + Rng + EStep between esize_kernel and the step kernels; eke = e - RM and
+// the cut-off are recomputed / re-read instead of stored)
+__device__ __forceinline__ double region_ecut(const DevProblem &P, int ir, int imed) {
+    if (P.reg8 != nullptr) return imed >= 0 ? P.med[imed].ecut : 0.0;
+    return load_region(P, ir).ecut;
+}
 __device__ __forceinline__ void es_put(const EStepQueue &S, unsigned s, const Part &p, const Rng &g, const EStep &e) {
-    S.d[0][s] = p.x; S.d[1][s] = p.y; S.d[2][s] = p.z; S.d[3][s] = p.u; S.d[4][s] = p.v; S.d[5][s] = p.w; S.d[6][s] = p.e; S.d[7][s] = p.wt;
-    S.d[8][s] = e.eke; S.d[9][s] = e.elke; S.d[10][s] = e.demfp; S.d[11][s] = e.sig0; S.d[12][s] = e.total_tstep; S.d[13][s] = e.range;
-    S.d[14][s] = e.tustep; S.d[15][s] = e.tperp; S.d[16][s] = e.rhof; S.d[17][s] = e.ecut; S.d[18][s] = e.dedx; S.d[19][s] = e.blccl;
-    S.d[20][s] = e.ssmfp;
-    S.w[0][s] = make_uint4((unsigned)p.ir, (unsigned)p.iq, (unsigned)e.lelke, (unsigned)e.imed);
-    S.w[1][s] = make_uint4(g.h0, g.h1, g.stream, g.ndraws());
+    S.v[0][s] = make_double2(p.x, p.y); S.v[1][s] = make_double2(p.z, p.u); S.v[2][s] = make_double2(p.v, p.w);
+    S.v[3][s] = make_double2(p.e, e.total_tstep); S.v[4][s] = make_double2(e.range, e.tustep);
+    S.v[5][s] = make_double2(e.tperp, __hiloint2double(__float_as_int((float)e.elke), __float_as_int((float)p.wt)));
+    S.f[s] = make_float4((float)e.demfp, (float)e.sig0, (float)e.rhof, (float)e.dedx);
+    S.m[s] = make_uint4((unsigned)__float_as_int((float)e.blccl), (unsigned)__float_as_int((float)e.ssmfp), (unsigned)p.ir,
+                        (unsigned)(p.iq + 1) | ((unsigned)(e.imed + 1) << 2) | ((unsigned)e.lelke << 16));
+    S.rng[s] = make_uint4(g.h0, g.h1, g.stream, g.ndraws());
 }
 __device__ __forceinline__ void es_get(const EStepQueue &S, unsigned s, Part &p, Rng &g, EStep &e, const DevProblem &P) {
-    p.x = S.d[0][s]; p.y = S.d[1][s]; p.z = S.d[2][s]; p.u = S.d[3][s]; p.v = S.d[4][s]; p.w = S.d[5][s]; p.e = S.d[6][s]; p.wt = S.d[7][s];
-    e.eke = S.d[8][s]; e.elke = S.d[9][s]; e.demfp = S.d[10][s]; e.sig0 = S.d[11][s]; e.total_tstep = S.d[12][s]; e.range = S.d[13][s];
-    e.tustep = S.d[14][s]; e.tperp = S.d[15][s]; e.rhof = S.d[16][s]; e.ecut = S.d[17][s]; e.dedx = S.d[18][s]; e.blccl = S.d[19][s];
-    e.ssmfp = S.d[20][s];
-    const uint4 a = S.w[0][s], r = S.w[1][s];
-    p.ir = (int)a.x; p.iq = (int)a.y; e.lelke = (int)a.z; e.imed = (int)a.w;
+    const uint4 m = S.m[s];
+    const double2 v0 = S.v[0][s], v1 = S.v[1][s], v2 = S.v[2][s], v3 = S.v[3][s], v4 = S.v[4][s], v5 = S.v[5][s];
+    const float4 f = S.f[s];
+    const uint4 r = S.rng[s];
+    p.ir = (int)m.z; p.iq = (int)(m.w & 3u) - 1; e.imed = (int)((m.w >> 2) & 15u) - 1; e.lelke = (int)m.w >> 16;
+    p.x = v0.x; p.y = v0.y; p.z = v1.x; p.u = v1.y; p.v = v2.x; p.w = v2.y; p.e = v3.x;
+    e.total_tstep = v3.y; e.range = v4.x; e.tustep = v4.y; e.tperp = v5.x;
+    p.wt = (double)__int_as_float(__double2loint(v5.y)); e.elke = (double)__int_as_float(__double2hiint(v5.y));
+    e.demfp = (double)f.x; e.sig0 = (double)f.y; e.rhof = (double)f.z; e.dedx = (double)f.w;
+    e.blccl = (double)__int_as_float((int)m.x); e.ssmfp = (double)__int_as_float((int)m.y);
+    e.eke = p.e - RM;
+    e.ecut = region_ecut(P, p.ir, e.imed);
     g.seed(P.seed0, P.seed1, ((unsigned long long)r.y << 32) | r.x, r.z, r.w);
 }
 
@@ -450,10 +465,10 @@ __device__ __forceinline__ int estep_size(const DevProblem &P, Rng &g, Part &p, 
     const ElecBin *B0 = P.ebin + (size_t)qel * P.nmed * MXEKE + imed * MXEKE;
     const double rhof = R.rhof, eke = e.eke;
     const double rinv = 1.0 / rhof;
-    g.align();
+    const uint4 blk = g.block();                               // one draw is used; block-wise so the state stays in registers
 #if OMC_WAVE_F32
     // mixed precision (see omc_physics_f32.cuh): logs and ratios in fp32, energy / length sums in fp64
-    float rf = nextf(g);
+    float rf = (float)(blk.x >> 8) * (1.0f / 16777216.0f);
     if (rf == 0.0f) rf = 1.0E-30f;
     e.demfp = fmax((double)(-__logf(rf)), 1.0E-5);
     const double elke = flog(eke);
@@ -498,7 +513,7 @@ __device__ __forceinline__ int estep_size(const DevProblem &P, Rng &g, Part &p, 
         e.range = (drange_m(B, eke, ekei, elke, elkei) + __ldg(&B->range_ep)) * rinv;
     }
     double tustep = fmin(fmin(tstep, tmxs), e.range);
-    const double tperp = hownear(P, p);
+    const double tperp = hownear_i(P, p);
     const float xccl = (float)(rhof * M.xcc);
     const float p2 = (float)(eke * (eke + 2.0 * RM));
     const float beta2 = fdiv(p2, p2 + RMf * RMf);
@@ -509,7 +524,7 @@ __device__ __forceinline__ int estep_size(const DevProblem &P, Rng &g, Part &p, 
     const double blccl = (double)blcclf;
     const double ssmfp = (double)fdiv(beta2, blcclf);
 #else
-    double r = g.next();
+    double r = (double)blk.x * (1.0 / 4294967296.0);
     if (r == 0.0) r = 1.0E-30;
     e.demfp = fmax(-log(r), 1.0E-5);
     const double elke = log(eke);
@@ -553,7 +568,7 @@ __device__ __forceinline__ int estep_size(const DevProblem &P, Rng &g, Part &p, 
         e.range = (drange(B, eke, ekei, elke, elkei) + __ldg(&B->range_ep)) * rinv;
     }
     double tustep = fmin(fmin(tstep, tmxs), e.range);
-    const double tperp = hownear(P, p);
+    const double tperp = hownear_i(P, p);
     double blccl = rhof * M.blcc;
     const double xccl = rhof * M.xcc;
     const double p2 = eke * (eke + 2.0 * RM);
@@ -718,44 +733,48 @@ __device__ __forceinline__ void flush_tally(const DevProblem &P, Tally &t, doubl
     }
 }
 
-// append to the step-class queue `cls` of parity `par`
-// (two branches on purpose: q_reserve() aggregates over the lanes that are active TOGETHER)
-__device__ __forceinline__ void es_push(const WaveArgs &A, WaveCtl *ctl, int par, int cls, const Part &p, const Rng &g, const EStep &e) {
-    if (cls == CLS_CH) {
-        const unsigned slot = q_reserve(&ctl->n_ch[par]);
-        if (slot < A.Q.ch[par].cap) es_put(A.Q.ch[par], slot, p, g, e);
-        else atomicAdd(&ctl->overflow, 1u);
-    } else {
-        const unsigned slot = q_reserve(&ctl->n_bca[par]);
-        if (slot < A.Q.bca[par].cap) es_put(A.Q.bca[par], slot, p, g, e);
-        else atomicAdd(&ctl->overflow, 1u);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // electron kernels.  esize_kernel sizes the next step of every electron in E[cur] and sorts it into the CH or BCA
-// queue of this wave; the step kernels push survivors back to E[next].
-// OMC_FUSE_ESIZE=1 (experiment, measured SLOWER on B200: 5.28e7 vs 5.67e7 histories/s): the step kernels size the
-// next step of a surviving electron in registers and push it straight into the step-class queue of the next
-// wave (one 200-byte record per step instead of a particle record plus a step record).  It removes a third of
-// the queue traffic, but the kernels are latency bound, not bandwidth bound, and the longer per-thread
-// dependent chain plus the extra divergence (finished lanes idle through the sizing code) cost more.
+// class of the step queue; the step kernels push survivors back to E[next].
+// (Measured alternative, not kept: sizing the next step of a surviving electron inside the step kernels and
+// pushing it straight into the next wave's class queue removes a third of the queue traffic but ran 7 % SLOWER
+// on B200 -- 5.28e7 vs 5.67e7 histories/s: the kernels are latency bound, not bandwidth bound, and the longer
+// per-thread dependent chain plus finished lanes idling through the sizing code cost more.)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT, OMC_MB_ESIZE) esize_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ WaveArgs A) {
     WaveCtl *ctl = A.ctl;
     const int par = (int)ctl->parity;
-    const unsigned n = min(ctl->n_e[par], A.Q.e[0].cap);
+    const PartQueue &q = A.Q.e[par];
+    const EStepQueue &S = A.Q.es;
+    const unsigned n = min(ctl->n_e[par], q.cap);
+    const unsigned lane = threadIdx.x & 31u, stride = gridDim.x * blockDim.x;
+    const unsigned lt = (1u << lane) - 1u;
     Tally t = {0, 0, 0};
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        Part p; Rng g; EStep e; double aux; int tag, st;
-        q_load(A.Q.e[par], i, p, g, P, aux, tag);
-        const int cls = estep_size(P, g, p, e, t, st);
-        if (cls == CLS_NONE) {
-            if (st > 0) q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st);
-            continue;
+    // warp-uniform loop: all 32 lanes stay converged through the slot reservation and the store
+    for (unsigned base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const unsigned i = base + lane;
+        Part p; Rng g; EStep e;
+        int cls = CLS_NONE, st = 0;
+        if (i < n) {
+            int tag;
+            q_load_part(q, i, p, tag);
+            const uint4 r = q.rng[i];
+            g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
+            cls = estep_size(P, g, p, e, t, st);
         }
-        // (two branches on purpose: q_reserve() aggregates over the lanes that are active TOGETHER)
-        es_push(A, ctl, par, cls, p, g, e);                    // into the step-class queues of THIS wave
+        // one reservation per (warp, class): lane 0 asks for the CH slots, lane 1 for the BCA slots, together
+        const unsigned m_ch = __ballot_sync(0xffffffffu, cls == CLS_CH), m_bca = __ballot_sync(0xffffffffu, cls == CLS_BCA);
+        unsigned b = 0;
+        if (lane == 0 && m_ch) b = atomicAdd(&ctl->n_ch, (unsigned)__popc(m_ch));
+        if (lane == 1 && m_bca) b = atomicAdd(&ctl->n_bca, (unsigned)__popc(m_bca));
+        const unsigned b_ch = __shfl_sync(0xffffffffu, b, 0), b_bca = __shfl_sync(0xffffffffu, b, 1);
+        if (cls != CLS_NONE) {
+            const unsigned k = (cls == CLS_CH) ? b_ch + __popc(m_ch & lt) : b_bca + __popc(m_bca & lt);
+            if (k < S.cap) es_put(S, (cls == CLS_CH) ? k : 2u * S.cap - 1u - k, p, g, e);
+            else atomicAdd(&ctl->overflow, 1u);
+        } else if (st > 0) {
+            q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st);
+        }
     }
     flush_tally(P, t, 0.0);
 }
@@ -764,25 +783,15 @@ template <int CLS>
 __global__ void __launch_bounds__(NT, (CLS == 1 ? OMC_MB_ECH : OMC_MB_EBCA)) edo_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ WaveArgs A) {
     WaveCtl *ctl = A.ctl;
     const int par = (int)ctl->parity;
-    const EStepQueue &S = (CLS == CLS_CH) ? A.Q.ch[par] : A.Q.bca[par];
-    const unsigned n = min(CLS == CLS_CH ? ctl->n_ch[par] : ctl->n_bca[par], S.cap);
+    const EStepQueue &S = A.Q.es;
+    const unsigned n = min(CLS == CLS_CH ? ctl->n_ch : ctl->n_bca, S.cap);
     Tally t = {0, 0, 0};
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Part p; Rng g; EStep e;
-        es_get(S, i, p, g, e, P);
+        es_get(S, (CLS == CLS_CH) ? i : 2u * S.cap - 1u - i, p, g, e, P);
         const int st = estep_do(P, g, p, e, CLS, t);
-#if OMC_FUSE_ESIZE
-        if (st == 0) {                                         // keeps travelling: size the next step right here
-            int st2;
-            const int cls = estep_size(P, g, p, e, t, st2);    // (st2: -1 finished / TAG_RANNIH when below the cut-off)
-            if (cls != CLS_NONE) es_push(A, ctl, par ^ 1, cls, p, g, e);
-            else if (st2 > 0) q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st2);
-            continue;
-        }
-#else
         if (st == 0) q_push(A.Q.e[par ^ 1], &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
-#endif
-        if (st > 0) q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st);
+        else if (st > 0) q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st);
     }
     flush_tally(P, t, 0.0);
 }
@@ -838,8 +847,8 @@ __global__ void advance_kernel(const __grid_constant__ DevProblem P, WaveCtl *c)
     const int par = (int)c->parity, nxt = par ^ 1;
     c->hist_next += c->n_src;
     P.counters->histories += c->n_src;
-    c->n_p[par] = 0; c->n_e[par] = 0; c->n_ip[par] = 0; c->n_ie[par] = 0; c->n_ch[par] = 0; c->n_bca[par] = 0;
-    const unsigned live = c->n_p[nxt] + c->n_e[nxt] + c->n_ip[nxt] + c->n_ie[nxt] + c->n_ch[nxt] + c->n_bca[nxt];
+    c->n_p[par] = 0; c->n_e[par] = 0; c->n_ip[par] = 0; c->n_ie[par] = 0; c->n_ch = 0; c->n_bca = 0;
+    const unsigned live = c->n_p[nxt] + c->n_e[nxt] + c->n_ip[nxt] + c->n_ie[nxt];
     const unsigned long long left = c->hist_end - c->hist_next;
     const unsigned room = (live < c->target) ? c->target - live : 0u;
     c->n_src = (unsigned)(left < (unsigned long long)room ? left : (unsigned long long)room);
