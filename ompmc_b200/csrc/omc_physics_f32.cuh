@@ -283,6 +283,264 @@ static __device__ __noinline__ double msdist_f(const DevProblem &P, Rng &g, cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// Block-draw version of the condensed-history step for edo_kernel<CH>.  ncu on the versions above: the Rng object
+// is passed by reference through __noinline__ samplers, so it lives in LOCAL memory (LDL + STL = 12.6 % of the
+// executed instructions), its word-select chain is another 11 %, and the Philox block function runs at 14 of 32
+// lanes because lanes reach their refills at different draw sites (8 partial executions per warp and step).
+// Here every random number comes from a whole Philox block drawn at a fixed program point by all lanes together
+// (Rng::block(), register-only); words that a lane does not need are dropped.  Same algorithm and distributions as
+// msdist()/mscat()/spinRejection() (src/ompmc.c:3097-3168, 3606-3976); statistically neutral differences: the
+// four table-index rounding decisions (mscat :3702-3724, spinRejection :3104-3150) are always made, up front, from
+// 16-bit halves of two words; the dead interpolation draw of mscat (Q1) is not generated.
+//   block G0 = {sprob pass 0, sprob pass 1, eta of msdist, rfict of the caller's sigma-ratio test}
+//   block G1 = {ms i|j rounding, spin i|j rounding, first (u, r) pair}
+//   further (u, r) pairs two per block; both azimuths from one block {x1, y1, x2, y2} per round
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float u24(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float u16lo(uint32_t w) { return (float)(w & 0xffffu) * (1.0f / 65536.0f); }
+__device__ __forceinline__ float u16hi(uint32_t w) { return (float)(w >> 16) * (1.0f / 65536.0f); }
+
+// spinRejection() index part, :3104-3150: the (i, j) row of the Mott table for this step
+__device__ __forceinline__ const float *spin_row(const DevProblem &P, int imed, int qel, float elke, float beta2, float q1, float ri, float rj) {
+    int i;
+    float ai;
+    const float b2min = (float)P.b2spin_min, espml = (float)P.espml;
+    if (beta2 >= b2min) {
+        ai = (beta2 - b2min) * (float)P.dbeta2i;
+        i = (int)ai; ai -= (float)i; i += 16;
+        if (i > 30) { i = 30; ai = 1.0f; }                     // beta2 -> 1 in fp32
+    } else if (elke > espml) {
+        ai = (elke - espml) * (float)P.dleneri;
+        i = (int)ai; ai -= (float)i;
+    } else {
+        i = 0; ai = -1.0f;
+    }
+    if (ri < ai) i += 1;
+    float qq1 = 2.0f * q1;
+    qq1 = fdiv(qq1, 1.0f + qq1);
+    float aj = qq1 * (float)P.dqq1i;
+    int j = (int)aj;
+    if (j >= 15) {
+        j = 15;
+    } else {
+        aj -= (float)j;
+        if (rj < aj) j += 1;
+    }
+    return P.spin_rej_f + (((size_t)(imed * 2 + qel) * OMC_SPIN_NE + i) * OMC_SPIN_NQ + j) * OMC_SPIN_NU;
+}
+// spinRejection() value part, :3152-3167, argument omc = 1 - cos(theta)
+__device__ __forceinline__ float spin_rej_row(const float *row, float omc_) {
+    const float xi = sqrtf(0.5f * omc_);
+    float ak = xi * 31.0f;
+    int k = (int)ak;
+    if (k > 30) k = 30;
+    ak -= (float)k;
+    return (1.0f - ak) * __ldg(row + k) + ak * __ldg(row + k + 1);
+}
+
+// source of (u, r) word pairs: the pair left over in G1 first, then two pairs per fresh block
+struct PairSrc {
+    uint4 b;
+    uint32_t a0, a1;
+    int have, nb;
+    __device__ __forceinline__ void next(Rng &g, uint32_t &u, uint32_t &r) {
+        if (have) { u = a0; r = a1; have = 0; return; }
+        if (nb >= 2) { b = g.block(); nb = 0; }
+        u = nb ? b.z : b.x; r = nb ? b.w : b.y;
+        nb += 1;
+    }
+};
+
+__device__ __forceinline__ double msdist_b(const DevProblem &P, Rng &g, const Part &p, int imed, int qel, double rhof_d, double de_d,
+                                           double tustep_d, double eke_d, double &xf, double &yf, double &zf, double &uf, double &vf,
+                                           double &wf, uint32_t &w_rfict) {
+    const MedRec &M = P.med[imed];
+    const float rhof = (float)rhof_d, de = (float)de_d, tustep = (float)tustep_d, eke = (float)eke_d;
+    const float xcc = (float)M.xcc, blcc = (float)M.blcc;
+    float e = eke - 0.5f * de;
+    const float tau = e * (1.0f / RMf), tau2 = tau * tau;
+    const float epsilon = fdiv(de, eke), epsilonp = fdiv(de, e);
+    e *= (1.0f - (epsilonp * epsilonp) * fdiv(6.0f + 10.0f * tau + 5.0f * tau2, 24.0f * tau2 + 72.0f * tau + 48.0f));
+    const float p2 = e * (e + 2.0f * RMf);
+    const float beta2 = fdiv(p2, p2 + (RMf * RMf));
+    float chia2 = fdiv(xcc, 4.0f * p2 * blcc);
+    float lambda = fdiv(0.5f * tustep * rhof * blcc, beta2);
+    const float t12 = fdiv(epsilonp, (tau + 1.0f) * (tau + 2.0f));
+    const float temp2 = 0.166666f * (4.0f + tau * (6.0f + tau * (7.0f + tau * (4.0f + tau)))) * t12 * t12;
+    lambda *= (1.0f - temp2);
+    float elke = __logf(e);
+    int lelke = (int)(elke * (float)M.eke1 + (float)M.eke0) - 1;
+    if (lelke < 0) { lelke = 0; elke = (float)((1.0 - M.eke0) / M.eke1); }
+    const ElecBin *B = P.ebin + (size_t)qel * P.nmed * MXEKE + imed * MXEKE + lelke;
+    const float etap = elke * (float)__ldg(&B->eta1) + (float)__ldg(&B->eta0);
+    const float xi_corr = elke * (float)__ldg(&B->q1c1) + (float)__ldg(&B->q1c0);
+    float gamma = elke * (float)__ldg(&B->q2c1) + (float)__ldg(&B->q2c0);
+    const float ms_corr = elke * (float)__ldg(&B->blcce1) + (float)__ldg(&B->blcce0);
+    chia2 *= etap;
+    lambda = fdiv(lambda, etap * (1.0f + chia2));
+    lambda *= ms_corr;
+    const float chilog = __logf(1.0f + frcp(chia2));
+    const float q1 = 2.0f * chia2 * (chilog * (1.0f + chia2) - 1.0f);
+    gamma = fdiv(6.0f * chia2 * (1.0f + chia2) * (chilog * (1.0f + 2.0f * chia2) - 2.0f), q1) * gamma;
+    float xi = q1 * lambda;
+
+    const uint4 g0 = g.block();
+    const uint4 g1 = g.block();
+    w_rfict = g0.w;
+    // table rows of this step: mscat :3694-3735 (find_index), spinRejection :3104-3150 (spin_index)
+    const float explambda = __expf(-lambda);
+    const float llmbda = __logf(lambda);
+    int mi, mj;
+    {
+        float ai = llmbda * (float)P.dllambi;
+        mi = (int)ai; ai -= (float)mi;
+        if (u16lo(g1.x) < ai) mi += 1;
+        mi = max(0, min(mi, 63));
+        if (xi < 1.0E-3f) {
+            mj = 0;
+        } else if (xi < 0.5f) {
+            float aj = xi * (float)P.dqmsi;
+            mj = (int)aj; aj -= (float)mj;
+            if (u16hi(g1.x) < aj) mj += 1;
+        } else {
+            mj = 7;
+        }
+    }
+    float omega2;
+    if (llmbda < 2.2299f)
+        omega2 = chia2 * (lambda + 4.0f) * (1.347006f + llmbda * (0.209364f - llmbda * (0.45525f - llmbda * (0.50142f - 0.081234f * llmbda))));
+    else
+        omega2 = chia2 * (lambda + 4.0f) * (-2.77164f + llmbda * (2.94874f - llmbda * (0.1535754f - llmbda * 0.00552888f)));
+    const MsEntryF *tab = P.ms_f + (mi * OMC_MS_NQ + mj) * OMC_MS_NU;
+    const float *row = spin_row(P, imed, qel, elke, beta2, xi, u16lo(g1.y), u16hi(g1.y));
+
+    PairSrc ps;
+    ps.a0 = g1.z; ps.a1 = g1.w; ps.have = 1; ps.nb = 2;
+    float w1 = 1.0f, sint1 = 0.0f, w2 = 1.0f, sint2 = 0.0f;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        const float sprob = u24(pass ? g0.y : g0.x);
+        float c = 1.0f, sv = 0.0f;
+        // regime of mscat(): 0 no scattering (or Q7), 1 single scattering, 2 table, 3 plural scattering (lambda <= 1)
+        int regime = 2;
+        if (lambda <= 13.8f) {
+            if (sprob < explambda) regime = 0;
+            else if (sprob < (1.0f + lambda) * explambda) regime = 1;
+            else if (lambda <= 1.0f) regime = 3;
+        } else if (!(lambda <= 1.0E5f)) {
+            regime = 0;
+        }
+        if (regime == 1 || regime == 2) {
+            float x;
+            for (;;) {
+                uint32_t wu, wr;
+                ps.next(g, wu, wr);
+                const float u = u24(wu);
+                if (regime == 1) {
+                    x = fdiv(2.0f * chia2 * u, 1.0f - u + chia2);
+                } else {
+                    float ak = u * 31.0f;
+                    int k = (int)ak;
+                    ak -= (float)k;
+                    const float4 t0 = __ldg(reinterpret_cast<const float4 *>(tab + k));   // {ums, wms, ims, fms}
+                    if (ak > t0.y) k = __float_as_int(t0.z);
+                    const float um = __ldg(&tab[k].ums);
+                    x = fdiv(omega2 * um, 1.0f + 0.5f * omega2 - um);
+                    if (x > 1.99999f) x = 1.99999f;
+                }
+                if (!(u24(wr) > spin_rej_row(row, x))) break;
+            }
+            c = 1.0f - x;
+            sv = sqrtf(x * (2.0f - x));
+        } else if (regime == 3) {                              // :3652-3682, rare in a condensed-history step
+            int icount = 0;
+            float wprob = explambda, wsum = explambda;
+            do {
+                icount += 1;
+                if (icount > 20) break;
+                wprob = wprob * lambda / (float)icount;
+                wsum = wsum + wprob;
+                float x;
+                for (;;) {
+                    uint32_t wu, wr;
+                    ps.next(g, wu, wr);
+                    const float u = u24(wu);
+                    x = fdiv(2.0f * chia2 * u, 1.0f - u + chia2);
+                    if (!(u24(wr) > spin_rej_row(row, x))) break;
+                }
+                const float cosz = 1.0f - x;
+                float sinz = x * (2.0f - x);
+                if (sinz > 1.0E-20f) {
+                    sinz = sqrtf(sinz);
+                    uint32_t wu, wr;
+                    ps.next(g, wu, wr);
+                    const float phi = u24(wu) * 6.2831853f;
+                    c = c * cosz - sv * sinz * __cosf(phi);
+                    sv = sqrtf(fmaxf(0.0f, (1.0f - c) * (1.0f + c)));
+                }
+            } while (wsum <= sprob);
+        }
+        if (pass == 0) { w1 = c; sint1 = sv; } else { w2 = c; sint2 = sv; }
+    }
+    // both azimuths, selectAzimuthalAngle() :101-122, from one block per round
+    float cphi1 = 1.0f, sphi1 = 0.0f, cphi2 = 1.0f, sphi2 = 0.0f;
+    {
+        bool ok1 = false, ok2 = false;
+        do {
+            const uint4 ba = g.block();
+            if (!ok1) {
+                const float x = 2.0f * u24(ba.x) - 1.0f, y = u24(ba.y), x2 = x * x, y2 = y * y, r2 = x2 + y2;
+                if (r2 <= 1.0f && r2 > 0.0f) { const float ir2 = frcp(r2); cphi1 = (x2 - y2) * ir2; sphi1 = 2.0f * x * y * ir2; ok1 = true; }
+            }
+            if (!ok2) {
+                const float x = 2.0f * u24(ba.z) - 1.0f, y = u24(ba.w), x2 = x * x, y2 = y * y, r2 = x2 + y2;
+                if (r2 <= 1.0f && r2 > 0.0f) { const float ir2 = frcp(r2); cphi2 = (x2 - y2) * ir2; sphi2 = 2.0f * x * y * ir2; ok2 = true; }
+            }
+        } while (!(ok1 && ok2));
+    }
+    const float u2 = sint2 * cphi2, v2 = sint2 * sphi2;
+    float u2p = w1 * u2 + sint1 * w2;
+    float us = u2p * cphi1 - v2 * sphi1, vs = u2p * sphi1 + v2 * cphi1, ws = w1 * w2 - sint1 * u2;
+    xi *= 2.0f * xi_corr;
+    const float eta = u24(g0.z);
+    const float eta1 = 0.5f * (1.0f - eta);
+    float delta = 0.9082483f - (0.1020621f - 0.0263747f * gamma) * xi;
+    float temp1 = 2.0f + tau;
+    float temp = fdiv(2.0f + tau * temp1, (tau + 1.0f) * temp1);
+    const float c1 = chilog * (1.0f + chia2) - 1.0f, c2 = chilog * (1.0f + 2.0f * chia2) - 2.0f;
+    temp -= fdiv(tau + 1.0f, (tau + 2.0f) * c1);
+    temp *= epsilonp;
+    temp1 = 1.0f - temp;
+    delta += 0.40824829f * (fdiv(epsilon * (tau + 1.0f), (tau + 2.0f) * c1 * c2) - 0.25f * (temp * temp));
+    const float b = eta * delta, cc = eta * (1.0f - delta);
+    const float w1v2 = w1 * v2;
+    float ut = b * sint1 * cphi1 + cc * (cphi1 * u2 - sphi1 * w1v2) + eta1 * us * temp1;
+    float vt = b * sint1 * sphi1 + cc * (sphi1 * u2 + cphi1 * w1v2) + eta1 * vs * temp1;
+    float wt = eta1 * (1.0f + temp) + b * w1 + cc * w2 + eta1 * ws * temp1;
+    const float ustep = tustep * sqrtf(ut * ut + vt * vt + wt * wt);
+    const float u0 = (float)p.u, v0 = (float)p.v, w0 = (float)p.w;
+    const float sint02 = u0 * u0 + v0 * v0;
+    if (sint02 > 1.0E-20f) {
+        const float sint0i = rsqrtf(sint02), sint0 = sint02 * sint0i;
+        const float cphi0 = sint0i * u0, sphi0 = sint0i * v0;
+        u2p = w0 * us + sint0 * ws;
+        ws = w0 * ws - sint0 * us;
+        us = u2p * cphi0 - vs * sphi0;
+        vs = u2p * sphi0 + vs * cphi0;
+        u2p = w0 * ut + sint0 * wt;
+        wt = w0 * wt - sint0 * ut;
+        ut = u2p * cphi0 - vt * sphi0;
+        vt = u2p * sphi0 + vt * cphi0;
+    } else {
+        wt = w0 * wt; ws = w0 * ws;
+    }
+    const float nrm = rsqrtf(us * us + vs * vs + ws * ws);
+    xf = p.x + tustep_d * (double)ut; yf = p.y + tustep_d * (double)vt; zf = p.z + tustep_d * (double)wt;
+    uf = (double)(us * nrm); vf = (double)(vs * nrm); wf = (double)(ws * nrm);
+    return (double)ustep;
+}
+
+// ---------------------------------------------------------------------------------------------
 // CSDA helpers in mixed precision: energies and path lengths are fp64 quantities, but the series below only
 // needs RATIOS to ~1e-7, so the logs / divisions (software sequences in fp64) are done in fp32.  Differences of
 // nearly equal energies are taken in fp64 BEFORE the conversion (no cancellation in fp32).

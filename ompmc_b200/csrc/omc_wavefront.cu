@@ -36,6 +36,9 @@
 #define OMC_WAVE_F32 1     // 1: fp32 angle samplers (omc_physics_f32.cuh); 0: the fp64 ones of the lock-step kernel
 #endif
 
+#ifndef OMC_CH_BLOCK_RNG
+#define OMC_CH_BLOCK_RNG 1   // 1: condensed-history step with whole-block draws, Rng in registers (msdist_b); 0: msdist_f
+#endif
 #ifndef OMC_WARP_AGGREGATE_DOSE
 #define OMC_WARP_AGGREGATE_DOSE 0
 #endif
@@ -48,7 +51,7 @@
 #define OMC_MB_ESIZE 5
 #endif
 #ifndef OMC_MB_ECH
-#define OMC_MB_ECH 6
+#define OMC_MB_ECH 5
 #endif
 #ifndef OMC_MB_EBCA
 #define OMC_MB_EBCA 6
@@ -425,6 +428,7 @@ __device__ __forceinline__ void es_put(const EStepQueue &S, unsigned s, const Pa
                         (unsigned)(p.iq + 1) | ((unsigned)(e.imed + 1) << 2) | ((unsigned)e.lelke << 16));
     S.rng[s] = make_uint4(g.h0, g.h1, g.stream, g.ndraws());
 }
+template <bool BLOCKS>
 __device__ __forceinline__ void es_get(const EStepQueue &S, unsigned s, Part &p, Rng &g, EStep &e, const DevProblem &P) {
     const uint4 m = S.m[s];
     const double2 v0 = S.v[0][s], v1 = S.v[1][s], v2 = S.v[2][s], v3 = S.v[3][s], v4 = S.v[4][s], v5 = S.v[5][s];
@@ -438,7 +442,8 @@ __device__ __forceinline__ void es_get(const EStepQueue &S, unsigned s, Part &p,
     e.blccl = (double)__int_as_float((int)m.x); e.ssmfp = (double)__int_as_float((int)m.y);
     e.eke = p.e - RM;
     e.ecut = region_ecut(P, p.ir, e.imed);
-    g.seed(P.seed0, P.seed1, ((unsigned long long)r.y << 32) | r.x, r.z, r.w);
+    if (BLOCKS) g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
+    else g.seed(P.seed0, P.seed1, ((unsigned long long)r.y << 32) | r.x, r.z, r.w);
 }
 
 // Phase A: cut-off test, distance to the next discrete interaction, step-size restrictions.
@@ -591,12 +596,17 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
     const double rhof = e.rhof, eke0 = e.eke;
     bool call_howfar, do_single = false;
     double xf = 0, yf = 0, zf = 0, uf = 0, vf = 0, wf = 0;
+    uint32_t w_rfict = 0;                                      // (block-draw CH step: the word kept for the sigma-ratio test)
     const ElecBin *B0 = (imed >= 0) ? P.ebin + (size_t)qel * P.nmed * MXEKE + imed * MXEKE : nullptr;
     if (cls == CLS_CH) {                                       // condensed-history step, :4973-4996
         call_howfar = false;
 #if OMC_WAVE_F32
         de = eloss_m(B0, P.med[imed], rhof, 1.0 / rhof, tustep, e.range, eke0, e.elke, e.lelke);
+#if OMC_CH_BLOCK_RNG
+        ustep = msdist_b(P, g, p, imed, qel, rhof, de, tustep, eke0, xf, yf, zf, uf, vf, wf, w_rfict);
+#else
         ustep = msdist_f(P, g, p, imed, qel, rhof, de, tustep, eke0, xf, yf, zf, uf, vf, wf);
+#endif
 #else
         de = eloss(B0, P.med[imed], rhof, tustep, e.range, eke0, e.elke, e.lelke);
         ustep = msdist<true>(P, g, p, imed, qel, rhof, de, tustep, eke0, xf, yf, zf, uf, vf, wf);
@@ -703,11 +713,20 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
     // fictitious cross-section rejection, :5354-5372
     const ElecBin *B = B0 + lelke;
     const double sigf = pwl(elke, __ldg(&B->sig1), __ldg(&B->sig0)) / pwl(elke, __ldg(&B->dedx1), __ldg(&B->dedx0));
-    g.align();
-    const double rfict = g.next();
-    if (rfict >= sigf / e.sig0) return 0;
     const double br1 = pwl(elke, __ldg(&B->bra1), __ldg(&B->bra0));   // :5375-5429
-    const double r = g.next();
+    double r;
+#if OMC_WAVE_F32 && OMC_CH_BLOCK_RNG
+    if (cls == CLS_CH) {
+        if ((double)w_rfict * (1.0 / 4294967296.0) >= sigf / e.sig0) return 0;
+        r = (double)g.block().x * (1.0 / 4294967296.0);
+    } else
+#endif
+    {
+        g.align();
+        const double rfict = g.next();
+        if (rfict >= sigf / e.sig0) return 0;
+        r = g.next();
+    }
     if (iq < 0) {
         if (r <= br1) return TAG_BREMS;
         if (p.e <= M.thmoll) return (br1 <= 0) ? 0 : TAG_BREMS;
@@ -788,7 +807,7 @@ __global__ void __launch_bounds__(NT, (CLS == 1 ? OMC_MB_ECH : OMC_MB_EBCA)) edo
     Tally t = {0, 0, 0};
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Part p; Rng g; EStep e;
-        es_get(S, (CLS == CLS_CH) ? i : 2u * S.cap - 1u - i, p, g, e, P);
+        es_get<(CLS == CLS_CH) && OMC_WAVE_F32 && OMC_CH_BLOCK_RNG>(S, (CLS == CLS_CH) ? i : 2u * S.cap - 1u - i, p, g, e, P);
         const int st = estep_do(P, g, p, e, CLS, t);
         if (st == 0) q_push(A.Q.e[par ^ 1], &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
         else if (st > 0) q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st);
