@@ -181,7 +181,7 @@ __device__ __forceinline__ void decode_region(const DevProblem &P, int irl, int 
     iry = ((irl - 1 - irx) - irz * P.ijmax) / P.isize;
 }
 
-OMC_FN void howfar(const DevProblem &P, const Part &p, int &idisc, int &irnew, double &ustep) {
+__device__ __forceinline__ void howfar_i(const DevProblem &P, const Part &p, int &idisc, int &irnew, double &ustep) {
     const int irl = p.ir;
     if (irl == 0) { idisc = 1; return; }
     int irx, iry, irz;
@@ -209,6 +209,7 @@ OMC_FN void howfar(const DevProblem &P, const Part &p, int &idisc, int &irnew, d
         if (dist < ustep) { ustep = dist; irnew = (iry != 0) ? irl - P.isize : 0; }
     }
 }
+OMC_FN void howfar(const DevProblem &P, const Part &p, int &idisc, int &irnew, double &ustep) { howfar_i(P, p, idisc, irnew, ustep); }
 
 __device__ __forceinline__ double hownear_i(const DevProblem &P, const Part &p) {
     const int irl = p.ir;

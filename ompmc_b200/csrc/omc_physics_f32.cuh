@@ -301,7 +301,8 @@ __device__ __forceinline__ float u16lo(uint32_t w) { return (float)(w & 0xffffu)
 __device__ __forceinline__ float u16hi(uint32_t w) { return (float)(w >> 16) * (1.0f / 65536.0f); }
 
 // spinRejection() index part, :3104-3150: the (i, j) row of the Mott table for this step
-__device__ __forceinline__ const float *spin_row(const DevProblem &P, int imed, int qel, float elke, float beta2, float q1, float ri, float rj) {
+__device__ __forceinline__ const float *spin_row(const DevProblem &P, int imed, int qel, float elke, float beta2, float q1, float ri, float rj,
+                                                 bool is_single = false) {
     int i;
     float ai;
     const float b2min = (float)P.b2spin_min, espml = (float)P.espml;
@@ -316,15 +317,18 @@ __device__ __forceinline__ const float *spin_row(const DevProblem &P, int imed, 
         i = 0; ai = -1.0f;
     }
     if (ri < ai) i += 1;
-    float qq1 = 2.0f * q1;
-    qq1 = fdiv(qq1, 1.0f + qq1);
-    float aj = qq1 * (float)P.dqq1i;
-    int j = (int)aj;
-    if (j >= 15) {
-        j = 15;
-    } else {
-        aj -= (float)j;
-        if (rj < aj) j += 1;
+    int j = 0;
+    if (!is_single) {
+        float qq1 = 2.0f * q1;
+        qq1 = fdiv(qq1, 1.0f + qq1);
+        float aj = qq1 * (float)P.dqq1i;
+        j = (int)aj;
+        if (j >= 15) {
+            j = 15;
+        } else {
+            aj -= (float)j;
+            if (rj < aj) j += 1;
+        }
     }
     return P.spin_rej_f + (((size_t)(imed * 2 + qel) * OMC_SPIN_NE + i) * OMC_SPIN_NQ + j) * OMC_SPIN_NU;
 }
@@ -350,6 +354,35 @@ struct PairSrc {
         nb += 1;
     }
 };
+
+// sscat() + the azimuth of uphi21(), src/ompmc.c:3170-3199 / :101-122, for the boundary-crossing step: (u, r)
+// pairs two per block; `wi` = the word whose low half rounds the spin-table energy index
+__device__ __forceinline__ void sscat_b(const DevProblem &P, Rng &g, int imed, int qel, float chia2, float elke, float beta2, uint32_t wi,
+                                        float &cost, float &sint, float &cphi, float &sphi) {
+    const float *row = spin_row(P, imed, qel, elke, beta2, 0.0f, u16lo(wi), 0.0f, true);
+    PairSrc ps;
+    ps.a0 = ps.a1 = 0u; ps.have = 0; ps.nb = 2;
+    float x;
+    for (;;) {
+        uint32_t wu, wr;
+        ps.next(g, wu, wr);
+        const float u = u24(wu);
+        x = fdiv(2.0f * chia2 * u, 1.0f - u + chia2);
+        if (!(u24(wr) > spin_rej_row(row, x))) break;
+    }
+    cost = 1.0f - x;
+    sint = sqrtf(x * (2.0f - x));
+    for (;;) {
+        uint32_t wu, wr;
+        ps.next(g, wu, wr);
+        const float xx = 2.0f * u24(wu) - 1.0f, y = u24(wr), x2 = xx * xx, y2 = y * y, r2 = x2 + y2;
+        if (r2 <= 1.0f && r2 > 0.0f) {
+            const float ir2 = frcp(r2);
+            cphi = (x2 - y2) * ir2; sphi = 2.0f * xx * y * ir2;
+            break;
+        }
+    }
+}
 
 __device__ __forceinline__ double msdist_b(const DevProblem &P, Rng &g, const Part &p, int imed, int qel, double rhof_d, double de_d,
                                            double tustep_d, double eke_d, double &xf, double &yf, double &zf, double &uf, double &vf,

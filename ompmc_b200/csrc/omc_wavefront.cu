@@ -597,6 +597,7 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
     bool call_howfar, do_single = false;
     double xf = 0, yf = 0, zf = 0, uf = 0, vf = 0, wf = 0;
     uint32_t w_rfict = 0;                                      // (block-draw CH step: the word kept for the sigma-ratio test)
+    uint4 g0 = make_uint4(0u, 0u, 0u, 0u);                     // (block-draw BCA step: its first block)
     const ElecBin *B0 = (imed >= 0) ? P.ebin + (size_t)qel * P.nmed * MXEKE + imed * MXEKE : nullptr;
     if (cls == CLS_CH) {                                       // condensed-history step, :4973-4996
         call_howfar = false;
@@ -614,8 +615,13 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
     } else if (imed == -1) {                                   // :4815-4821
         ustep = tustep; call_howfar = true;
     } else {                                                   // exact boundary crossing, :4997-5057
+#if OMC_WAVE_F32 && OMC_CH_BLOCK_RNG
+        g0 = g.block();                                        // {lambda, spin index rounding, rfict, branch}
+        double r = (double)g0.x * (1.0 / 4294967296.0);
+#else
         g.align();
         double r = g.next();
+#endif
         if (r < 1.0E-30) r = 1.0E-30;
         const double lambda = (-1.0) * log(1.0 - r);
         double lambda_max = 0.5 * e.blccl * RM / e.dedx;
@@ -628,7 +634,7 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
     }
     const int irl = p.ir;
     int irnew = irl, idisc = 0;
-    if (call_howfar) howfar(P, p, idisc, irnew, ustep);
+    if (call_howfar) howfar_i(P, p, idisc, irnew, ustep);
     if (idisc > 0) {                                           // :5061-5088 (no annihilation quanta: edep > eie)
         deposit32(P, t, p.ir, p.wt * ((iq > 0) ? p.e + RM : p.e - RM));
         return -1;
@@ -666,6 +672,15 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
             const int lelkems = elec_interval(M, elkems);
             chia2 *= pwl(elkems, __ldg(&B0[lelkems].eta1), __ldg(&B0[lelkems].eta0));
             double costhe, sinthe;
+            Frame fr;
+#if OMC_WAVE_F32 && OMC_CH_BLOCK_RNG
+            float cf, sf, cphi, sphi;
+            sscat_b(P, g, imed, qel, (float)chia2, (float)elkems, (float)beta2, g0.y, cf, sf, cphi, sphi);
+            costhe = (double)cf; sinthe = (double)sf;
+            fr.cphi = (double)cphi; fr.sphi = (double)sphi;
+            fr.A = p.u; fr.B = p.v; fr.C = p.w;
+            frame_apply(fr, costhe, sinthe, p);
+#else
             g.align();
 #if OMC_WAVE_F32
             float cf, sf;
@@ -675,8 +690,8 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
             sscat(P, g, imed, qel, chia2, elkems, beta2, costhe, sinthe);
 #endif
             g.align();
-            Frame fr;
             uphi21(g, fr, costhe, sinthe, p);
+#endif
         }
         uf = p.u; vf = p.v; wf = p.w;
     } else {
@@ -719,14 +734,18 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
     if (cls == CLS_CH) {
         if ((double)w_rfict * (1.0 / 4294967296.0) >= sigf / e.sig0) return 0;
         r = (double)g.block().x * (1.0 / 4294967296.0);
-    } else
-#endif
+    } else {
+        if ((double)g0.z * (1.0 / 4294967296.0) >= sigf / e.sig0) return 0;
+        r = (double)g0.w * (1.0 / 4294967296.0);
+    }
+#else
     {
         g.align();
         const double rfict = g.next();
         if (rfict >= sigf / e.sig0) return 0;
         r = g.next();
     }
+#endif
     if (iq < 0) {
         if (r <= br1) return TAG_BREMS;
         if (p.e <= M.thmoll) return (br1 <= 0) ? 0 : TAG_BREMS;
@@ -807,7 +826,7 @@ __global__ void __launch_bounds__(NT, (CLS == 1 ? OMC_MB_ECH : OMC_MB_EBCA)) edo
     Tally t = {0, 0, 0};
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Part p; Rng g; EStep e;
-        es_get<(CLS == CLS_CH) && OMC_WAVE_F32 && OMC_CH_BLOCK_RNG>(S, (CLS == CLS_CH) ? i : 2u * S.cap - 1u - i, p, g, e, P);
+        es_get<OMC_WAVE_F32 && OMC_CH_BLOCK_RNG>(S, (CLS == CLS_CH) ? i : 2u * S.cap - 1u - i, p, g, e, P);
         const int st = estep_do(P, g, p, e, CLS, t);
         if (st == 0) q_push(A.Q.e[par ^ 1], &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
         else if (st > 0) q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st);
