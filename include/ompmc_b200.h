@@ -181,6 +181,15 @@ int omc_gpu_synchronize(omc_gpu_handle h);
 /* ---- results ----------------------------------------------------------------------------- */
 /* score.accum_endep / score.accum_endep2 / score.ensrc (omc_dosxyz.c:636-645); each [nreg] fp64; any may be NULL */
 int omc_gpu_get_tallies(omc_gpu_handle h, double *accum_endep, double *accum_endep2, double *ensrc);
+/* accumulateResults(iout, nhist, nbatch) (omc_dosxyz.c:719-799; omc_matrad.c passes the total history count,
+ * omc_dosxyz.c:1282 the per-batch one) evaluated ON THE DEVICE from the resident tallies: batch mean, batch-method
+ * relative uncertainty, MeV -> Gy with the voxel mass (iout != 0), dose 0 / uncertainty 0.9999999 where the density
+ * is below 0.044 g/cm3 or nothing was scored.  med_densities = geometry.med_densities [nvox] (g/cm3).  dose and
+ * unc are indexed like score.accum_endep (element irl = 1 + ix + iy*isize + iz*isize*jsize; element 0 is copied
+ * through), so a user code passes score.accum_endep / score.accum_endep2 and calls its outputResults() unchanged.
+ * The device tallies are not modified. */
+int omc_gpu_accumulate_results(omc_gpu_handle h, int iout, int nhist, int nbatch, const double *med_densities, double *dose,
+                               double *unc);
 /* score.endep of the running batch, [nreg] fp64 (before accum_batch) */
 int omc_gpu_get_batch_grid(omc_gpu_handle h, double *endep);
 /* memset of the three grids (initScore(), omc_dosxyz.c:647-665; omc_matrad.c:1482 zeroes accum only: which = 1) */

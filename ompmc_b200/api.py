@@ -88,7 +88,7 @@ class Counters(C.Structure):
 EXPORTS = ["omc_gpu_create", "omc_gpu_destroy", "omc_gpu_last_error", "omc_gpu_set_media", "omc_gpu_set_geometry",
            "omc_gpu_set_source_dosxyz", "omc_gpu_set_source_matrad", "omc_gpu_set_vrt", "omc_gpu_set_seed", "omc_gpu_set_option",
            "omc_gpu_run_histories", "omc_gpu_accum_batch", "omc_gpu_run_batch", "omc_gpu_synchronize", "omc_gpu_get_tallies",
-           "omc_gpu_get_batch_grid", "omc_gpu_reset_tallies", "omc_gpu_device_ptrs", "omc_gpu_stream", "omc_gpu_get_counters",
+           "omc_gpu_get_batch_grid", "omc_gpu_accumulate_results", "omc_gpu_reset_tallies", "omc_gpu_device_ptrs", "omc_gpu_stream", "omc_gpu_get_counters",
            "omc_gpu_get_history_records", "omc_gpu_test_geometry", "omc_gpu_test_rng", "omc_gpu_test_particles",
            "omc_gpu_abi_sizeof"]
 
@@ -114,6 +114,7 @@ def load_library() -> C.CDLL:
     lib.omc_gpu_synchronize.argtypes = [H]
     lib.omc_gpu_get_tallies.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.omc_gpu_get_batch_grid.argtypes = [H, C.c_void_p]
+    lib.omc_gpu_accumulate_results.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.omc_gpu_reset_tallies.argtypes = [H, C.c_int]
     lib.omc_gpu_device_ptrs.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
     lib.omc_gpu_stream.argtypes = [H]; lib.omc_gpu_stream.restype = C.c_void_p
@@ -256,6 +257,15 @@ class GpuTransport:
         return a, a2, e.value
 
     get_accum = get_tallies
+
+    def accumulate_results(self, med_densities: np.ndarray, nhist: int, nbatch: int, iout: int = 1):
+        """accumulateResults() on the device (omc_dosxyz.c:719-799): (dose[nvox], rel_sigma[nvox])."""
+        dens = np.ascontiguousarray(med_densities, dtype=np.float64)
+        assert dens.size == self.nreg - 1
+        dose = np.zeros(self.nreg); unc = np.zeros(self.nreg)
+        self._ck(self.lib.omc_gpu_accumulate_results(self.h, int(iout), int(nhist), int(nbatch), dens.ctypes.data, dose.ctypes.data,
+                                                     unc.ctypes.data), "omc_gpu_accumulate_results")
+        return dose[1:], unc[1:]
 
     def reset_tallies(self, which: int = 0):
         self._ck(self.lib.omc_gpu_reset_tallies(self.h, which), "omc_gpu_reset_tallies")

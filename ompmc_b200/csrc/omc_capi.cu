@@ -68,6 +68,9 @@ struct omc_gpu_ctx {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned drain_threshold = 32768;
+    // omc_gpu_accumulate_results scratch
+    double *res_dens = nullptr, *res_dose = nullptr, *res_unc = nullptr;
+    int res_nreg = -1;
 };
 
 #define CK(call)                                                                                         \
@@ -110,7 +113,7 @@ static void free_pool(std::vector<void *> &pool) {
     pool.clear();
 }
 
-static int alloc_queue(omc_gpu_handle h, PartQueue &q, unsigned cap, bool photons) {
+static int alloc_queue(omc_gpu_handle h, PartQueue &q, unsigned cap, bool photons, bool electrons = false) {
     q.cap = cap;
     double2 **f[4] = {&q.xy, &q.zu, &q.vw, &q.ew};
     for (auto pp : f) {
@@ -121,6 +124,11 @@ static int alloc_queue(omc_gpu_handle h, PartQueue &q, unsigned cap, bool photon
     if (photons) {
         CK(cudaMalloc((void **)&q.aux, (size_t)cap * sizeof(double2)));
         h->wave_bufs.push_back(q.aux);
+    }
+    q.rm = nullptr;
+    if (electrons) {
+        CK(cudaMalloc((void **)&q.rm, (size_t)cap * sizeof(int2)));
+        h->wave_bufs.push_back(q.rm);
     }
     CK(cudaMalloc((void **)&q.irq, (size_t)cap * sizeof(int2)));
     h->wave_bufs.push_back(q.irq);
@@ -154,7 +162,7 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
         h->pool_cap = 0;
         for (int i = 0; i < 2; i++) {
             if (alloc_queue(h, h->wq.p[i], cap, true)) return 1;
-            if (alloc_queue(h, h->wq.e[i], cap, false)) return 1;
+            if (alloc_queue(h, h->wq.e[i], cap, false, true)) return 1;
             if (alloc_queue(h, h->wq.ip[i], cap, false)) return 1;
             if (alloc_queue(h, h->wq.ie[i], cap, false)) return 1;
         }
@@ -291,6 +299,7 @@ void omc_gpu_destroy(omc_gpu_handle h) {
     if (h->ctl_host) cudaFreeHost(h->ctl_host);
     cudaFree(h->P.endep); cudaFree(h->P.endep32); cudaFree(h->accum); cudaFree(h->accum2);
     cudaFree(h->P.counters); cudaFree(h->P.ensrc); cudaFree(h->stack); cudaFree(h->records);
+    cudaFree(h->res_dens); cudaFree(h->res_dose); cudaFree(h->res_unc);
     if (h->stream2) { cudaStreamDestroy(h->stream2); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
     cudaStreamDestroy(h->stream);
     delete h;
@@ -652,6 +661,32 @@ int omc_gpu_get_tallies(omc_gpu_handle h, double *accum, double *accum2, double 
     if (accum) CK(cudaMemcpy(accum, h->accum, n, cudaMemcpyDeviceToHost));
     if (accum2) CK(cudaMemcpy(accum2, h->accum2, n, cudaMemcpyDeviceToHost));
     if (ensrc) CK(cudaMemcpy(ensrc, h->P.ensrc, sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int omc_gpu_accumulate_results(omc_gpu_handle h, int iout, int nhist, int nbatch, const double *med_densities, double *dose,
+                               double *unc) {
+    if (!h || !h->have_geom || !med_densities || !dose || !unc) return 2;
+    if (nbatch < 2) return fail(h, "accumulateResults needs at least two batches (batch-method uncertainty)");
+    if (nhist < 1) return fail(h, "accumulateResults: history count must be positive");
+    int rc = omc_gpu_synchronize(h);
+    if (rc) return rc;
+    const size_t nreg = (size_t)h->P.nreg, nvox = nreg - 1;
+    if (h->res_nreg != h->P.nreg) {
+        cudaFree(h->res_dens); cudaFree(h->res_dose); cudaFree(h->res_unc);
+        h->res_dens = h->res_dose = h->res_unc = nullptr; h->res_nreg = -1;
+        CK(cudaMalloc((void **)&h->res_dens, (nvox ? nvox : 1) * sizeof(double)));
+        CK(cudaMalloc((void **)&h->res_dose, nreg * sizeof(double)));
+        CK(cudaMalloc((void **)&h->res_unc, nreg * sizeof(double)));
+        h->res_nreg = h->P.nreg;
+    }
+    CK(cudaMemcpyAsync(h->res_dens, med_densities, nvox * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    launch_results(h->P, h->accum, h->accum2, h->res_dens, iout, nhist, nbatch, h->res_dose, h->res_unc, h->stream);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dose, h->res_dose, nreg * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(unc, h->res_unc, nreg * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -12,6 +12,8 @@ void launch_test_geometry(const DevProblem &P, int n, const double *xyzuvw, cons
                           int *irnew, double *ustep_out, double *tperp, cudaStream_t stream);
 void launch_test_rng(uint32_t s0, uint32_t s1, unsigned long long hist, int n, double *out, cudaStream_t stream);
 void launch_accum(double *endep, double *accum, double *accum2, long long n, cudaStream_t stream);
+void launch_results(const DevProblem &P, const double *accum, const double *accum2, const double *dens, int iout, int nhist, int nbatch,
+                    double *dose, double *unc, cudaStream_t stream);
 
 
 // ---- omc_wavefront.cu ---------------------------------------------------------------------------
@@ -22,6 +24,7 @@ void launch_accum(double *endep, double *accum, double *accum2, long long n, cud
 struct PartQueue {
     double2 *xy, *zu, *vw, *ew;
     double2 *aux;
+    int2 *rm;        // electron queues only (else nullptr): voxel record {float rhof, int med} of region ir, med = -2: not known
     int2 *irq;
     uint4 *rng;
     unsigned cap;

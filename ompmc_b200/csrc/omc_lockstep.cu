@@ -641,4 +641,47 @@ void launch_accum(double *endep, double *accum, double *accum2, long long n, cud
     accum_kernel<<<blocks, 256, 0, stream>>>(endep, accum, accum2, n);
 }
 
+// accumulateResults(), omc_dosxyz.c:719-799, same operation order (this file is compiled with -fmad=false)
+__global__ void results_kernel(const double *__restrict__ accum, const double *__restrict__ accum2, const double *__restrict__ dens,
+                               const double *__restrict__ xb, const double *__restrict__ yb, const double *__restrict__ zb, int isize,
+                               int jsize, int ksize, int iout, double inc_fluence, double nbatch, double *__restrict__ dose,
+                               double *__restrict__ unc) {
+    const long long nvox = (long long)isize * jsize * ksize;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(v % isize), iy = (int)((v / isize) % jsize), iz = (int)(v / ((long long)isize * jsize));
+        const long long irl = v + 1;
+        double endep = accum[irl], endep2 = accum2[irl], unc_endep;
+        endep /= nbatch;
+        endep2 /= nbatch;
+        if (endep != 0.0) {
+            unc_endep = endep2 - endep * endep;
+            unc_endep /= (nbatch - 1.0);
+            unc_endep = sqrt(unc_endep) / endep;
+        } else {
+            endep = 0.0;
+            unc_endep = 0.9999999;
+        }
+        if (iout) {
+            double mass = (xb[ix + 1] - xb[ix]) * (yb[iy + 1] - yb[iy]) * (zb[iz + 1] - zb[iz]);
+            mass *= dens[v];
+            endep *= 1.602E-10 / (mass * inc_fluence);
+        } else {
+            endep /= inc_fluence;
+        }
+        if (dens[v] < 0.044) { endep = 0.0; unc_endep = 0.9999999; }   // "zero dose in air", :782-796
+        dose[irl] = endep;
+        unc[irl] = unc_endep;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { dose[0] = accum[0]; unc[0] = accum2[0]; }
+}
+void launch_results(const DevProblem &P, const double *accum, const double *accum2, const double *dens, int iout, int nhist, int nbatch,
+                    double *dose, double *unc, cudaStream_t stream) {
+    const long long nvox = (long long)P.nreg - 1;
+    int blocks = (int)((nvox + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    results_kernel<<<blocks, 256, 0, stream>>>(accum, accum2, dens, P.xb, P.yb, P.zb, P.isize, P.jsize, P.ksize, iout, (double)nhist,
+                                               (double)nbatch, dose, unc);
+}
+
 }  // namespace omc

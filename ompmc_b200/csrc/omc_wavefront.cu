@@ -103,6 +103,16 @@ __device__ __forceinline__ void q_push(const PartQueue &q, unsigned *count, Wave
     q_store(q, slot, p, g, aux, tag, aux2);
 }
 
+// push into an electron queue together with the voxel record of p.ir as the producer knows it (saves esize_kernel the
+// dependent random load ir -> voxel record, its top stall); med = -2: not known
+__device__ __forceinline__ void q_push_e(const PartQueue &q, unsigned *count, WaveCtl *ctl, const Part &p, const Rng &g, int tag,
+                                         float rhof, int med) {
+    const unsigned slot = q_reserve(count);
+    if (slot >= q.cap) { atomicAdd(&ctl->overflow, 1u); return; }
+    q_store(q, slot, p, g, 0.0, tag);
+    q.rm[slot] = make_int2(__float_as_int(rhof), med);
+}
+
 // sub-stream of a particle created by `parent` (a function of the parent's stream position only)
 __device__ __forceinline__ void child_rng(const Rng &parent, Rng &c, unsigned k) {
     unsigned s = parent.stream * 0x9E3779B1u + parent.ndraws() * 0x85EBCA77u + (k + 1u) * 0xC2B2AE3Du;
@@ -321,6 +331,7 @@ __device__ void p_interact_chunk(const DevProblem &P, const WaveArgs &A, int par
     g.align();
     const RegionRec R = load_region_w(P, p.ir);
     const int imed = R.med;
+    const float rho_f = (float)R.rhof;
     // photon splitting: scattered photons are kept for the surviving copy only and get the full weight back;
     // charged secondaries of every copy are kept with the copy's weight wt/nsplit (:2072-2093)
     const bool surv = (tag & 16) != 0;
@@ -335,15 +346,15 @@ __device__ void p_interact_chunk(const DevProblem &P, const WaveArgs &A, int par
         compton(g, p, q);
         child_rng(g, gq, 0);
         if (surv) { p.wt *= back; q_push(pn, &ctl->n_p[par ^ 1], ctl, p, g, -1.0, TAG_NONE); }
-        q_push(en, &ctl->n_e[par ^ 1], ctl, q, gq, 0.0, TAG_NONE);
+        q_push_e(en, &ctl->n_e[par ^ 1], ctl, q, gq, TAG_NONE, rho_f, imed);
     } else if (type == TAG_PAIR) {
         pair(P, g, p, q, imed);
         child_rng(g, gq, 0);
-        q_push(en, &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
-        q_push(en, &ctl->n_e[par ^ 1], ctl, q, gq, 0.0, TAG_NONE);
+        q_push_e(en, &ctl->n_e[par ^ 1], ctl, p, g, TAG_NONE, rho_f, imed);
+        q_push_e(en, &ctl->n_e[par ^ 1], ctl, q, gq, TAG_NONE, rho_f, imed);
     } else if (type == TAG_PHOTO) {
         photo(g, p, R.ecut);
-        q_push(en, &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
+        q_push_e(en, &ctl->n_e[par ^ 1], ctl, p, g, TAG_NONE, rho_f, imed);
     } else {                                                   // Rayleigh (surviving copy only): direction change
         const MedRec &M = P.med[imed];
         const double gle = log(p.e);
@@ -363,24 +374,26 @@ __device__ void e_interact_chunk(const DevProblem &P, const WaveArgs &A, int par
     Part p, q; Rng g, gq; double aux; int tag;
     q_load(A.Q.ie[par], i, p, g, P, aux, tag);
     g.align();
-    const int imed = load_region_w(P, p.ir).med;
+    double rho_d; int imed;
+    load_region_rm(P, p.ir, rho_d, imed);
+    const float rho_f = (float)rho_d;
     if (tag == TAG_MOLLER) {
         const bool created = moller(P, g, p, q, imed);
-        q_push(en, &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
+        q_push_e(en, &ctl->n_e[par ^ 1], ctl, p, g, TAG_NONE, rho_f, imed);
         if (created) {
             child_rng(g, gq, 0);
-            q_push(en, &ctl->n_e[par ^ 1], ctl, q, gq, 0.0, TAG_NONE);
+            q_push_e(en, &ctl->n_e[par ^ 1], ctl, q, gq, TAG_NONE, rho_f, imed);
         }
     } else if (tag == TAG_BREMS) {
         brems(P, g, p, q, imed, P.nsplit);                     // incl. Russian roulette of the photon when nsplit > 1
         child_rng(g, gq, 0);
-        q_push(en, &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
+        q_push_e(en, &ctl->n_e[par ^ 1], ctl, p, g, TAG_NONE, rho_f, imed);
         if (q.wt != 0.0) q_push(pn, &ctl->n_p[par ^ 1], ctl, q, gq, -1.0, TAG_NONE);
     } else if (tag == TAG_BHABHA) {
         bhabha(P, g, p, q, imed);
         child_rng(g, gq, 0);
-        q_push(en, &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
-        q_push(en, &ctl->n_e[par ^ 1], ctl, q, gq, 0.0, TAG_NONE);
+        q_push_e(en, &ctl->n_e[par ^ 1], ctl, p, g, TAG_NONE, rho_f, imed);
+        q_push_e(en, &ctl->n_e[par ^ 1], ctl, q, gq, TAG_NONE, rho_f, imed);
     } else {                                                   // annihilation in flight / at rest
         if (tag == TAG_ANNIH) annih(g, p, q, P.nsplit);
         else rannih(g, p, q, P.nsplit);
@@ -399,7 +412,7 @@ __device__ void source_chunk(const DevProblem &P, const WaveArgs &A, int par, un
     Part p;
     ensrc += init_history(P, g, p, A.ibeamlet);
     if (p.iq == 0) q_push(A.Q.p[par ^ 1], &ctl->n_p[par ^ 1], ctl, p, g, -1.0, TAG_NONE);
-    else q_push(A.Q.e[par ^ 1], &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
+    else q_push_e(A.Q.e[par ^ 1], &ctl->n_e[par ^ 1], ctl, p, g, TAG_NONE, 0.0f, -2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -448,8 +461,14 @@ __device__ __forceinline__ void es_get(const EStepQueue &S, unsigned s, Part &p,
 
 // Phase A: cut-off test, distance to the next discrete interaction, step-size restrictions.
 // Returns the step class, or CLS_NONE with `st` = -1 (finished) / TAG_RANNIH.
-__device__ __forceinline__ int estep_size(const DevProblem &P, Rng &g, Part &p, EStep &e, Tally &t, int &st) {
-    const RegionRec R = load_region_w(P, p.ir);
+__device__ __forceinline__ int estep_size(const DevProblem &P, Rng &g, Part &p, EStep &e, Tally &t, int &st, int2 rm) {
+    RegionRec R;
+    if (rm.y > -2 && P.reg8 != nullptr) {                      // voxel record handed over by the producer
+        R.rhof = (double)__int_as_float(rm.x); R.med = rm.y; R.pcut = 0.0; R.pad = 0;
+        R.ecut = (rm.y >= 0) ? P.med[rm.y].ecut : 0.0;
+    } else {
+        R = load_region_w(P, p.ir);
+    }
     const int imed = R.med, iq = p.iq, qel = (1 + iq) / 2;
     const double eie = p.e;
     t.nestep++;
@@ -590,7 +609,9 @@ __device__ __forceinline__ int estep_size(const DevProblem &P, Rng &g, Part &p, 
 }
 
 // Phase B: take the step.  Returns 0 = keep travelling, -1 = finished, TAG_* = interaction due.
-__device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, const EStep &e, int cls, Tally &t) {
+// (rho_out, med_out) = voxel record of the region the electron ends in, when known (med_out = -2 otherwise)
+__device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, const EStep &e, int cls, Tally &t, float &rho_out, int &med_out) {
+    rho_out = (float)e.rhof; med_out = e.imed;
     const int iq = p.iq, qel = (1 + iq) / 2, imed = e.imed;
     double eie = p.e, ustep, tustep = e.tustep, tvstep, de = 0.0;
     const double rhof = e.rhof, eke0 = e.eke;
@@ -645,7 +666,8 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
         if (ustep != 0.0) { p.x += p.u * ustep; p.y += p.v * ustep; p.z += p.w * ustep; }
         if (irnew != irl) {
             p.ir = irnew;
-            ecut = load_region_w(P, irnew).ecut;
+            const RegionRec R = load_region_w(P, irnew);
+            ecut = R.ecut; rho_out = (float)R.rhof; med_out = R.med;
         }
         if (eie <= ecut) {
             deposit32(P, t, p.ir, p.wt * (eie - RM));
@@ -716,6 +738,7 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
         p.ir = irnew;
         const RegionRec R = load_region_w(P, irnew);
         imed_new = R.med; ecut = R.ecut;
+        rho_out = (float)R.rhof; med_out = R.med;
     }
     if (eie <= ecut) {
         deposit32(P, t, p.ir, p.wt * (eie - RM));
@@ -796,9 +819,10 @@ __global__ void __launch_bounds__(NT, OMC_MB_ESIZE) esize_kernel(const __grid_co
         if (i < n) {
             int tag;
             q_load_part(q, i, p, tag);
+            const int2 rm = q.rm[i];
             const uint4 r = q.rng[i];
             g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
-            cls = estep_size(P, g, p, e, t, st);
+            cls = estep_size(P, g, p, e, t, st, rm);
         }
         // one reservation per (warp, class): lane 0 asks for the CH slots, lane 1 for the BCA slots, together
         const unsigned m_ch = __ballot_sync(0xffffffffu, cls == CLS_CH), m_bca = __ballot_sync(0xffffffffu, cls == CLS_BCA);
@@ -827,8 +851,9 @@ __global__ void __launch_bounds__(NT, (CLS == 1 ? OMC_MB_ECH : OMC_MB_EBCA)) edo
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Part p; Rng g; EStep e;
         es_get<OMC_WAVE_F32 && OMC_CH_BLOCK_RNG>(S, (CLS == CLS_CH) ? i : 2u * S.cap - 1u - i, p, g, e, P);
-        const int st = estep_do(P, g, p, e, CLS, t);
-        if (st == 0) q_push(A.Q.e[par ^ 1], &ctl->n_e[par ^ 1], ctl, p, g, 0.0, TAG_NONE);
+        float rho_new; int med_new;
+        const int st = estep_do(P, g, p, e, CLS, t, rho_new, med_new);
+        if (st == 0) q_push_e(A.Q.e[par ^ 1], &ctl->n_e[par ^ 1], ctl, p, g, TAG_NONE, rho_new, med_new);
         else if (st > 0) q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st);
     }
     flush_tally(P, t, 0.0);
@@ -850,31 +875,27 @@ __global__ void __launch_bounds__(NT, OMC_MB_MISC) misc_kernel(const __grid_cons
     const unsigned cnt0 = min(ctl->n_ie[par], cap), cnt1 = min(ctl->n_ip[par], cap), cnt2 = ctl->n_src, cnt3 = min(ctl->n_p[par], cap);
     Tally t = {0, 0, 0};
     double ensrc = 0.0;
-    unsigned open = 0xf, rr = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);   // (lane 0) classes that may still have chunks; pull phase
-    for (;;) {
-        unsigned type = 4, chunk = 0;
-        if (lane == 0) {
-            for (int tries = 0; tries < 4 && open; tries++) {
-                const unsigned c = rr & 3u;
-                rr++;
-                if (!(open & (1u << c))) continue;
-                const unsigned cnt = c == 0 ? cnt0 : (c == 1 ? cnt1 : (c == 2 ? cnt2 : cnt3));
-                const unsigned tk = atomicAdd(&ctl->tk[c], 1u);
-                if ((unsigned long long)tk * CH < cnt) { type = c; chunk = tk; break; }
-                open &= ~(1u << c);
-            }
+    // All warps of the machine work through the classes in the same order (heaviest first), so that at any time
+    // nearly every warp of an SM runs the same code: with each warp picking classes round-robin the kernel's top
+    // stall was instruction fetch (ncu: stall_no_instruction 5.6 warps per issue).
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        const unsigned c = (k == 0) ? 3u : (k == 1) ? 1u : (k == 2) ? 0u : 2u;
+        const unsigned cnt = c == 0 ? cnt0 : (c == 1 ? cnt1 : (c == 2 ? cnt2 : cnt3));
+        for (;;) {
+            unsigned chunk = 0;
+            if (lane == 0) chunk = atomicAdd(&ctl->tk[c], 1u);
+            chunk = __shfl_sync(0xffffffffu, chunk, 0);
+            if ((unsigned long long)chunk * CH >= cnt) break;
+            const unsigned i = chunk * CH + lane;
+            if (c == 3) {
+                if (A.woodcock) photon_chunk_wc(P, A, par, i, cnt3, t);
+                else photon_chunk(P, A, par, i, cnt3, t);
+            } else if (c == 2) source_chunk(P, A, par, i, cnt2, ensrc);
+            else if (c == 1) p_interact_chunk(P, A, par, i, cnt1);
+            else e_interact_chunk(P, A, par, i, cnt0);
+            __syncwarp();
         }
-        type = __shfl_sync(0xffffffffu, type, 0);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        if (type == 4) break;
-        const unsigned i = chunk * CH + lane;
-        if (type == 3) {
-            if (A.woodcock) photon_chunk_wc(P, A, par, i, cnt3, t);
-            else photon_chunk(P, A, par, i, cnt3, t);
-        } else if (type == 2) source_chunk(P, A, par, i, cnt2, ensrc);
-        else if (type == 1) p_interact_chunk(P, A, par, i, cnt1);
-        else e_interact_chunk(P, A, par, i, cnt0);
-        __syncwarp();
     }
     flush_tally(P, t, ensrc);
 }

@@ -218,7 +218,13 @@ int main(int argc, char **argv) {
     double etot = 0.0;
     for (int irl = 1; irl < gridsize + 1; irl++) etot += accum[irl];
     printf("Fraction of incident energy deposited in the phantom: %5.4f\n", etot / ensrc);
-    accumulate_results(&g, dens, accum, accum2, 1, nperbatch, nbatch);          /* iout = 1, nperbatch: omc_dosxyz.c:1281-1282 */
+    /* accumulateResults(iout = 1, nperbatch, nbatch), omc_dosxyz.c:1281-1282: on the device by default (the tallies are
+     * resident there); OMC_HOST_RESULTS=1 runs the host restatement above instead -- same numbers, bit for bit */
+    if (getenv("OMC_HOST_RESULTS") && atoi(getenv("OMC_HOST_RESULTS")) == 1) {
+        accumulate_results(&g, dens, accum, accum2, 1, nperbatch, nbatch);
+    } else if (omc_gpu_accumulate_results(gpu, 1, nperbatch, nbatch, dens, accum, accum2)) {
+        die("omc_gpu_accumulate_results");
+    }
     if (write_3ddose(stem, &g, accum, accum2)) return EXIT_FAILURE;
     omc_gpu_destroy(gpu);
     printf("Total execution time : %8.5f seconds\n", now_s() - tbegin);

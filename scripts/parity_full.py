@@ -91,14 +91,27 @@ def main():
         print(name, res[name], flush=True)
     g.close()
 
-    ref, kind = bench.cpu_reference_transport(prob)       # RANMAR, all host threads, the reference's own batch loop
-    ref.reset_score()
-    t0 = time.time()
-    ref.time_batches(0, per, nb)
-    dt = time.time() - t0
-    m, v, e = stats(ref.get_accum, nb)
-    runs["reference"] = (m, v, e)
-    res["reference"] = {"hist_per_s": per * nb / dt, "seconds": dt, "kind": kind, "threads": ref.num_threads()}
+    # The reference run is by far the most expensive part (minutes of all host cores); its batch statistics are
+    # cached (oracle/_ref/cache travels to the GPU box, gpurun_out/ comes back from it) and reused by later runs.
+    cname = f"ref_{wl}_{per * nb}.npz"
+    cpath = os.path.join(ROOT, "oracle", "_ref", "cache", cname)
+    if os.path.exists(cpath):
+        z = np.load(cpath)
+        runs["reference"] = (z["mean"].astype(np.float64), z["var"].astype(np.float64), float(z["ensrc"]))
+        res["reference"] = json.loads(str(z["info"]))
+        res["reference"]["cached"] = cname
+    else:
+        ref, kind = bench.cpu_reference_transport(prob)       # RANMAR, all host threads, the reference's own batch loop
+        ref.reset_score()
+        t0 = time.time()
+        ref.time_batches(0, per, nb)
+        dt = time.time() - t0
+        m, v, e = stats(ref.get_accum, nb)
+        runs["reference"] = (m, v, e)
+        res["reference"] = {"hist_per_s": per * nb / dt, "seconds": dt, "kind": kind, "threads": ref.num_threads()}
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        np.savez_compressed(os.path.join(ROOT, "gpurun_out", cname), mean=m.astype(np.float32), var=v.astype(np.float32), ensrc=e,
+                            info=json.dumps(res["reference"]))
     print("reference", res["reference"], flush=True)
 
     spacing = (10 * np.diff(ph.xbounds)[0], 10 * np.diff(ph.ybounds)[0], 10 * np.diff(ph.zbounds)[0])

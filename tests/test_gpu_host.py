@@ -41,3 +41,35 @@ def test_c_driver_matches_python_path(gpu, tmp_path, kernel):
         first = f.readline()
     assert first == "%5d%5d%5d\n" % (ph.isize, ph.jsize, ph.ksize)
     gpu.set_option("kernel", 1)
+
+
+def test_device_accumulate_results(gpu, tmp_path):
+    """omc_gpu_accumulate_results (accumulateResults() on the device, omc_dosxyz.c:719-799) against the host restatements:
+    numpy (last-ulp: other operation order) and the C driver's, whose .3ddose must be byte-identical either way."""
+    prob, ph, cfg = golden_problem("golden_tissue4_6MV")
+    gpu.load_problem(prob)
+    gpu.set_option("kernel", 0)
+    gpu.reset_tallies()
+    nhist, nb, nper = P.batch_plan("20000", "5")
+    for ib in range(nb):
+        gpu.run_batch(ib * nper, nper)
+    a, a2, _ = gpu.get_tallies()
+    for iout, n in ((1, nper), (0, nhist)):
+        d_py, u_py = P.accumulate_results(ph, a, a2, n, nb, iout=iout)
+        d_gpu, u_gpu = gpu.accumulate_results(ph.med_densities, n, nb, iout=iout)
+        np.testing.assert_allclose(d_gpu, d_py, rtol=1e-14, atol=0)
+        np.testing.assert_allclose(u_gpu, u_py, rtol=1e-13, atol=0)
+        assert ((d_gpu == 0) == (d_py == 0)).all() and ((u_gpu == 0.9999999) == (u_py == 0.9999999)).all()
+    a_again, a2_again, _ = gpu.get_tallies()
+    assert np.array_equal(a, a_again) and np.array_equal(a2, a2_again)       # the device tallies are left alone
+    gpu.set_option("kernel", 1)
+    blob = str(tmp_path / "p.blob")
+    P.save_blob(blob, prob)
+    outs = []
+    for host in ("0", "1"):
+        stem = str(tmp_path / ("out" + host))
+        r = subprocess.run([build.HOST_EXE, "-p", blob, "-n", "20000", "-b", "5", "-o", stem, "-k", "0"], capture_output=True, text=True,
+                           env=dict(os.environ, OMC_HOST_RESULTS=host))
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(open(stem + ".3ddose", "rb").read())
+    assert outs[0] == outs[1]
