@@ -217,8 +217,8 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
         const WaveCtl &s = *h->ctl_host;
         if (h->trace)
             fprintf(stderr, "wave %llu live %u n_src %u P %u E %u IP %u IE %u hist_next %llu\n", wave + every, s.live, s.n_src,
-                    s.n_p[s.parity], s.n_e[s.parity], s.n_ip[s.parity], s.n_ie[s.parity], s.hist_next);
-        if (s.overflow) {
+                    s.n_p[s.parity].v, s.n_e[s.parity].v, s.n_ip[s.parity].v, s.n_ie[s.parity].v, s.hist_next);
+        if (s.overflow.v) {
             h->err = "particle queue overflow on the device: increase option pool_size";
             rc = 7;
             break;
@@ -245,8 +245,8 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
         }
         DrainArgs D;
         D.q[0] = h->wq.p[par]; D.q[1] = h->wq.e[par]; D.q[2] = h->wq.ip[par]; D.q[3] = h->wq.ie[par];
-        D.count[0] = &h->ctl->n_p[par]; D.count[1] = &h->ctl->n_e[par]; D.count[2] = &h->ctl->n_ip[par]; D.count[3] = &h->ctl->n_ie[par];
-        D.ticket = &h->ctl->drain_ticket;
+        D.count[0] = &h->ctl->n_p[par].v; D.count[1] = &h->ctl->n_e[par].v; D.count[2] = &h->ctl->n_ip[par].v; D.count[3] = &h->ctl->n_ie[par].v;
+        D.ticket = &h->ctl->drain_ticket.v;
         launch_drain(P, D, h->stack, depth, blocks, h->stream);
         h->launches += 1;
     }

@@ -33,12 +33,20 @@ constexpr size_t PART_QUEUE_BYTES_PER_SLOT = 4 * sizeof(double2) + sizeof(int2) 
 
 constexpr int WAVE_THREADS = 128;   // threads per block == particles per chunk
 
+// A counter alone in its 256-byte line: every hot counter of a wave is hit by one atomic per warp and iteration from
+// the whole machine, and the L2 atomic unit serialises per line (all counters in ONE line made the reservation
+// atomics the top stall of esize_kernel).
+struct alignas(256) PadU {
+    unsigned v;
+};
+
 struct WaveCtl {
-    unsigned n_p[2], n_e[2], n_ip[2], n_ie[2];   // queue fill counts, [parity]: cur = parity, next = parity ^ 1
-    unsigned n_ch, n_bca;                        // step-class queues, filled and drained inside one wave
-    unsigned tk[5];                              // chunk tickets per class (misc_kernel)
+    PadU n_p[2], n_e[2], n_ip[2], n_ie[2];       // queue fill counts, [parity]: cur = parity, next = parity ^ 1
+    PadU n_ch, n_bca;                            // step-class queues, filled and drained inside one wave
+    PadU tk[5];                                  // chunk tickets per class (misc_kernel)
+    PadU overflow, drain_ticket;
     unsigned n_src;                              // histories injected by the current wave
-    unsigned parity, target, overflow, live, waves, drain_ticket;
+    unsigned parity, target, live, waves;
     unsigned long long hist_next, hist_end;
 };
 

@@ -99,7 +99,7 @@ __device__ __forceinline__ unsigned q_reserve(unsigned *count) {
 __device__ __forceinline__ void q_push(const PartQueue &q, unsigned *count, WaveCtl *ctl, const Part &p, const Rng &g, double aux,
                                        int tag, double aux2 = 0.0) {
     const unsigned slot = q_reserve(count);
-    if (slot >= q.cap) { atomicAdd(&ctl->overflow, 1u); return; }
+    if (slot >= q.cap) { atomicAdd(&ctl->overflow.v, 1u); return; }
     q_store(q, slot, p, g, aux, tag, aux2);
 }
 
@@ -108,7 +108,7 @@ __device__ __forceinline__ void q_push(const PartQueue &q, unsigned *count, Wave
 __device__ __forceinline__ void q_push_e(const PartQueue &q, unsigned *count, WaveCtl *ctl, const Part &p, const Rng &g, int tag,
                                          float rhof, int med) {
     const unsigned slot = q_reserve(count);
-    if (slot >= q.cap) { atomicAdd(&ctl->overflow, 1u); return; }
+    if (slot >= q.cap) { atomicAdd(&ctl->overflow.v, 1u); return; }
     q_store(q, slot, p, g, 0.0, tag);
     q.rm[slot] = make_int2(__float_as_int(rhof), med);
 }
@@ -236,7 +236,7 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, int par, un
             {
                 Rng gq;
                 child_rng(g, gq, (unsigned)isplit);
-                q_push(A.Q.ip[par ^ 1], &ctl->n_ip[par ^ 1], ctl, p, gq, -1.0, TAG_NONE | (surv ? 16 : 0));
+                q_push(A.Q.ip[par ^ 1], &ctl->n_ip[par ^ 1].v, ctl, p, gq, -1.0, TAG_NONE | (surv ? 16 : 0));
             }
             isplit += 1;
             const double eta_new = eta - d_eta;
@@ -245,8 +245,8 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, int par, un
             eta = eta_new;
         }
     }
-    if (hit) q_push(A.Q.ip[par ^ 1], &ctl->n_ip[par ^ 1], ctl, p, g, -1.0, TAG_NONE | 16);
-    else q_push(A.Q.p[par ^ 1], &ctl->n_p[par ^ 1], ctl, p, g, dpmfp, isplit | (isurv << 8), eta);
+    if (hit) q_push(A.Q.ip[par ^ 1], &ctl->n_ip[par ^ 1].v, ctl, p, g, -1.0, TAG_NONE | 16);
+    else q_push(A.Q.p[par ^ 1], &ctl->n_p[par ^ 1].v, ctl, p, g, dpmfp, isplit | (isurv << 8), eta);
 }
 
 // chunk P, Woodcock flight (nsplit == 1): the distance to the next TENTATIVE collision is sampled with the
@@ -317,8 +317,8 @@ __device__ void photon_chunk_wc(const DevProblem &P, const WaveArgs &A, int par,
         if (med != medc) { sigc = phot_sig0(P, med, gle); medc = med; }
         if ((double)w1 * (1.0 / 4294967296.0) * smaj < sigc * rhof) { hit = true; break; }
     }
-    if (hit) q_push(A.Q.ip[par ^ 1], &ctl->n_ip[par ^ 1], ctl, p, g, -1.0, TAG_NONE | 16);
-    else q_push(A.Q.p[par ^ 1], &ctl->n_p[par ^ 1], ctl, p, g, entered ? -2.0 : -1.0, TAG_NONE);
+    if (hit) q_push(A.Q.ip[par ^ 1], &ctl->n_ip[par ^ 1].v, ctl, p, g, -1.0, TAG_NONE | 16);
+    else q_push(A.Q.p[par ^ 1], &ctl->n_p[par ^ 1].v, ctl, p, g, entered ? -2.0 : -1.0, TAG_NONE);
 }
 
 // chunk IP: photon interactions
@@ -345,16 +345,16 @@ __device__ void p_interact_chunk(const DevProblem &P, const WaveArgs &A, int par
     if (type == TAG_COMPTON) {
         compton(g, p, q);
         child_rng(g, gq, 0);
-        if (surv) { p.wt *= back; q_push(pn, &ctl->n_p[par ^ 1], ctl, p, g, -1.0, TAG_NONE); }
-        q_push_e(en, &ctl->n_e[par ^ 1], ctl, q, gq, TAG_NONE, rho_f, imed);
+        if (surv) { p.wt *= back; q_push(pn, &ctl->n_p[par ^ 1].v, ctl, p, g, -1.0, TAG_NONE); }
+        q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, q, gq, TAG_NONE, rho_f, imed);
     } else if (type == TAG_PAIR) {
         pair(P, g, p, q, imed);
         child_rng(g, gq, 0);
-        q_push_e(en, &ctl->n_e[par ^ 1], ctl, p, g, TAG_NONE, rho_f, imed);
-        q_push_e(en, &ctl->n_e[par ^ 1], ctl, q, gq, TAG_NONE, rho_f, imed);
+        q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, p, g, TAG_NONE, rho_f, imed);
+        q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, q, gq, TAG_NONE, rho_f, imed);
     } else if (type == TAG_PHOTO) {
         photo(g, p, R.ecut);
-        q_push_e(en, &ctl->n_e[par ^ 1], ctl, p, g, TAG_NONE, rho_f, imed);
+        q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, p, g, TAG_NONE, rho_f, imed);
     } else {                                                   // Rayleigh (surviving copy only): direction change
         const MedRec &M = P.med[imed];
         const double gle = log(p.e);
@@ -362,7 +362,7 @@ __device__ void p_interact_chunk(const DevProblem &P, const WaveArgs &A, int par
         const PhotBin *B = P.phot + imed * MXGE + lgle;
         p.wt *= back;
         rayleigh(P, g, p, pwl(gle, __ldg(&B->pmax1), __ldg(&B->pmax0)), p.e);
-        q_push(pn, &ctl->n_p[par ^ 1], ctl, p, g, -1.0, TAG_NONE);
+        q_push(pn, &ctl->n_p[par ^ 1].v, ctl, p, g, -1.0, TAG_NONE);
     }
 }
 
@@ -379,27 +379,27 @@ __device__ void e_interact_chunk(const DevProblem &P, const WaveArgs &A, int par
     const float rho_f = (float)rho_d;
     if (tag == TAG_MOLLER) {
         const bool created = moller(P, g, p, q, imed);
-        q_push_e(en, &ctl->n_e[par ^ 1], ctl, p, g, TAG_NONE, rho_f, imed);
+        q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, p, g, TAG_NONE, rho_f, imed);
         if (created) {
             child_rng(g, gq, 0);
-            q_push_e(en, &ctl->n_e[par ^ 1], ctl, q, gq, TAG_NONE, rho_f, imed);
+            q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, q, gq, TAG_NONE, rho_f, imed);
         }
     } else if (tag == TAG_BREMS) {
         brems(P, g, p, q, imed, P.nsplit);                     // incl. Russian roulette of the photon when nsplit > 1
         child_rng(g, gq, 0);
-        q_push_e(en, &ctl->n_e[par ^ 1], ctl, p, g, TAG_NONE, rho_f, imed);
-        if (q.wt != 0.0) q_push(pn, &ctl->n_p[par ^ 1], ctl, q, gq, -1.0, TAG_NONE);
+        q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, p, g, TAG_NONE, rho_f, imed);
+        if (q.wt != 0.0) q_push(pn, &ctl->n_p[par ^ 1].v, ctl, q, gq, -1.0, TAG_NONE);
     } else if (tag == TAG_BHABHA) {
         bhabha(P, g, p, q, imed);
         child_rng(g, gq, 0);
-        q_push_e(en, &ctl->n_e[par ^ 1], ctl, p, g, TAG_NONE, rho_f, imed);
-        q_push_e(en, &ctl->n_e[par ^ 1], ctl, q, gq, TAG_NONE, rho_f, imed);
+        q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, p, g, TAG_NONE, rho_f, imed);
+        q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, q, gq, TAG_NONE, rho_f, imed);
     } else {                                                   // annihilation in flight / at rest
         if (tag == TAG_ANNIH) annih(g, p, q, P.nsplit);
         else rannih(g, p, q, P.nsplit);
         child_rng(g, gq, 0);
-        if (p.wt != 0.0) q_push(pn, &ctl->n_p[par ^ 1], ctl, p, g, -1.0, TAG_NONE);
-        if (q.wt != 0.0) q_push(pn, &ctl->n_p[par ^ 1], ctl, q, gq, -1.0, TAG_NONE);
+        if (p.wt != 0.0) q_push(pn, &ctl->n_p[par ^ 1].v, ctl, p, g, -1.0, TAG_NONE);
+        if (q.wt != 0.0) q_push(pn, &ctl->n_p[par ^ 1].v, ctl, q, gq, -1.0, TAG_NONE);
     }
 }
 
@@ -411,8 +411,8 @@ __device__ void source_chunk(const DevProblem &P, const WaveArgs &A, int par, un
     g.seed(P.seed0, P.seed1, ctl->hist_next + i, 0u);
     Part p;
     ensrc += init_history(P, g, p, A.ibeamlet);
-    if (p.iq == 0) q_push(A.Q.p[par ^ 1], &ctl->n_p[par ^ 1], ctl, p, g, -1.0, TAG_NONE);
-    else q_push_e(A.Q.e[par ^ 1], &ctl->n_e[par ^ 1], ctl, p, g, TAG_NONE, 0.0f, -2);
+    if (p.iq == 0) q_push(A.Q.p[par ^ 1], &ctl->n_p[par ^ 1].v, ctl, p, g, -1.0, TAG_NONE);
+    else q_push_e(A.Q.e[par ^ 1], &ctl->n_e[par ^ 1].v, ctl, p, g, TAG_NONE, 0.0f, -2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -807,7 +807,7 @@ __global__ void __launch_bounds__(NT, OMC_MB_ESIZE) esize_kernel(const __grid_co
     const int par = (int)ctl->parity;
     const PartQueue &q = A.Q.e[par];
     const EStepQueue &S = A.Q.es;
-    const unsigned n = min(ctl->n_e[par], q.cap);
+    const unsigned n = min(ctl->n_e[par].v, q.cap);
     const unsigned lane = threadIdx.x & 31u, stride = gridDim.x * blockDim.x;
     const unsigned lt = (1u << lane) - 1u;
     Tally t = {0, 0, 0};
@@ -827,15 +827,15 @@ __global__ void __launch_bounds__(NT, OMC_MB_ESIZE) esize_kernel(const __grid_co
         // one reservation per (warp, class): lane 0 asks for the CH slots, lane 1 for the BCA slots, together
         const unsigned m_ch = __ballot_sync(0xffffffffu, cls == CLS_CH), m_bca = __ballot_sync(0xffffffffu, cls == CLS_BCA);
         unsigned b = 0;
-        if (lane == 0 && m_ch) b = atomicAdd(&ctl->n_ch, (unsigned)__popc(m_ch));
-        if (lane == 1 && m_bca) b = atomicAdd(&ctl->n_bca, (unsigned)__popc(m_bca));
+        if (lane == 0 && m_ch) b = atomicAdd(&ctl->n_ch.v, (unsigned)__popc(m_ch));
+        if (lane == 1 && m_bca) b = atomicAdd(&ctl->n_bca.v, (unsigned)__popc(m_bca));
         const unsigned b_ch = __shfl_sync(0xffffffffu, b, 0), b_bca = __shfl_sync(0xffffffffu, b, 1);
         if (cls != CLS_NONE) {
             const unsigned k = (cls == CLS_CH) ? b_ch + __popc(m_ch & lt) : b_bca + __popc(m_bca & lt);
             if (k < S.cap) es_put(S, (cls == CLS_CH) ? k : 2u * S.cap - 1u - k, p, g, e);
-            else atomicAdd(&ctl->overflow, 1u);
+            else atomicAdd(&ctl->overflow.v, 1u);
         } else if (st > 0) {
-            q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st);
+            q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1].v, ctl, p, g, 0.0, st);
         }
     }
     flush_tally(P, t, 0.0);
@@ -846,15 +846,33 @@ __global__ void __launch_bounds__(NT, (CLS == 1 ? OMC_MB_ECH : OMC_MB_EBCA)) edo
     WaveCtl *ctl = A.ctl;
     const int par = (int)ctl->parity;
     const EStepQueue &S = A.Q.es;
-    const unsigned n = min(CLS == CLS_CH ? ctl->n_ch : ctl->n_bca, S.cap);
+    const unsigned n = min(CLS == CLS_CH ? ctl->n_ch.v : ctl->n_bca.v, S.cap);
+    const PartQueue &qe = A.Q.e[par ^ 1], &qi = A.Q.ie[par ^ 1];
+    const unsigned lane = threadIdx.x & 31u, stride = gridDim.x * blockDim.x, lt = (1u << lane) - 1u;
     Tally t = {0, 0, 0};
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    // warp-uniform loop; one converged reservation per warp for both output queues (lane 0: E, lane 1: IE)
+    for (unsigned base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const unsigned i = base + lane;
         Part p; Rng g; EStep e;
-        es_get<OMC_WAVE_F32 && OMC_CH_BLOCK_RNG>(S, (CLS == CLS_CH) ? i : 2u * S.cap - 1u - i, p, g, e, P);
-        float rho_new; int med_new;
-        const int st = estep_do(P, g, p, e, CLS, t, rho_new, med_new);
-        if (st == 0) q_push_e(A.Q.e[par ^ 1], &ctl->n_e[par ^ 1], ctl, p, g, TAG_NONE, rho_new, med_new);
-        else if (st > 0) q_push(A.Q.ie[par ^ 1], &ctl->n_ie[par ^ 1], ctl, p, g, 0.0, st);
+        float rho_new = 0.0f; int med_new = -2, st = -1;
+        if (i < n) {
+            es_get<OMC_WAVE_F32 && OMC_CH_BLOCK_RNG>(S, (CLS == CLS_CH) ? i : 2u * S.cap - 1u - i, p, g, e, P);
+            st = estep_do(P, g, p, e, CLS, t, rho_new, med_new);
+        }
+        const unsigned m_e = __ballot_sync(0xffffffffu, st == 0), m_i = __ballot_sync(0xffffffffu, st > 0);
+        unsigned b = 0;
+        if (lane == 0 && m_e) b = atomicAdd(&ctl->n_e[par ^ 1].v, (unsigned)__popc(m_e));
+        if (lane == 1 && m_i) b = atomicAdd(&ctl->n_ie[par ^ 1].v, (unsigned)__popc(m_i));
+        const unsigned b_e = __shfl_sync(0xffffffffu, b, 0), b_i = __shfl_sync(0xffffffffu, b, 1);
+        if (st == 0) {
+            const unsigned slot = b_e + __popc(m_e & lt);
+            if (slot < qe.cap) { q_store(qe, slot, p, g, 0.0, TAG_NONE); qe.rm[slot] = make_int2(__float_as_int(rho_new), med_new); }
+            else atomicAdd(&ctl->overflow.v, 1u);
+        } else if (st > 0) {
+            const unsigned slot = b_i + __popc(m_i & lt);
+            if (slot < qi.cap) q_store(qi, slot, p, g, 0.0, st);
+            else atomicAdd(&ctl->overflow.v, 1u);
+        }
     }
     flush_tally(P, t, 0.0);
 }
@@ -872,7 +890,7 @@ __global__ void __launch_bounds__(NT, OMC_MB_MISC) misc_kernel(const __grid_cons
     // chunk classes: 0 electron interactions, 1 photon interactions, 2 source, 3 photon flights
     // (counts are clamped to the queue capacity: after an overflow the counters run past it)
     const unsigned cap = A.Q.p[0].cap;
-    const unsigned cnt0 = min(ctl->n_ie[par], cap), cnt1 = min(ctl->n_ip[par], cap), cnt2 = ctl->n_src, cnt3 = min(ctl->n_p[par], cap);
+    const unsigned cnt0 = min(ctl->n_ie[par].v, cap), cnt1 = min(ctl->n_ip[par].v, cap), cnt2 = ctl->n_src, cnt3 = min(ctl->n_p[par].v, cap);
     Tally t = {0, 0, 0};
     double ensrc = 0.0;
     // All warps of the machine work through the classes in the same order (heaviest first), so that at any time
@@ -884,7 +902,7 @@ __global__ void __launch_bounds__(NT, OMC_MB_MISC) misc_kernel(const __grid_cons
         const unsigned cnt = c == 0 ? cnt0 : (c == 1 ? cnt1 : (c == 2 ? cnt2 : cnt3));
         for (;;) {
             unsigned chunk = 0;
-            if (lane == 0) chunk = atomicAdd(&ctl->tk[c], 1u);
+            if (lane == 0) chunk = atomicAdd(&ctl->tk[c].v, 1u);
             chunk = __shfl_sync(0xffffffffu, chunk, 0);
             if ((unsigned long long)chunk * CH >= cnt) break;
             const unsigned i = chunk * CH + lane;
@@ -906,16 +924,16 @@ __global__ void advance_kernel(const __grid_constant__ DevProblem P, WaveCtl *c)
     const int par = (int)c->parity, nxt = par ^ 1;
     c->hist_next += c->n_src;
     P.counters->histories += c->n_src;
-    c->n_p[par] = 0; c->n_e[par] = 0; c->n_ip[par] = 0; c->n_ie[par] = 0; c->n_ch = 0; c->n_bca = 0;
-    const unsigned live = c->n_p[nxt] + c->n_e[nxt] + c->n_ip[nxt] + c->n_ie[nxt];
+    c->n_p[par].v = 0; c->n_e[par].v = 0; c->n_ip[par].v = 0; c->n_ie[par].v = 0; c->n_ch.v = 0; c->n_bca.v = 0;
+    const unsigned live = c->n_p[nxt].v + c->n_e[nxt].v + c->n_ip[nxt].v + c->n_ie[nxt].v;
     const unsigned long long left = c->hist_end - c->hist_next;
     const unsigned room = (live < c->target) ? c->target - live : 0u;
     c->n_src = (unsigned)(left < (unsigned long long)room ? left : (unsigned long long)room);
     c->live = live;
-    c->tk[0] = c->tk[1] = c->tk[2] = c->tk[3] = c->tk[4] = 0;
+    c->tk[0].v = c->tk[1].v = c->tk[2].v = c->tk[3].v = c->tk[4].v = 0;
     c->parity = (unsigned)nxt;
     c->waves += 1;
-    if (c->overflow) P.counters->errors = c->overflow;
+    if (c->overflow.v) P.counters->errors = c->overflow.v;
 }
 
 // fold the fp32 chunk grid into the fp64 batch grid
