@@ -38,6 +38,8 @@ WORKLOADS = {
     # name: (media blob, phantom builder, spectrum key, collimator, ssd, ecut)
     "prostate6mv": dict(media="media_700_tissue4.blob", phantom=lambda: P.tissue_phantom((183, 183, 90), (0.3, 0.3, 0.3), "prostate"),
                         spectrum="var_6MV", coll=(-5, 5, -5, 5), ssd=90.0, ecut=0.700, desc="PROSTATE-like 183x183x90 @3mm, 4 media 700icru, var_6MV, 10x10 cm2, SSD 90, nsplit 1"),
+    "tg119_6mv": dict(media="media_700_tissue4.blob", phantom=lambda: P.tissue_phantom((167, 167, 129), (0.3, 0.3, 0.25), "tg119"),
+                      spectrum="var_6MV", coll=(-5, 5, -5, 5), ssd=90.0, ecut=0.700, desc="TG119-like 167x167x129 @3x3x2.5mm, 4 media 700icru, var_6MV, 10x10 cm2, SSD 90, nsplit 1"),
     "water6mv": dict(media="media_700_water.blob", phantom=lambda: P.water_phantom("H2O700ICRU", (61, 61, 60), (0.5, 0.5, 0.5)),
                      spectrum="mohan6", coll=(-5, 5, -5, 5), ssd=100.0, ecut=0.700, desc="WATER 61x61x60 @5mm, H2O700ICRU, mohan6, 10x10 cm2, SSD 100, nsplit 1"),
 }

@@ -65,8 +65,8 @@ struct omc_gpu_ctx {
     int max_virtual = 8;          // Woodcock: tentative collisions per photon per wave
     unsigned long long waves = 0;
     int trace = 0, use_graph = 1, overlap = 1, source_kind = 0;
-    cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream2 = nullptr, stream3 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork3 = nullptr, ev_join3 = nullptr;
     unsigned drain_threshold = 32768;
     // omc_gpu_accumulate_results scratch
     double *res_dens = nullptr, *res_dose = nullptr, *res_unc = nullptr;
@@ -171,8 +171,11 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
     }
     if (!h->stream2) {
         CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_fork3, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
     }
     if (!h->ctl) {
         CK(cudaMalloc((void **)&h->ctl, sizeof(WaveCtl)));
@@ -191,6 +194,9 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
     L.max_cross = h->max_cross; L.electron_iters = h->electron_iters; L.ibeamlet = ibeamlet;
     L.woodcock = (h->photon_tracking == 1 && P.nsplit == 1) ? 1 : 0;
     L.max_virtual = h->max_virtual > 0 ? ((h->max_virtual + 1) & ~1) : 8;   // even: whole Philox blocks, so results do not depend on it
+    WaveStreams W;
+    W.s = h->stream; W.s2 = h->overlap ? h->stream2 : nullptr; W.s3 = h->stream3;
+    W.fork = h->ev_fork; W.join = h->ev_join; W.fork3 = h->ev_fork3; W.join3 = h->ev_join3;
     const int every = h->check_every > 0 ? h->check_every : 1;
     // `every` waves are captured once into a CUDA graph (all launch parameters are wave-invariant: cur/next
     // parity lives in WaveCtl on the device), so the host issues one graph launch per `every` waves
@@ -198,7 +204,7 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
     cudaGraphExec_t gexec = nullptr;
     if (h->use_graph) {
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        for (int k = 0; k < every; k++) launch_wave(P, h->ctl, h->wq, L, h->stream, h->overlap ? h->stream2 : nullptr, h->ev_fork, h->ev_join);
+        for (int k = 0; k < every; k++) launch_wave(P, h->ctl, h->wq, L, W);
         CK(cudaStreamEndCapture(h->stream, &graph));
         CK(cudaGraphInstantiate(&gexec, graph, 0));
     }
@@ -208,7 +214,7 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
         if (gexec) {
             CK(cudaGraphLaunch(gexec, h->stream));
         } else {
-            for (int k = 0; k < every; k++) launch_wave(P, h->ctl, h->wq, L, h->stream, h->overlap ? h->stream2 : nullptr, h->ev_fork, h->ev_join);
+            for (int k = 0; k < every; k++) launch_wave(P, h->ctl, h->wq, L, W);
         }
         h->launches += 5ull * every;
         h->waves += every;
@@ -300,7 +306,10 @@ void omc_gpu_destroy(omc_gpu_handle h) {
     cudaFree(h->P.endep); cudaFree(h->P.endep32); cudaFree(h->accum); cudaFree(h->accum2);
     cudaFree(h->P.counters); cudaFree(h->P.ensrc); cudaFree(h->stack); cudaFree(h->records);
     cudaFree(h->res_dens); cudaFree(h->res_dose); cudaFree(h->res_unc);
-    if (h->stream2) { cudaStreamDestroy(h->stream2); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
+    if (h->stream2) {
+        cudaStreamDestroy(h->stream2); cudaStreamDestroy(h->stream3);
+        cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_fork3); cudaEventDestroy(h->ev_join3);
+    }
     cudaStreamDestroy(h->stream);
     delete h;
 }

@@ -83,8 +83,13 @@ struct DrainArgs {
     unsigned *ticket;
 };
 void launch_drain(const DevProblem &P, const DrainArgs &D, Part *stack, int depth, int blocks, cudaStream_t stream);
-void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, cudaStream_t s, cudaStream_t s2,
-                 cudaEvent_t fork, cudaEvent_t join);
+// streams / events of one wave: s = electron chain; s2 = misc_kernel; s3 = the boundary-crossing step kernel, which runs
+// beside the condensed-history one (both only read the step queue); s2 == nullptr: everything in order on s
+struct WaveStreams {
+    cudaStream_t s, s2, s3;
+    cudaEvent_t fork, join, fork3, join3;
+};
+void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, const WaveStreams &W);
 void launch_flush(float *g32, double *g64, long long n, cudaStream_t s);
 
 }  // namespace omc

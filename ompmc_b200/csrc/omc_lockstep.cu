@@ -541,7 +541,10 @@ __global__ void __launch_bounds__(128) drain_kernel(const __grid_constant__ DevP
             const RegionRec R = load_region(P, p.ir);
             const int imed = R.med;
             int type = tag & 15;                              // (bit 4 = survivor flag of photon splitting, always set here)
-            if (type == 0) type = photon_interaction_type(P, c.g, imed, log(p.e), p.e);   // choice deferred by the flight chunk
+            if (type == 0) {                                  // choice deferred by the flight chunk
+                const double r1 = c.g.next(), r2 = c.g.next();
+                type = photon_interaction_type(P, imed, log(p.e), p.e, r1, r2);
+            }
             switch (type) {
                 case 1: compton(c.g, p, s2); two = true; break;
                 case 2: pair(P, c.g, p, s2, imed); two = true; break;

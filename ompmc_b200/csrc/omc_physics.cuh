@@ -137,14 +137,14 @@ __device__ __forceinline__ double phot_sig0(const DevProblem &P, int imed, doubl
 }
 
 // interaction choice at a photon interaction site, photon() src/ompmc.c:2027-2067: 1 Compton, 2 pair, 3 photo, 4 Rayleigh
-__device__ __forceinline__ int photon_interaction_type(const DevProblem &P, Rng &g, int imed, double gle, double eig) {
+// (r1, r2: the Rayleigh test and the branching draw)
+__device__ __forceinline__ int photon_interaction_type(const DevProblem &P, int imed, double gle, double eig, double r1, double r2) {
     const MedRec &M = P.med[imed];
     const int lgle = (int)(gle * M.ge1 + M.ge0) - 1;
     const PhotBin *B = P.phot + imed * MXGE + lgle;
     const double coh = pwl(gle, __ldg(&B->cohe1), __ldg(&B->cohe0));
-    double r = g.next();
-    if (r <= 1.0 - coh) return 4;
-    r = g.next();
+    if (r1 <= 1.0 - coh) return 4;
+    const double r = r2;
     const double gbr1 = pwl(gle, __ldg(&B->gbr11), __ldg(&B->gbr10));
     if (r <= gbr1 && eig > 2.0 * RM) return 2;
     const double gbr2 = pwl(gle, __ldg(&B->gbr21), __ldg(&B->gbr20));
@@ -283,8 +283,16 @@ OMC_FN void rayleigh(const DevProblem &P, Rng &g, Part &p, double pmax, double e
             r0 = g.next(); r0 *= pmax;
             int ibin = (int)r0 * dwi;
             int ib = __ldg(P.ray_i + ibin) - 1;
-            if ((__ldg(P.ray_i + ibin + 1) - 1) > ib)
-                while (r0 >= __ldg(P.ray_fcum + ib + 1)) ib++;
+            if ((__ldg(P.ray_i + ibin + 1) - 1) > ib) {
+                // the reference scans `while (r0 >= fcum[ib+1]) ib++` -- up to 99 dependent loads because ibin == 0
+                // always (Q2); fcum is a cumulative distribution, so bisection finds the same ib
+                int lo = ib, hi = OMC_MXRAYFF - 2;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (r0 < __ldg(P.ray_fcum + mid + 1)) hi = mid; else lo = mid + 1;
+                }
+                ib = lo;
+            }
             r0 = (r0 - __ldg(P.ray_fcum + ib)) * __ldg(P.ray_c + ib);
             xv = __ldg(P.ray_xgrid + ib) * exp(log(1.0 + r0) * __ldg(P.ray_b + ib));
         } while (xv >= xmax);

@@ -574,6 +574,110 @@ __device__ __forceinline__ double msdist_b(const DevProblem &P, Rng &g, const Pa
 }
 
 // ---------------------------------------------------------------------------------------------
+// Block-draw versions of the two interactions that make up 95 % of all discrete interactions at 6 MV (Compton 3.3
+// and Moller 4.9 per history): same fp64 sampling code as compton() / moller() in omc_physics.cuh
+// (src/ompmc.c:1670-1783, 4359-4435), random numbers from whole Philox blocks so that the generator state stays in
+// registers (one block per Klein-Nishina try, two Moller tries or two azimuth tries per block).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double u32d(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }
+
+// selectAzimuthalAngle(), src/ompmc.c:101-122
+__device__ __forceinline__ void azimuth_blk(Rng &g, double &cphi, double &sphi) {
+    for (;;) {
+        const uint4 b = g.block();
+        double x = 2.0 * u32d(b.x) - 1.0, y = u32d(b.y), x2 = x * x, y2 = y * y, r2 = x2 + y2;
+        if (r2 > 1.0 || r2 == 0.0) {
+            x = 2.0 * u32d(b.z) - 1.0; y = u32d(b.w); x2 = x * x; y2 = y * y; r2 = x2 + y2;
+            if (r2 > 1.0 || r2 == 0.0) continue;
+        }
+        r2 = 1.0 / r2;
+        cphi = (x2 - y2) * r2;
+        sphi = 2.0 * x * y * r2;
+        return;
+    }
+}
+
+__device__ __forceinline__ void compton_b(Rng &g, Part &p, Part &q) {
+    const double eig = p.e, ko = p.e / RM;
+    const double broi = 1.0 + 2.0 * ko, bro = 1.0 / broi;
+    double sinthe = 0.0, costhe = 0.0, br, aux, rejf3, temp;
+    const double alph1 = log(broi), alph2 = ko * (broi + 1.0) * (bro * bro), alpha = alph1 + alph2, rejmax = broi + bro;
+    do {
+        const uint4 b = g.block();
+        const double r1 = u32d(b.x), r2 = u32d(b.y), r3 = u32d(b.z);
+        if (ko > 2.0) {
+            if (r1 * alpha < alph1) br = exp(alph1 * r2) * bro;
+            else br = sqrt(r2 * (broi * broi) + (1.0 - r2)) * bro;
+            temp = (1.0 - br) / (ko * br);
+            sinthe = fmax(0.0, temp * (2.0 - temp));
+            aux = 1.0 + (br * br);
+            rejf3 = aux - br * sinthe;
+            if (r3 * aux > rejf3) { br = -1.0; continue; }
+        } else {
+            br = bro + (1.0 - bro) * r1;
+            temp = (1.0 - br) / (ko * br);
+            sinthe = fmax(0.0, temp * (2.0 - temp));
+            rejf3 = 1.0 + br * br - br * sinthe;
+            if (r2 * br * rejmax > rejf3) { br = -1.0; continue; }
+        }
+    } while ((br < bro) || (br > 1));
+    costhe = 1.0 - temp;
+    sinthe = sqrt(sinthe);
+    const double esg = br * eig, ese = eig - esg + RM;
+    p.e = esg;
+    Frame f;
+    azimuth_blk(g, f.cphi, f.sphi);
+    f.A = p.u; f.B = p.v; f.C = p.w;
+    frame_apply(f, costhe, sinthe, p);
+    aux = 1.0 + br * br - 2.0 * br * costhe;
+    if (aux > 1.0E-8) {
+        costhe = (1.0 - br * costhe) / sqrt(aux);
+        sinthe = (1.0 - costhe) * (1.0 + costhe);
+        sinthe = (sinthe > 0.0) ? -sqrt(sinthe) : 0.0;
+    } else {
+        costhe = 0.0; sinthe = -1.0;
+    }
+    uphi32(f, costhe, sinthe, q, p);
+    q.e = ese;
+    q.iq = -1;
+}
+
+__device__ __forceinline__ bool moller_b(const DevProblem &P, Rng &g, Part &p, Part &q, int imed) {
+    const MedRec &M = P.med[imed];
+    const double eie = p.e, ekin = eie - RM, te = M.te;
+    if (ekin <= 2.0 * te) return false;
+    const double t0 = ekin / RM, e0 = t0 + 1.0, extrae = eie - M.thmoll;
+    const double g2 = (t0 * t0) / (e0 * e0), g3 = (2.0 * t0 + 1.0) / (e0 * e0);
+    const double gmax = (1.0 + 1.25 * g2);
+    double br;
+    for (;;) {
+        const uint4 b = g.block();
+        br = te / (ekin - extrae * u32d(b.x));
+        double r = br / (1.0 - br);
+        if (!(u32d(b.y) * gmax > (1.0 + g2 * (br * br) + r * (r - g3)))) break;
+        br = te / (ekin - extrae * u32d(b.z));
+        r = br / (1.0 - br);
+        if (!(u32d(b.w) * gmax > (1.0 + g2 * (br * br) + r * (r - g3)))) break;
+    }
+    const double ekse2 = br * ekin, ese1 = eie - ekse2, ese2 = ekse2 + RM;
+    p.e = ese1;
+    q.e = ese2;
+    const double h1 = (eie + RM) / ekin;
+    double costh = h1 * (ese1 - RM) / (ese1 + RM);
+    double sinthe = sqrt(1.0 - costh), costhe = sqrt(costh);
+    Frame f;
+    azimuth_blk(g, f.cphi, f.sphi);
+    f.A = p.u; f.B = p.v; f.C = p.w;
+    frame_apply(f, costhe, sinthe, p);
+    q.iq = -1;
+    costh = h1 * (ese2 - RM) / (ese2 + RM);
+    sinthe = -sqrt(1.0 - costh);
+    costhe = sqrt(costh);
+    uphi32(f, costhe, sinthe, q, p);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // CSDA helpers in mixed precision: energies and path lengths are fp64 quantities, but the series below only
 // needs RATIOS to ~1e-7, so the logs / divisions (software sequences in fp64) are done in fp32.  Differences of
 // nearly equal energies are taken in fp64 BEFORE the conversion (no cancellation in fp32).

@@ -39,6 +39,9 @@
 #ifndef OMC_CH_BLOCK_RNG
 #define OMC_CH_BLOCK_RNG 1   // 1: condensed-history step with whole-block draws, Rng in registers (msdist_b); 0: msdist_f
 #endif
+#ifndef OMC_PREFETCH
+#define OMC_PREFETCH 1       // 1: the electron kernels prefetch the queue records of their NEXT loop iteration into L1
+#endif
 #ifndef OMC_WARP_AGGREGATE_DOSE
 #define OMC_WARP_AGGREGATE_DOSE 0
 #endif
@@ -83,6 +86,22 @@ __device__ __forceinline__ void q_store(const PartQueue &q, unsigned i, const Pa
     if (q.aux) q.aux[i] = make_double2(aux, aux2);             // photon queues only
     q.irq[i] = make_int2(p.ir, (p.iq & 0xffff) | (tag << 16));
     q.rng[i] = make_uint4(g.h0, g.h1, g.stream, g.ndraws());
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *p) {
+#if OMC_PREFETCH
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
+// the record of slot i of a particle queue / of the step queue (what the next grid-stride iteration will load)
+__device__ __forceinline__ void q_prefetch_e(const PartQueue &q, unsigned i) {
+    prefetch_l1(q.irq + i); prefetch_l1(q.rm + i); prefetch_l1(q.xy + i); prefetch_l1(q.zu + i); prefetch_l1(q.vw + i);
+    prefetch_l1(q.ew + i); prefetch_l1(q.rng + i);
+}
+__device__ __forceinline__ void es_prefetch(const EStepQueue &S, unsigned s) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) prefetch_l1(S.v[k] + s);
+    prefetch_l1(S.f + s); prefetch_l1(S.m + s); prefetch_l1(S.rng + s);
 }
 
 // warp-aggregated slot reservation: one atomic per (warp, queue) instead of one per lane
@@ -326,9 +345,12 @@ __device__ void p_interact_chunk(const DevProblem &P, const WaveArgs &A, int par
     if (i >= n) return;
     WaveCtl *ctl = A.ctl;
     const PartQueue &pn = A.Q.p[par ^ 1], &en = A.Q.e[par ^ 1];
-    Part p, q; Rng g, gq; double aux; int tag;
-    q_load(A.Q.ip[par], i, p, g, P, aux, tag);
-    g.align();
+    Part p, q; Rng g, gq; int tag;
+    q_load_part(A.Q.ip[par], i, p, tag);
+    {
+        const uint4 r = A.Q.ip[par].rng[i];
+        g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
+    }
     const RegionRec R = load_region_w(P, p.ir);
     const int imed = R.med;
     const float rho_f = (float)R.rhof;
@@ -338,31 +360,34 @@ __device__ void p_interact_chunk(const DevProblem &P, const WaveArgs &A, int par
     int type = tag & 15;
     const double back = (double)P.nsplit;
     if (type == TAG_NONE) {                                    // interaction choice, photon() :2027-2067
-        type = photon_interaction_type(P, g, imed, log(p.e), p.e);
+        const uint4 b = g.block();
+        type = photon_interaction_type(P, imed, log(p.e), p.e, u32d(b.x), u32d(b.y));
         if (!surv && type == TAG_RAYLEIGH) return;             // a Rayleigh-scattered non-survivor is simply dropped, :2030-2034
-        g.align();
     }
-    if (type == TAG_COMPTON) {
-        compton(g, p, q);
+    if (type == TAG_COMPTON) {                                 // the common one: block draws, generator in registers
+        compton_b(g, p, q);
         child_rng(g, gq, 0);
         if (surv) { p.wt *= back; q_push(pn, &ctl->n_p[par ^ 1].v, ctl, p, g, -1.0, TAG_NONE); }
         q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, q, gq, TAG_NONE, rho_f, imed);
-    } else if (type == TAG_PAIR) {
-        pair(P, g, p, q, imed);
-        child_rng(g, gq, 0);
-        q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, p, g, TAG_NONE, rho_f, imed);
+        return;
+    }
+    Rng g2 = g;                                                // rare ones: the word-by-word samplers shared with the lock-step kernel
+    if (type == TAG_PAIR) {
+        pair(P, g2, p, q, imed);
+        child_rng(g2, gq, 0);
+        q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, p, g2, TAG_NONE, rho_f, imed);
         q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, q, gq, TAG_NONE, rho_f, imed);
     } else if (type == TAG_PHOTO) {
-        photo(g, p, R.ecut);
-        q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, p, g, TAG_NONE, rho_f, imed);
+        photo(g2, p, R.ecut);
+        q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, p, g2, TAG_NONE, rho_f, imed);
     } else {                                                   // Rayleigh (surviving copy only): direction change
         const MedRec &M = P.med[imed];
         const double gle = log(p.e);
         const int lgle = (int)(gle * M.ge1 + M.ge0) - 1;
         const PhotBin *B = P.phot + imed * MXGE + lgle;
         p.wt *= back;
-        rayleigh(P, g, p, pwl(gle, __ldg(&B->pmax1), __ldg(&B->pmax0)), p.e);
-        q_push(pn, &ctl->n_p[par ^ 1].v, ctl, p, g, -1.0, TAG_NONE);
+        rayleigh(P, g2, p, pwl(gle, __ldg(&B->pmax1), __ldg(&B->pmax0)), p.e);
+        q_push(pn, &ctl->n_p[par ^ 1].v, ctl, p, g2, -1.0, TAG_NONE);
     }
 }
 
@@ -371,34 +396,40 @@ __device__ void e_interact_chunk(const DevProblem &P, const WaveArgs &A, int par
     if (i >= n) return;
     WaveCtl *ctl = A.ctl;
     const PartQueue &pn = A.Q.p[par ^ 1], &en = A.Q.e[par ^ 1];
-    Part p, q; Rng g, gq; double aux; int tag;
-    q_load(A.Q.ie[par], i, p, g, P, aux, tag);
-    g.align();
+    Part p, q; Rng g, gq; int tag;
+    q_load_part(A.Q.ie[par], i, p, tag);
+    {
+        const uint4 r = A.Q.ie[par].rng[i];
+        g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
+    }
     double rho_d; int imed;
     load_region_rm(P, p.ir, rho_d, imed);
     const float rho_f = (float)rho_d;
-    if (tag == TAG_MOLLER) {
-        const bool created = moller(P, g, p, q, imed);
+    if (tag == TAG_MOLLER) {                                   // the common one: block draws, generator in registers
+        const bool created = moller_b(P, g, p, q, imed);
         q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, p, g, TAG_NONE, rho_f, imed);
         if (created) {
             child_rng(g, gq, 0);
             q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, q, gq, TAG_NONE, rho_f, imed);
         }
-    } else if (tag == TAG_BREMS) {
-        brems(P, g, p, q, imed, P.nsplit);                     // incl. Russian roulette of the photon when nsplit > 1
-        child_rng(g, gq, 0);
-        q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, p, g, TAG_NONE, rho_f, imed);
+        return;
+    }
+    Rng g2 = g;
+    if (tag == TAG_BREMS) {
+        brems(P, g2, p, q, imed, P.nsplit);                    // incl. Russian roulette of the photon when nsplit > 1
+        child_rng(g2, gq, 0);
+        q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, p, g2, TAG_NONE, rho_f, imed);
         if (q.wt != 0.0) q_push(pn, &ctl->n_p[par ^ 1].v, ctl, q, gq, -1.0, TAG_NONE);
     } else if (tag == TAG_BHABHA) {
-        bhabha(P, g, p, q, imed);
-        child_rng(g, gq, 0);
-        q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, p, g, TAG_NONE, rho_f, imed);
+        bhabha(P, g2, p, q, imed);
+        child_rng(g2, gq, 0);
+        q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, p, g2, TAG_NONE, rho_f, imed);
         q_push_e(en, &ctl->n_e[par ^ 1].v, ctl, q, gq, TAG_NONE, rho_f, imed);
     } else {                                                   // annihilation in flight / at rest
-        if (tag == TAG_ANNIH) annih(g, p, q, P.nsplit);
-        else rannih(g, p, q, P.nsplit);
-        child_rng(g, gq, 0);
-        if (p.wt != 0.0) q_push(pn, &ctl->n_p[par ^ 1].v, ctl, p, g, -1.0, TAG_NONE);
+        if (tag == TAG_ANNIH) annih(g2, p, q, P.nsplit);
+        else rannih(g2, p, q, P.nsplit);
+        child_rng(g2, gq, 0);
+        if (p.wt != 0.0) q_push(pn, &ctl->n_p[par ^ 1].v, ctl, p, g2, -1.0, TAG_NONE);
         if (q.wt != 0.0) q_push(pn, &ctl->n_p[par ^ 1].v, ctl, q, gq, -1.0, TAG_NONE);
     }
 }
@@ -819,6 +850,7 @@ __global__ void __launch_bounds__(NT, OMC_MB_ESIZE) esize_kernel(const __grid_co
         if (i < n) {
             int tag;
             q_load_part(q, i, p, tag);
+            if (i + stride < n) q_prefetch_e(q, i + stride);
             const int2 rm = q.rm[i];
             const uint4 r = q.rng[i];
             g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
@@ -857,6 +889,7 @@ __global__ void __launch_bounds__(NT, (CLS == 1 ? OMC_MB_ECH : OMC_MB_EBCA)) edo
         float rho_new = 0.0f; int med_new = -2, st = -1;
         if (i < n) {
             es_get<OMC_WAVE_F32 && OMC_CH_BLOCK_RNG>(S, (CLS == CLS_CH) ? i : 2u * S.cap - 1u - i, p, g, e, P);
+            if (i + stride < n) es_prefetch(S, (CLS == CLS_CH) ? i + stride : 2u * S.cap - 1u - (i + stride));
             st = estep_do(P, g, p, e, CLS, t, rho_new, med_new);
         }
         const unsigned m_e = __ballot_sync(0xffffffffu, st == 0), m_i = __ballot_sync(0xffffffffu, st > 0);
@@ -956,22 +989,23 @@ void wave_blocks_per_sm(int out[4]) {
 }
 
 // One wave.  misc_kernel (photons / interactions / source) and the electron chain touch disjoint inputs and
-// append to the same output queues through atomic counters, so they run as two parallel branches (second
-// stream `s2` forked and joined with events; under stream capture this becomes a fork/join in the graph).
-void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, cudaStream_t s, cudaStream_t s2,
-                 cudaEvent_t fork, cudaEvent_t join) {
+// append to the same output queues through atomic counters, so they run as parallel branches; so do the two step
+// kernels after esize_kernel (forked and joined with events; under stream capture this becomes a fork/join graph).
+void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, const WaveStreams &W) {
     WaveArgs A;
     A.ctl = ctl; A.Q = Q; A.max_cross = L.max_cross; A.electron_iters = L.electron_iters; A.ibeamlet = L.ibeamlet;
     A.woodcock = L.woodcock; A.max_virtual = L.max_virtual;
-    const bool par = (s2 != nullptr);
-    cudaStream_t sm = par ? s2 : s;
-    if (par) { cudaEventRecord(fork, s); cudaStreamWaitEvent(s2, fork, 0); }
+    const bool par = (W.s2 != nullptr);
+    cudaStream_t s = W.s, sm = par ? W.s2 : s, sb = par ? W.s3 : s;
+    if (par) { cudaEventRecord(W.fork, s); cudaStreamWaitEvent(W.s2, W.fork, 0); }
     misc_kernel<<<L.blocks[0], NT, 0, sm>>>(P, A);
-    if (par) cudaEventRecord(join, s2);
+    if (par) cudaEventRecord(W.join, W.s2);
     esize_kernel<<<L.blocks[1], NT, 0, s>>>(P, A);
+    if (par) { cudaEventRecord(W.fork3, s); cudaStreamWaitEvent(W.s3, W.fork3, 0); }
+    edo_kernel<CLS_BCA><<<L.blocks[3], NT, 0, sb>>>(P, A);
+    if (par) cudaEventRecord(W.join3, W.s3);
     edo_kernel<CLS_CH><<<L.blocks[2], NT, 0, s>>>(P, A);
-    edo_kernel<CLS_BCA><<<L.blocks[3], NT, 0, s>>>(P, A);
-    if (par) cudaStreamWaitEvent(s, join, 0);
+    if (par) { cudaStreamWaitEvent(s, W.join, 0); cudaStreamWaitEvent(s, W.join3, 0); }
     advance_kernel<<<1, 32, 0, s>>>(P, ctl);
 }
 
