@@ -169,7 +169,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="prostate6mv", choices=list(WORKLOADS))
-    ap.add_argument("--hist-per-step", type=int, default=1 << 24, help="histories per step PER GPU")
+    # one step = one statistical batch; 1 % sigma above half Dmax needs ~6e8 histories on this workload = 10 batches of ~6e7
+    ap.add_argument("--hist-per-step", type=int, default=1 << 26, help="histories per step PER GPU")
     ap.add_argument("--kernel", type=int, default=-1, help="-1 production default, 0 lock-step, 1 wavefront")
     ap.add_argument("--nsplit", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")

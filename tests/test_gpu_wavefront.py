@@ -166,7 +166,7 @@ def test_wavefront_scheduling_independence(gpu):
         gpu.reset_tallies()
         gpu.run_histories(0, 50000)
         runs.append((gpu.get_endep()[1:], gpu.counters()))
-    gpu.set_option("drain_threshold", 32768)
+    gpu.set_option("drain_threshold", 8192)
     assert runs[0][1] == runs[1][1]
     np.testing.assert_allclose(runs[0][0], runs[1][0], rtol=2e-4, atol=1e-4 * g0.max())
     assert abs(runs[0][0].sum() - g0.sum()) < 0.01 * g0.sum()
