@@ -101,6 +101,28 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class quiet_stdout:
+    """The reference prints from C (printf: 'RNG seeds ...', 'Warning!, negative ustep'); keep it off our stdout,
+    where exactly one JSON line is expected."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+        return self
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved); os.close(self.null)
+        return False
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -119,13 +141,18 @@ def alg_bytes_per_history(work: dict) -> float:
 def cpu_reference_transport(prob):
     """The unmodified reference on all host threads when oracle/_ref was built, else the oracle port."""
     from oracle import cpudrv
+    # The reference forces omp_get_num_procs() threads (omc_dosxyz.c:1184-1191); torchrun exports OMP_NUM_THREADS=1 to its
+    # children, which must not throttle the baseline: ask for every core this process may run on.
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if cpudrv.have_ref(omp=True):
         tr, kind = cpudrv.RefTransport(omp=True), "reference"
+        tr.set_num_threads(ncores)
         tr.load_problem(prob)
         tr.set_rng("ranmar")         # the reference's own generator
     else:
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, capture_output=True)
         tr, kind = cpudrv.OracleTransport(), "port"
+        tr.set_num_threads(ncores)
         tr.load_problem(prob)
         tr.set_rng("ranmar")
     return tr, kind
@@ -136,20 +163,21 @@ def run_reference_arm(args) -> None:
     if rank != 0:
         return
     prob, ph, w = build_workload(args.workload, args.nsplit)
-    tr, kind = cpu_reference_transport(prob)
-    cores = tr.num_threads()
-    # calibrate the per-step sample so the whole run ends within a few minutes
-    t = tr.time_batches(0, 4000, 1)
-    rate0 = 4000 / max(t, 1e-6)
-    budget = 90.0 / max(args.steps + args.warmup, 1)
-    nper = int(min(max(rate0 * min(budget, 6.0), 2000), 2_000_000))
-    first = 10_000
-    for i in range(args.warmup):
-        tr.time_batches(first, nper, 1); first += nper
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        tr.time_batches(first, nper, 1); first += nper
-    dt = time.perf_counter() - t0
+    with quiet_stdout():
+        tr, kind = cpu_reference_transport(prob)
+        cores = tr.num_threads()
+        # calibrate the per-step sample so the whole run ends within a few minutes
+        t = tr.time_batches(0, 4000, 1)
+        rate0 = 4000 / max(t, 1e-6)
+        budget = 90.0 / max(args.steps + args.warmup, 1)
+        nper = int(min(max(rate0 * min(budget, 6.0), 2000), 2_000_000))
+        first = 10_000
+        for i in range(args.warmup):
+            tr.time_batches(first, nper, 1); first += nper
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            tr.time_batches(first, nper, 1); first += nper
+        dt = time.perf_counter() - t0
     value = args.steps * nper / dt
     sample = f"{args.steps} batches x {nper} histories of the workload, RANMAR, schedule(dynamic)"
     line = {"impl": "reference", "metric": "histories/s", "value": value, "unit": "histories/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -320,10 +348,11 @@ def main() -> None:
         orc.reset_score()
         orc.run_histories(0, 40000)
         work = orc.work_per_history()
-        ref, kind = cpu_reference_transport(prob)
-        t = ref.time_batches(0, 4000, 1)
-        n = int(min(max(4000 / max(t, 1e-6) * 15.0, 4000), 4_000_000))
-        t = ref.time_batches(100000, n, 1)
+        with quiet_stdout():
+            ref, kind = cpu_reference_transport(prob)
+            t = ref.time_batches(0, 4000, 1)
+            n = int(min(max(4000 / max(t, 1e-6) * 15.0, 4000), 4_000_000))
+            t = ref.time_batches(100000, n, 1)
         line["cpu_baseline"] = {"value": n / t, "unit": "histories/s", "cores": ref.num_threads(), "kind": kind,
                                 "sample": f"1 batch of {n} histories of the same workload ({t:.1f} s), RANMAR, all host threads"}
     if work is None:
