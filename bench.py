@@ -249,13 +249,19 @@ def main() -> None:
         torch.cuda.synchronize()
 
     def step(i: int):
-        # batch i = history ids [i*H*world, (i+1)*H*world), rank r takes its contiguous slice
+        # batch i = history ids [i*H*world, (i+1)*H*world), rank r takes its contiguous slice.  Batches are pipelined
+        # (ompmc_b200/dist.py): batch i is started while the tail of batch i-1 is still in flight; i-1 is then
+        # summed over ranks and accumulated.
         with torch.cuda.stream(stream):
             flush.zero_()                                     # L2 flush between timed iterations
-        odist.run_batch_sharded(tr, i * H * world, H * world, rank, world, allreduce)
+        odist.start_batch_sharded(tr, i * H * world, H * world, rank, world, allreduce)
+
+    def finish():
+        odist.finish_batches_sharded(tr, rank, world, allreduce)
 
     for i in range(args.warmup):
         step(i)
+    finish()
     barrier()
     tr.reset_tallies()
     sampler = ClockSampler(local)
@@ -266,6 +272,7 @@ def main() -> None:
     ev0.record(stream)
     for i in range(args.steps):
         step(args.warmup + i)
+    finish()                                                  # the tail of the last batch belongs to the timed region
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -276,18 +283,13 @@ def main() -> None:
     kms = 0.0
     ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nk = max(2, min(args.steps, 4))
-    for i in range(nk):
-        with torch.cuda.stream(stream):
-            flush.zero_()
-        ka.record(stream)
-        lo, n = odist.shard_range((args.warmup + args.steps + i) * H * world, H * world, rank, world)
-        tr.run_histories(lo, n)
-        kb.record(stream)
-        tr.synchronize()
-        kms += ka.elapsed_time(kb)
-        if world > 1:
-            allreduce(tr)             # keep these batches comparable with the reduced ones in the sigma estimate
-        tr.accum_batch()
+    ka.record(stream)
+    for i in range(nk):                                        # same pipelined batches, no L2 flush: the launch group of the roofline
+        odist.start_batch_sharded(tr, (args.warmup + args.steps + i) * H * world, H * world, rank, world, allreduce)
+    finish()
+    kb.record(stream)
+    torch.cuda.synchronize()
+    kms = ka.elapsed_time(kb)
     kernel_ms = kms / nk
     launches_per_step = cnt["kernel_launches"] / max(args.steps, 1)
 

@@ -174,8 +174,20 @@ int omc_gpu_set_option(omc_gpu_handle h, const char *key, long long value);
 int omc_gpu_run_histories(omc_gpu_handle h, long long first_history, long long nhist, int ibeamlet);
 /* accumEndep() (omc_dosxyz.c:696-717): accum += e, accum2 += e*e, zero the batch grid. */
 int omc_gpu_accum_batch(omc_gpu_handle h);
-/* convenience: run_histories + accum_batch == one iteration of the reference batch loop */
+/* One iteration of the reference batch loop ({initHistory(); shower();} x nhist + accumEndep(), omc_dosxyz.c:1237-1263).
+ * With the wavefront kernels consecutive calls are PIPELINED: the call returns when all its histories have been
+ * started and every earlier batch is complete and accumulated; the tail of this batch keeps running underneath the
+ * next call (each particle scores into the grid of the batch its history id belongs to) and is completed and
+ * accumulated by the next call or by whichever call reads results (get_tallies, accumulate_results, synchronize...). */
 int omc_gpu_run_batch(omc_gpu_handle h, long long first_history, long long nhist, int ibeamlet);
+/* The same pipelining with the accumulation left to the caller (multi-GPU: the batch grid is summed over ranks before
+ * accumEndep() squares it): start_batch returns when its histories are all started and the PREVIOUS started batch is
+ * complete; omc_gpu_completed_batches() = how many complete batch grids wait for omc_gpu_accum_batch(), which takes
+ * them oldest first (omc_gpu_device_ptrs / omc_gpu_get_batch_grid address the oldest one); omc_gpu_finish_batches
+ * completes the batch in flight.  At most two batches may be waiting / in flight together. */
+int omc_gpu_start_batch(omc_gpu_handle h, long long first_history, long long nhist, int ibeamlet);
+int omc_gpu_finish_batches(omc_gpu_handle h);
+int omc_gpu_completed_batches(omc_gpu_handle h);
 int omc_gpu_synchronize(omc_gpu_handle h);
 
 /* ---- results ----------------------------------------------------------------------------- */

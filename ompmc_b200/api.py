@@ -87,7 +87,8 @@ class Counters(C.Structure):
 
 EXPORTS = ["omc_gpu_create", "omc_gpu_destroy", "omc_gpu_last_error", "omc_gpu_set_media", "omc_gpu_set_geometry",
            "omc_gpu_set_source_dosxyz", "omc_gpu_set_source_matrad", "omc_gpu_set_vrt", "omc_gpu_set_seed", "omc_gpu_set_option",
-           "omc_gpu_run_histories", "omc_gpu_accum_batch", "omc_gpu_run_batch", "omc_gpu_synchronize", "omc_gpu_get_tallies",
+           "omc_gpu_run_histories", "omc_gpu_accum_batch", "omc_gpu_run_batch", "omc_gpu_start_batch", "omc_gpu_finish_batches",
+           "omc_gpu_completed_batches", "omc_gpu_synchronize", "omc_gpu_get_tallies",
            "omc_gpu_get_batch_grid", "omc_gpu_accumulate_results", "omc_gpu_reset_tallies", "omc_gpu_device_ptrs", "omc_gpu_stream", "omc_gpu_get_counters",
            "omc_gpu_get_history_records", "omc_gpu_test_geometry", "omc_gpu_test_rng", "omc_gpu_test_particles",
            "omc_gpu_abi_sizeof"]
@@ -111,6 +112,9 @@ def load_library() -> C.CDLL:
     lib.omc_gpu_run_histories.argtypes = [H, C.c_longlong, C.c_longlong, C.c_int]
     lib.omc_gpu_accum_batch.argtypes = [H]
     lib.omc_gpu_run_batch.argtypes = [H, C.c_longlong, C.c_longlong, C.c_int]
+    lib.omc_gpu_start_batch.argtypes = [H, C.c_longlong, C.c_longlong, C.c_int]
+    lib.omc_gpu_finish_batches.argtypes = [H]
+    lib.omc_gpu_completed_batches.argtypes = [H]
     lib.omc_gpu_synchronize.argtypes = [H]
     lib.omc_gpu_get_tallies.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.omc_gpu_get_batch_grid.argtypes = [H, C.c_void_p]
@@ -242,6 +246,17 @@ class GpuTransport:
 
     def run_batch(self, first: int, n: int, ibeamlet: int = -1):
         self._ck(self.lib.omc_gpu_run_batch(self.h, first, n, ibeamlet), "omc_gpu_run_batch")
+
+    def start_batch(self, first: int, n: int, ibeamlet: int = -1):
+        """Pipelined batch, accumulation left to the caller (see include/ompmc_b200.h)."""
+        self.set_option("record_histories", 0)
+        self._ck(self.lib.omc_gpu_start_batch(self.h, first, n, ibeamlet), "omc_gpu_start_batch")
+
+    def finish_batches(self):
+        self._ck(self.lib.omc_gpu_finish_batches(self.h), "omc_gpu_finish_batches")
+
+    def completed_batches(self) -> int:
+        return int(self.lib.omc_gpu_completed_batches(self.h))
 
     def synchronize(self):
         self._ck(self.lib.omc_gpu_synchronize(self.h), "omc_gpu_synchronize")

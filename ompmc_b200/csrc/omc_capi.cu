@@ -71,6 +71,11 @@ struct omc_gpu_ctx {
     // omc_gpu_accumulate_results scratch
     double *res_dens = nullptr, *res_dose = nullptr, *res_unc = nullptr;
     int res_nreg = -1;
+    // batch pipelining (see wave_run)
+    int run_grid = -1, last_ibeamlet = -1;
+    std::vector<int> done_q;
+    bool auto_acc[2] = {false, false};
+    bool pipeline_next = false, pipeline_auto = false;   // how the next omc_gpu_run_histories() body is to run (set by the callers below)
 };
 
 #define CK(call)                                                                                         \
@@ -152,14 +157,18 @@ static int alloc_estep_queue(omc_gpu_handle h, EStepQueue &q, unsigned cap) {
     return 0;
 }
 
-// Drive waves until every history of [first, first+nhist) has been started and all queues drained.
-static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int ibeamlet) {
-    DevProblem &P = h->P;
+// ---- wavefront driver -------------------------------------------------------------------------------
+// Two dose grids (fp32 chunk grid + fp64 batch grid each) let the NEXT batch start while the tail of the previous
+// one is still in the queues: a particle scores into the grid of the batch its history id belongs to
+// (WaveCtl::hist_split).  h->run_grid = grid of the batch whose tail is in flight (-1: queues empty);
+// h->done_q = grids of completed batches that have not been accumulated yet (accumEndep), oldest first.
+static int wave_prepare(omc_gpu_handle h) {
     const unsigned target = h->pool_target;
     const unsigned cap = h->pool_cap_opt ? h->pool_cap_opt : 2u * target + 65536u;
     if (h->pool_cap != cap) {
         free_pool(h->wave_bufs);
         h->pool_cap = 0;
+        h->run_grid = -1;                         // (whatever was in flight is gone with the queues)
         for (int i = 0; i < 2; i++) {
             if (alloc_queue(h, h->wq.p[i], cap, true)) return 1;
             if (alloc_queue(h, h->wq.e[i], cap, false, true)) return 1;
@@ -180,13 +189,57 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
     if (!h->ctl) {
         CK(cudaMalloc((void **)&h->ctl, sizeof(WaveCtl)));
         CK(cudaMallocHost((void **)&h->ctl_host, sizeof(WaveCtl)));
+        memset(h->ctl_host, 0, sizeof(WaveCtl));
     }
-    WaveCtl c;
-    memset(&c, 0, sizeof c);
-    c.target = target;
-    c.hist_next = (unsigned long long)first; c.hist_end = (unsigned long long)(first + nhist);
-    c.n_src = (unsigned)((unsigned long long)nhist < (unsigned long long)target ? nhist : target);
-    CK(cudaMemcpyAsync(h->ctl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+static int grid_done(omc_gpu_handle h, int g) {      // fold the fp32 chunk grid of a completed batch into its fp64 batch grid
+    const size_t off = (size_t)g * h->P.nreg;
+    launch_flush(h->P.endep32 + off, h->P.endep + off, h->P.nreg, h->stream);
+    h->launches += 1;
+    h->done_q.push_back(g);
+    return 0;
+}
+
+static bool in_done(omc_gpu_handle h, int g) {
+    for (int d : h->done_q) if (d == g) return true;
+    return false;
+}
+
+// start == true : inject histories [first, first+nhist) and return once all of them are started AND the previous batch
+//                 (if its tail was in flight) is complete; the tail of the new batch stays in the queues.
+// start == false: run what is in the queues to the end (waves, then drain_kernel for the last few particles).
+// g_new: dose grid of the new batch (start only).
+static int wave_run(omc_gpu_handle h, bool start, long long first, long long nhist, int ibeamlet, int g_new) {
+    DevProblem &P = h->P;
+    if (!start && h->run_grid < 0) return 0;
+    if (wave_prepare(h)) return 1;
+    const unsigned target = h->pool_target;
+    int g_old = h->run_grid;
+    bool old_pending = false;
+    if (start) {
+        if (g_old < 0) {                                        // empty pipeline
+            WaveCtl c;
+            memset(&c, 0, sizeof c);
+            c.target = target;
+            c.hist_next = (unsigned long long)first; c.hist_end = (unsigned long long)(first + nhist);
+            c.hist_split = (unsigned long long)first; c.grid_new = (unsigned)g_new; c.old_done = 1;
+            c.n_src = (unsigned)((unsigned long long)nhist < (unsigned long long)target ? nhist : target);
+            CK(cudaMemcpyAsync(h->ctl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
+        } else {                                                // previous batch still in flight: it becomes "old"
+            launch_rearm(h->ctl, (unsigned long long)first, (unsigned long long)nhist, h->stream);
+            old_pending = true;
+        }
+        h->last_ibeamlet = ibeamlet;
+    } else {
+        const WaveCtl &s0 = *h->ctl_host;                       // status as of the last check
+        if (s0.live == 0 && s0.n_src == 0 && s0.hist_next >= s0.hist_end) {
+            h->run_grid = -1;
+            return grid_done(h, g_old);
+        }
+        ibeamlet = h->last_ibeamlet;
+    }
     WaveLaunch L;
     int occ[4];
     wave_blocks_per_sm(occ);
@@ -222,20 +275,37 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
         CK(cudaStreamSynchronize(h->stream));
         const WaveCtl &s = *h->ctl_host;
         if (h->trace)
-            fprintf(stderr, "wave %llu live %u n_src %u P %u E %u IP %u IE %u hist_next %llu\n", wave + every, s.live, s.n_src,
-                    s.n_p[s.parity].v, s.n_e[s.parity].v, s.n_ip[s.parity].v, s.n_ie[s.parity].v, s.hist_next);
+            fprintf(stderr, "wave %llu live %u n_src %u P %u E %u IP %u IE %u hist_next %llu old %u/%u\n", wave + every, s.live, s.n_src,
+                    s.n_p[s.parity].v, s.n_e[s.parity].v, s.n_ip[s.parity].v, s.n_ie[s.parity].v, s.hist_next, s.has_old, s.old_done);
         if (s.overflow.v) {
             h->err = "particle queue overflow on the device: increase option pool_size";
             rc = 7;
             break;
         }
+        if (old_pending && s.old_done) {                        // the previous batch has left the queues: its grid is final
+            grid_done(h, g_old);
+            old_pending = false;
+        }
         const bool exhausted = s.hist_next >= s.hist_end && s.n_src == 0;
-        if (exhausted && s.live == 0) break;
-        if (exhausted && s.live <= h->drain_threshold && P.nsplit == 1) { drained = true; break; }   // (split photons in flight cannot be handed over)
+        if (start) {
+            // the tail of the new batch stays in flight; it is always the NEXT call that completes a batch, even an
+            // already empty one, so that every rank of a multi-GPU run sees the same sequence of completed batches
+            if (exhausted && !old_pending) break;
+        } else if (exhausted && s.live == 0) {
+            break;
+        } else if (exhausted && s.live <= h->drain_threshold && P.nsplit == 1) {   // (split photons in flight cannot be handed over)
+            drained = true;
+            break;
+        }
         if (wave > 50000000ull) { rc = fail(h, "wavefront did not terminate"); break; }
     }
     if (gexec) { cudaGraphExecDestroy(gexec); cudaGraphDestroy(graph); }
-    if (rc) return rc;
+    if (rc) { h->run_grid = -1; return rc; }
+    if (start) {
+        h->run_grid = g_new;
+        CK(cudaGetLastError());
+        return 0;
+    }
     if (drained) {
         // few particles left: one thread follows each to the end (omc_lockstep.cu: drain_kernel)
         const int par = (int)h->ctl_host->parity;
@@ -253,13 +323,72 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
         D.q[0] = h->wq.p[par]; D.q[1] = h->wq.e[par]; D.q[2] = h->wq.ip[par]; D.q[3] = h->wq.ie[par];
         D.count[0] = &h->ctl->n_p[par].v; D.count[1] = &h->ctl->n_e[par].v; D.count[2] = &h->ctl->n_ip[par].v; D.count[3] = &h->ctl->n_ie[par].v;
         D.ticket = &h->ctl->drain_ticket.v;
-        launch_drain(P, D, h->stack, depth, blocks, h->stream);
+        CK(cudaMemsetAsync(&h->ctl->drain_ticket.v, 0, sizeof(unsigned), h->stream));
+        DevProblem Pd = P;                                      // the drain scores straight into the fp64 grid of this batch
+        Pd.endep = P.endep + (size_t)g_old * P.nreg;
+        launch_drain(Pd, D, h->stack, depth, blocks, h->stream);
         h->launches += 1;
+        memset(h->ctl_host, 0, sizeof(WaveCtl));                // (status: nothing alive any more)
     }
-    launch_flush(P.endep32, P.endep, P.nreg, h->stream);
-    h->launches += 1;
+    h->run_grid = -1;
+    grid_done(h, g_old);
     CK(cudaGetLastError());
     return 0;
+}
+
+static int free_grid(omc_gpu_handle h) {
+    const int busy = h->run_grid;
+    for (int g = 0; g < 2; g++)
+        if (g != busy && !in_done(h, g)) return g;
+    return -1;
+}
+
+// accumEndep() of every completed batch that is waiting for it (oldest first); `only_auto`: just those started by
+// omc_gpu_run_batch(), which owes them an accumulation
+static int accum_done(omc_gpu_handle h, bool only_auto) {
+    std::vector<int> keep;
+    bool took = false;
+    for (int g : h->done_q) {
+        if ((only_auto && !h->auto_acc[g]) || (!only_auto && took)) { keep.push_back(g); continue; }   // explicit call: the oldest one only
+        took = true;
+        const size_t off = (size_t)g * h->P.nreg;
+        launch_accum(h->P.endep + off, h->accum, h->accum2, h->P.nreg, h->stream);
+        h->launches += 1;
+        h->auto_acc[g] = false;
+    }
+    h->done_q = keep;
+    if (cudaGetLastError() != cudaSuccess) { h->err = "accum kernel launch failed"; return 1; }
+    return 0;
+}
+
+// complete whatever is in flight and settle the accumulations owed by omc_gpu_run_batch()
+static int flush_all(omc_gpu_handle h) {
+    if (h->run_grid >= 0) {
+        int rc = wave_run(h, false, 0, 0, -1, -1);
+        if (rc) return rc;
+    }
+    return accum_done(h, true);
+}
+
+// histories [first, first+nhist) through the wavefront kernels.  pipelined: leave the tail of this batch in flight
+// (omc_gpu_start_batch / omc_gpu_run_batch); otherwise run it to the end (omc_gpu_run_histories).
+static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int ibeamlet, bool pipelined, bool auto_acc) {
+    int g;
+    if (!pipelined) {
+        int rc = flush_all(h);
+        if (rc) return rc;
+        // several un-accumulated calls in a row keep adding into the same batch grid, as they always did
+        if (!h->done_q.empty()) { g = h->done_q.back(); h->done_q.pop_back(); }
+        else g = 0;
+    } else {
+        g = free_grid(h);
+        if (g < 0) return fail(h, "two batches are waiting for omc_gpu_accum_batch(): accumulate before starting another one");
+    }
+    h->auto_acc[g] = auto_acc;
+    int rc = wave_run(h, true, first, nhist, ibeamlet, g);
+    if (rc) return rc;
+    if (!pipelined) rc = wave_run(h, false, 0, 0, -1, -1);
+    return rc;
 }
 
 extern "C" {
@@ -473,8 +602,8 @@ int omc_gpu_set_geometry(omc_gpu_handle h, const omc_geometry *g) {
     if (h->tally_nreg != P.nreg) {
         cudaFree(P.endep); cudaFree(P.endep32); cudaFree(h->accum); cudaFree(h->accum2);
         P.endep = nullptr; P.endep32 = nullptr; h->accum = h->accum2 = nullptr;
-        CK(cudaMalloc((void **)&P.endep, (size_t)P.nreg * sizeof(double)));
-        CK(cudaMalloc((void **)&P.endep32, (size_t)P.nreg * sizeof(float)));
+        CK(cudaMalloc((void **)&P.endep, (size_t)2 * P.nreg * sizeof(double)));      // two batch grids (pipelining), grid g at g * nreg
+        CK(cudaMalloc((void **)&P.endep32, (size_t)2 * P.nreg * sizeof(float)));
         CK(cudaMalloc((void **)&h->accum, (size_t)P.nreg * sizeof(double)));
         CK(cudaMalloc((void **)&h->accum2, (size_t)P.nreg * sizeof(double)));
         h->tally_nreg = P.nreg;
@@ -607,6 +736,14 @@ int omc_gpu_run_histories(omc_gpu_handle h, long long first, long long nhist, in
     }
     h->last_nhist = nhist;
     if (h->kernel == OMC_KERNEL_LOCKSTEP) {
+        {                                                      // the lock-step kernel always scores into batch grid 0
+            int rc = flush_all(h);
+            if (rc) return rc;
+            bool has0 = false;
+            for (int d : h->done_q) has0 |= (d == 0);
+            if (!has0) h->done_q.push_back(0);
+            h->auto_acc[0] = h->pipeline_auto;
+        }
         const int tpb = h->threads_per_block;
         int blocks_cap = h->max_blocks > 0 ? h->max_blocks : h->sm_count * lockstep_blocks_per_sm(tpb);
         long long want = (nhist + tpb - 1) / tpb;
@@ -625,7 +762,7 @@ int omc_gpu_run_histories(omc_gpu_handle h, long long first, long long nhist, in
     } else if (h->kernel == OMC_KERNEL_WAVEFRONT) {
         if (P.nsplit > 255) return fail(h, "wavefront kernels support nsplit <= 255; use the lock-step kernel beyond");
         if (h->record) return fail(h, "per-history records are a lock-step kernel feature");
-        int rc = run_wavefront(h, first, nhist, ibeamlet);
+        int rc = run_wavefront(h, first, nhist, ibeamlet, h->pipeline_next, h->pipeline_auto);
         if (rc) return rc;
     } else {
         return fail(h, "unknown kernel");
@@ -636,21 +773,57 @@ int omc_gpu_run_histories(omc_gpu_handle h, long long first, long long nhist, in
 int omc_gpu_accum_batch(omc_gpu_handle h) {
     if (!h || !h->have_geom) return 2;
     CK(cudaSetDevice(h->device));
-    launch_accum(h->P.endep, h->accum, h->accum2, h->P.nreg, h->stream);
-    h->launches += 1;
-    CK(cudaGetLastError());
+    if (h->done_q.empty() && h->run_grid >= 0) {               // the batch that was started is still in flight: complete it
+        int rc = wave_run(h, false, 0, 0, -1, -1);
+        if (rc) return rc;
+    }
+    if (h->done_q.empty()) {                                   // nothing was run: accumEndep() of an empty batch grid
+        launch_accum(h->P.endep, h->accum, h->accum2, h->P.nreg, h->stream);
+        h->launches += 1;
+        CK(cudaGetLastError());
+        return 0;
+    }
+    return accum_done(h, false);
+}
+
+int omc_gpu_start_batch(omc_gpu_handle h, long long first, long long nhist, int ibeamlet) {
+    if (!h) return 2;
+    const bool wave = (h->kernel == OMC_KERNEL_WAVEFRONT) && !h->record;
+    h->pipeline_next = wave; h->pipeline_auto = false;
+    int rc = omc_gpu_run_histories(h, first, nhist, ibeamlet);
+    h->pipeline_next = false;
+    return rc;
+}
+
+int omc_gpu_finish_batches(omc_gpu_handle h) {
+    if (!h || !h->have_geom) return 2;
+    CK(cudaSetDevice(h->device));
+    if (h->run_grid >= 0) return wave_run(h, false, 0, 0, -1, -1);
     return 0;
 }
 
+int omc_gpu_completed_batches(omc_gpu_handle h) { return h ? (int)h->done_q.size() : -1; }
+
 int omc_gpu_run_batch(omc_gpu_handle h, long long first, long long nhist, int ibeamlet) {
+    if (!h) return 2;
+    // pipelined with the wavefront kernels: on return the histories are all started and every EARLIER batch is
+    // accumulated; this batch is completed and accumulated by the next call or by whatever reads results
+    const bool wave = (h->kernel == OMC_KERNEL_WAVEFRONT) && !h->record;
+    h->pipeline_next = wave; h->pipeline_auto = true;
     int rc = omc_gpu_run_histories(h, first, nhist, ibeamlet);
+    h->pipeline_next = false; h->pipeline_auto = false;
     if (rc) return rc;
-    return omc_gpu_accum_batch(h);
+    if (!wave) return omc_gpu_accum_batch(h);
+    return accum_done(h, true);
 }
 
 int omc_gpu_synchronize(omc_gpu_handle h) {
     if (!h) return 2;
     CK(cudaSetDevice(h->device));
+    if (h->have_geom) {
+        int rc = flush_all(h);
+        if (rc) return rc;
+    }
     CK(cudaStreamSynchronize(h->stream));
     Counters c;
     CK(cudaMemcpy(&c, h->P.counters, sizeof c, cudaMemcpyDeviceToHost));
@@ -703,7 +876,8 @@ int omc_gpu_get_batch_grid(omc_gpu_handle h, double *endep) {
     if (!h || !h->have_geom || !endep) return 2;
     int rc = omc_gpu_synchronize(h);
     if (rc) return rc;
-    CK(cudaMemcpy(endep, h->P.endep, (size_t)h->P.nreg * sizeof(double), cudaMemcpyDeviceToHost));
+    const int g = h->done_q.empty() ? 0 : h->done_q.front();   // the completed batch waiting for accumEndep(), else grid 0
+    CK(cudaMemcpy(endep, h->P.endep + (size_t)g * h->P.nreg, (size_t)h->P.nreg * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -711,11 +885,18 @@ int omc_gpu_reset_tallies(omc_gpu_handle h, int which) {
     if (!h || !h->have_geom) return 2;
     CK(cudaSetDevice(h->device));
     const size_t n = (size_t)h->P.nreg;
+    if (which == 0) {                       // everything starts over: particles still in flight are dropped with their grids
+        h->run_grid = -1; h->done_q.clear(); h->auto_acc[0] = h->auto_acc[1] = false;
+        if (h->ctl_host) memset(h->ctl_host, 0, sizeof(WaveCtl));
+    } else {                                // omc_matrad.c:1482 zeroes accum_endep between beamlets: settle what is owed first
+        int rc = flush_all(h);
+        if (rc) return rc;
+    }
     CK(cudaMemsetAsync(h->accum, 0, n * sizeof(double), h->stream));
     if (which == 0) {
         CK(cudaMemsetAsync(h->accum2, 0, n * sizeof(double), h->stream));
-        CK(cudaMemsetAsync(h->P.endep, 0, n * sizeof(double), h->stream));
-        CK(cudaMemsetAsync(h->P.endep32, 0, n * sizeof(float), h->stream));
+        CK(cudaMemsetAsync(h->P.endep, 0, 2 * n * sizeof(double), h->stream));
+        CK(cudaMemsetAsync(h->P.endep32, 0, 2 * n * sizeof(float), h->stream));
         CK(cudaMemsetAsync(h->P.ensrc, 0, sizeof(double), h->stream));
         CK(cudaMemsetAsync(h->P.counters, 0, sizeof(Counters), h->stream));
         h->launches = 0;
@@ -726,7 +907,7 @@ int omc_gpu_reset_tallies(omc_gpu_handle h, int which) {
 
 int omc_gpu_device_ptrs(omc_gpu_handle h, void **endep, void **accum, void **accum2, long long *nreg) {
     if (!h || !h->have_geom) return 2;
-    if (endep) *endep = h->P.endep;
+    if (endep) *endep = h->P.endep + (size_t)(h->done_q.empty() ? 0 : h->done_q.front()) * h->P.nreg;
     if (accum) *accum = h->accum;
     if (accum2) *accum2 = h->accum2;
     if (nreg) *nreg = h->P.nreg;
@@ -750,6 +931,10 @@ void *omc_gpu_stream(omc_gpu_handle h) { return h ? (void *)h->stream : nullptr;
 int omc_gpu_get_counters(omc_gpu_handle h, omc_gpu_counters *out) {
     if (!h || !out) return 2;
     CK(cudaSetDevice(h->device));
+    if (h->have_geom) {
+        int rc = flush_all(h);
+        if (rc) return rc;
+    }
     CK(cudaStreamSynchronize(h->stream));
     static_assert(sizeof(Counters) == sizeof(omc_gpu_counters), "counter layouts must match");
     CK(cudaMemcpy(out, h->P.counters, sizeof(Counters), cudaMemcpyDeviceToHost));

@@ -45,8 +45,13 @@ struct WaveCtl {
     PadU n_ch, n_bca;                            // step-class queues, filled and drained inside one wave
     PadU tk[5];                                  // chunk tickets per class (misc_kernel)
     PadU overflow, drain_ticket;
+    PadU old_seen;                               // particles of the PREVIOUS batch met by the consumers of this wave
     unsigned n_src;                              // histories injected by the current wave
     unsigned parity, target, live, waves;
+    // batch pipelining: histories with id < hist_split belong to the previous batch, whose tail is still in flight
+    // while this batch is injected; they score into dose grid (grid_new ^ 1), everything else into grid_new
+    unsigned has_old, old_done, grid_new, pad_;
+    unsigned long long hist_split;
     unsigned long long hist_next, hist_end;
 };
 
@@ -91,5 +96,7 @@ struct WaveStreams {
 };
 void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, const WaveStreams &W);
 void launch_flush(float *g32, double *g64, long long n, cudaStream_t s);
+// start the next batch while the tail of the previous one is still in the queues (see WaveCtl::hist_split)
+void launch_rearm(WaveCtl *ctl, unsigned long long first, unsigned long long nhist, cudaStream_t s);
 
 }  // namespace omc

@@ -145,8 +145,30 @@ struct Tally {
     unsigned ndep, nestep, npstep;
 };
 
+// Which of the two dose grids a particle scores into (batch pipelining, WaveCtl::hist_split), wave-uniform part
+struct BatchSel {
+    unsigned long long split;
+    float *g_new, *g_old;
+    unsigned has_old;
+    __device__ __forceinline__ void init(const DevProblem &P, const WaveCtl *c) {
+        split = c->hist_split; has_old = c->has_old;
+        g_new = P.endep32 + (size_t)c->grid_new * P.nreg;
+        g_old = P.endep32 + (size_t)(c->grid_new ^ 1u) * P.nreg;
+    }
+    __device__ __forceinline__ bool is_old(uint32_t h0, uint32_t h1) const {
+        return has_old && ((((unsigned long long)h1) << 32) | h0) < split;
+    }
+    __device__ __forceinline__ float *grid(bool old) const { return old ? g_old : g_new; }
+    // consumers count the previous batch's particles they meet; zero in a whole wave = that batch is complete
+    __device__ __forceinline__ void count(WaveCtl *c, unsigned mask, bool old) const {
+        if (!has_old) return;
+        const unsigned m = __ballot_sync(mask, old);
+        if (m && (threadIdx.x & 31) == __ffs(mask) - 1) atomicAdd(&c->old_seen.v, (unsigned)__popc(m));
+    }
+};
+
 // ausgab(): fp32 chunk grid (north_star (d)); optionally warp-aggregated when lanes hit the same voxel
-__device__ __forceinline__ void deposit32(const DevProblem &P, Tally &t, int ir, double en) {
+__device__ __forceinline__ void deposit32(float *grid32, Tally &t, int ir, double en) {
     t.ndep++;
 #if OMC_WARP_AGGREGATE_DOSE
     const unsigned m = __activemask();
@@ -159,9 +181,9 @@ __device__ __forceinline__ void deposit32(const DevProblem &P, Tally &t, int ir,
         const float o = __shfl_sync(peers, v, src);
         if (lane == leader) v += o;
     }
-    if (lane == leader) atomicAdd(P.endep32 + ir, v);
+    if (lane == leader) atomicAdd(grid32 + ir, v);
 #else
-    atomicAdd(P.endep32 + ir, (float)en);
+    atomicAdd(grid32 + ir, (float)en);
 #endif
 }
 
@@ -177,11 +199,14 @@ struct WaveArgs {
 // ---------------------------------------------------------------------------------------------
 // chunk P: photon free flight, photon() src/ompmc.c:1884-2067 for nsplit == 1
 // ---------------------------------------------------------------------------------------------
-__device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, int par, unsigned i, unsigned n, Tally &t) {
+__device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, const BatchSel &BS, int par, unsigned i, unsigned n, Tally &t) {
     if (i >= n) return;
     WaveCtl *ctl = A.ctl;
     Part p; Rng g; double dpmfp; int tag;
     q_load(A.Q.p[par], i, p, g, P, dpmfp, tag);
+    const bool old = BS.is_old(g.h0, g.h1);
+    BS.count(ctl, __activemask(), old);
+    float *dg = BS.grid(old);
     RegionRec R = load_region_w(P, p.ir);
     // uniform photon splitting, :1903-1945: the record is the ray of nsplit copies of weight wt/nsplit whose
     // interaction depths are stratified (eta'_k = eta'_0 - k/nsplit); copy `isplit` is the one in flight.
@@ -190,7 +215,7 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, int par, un
     int isplit = tag & 0xff, isurv = (tag >> 8) & 0xff;
     double eta = A.Q.p[par].aux[i].y;
     if (dpmfp < 0.0) {                                         // fresh photon: cut-off test + number of mfp
-        if (p.e <= R.pcut || p.wt == 0) { deposit32(P, t, p.ir, p.wt * p.e); return; }
+        if (p.e <= R.pcut || p.wt == 0) { deposit32(dg, t, p.ir, p.wt * p.e); return; }
         g.align();
         const double r = g.next();
         eta = 1.0 - r / (double)nsplit;                        // eta' of the first copy
@@ -274,7 +299,7 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, int par, un
 // voxel-to-voxel march (photon() src/ompmc.c:1951-2019: mean free paths accumulated over the voxels crossed),
 // but a flight costs a few voxel look-ups instead of one per voxel crossed, and there is no dependent chain of
 // voxel-record loads.  Draws are consumed in whole Philox blocks: {distance, accept} x 2 per block.
-__device__ void photon_chunk_wc(const DevProblem &P, const WaveArgs &A, int par, unsigned i, unsigned n, Tally &t) {
+__device__ void photon_chunk_wc(const DevProblem &P, const WaveArgs &A, const BatchSel &BS, int par, unsigned i, unsigned n, Tally &t) {
     if (i >= n) return;
     WaveCtl *ctl = A.ctl;
     const PartQueue &q = A.Q.p[par];
@@ -287,12 +312,15 @@ __device__ void photon_chunk_wc(const DevProblem &P, const WaveArgs &A, int par,
         const uint4 r = q.rng[i];
         g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
     }
+    const bool old = BS.is_old(g.h0, g.h1);
+    BS.count(ctl, __activemask(), old);
+    float *dg = BS.grid(old);
     if (p.ir == 0) return;                                     // outside the phantom: howfar() discards (idisc)
     {   // cut-off test of photon() :1884 (a flight that spans several waves repeats it, harmlessly)
         double rhof; int med;
         load_region_rm(P, p.ir, rhof, med);
         const double pcut = (P.reg8 != nullptr) ? (med >= 0 ? P.med[med].pcut : 0.0) : load_region(P, p.ir).pcut;
-        if (p.e <= pcut || p.wt == 0) { deposit32(P, t, p.ir, p.wt * p.e); return; }
+        if (p.e <= pcut || p.wt == 0) { deposit32(dg, t, p.ir, p.wt * p.e); return; }
     }
     const double gle = log(p.e);
     double smaj = 0.0;
@@ -341,7 +369,7 @@ __device__ void photon_chunk_wc(const DevProblem &P, const WaveArgs &A, int par,
 }
 
 // chunk IP: photon interactions
-__device__ void p_interact_chunk(const DevProblem &P, const WaveArgs &A, int par, unsigned i, unsigned n) {
+__device__ void p_interact_chunk(const DevProblem &P, const WaveArgs &A, const BatchSel &BS, int par, unsigned i, unsigned n) {
     if (i >= n) return;
     WaveCtl *ctl = A.ctl;
     const PartQueue &pn = A.Q.p[par ^ 1], &en = A.Q.e[par ^ 1];
@@ -351,6 +379,7 @@ __device__ void p_interact_chunk(const DevProblem &P, const WaveArgs &A, int par
         const uint4 r = A.Q.ip[par].rng[i];
         g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
     }
+    BS.count(ctl, __activemask(), BS.is_old(g.h0, g.h1));
     const RegionRec R = load_region_w(P, p.ir);
     const int imed = R.med;
     const float rho_f = (float)R.rhof;
@@ -392,7 +421,7 @@ __device__ void p_interact_chunk(const DevProblem &P, const WaveArgs &A, int par
 }
 
 // chunk IE: discrete electron / positron interactions
-__device__ void e_interact_chunk(const DevProblem &P, const WaveArgs &A, int par, unsigned i, unsigned n) {
+__device__ void e_interact_chunk(const DevProblem &P, const WaveArgs &A, const BatchSel &BS, int par, unsigned i, unsigned n) {
     if (i >= n) return;
     WaveCtl *ctl = A.ctl;
     const PartQueue &pn = A.Q.p[par ^ 1], &en = A.Q.e[par ^ 1];
@@ -402,6 +431,7 @@ __device__ void e_interact_chunk(const DevProblem &P, const WaveArgs &A, int par
         const uint4 r = A.Q.ie[par].rng[i];
         g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
     }
+    BS.count(ctl, __activemask(), BS.is_old(g.h0, g.h1));
     double rho_d; int imed;
     load_region_rm(P, p.ir, rho_d, imed);
     const float rho_f = (float)rho_d;
@@ -492,7 +522,7 @@ __device__ __forceinline__ void es_get(const EStepQueue &S, unsigned s, Part &p,
 
 // Phase A: cut-off test, distance to the next discrete interaction, step-size restrictions.
 // Returns the step class, or CLS_NONE with `st` = -1 (finished) / TAG_RANNIH.
-__device__ __forceinline__ int estep_size(const DevProblem &P, Rng &g, Part &p, EStep &e, Tally &t, int &st, int2 rm) {
+__device__ __forceinline__ int estep_size(const DevProblem &P, float *dg, Rng &g, Part &p, EStep &e, Tally &t, int &st, int2 rm) {
     RegionRec R;
     if (rm.y > -2 && P.reg8 != nullptr) {                      // voxel record handed over by the producer
         R.rhof = (double)__int_as_float(rm.x); R.med = rm.y; R.pcut = 0.0; R.pad = 0;
@@ -505,7 +535,7 @@ __device__ __forceinline__ int estep_size(const DevProblem &P, Rng &g, Part &p, 
     t.nestep++;
     st = 0;
     if (eie <= R.ecut) {                                       // :4665-4687
-        deposit32(P, t, p.ir, p.wt * (eie - RM));
+        deposit32(dg, t, p.ir, p.wt * (eie - RM));
         st = (iq > 0) ? TAG_RANNIH : -1;
         return CLS_NONE;
     }
@@ -641,7 +671,8 @@ __device__ __forceinline__ int estep_size(const DevProblem &P, Rng &g, Part &p, 
 
 // Phase B: take the step.  Returns 0 = keep travelling, -1 = finished, TAG_* = interaction due.
 // (rho_out, med_out) = voxel record of the region the electron ends in, when known (med_out = -2 otherwise)
-__device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, const EStep &e, int cls, Tally &t, float &rho_out, int &med_out) {
+__device__ __forceinline__ int estep_do(const DevProblem &P, float *dg, Rng &g, Part &p, const EStep &e, int cls, Tally &t, float &rho_out,
+                                        int &med_out) {
     rho_out = (float)e.rhof; med_out = e.imed;
     const int iq = p.iq, qel = (1 + iq) / 2, imed = e.imed;
     double eie = p.e, ustep, tustep = e.tustep, tvstep, de = 0.0;
@@ -688,7 +719,7 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
     int irnew = irl, idisc = 0;
     if (call_howfar) howfar_i(P, p, idisc, irnew, ustep);
     if (idisc > 0) {                                           // :5061-5088 (no annihilation quanta: edep > eie)
-        deposit32(P, t, p.ir, p.wt * ((iq > 0) ? p.e + RM : p.e - RM));
+        deposit32(dg, t, p.ir, p.wt * ((iq > 0) ? p.e + RM : p.e - RM));
         return -1;
     }
     if (ustep < 0) ustep = 0.0;
@@ -701,7 +732,7 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
             ecut = R.ecut; rho_out = (float)R.rhof; med_out = R.med;
         }
         if (eie <= ecut) {
-            deposit32(P, t, p.ir, p.wt * (eie - RM));
+            deposit32(dg, t, p.ir, p.wt * (eie - RM));
             return (iq > 0) ? TAG_RANNIH : -1;
         }
         return 0;
@@ -750,12 +781,12 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
     } else {
         tvstep = tustep;
     }
-    deposit32(P, t, p.ir, p.wt * de);                          // :5245
+    deposit32(dg, t, p.ir, p.wt * de);                          // :5245
     p.x = xf; p.y = yf; p.z = zf; p.u = uf; p.v = vf; p.w = wf;
     eie -= de;
     p.e = eie;
     if (irnew == irl && eie <= ecut) {
-        deposit32(P, t, p.ir, p.wt * (eie - RM));
+        deposit32(dg, t, p.ir, p.wt * (eie - RM));
         return (iq > 0) ? TAG_RANNIH : -1;
     }
 #if OMC_WAVE_F32
@@ -772,7 +803,7 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, Rng &g, Part &p, co
         rho_out = (float)R.rhof; med_out = R.med;
     }
     if (eie <= ecut) {
-        deposit32(P, t, p.ir, p.wt * (eie - RM));
+        deposit32(dg, t, p.ir, p.wt * (eie - RM));
         return (iq > 0) ? TAG_RANNIH : -1;
     }
     if (imed_new != imed) return 0;                            // new medium: resample from the top
@@ -842,11 +873,14 @@ __global__ void __launch_bounds__(NT, OMC_MB_ESIZE) esize_kernel(const __grid_co
     const unsigned lane = threadIdx.x & 31u, stride = gridDim.x * blockDim.x;
     const unsigned lt = (1u << lane) - 1u;
     Tally t = {0, 0, 0};
+    BatchSel BS;
+    BS.init(P, ctl);
     // warp-uniform loop: all 32 lanes stay converged through the slot reservation and the store
     for (unsigned base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
         const unsigned i = base + lane;
         Part p; Rng g; EStep e;
         int cls = CLS_NONE, st = 0;
+        bool old = false;
         if (i < n) {
             int tag;
             q_load_part(q, i, p, tag);
@@ -854,8 +888,10 @@ __global__ void __launch_bounds__(NT, OMC_MB_ESIZE) esize_kernel(const __grid_co
             const int2 rm = q.rm[i];
             const uint4 r = q.rng[i];
             g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
-            cls = estep_size(P, g, p, e, t, st, rm);
+            old = BS.is_old(r.x, r.y);
+            cls = estep_size(P, BS.grid(old), g, p, e, t, st, rm);
         }
+        BS.count(ctl, 0xffffffffu, old);
         // one reservation per (warp, class): lane 0 asks for the CH slots, lane 1 for the BCA slots, together
         const unsigned m_ch = __ballot_sync(0xffffffffu, cls == CLS_CH), m_bca = __ballot_sync(0xffffffffu, cls == CLS_BCA);
         unsigned b = 0;
@@ -882,6 +918,8 @@ __global__ void __launch_bounds__(NT, (CLS == 1 ? OMC_MB_ECH : OMC_MB_EBCA)) edo
     const PartQueue &qe = A.Q.e[par ^ 1], &qi = A.Q.ie[par ^ 1];
     const unsigned lane = threadIdx.x & 31u, stride = gridDim.x * blockDim.x, lt = (1u << lane) - 1u;
     Tally t = {0, 0, 0};
+    BatchSel BS;
+    BS.init(P, ctl);
     // warp-uniform loop; one converged reservation per warp for both output queues (lane 0: E, lane 1: IE)
     for (unsigned base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
         const unsigned i = base + lane;
@@ -890,7 +928,7 @@ __global__ void __launch_bounds__(NT, (CLS == 1 ? OMC_MB_ECH : OMC_MB_EBCA)) edo
         if (i < n) {
             es_get<OMC_WAVE_F32 && OMC_CH_BLOCK_RNG>(S, (CLS == CLS_CH) ? i : 2u * S.cap - 1u - i, p, g, e, P);
             if (i + stride < n) es_prefetch(S, (CLS == CLS_CH) ? i + stride : 2u * S.cap - 1u - (i + stride));
-            st = estep_do(P, g, p, e, CLS, t, rho_new, med_new);
+            st = estep_do(P, BS.grid(BS.is_old(g.h0, g.h1)), g, p, e, CLS, t, rho_new, med_new);
         }
         const unsigned m_e = __ballot_sync(0xffffffffu, st == 0), m_i = __ballot_sync(0xffffffffu, st > 0);
         unsigned b = 0;
@@ -926,6 +964,8 @@ __global__ void __launch_bounds__(NT, OMC_MB_MISC) misc_kernel(const __grid_cons
     const unsigned cnt0 = min(ctl->n_ie[par].v, cap), cnt1 = min(ctl->n_ip[par].v, cap), cnt2 = ctl->n_src, cnt3 = min(ctl->n_p[par].v, cap);
     Tally t = {0, 0, 0};
     double ensrc = 0.0;
+    BatchSel BS;
+    BS.init(P, ctl);
     // All warps of the machine work through the classes in the same order (heaviest first), so that at any time
     // nearly every warp of an SM runs the same code: with each warp picking classes round-robin the kernel's top
     // stall was instruction fetch (ncu: stall_no_instruction 5.6 warps per issue).
@@ -940,11 +980,11 @@ __global__ void __launch_bounds__(NT, OMC_MB_MISC) misc_kernel(const __grid_cons
             if ((unsigned long long)chunk * CH >= cnt) break;
             const unsigned i = chunk * CH + lane;
             if (c == 3) {
-                if (A.woodcock) photon_chunk_wc(P, A, par, i, cnt3, t);
-                else photon_chunk(P, A, par, i, cnt3, t);
+                if (A.woodcock) photon_chunk_wc(P, A, BS, par, i, cnt3, t);
+                else photon_chunk(P, A, BS, par, i, cnt3, t);
             } else if (c == 2) source_chunk(P, A, par, i, cnt2, ensrc);
-            else if (c == 1) p_interact_chunk(P, A, par, i, cnt1);
-            else e_interact_chunk(P, A, par, i, cnt0);
+            else if (c == 1) p_interact_chunk(P, A, BS, par, i, cnt1);
+            else e_interact_chunk(P, A, BS, par, i, cnt0);
             __syncwarp();
         }
     }
@@ -963,6 +1003,10 @@ __global__ void advance_kernel(const __grid_constant__ DevProblem P, WaveCtl *c)
     const unsigned room = (live < c->target) ? c->target - live : 0u;
     c->n_src = (unsigned)(left < (unsigned long long)room ? left : (unsigned long long)room);
     c->live = live;
+    if (c->has_old) {                                          // nothing of the previous batch was met in this wave: it is complete
+        if (c->old_seen.v == 0) { c->has_old = 0; c->old_done = 1; }
+        c->old_seen.v = 0;
+    }
     c->tk[0].v = c->tk[1].v = c->tk[2].v = c->tk[3].v = c->tk[4].v = 0;
     c->parity = (unsigned)nxt;
     c->waves += 1;
@@ -1007,6 +1051,22 @@ void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const W
     edo_kernel<CLS_CH><<<L.blocks[2], NT, 0, s>>>(P, A);
     if (par) { cudaStreamWaitEvent(s, W.join, 0); cudaStreamWaitEvent(s, W.join3, 0); }
     advance_kernel<<<1, 32, 0, s>>>(P, ctl);
+}
+
+// Next batch into the running pipeline: new history range, the dose grids swap roles, whatever is still alive
+// belongs to the previous batch (ids below `first`).
+__global__ void rearm_kernel(WaveCtl *c, unsigned long long first, unsigned long long nhist) {
+    if (blockIdx.x || threadIdx.x) return;
+    c->hist_next = first; c->hist_end = first + nhist; c->hist_split = first;
+    c->grid_new ^= 1u;
+    c->has_old = (c->live > 0) ? 1u : 0u;
+    c->old_done = c->has_old ? 0u : 1u;
+    c->old_seen.v = 0;
+    const unsigned room = (c->live < c->target) ? c->target - c->live : 0u;
+    c->n_src = (unsigned)(nhist < (unsigned long long)room ? nhist : (unsigned long long)room);
+}
+void launch_rearm(WaveCtl *ctl, unsigned long long first, unsigned long long nhist, cudaStream_t s) {
+    rearm_kernel<<<1, 32, 0, s>>>(ctl, first, nhist);
 }
 
 void launch_flush(float *g32, double *g64, long long n, cudaStream_t s) {

@@ -54,3 +54,28 @@ def run_batch_sharded(tr, first: int, nperbatch: int, rank: int, world: int, all
     if world > 1:
         allreduce(tr)
     tr.accum_batch()
+
+
+def settle_completed(tr, world: int, allreduce=None) -> int:
+    """Sum over ranks and accumulate (accumEndep) every completed batch grid that is waiting, oldest first."""
+    n = 0
+    while tr.completed_batches() > 0:
+        if world > 1:
+            allreduce(tr)
+        tr.accum_batch()
+        n += 1
+    return n
+
+
+def start_batch_sharded(tr, first: int, nperbatch: int, rank: int, world: int, allreduce=None) -> None:
+    """Pipelined form of run_batch_sharded: this rank's slice of the batch is started while the tail of the previous
+    batch is still in flight; whatever batch completed meanwhile is reduced over ranks and accumulated.  Every rank
+    completes batch k-1 inside its start of batch k, so the collective calls line up across ranks."""
+    lo, n = shard_range(first, nperbatch, rank, world)
+    tr.start_batch(lo, max(n, 0)) if n > 0 else tr.finish_batches()
+    settle_completed(tr, world, allreduce)
+
+
+def finish_batches_sharded(tr, rank: int, world: int, allreduce=None) -> None:
+    tr.finish_batches()
+    settle_completed(tr, world, allreduce)

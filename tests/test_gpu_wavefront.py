@@ -173,6 +173,57 @@ def test_wavefront_scheduling_independence(gpu):
     assert runs[0][1]["histories"] == c0["histories"]
 
 
+def test_batch_pipelining_matches_serial_batches(gpu):
+    """omc_gpu_run_batch() pipelines consecutive batches (the next batch is injected while the tail of the previous one
+    is still in flight, each particle scoring into the grid of the batch its history id belongs to).  Per-particle RNG
+    streams make every history identical to the serial run, so accum AND accum2 (the per-batch squares: a particle
+    scored into the wrong batch would show there) agree to fp32 summation order.  Drain off on both sides."""
+    prob, ph = make_problem(CASES[1][1])
+    gpu.load_problem(prob)
+    gpu.set_option("kernel", 1)
+    gpu.set_option("drain_threshold", 0)
+    nb, per = 6, 30000
+    try:
+        gpu.reset_tallies()
+        for ib in range(nb):                                   # serial: each batch runs to the end, then accumEndep()
+            gpu.run_histories(ib * per, per)
+            gpu.accum_batch()
+        a0, b0, e0 = gpu.get_tallies()
+        c0 = gpu.counters()
+        gpu.set_option("pool_size", 1 << 15)                   # small pool: injection of a batch spans many waves
+        gpu.reset_tallies()
+        for ib in range(nb):
+            gpu.run_batch(ib * per, per)
+        a1, b1, e1 = gpu.get_tallies()
+        c1 = gpu.counters()
+        # explicit form: start_batch / completed_batches / accum_batch / finish_batches
+        gpu.reset_tallies()
+        for ib in range(nb):
+            gpu.start_batch(ib * per, per)
+            assert gpu.completed_batches() == (1 if ib > 0 else 0)
+            while gpu.completed_batches():
+                gpu.accum_batch()
+        gpu.finish_batches()
+        assert gpu.completed_batches() == 1
+        gpu.accum_batch()
+        a2, b2, e2 = gpu.get_tallies()
+        # two batches waiting -> a third start is refused
+        gpu.reset_tallies()
+        gpu.start_batch(0, 1000); gpu.start_batch(1000, 1000); gpu.finish_batches()
+        assert gpu.completed_batches() == 2
+        with pytest.raises(OmcGpuError):
+            gpu.start_batch(2000, 1000)
+    finally:
+        gpu.set_option("pool_size", 1 << 22); gpu.set_option("drain_threshold", 8192)
+        gpu.reset_tallies()
+    for a, b, e in ((a1, b1, e1), (a2, b2, e2)):
+        assert abs(e - e0) <= 1e-9 * e0
+        np.testing.assert_allclose(a[1:], a0[1:], rtol=3e-4, atol=1e-4 * a0.max())
+        np.testing.assert_allclose(b[1:], b0[1:], rtol=6e-4, atol=1e-4 * b0.max())
+    assert c1["histories"] == c0["histories"] == nb * per
+    assert c1["deposits"] == c0["deposits"] and c1["electron_steps"] == c0["electron_steps"]
+
+
 def test_wavefront_rejects_unsupported(gpu):
     prob, ph = make_problem(dict(CASES[0][1], nsplit=300))
     gpu.load_problem(prob)
