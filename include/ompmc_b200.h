@@ -202,6 +202,16 @@ int omc_gpu_get_tallies(omc_gpu_handle h, double *accum_endep, double *accum_end
  * The device tallies are not modified. */
 int omc_gpu_accumulate_results(omc_gpu_handle h, int iout, int nhist, int nbatch, const double *med_densities, double *dose,
                                double *unc);
+/* The beamlet loop of omc_matrad.c:1389-1493 for beamlets [ib0, ib0+nb) in ONE pass of the wavefront kernels: all their
+ * histories run concurrently (beamlet ib0+k owns history ids [first_history + k*nhist, +nhist) and its own fp32 dose
+ * grid), then accumulateResults(1, nhist, nbatch) + the relDoseThreshold test + the sparse column assembly
+ * (omc_matrad.c:1416-1477) run on the device.  nbatch only enters as the reference's normalisation: the
+ * batch-method uncertainty is never exported by omc_matrad (Q12), so no batch structure is kept.  jc[nb+1] receives
+ * the column starts (jc[0] = 0), *nnz_total their sum; rows (irl-1, ascending) and values of all columns stay on the
+ * device until omc_gpu_fetch_columns(ir[nnz_total], val[nnz_total]).  Needs nb * nreg * 4 bytes of device memory. */
+int omc_gpu_run_beamlets(omc_gpu_handle h, long long first_history, int nhist, int nbatch, int ib0, int nb, double rel_threshold,
+                         const double *med_densities, long long *jc, long long *nnz_total);
+int omc_gpu_fetch_columns(omc_gpu_handle h, long long *ir, double *val);
 /* score.endep of the running batch, [nreg] fp64 (before accum_batch) */
 int omc_gpu_get_batch_grid(omc_gpu_handle h, double *endep);
 /* memset of the three grids (initScore(), omc_dosxyz.c:647-665; omc_matrad.c:1482 zeroes accum only: which = 1) */

@@ -89,7 +89,7 @@ EXPORTS = ["omc_gpu_create", "omc_gpu_destroy", "omc_gpu_last_error", "omc_gpu_s
            "omc_gpu_set_source_dosxyz", "omc_gpu_set_source_matrad", "omc_gpu_set_vrt", "omc_gpu_set_seed", "omc_gpu_set_option",
            "omc_gpu_run_histories", "omc_gpu_accum_batch", "omc_gpu_run_batch", "omc_gpu_start_batch", "omc_gpu_finish_batches",
            "omc_gpu_completed_batches", "omc_gpu_synchronize", "omc_gpu_get_tallies",
-           "omc_gpu_get_batch_grid", "omc_gpu_accumulate_results", "omc_gpu_reset_tallies", "omc_gpu_device_ptrs", "omc_gpu_stream", "omc_gpu_get_counters",
+           "omc_gpu_get_batch_grid", "omc_gpu_accumulate_results", "omc_gpu_run_beamlets", "omc_gpu_fetch_columns", "omc_gpu_reset_tallies", "omc_gpu_device_ptrs", "omc_gpu_stream", "omc_gpu_get_counters",
            "omc_gpu_get_history_records", "omc_gpu_test_geometry", "omc_gpu_test_rng", "omc_gpu_test_particles",
            "omc_gpu_abi_sizeof"]
 
@@ -119,6 +119,9 @@ def load_library() -> C.CDLL:
     lib.omc_gpu_get_tallies.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.omc_gpu_get_batch_grid.argtypes = [H, C.c_void_p]
     lib.omc_gpu_accumulate_results.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.omc_gpu_run_beamlets.argtypes = [H, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
+                                         C.POINTER(C.c_longlong)]
+    lib.omc_gpu_fetch_columns.argtypes = [H, C.c_void_p, C.c_void_p]
     lib.omc_gpu_reset_tallies.argtypes = [H, C.c_int]
     lib.omc_gpu_device_ptrs.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
     lib.omc_gpu_stream.argtypes = [H]; lib.omc_gpu_stream.restype = C.c_void_p
@@ -246,6 +249,18 @@ class GpuTransport:
 
     def run_batch(self, first: int, n: int, ibeamlet: int = -1):
         self._ck(self.lib.omc_gpu_run_batch(self.h, first, n, ibeamlet), "omc_gpu_run_batch")
+
+    def run_beamlets(self, first: int, nhist: int, nbatch: int, ib0: int, nb: int, rel_threshold: float, med_densities: np.ndarray):
+        """Beamlets [ib0, ib0+nb) in one pass + device-side column assembly: (jc[nb+1], ir[nnz], val[nnz])."""
+        dens = np.ascontiguousarray(med_densities, dtype=np.float64)
+        assert dens.size == self.nreg - 1
+        jc = np.zeros(nb + 1, dtype=np.int64)
+        tot = C.c_longlong(0)
+        self._ck(self.lib.omc_gpu_run_beamlets(self.h, int(first), int(nhist), int(nbatch), int(ib0), int(nb), float(rel_threshold),
+                                               dens.ctypes.data, jc.ctypes.data, C.byref(tot)), "omc_gpu_run_beamlets")
+        ir = np.zeros(max(tot.value, 1), dtype=np.int64); val = np.zeros(max(tot.value, 1))
+        self._ck(self.lib.omc_gpu_fetch_columns(self.h, ir.ctypes.data, val.ctypes.data), "omc_gpu_fetch_columns")
+        return jc, ir[:tot.value], val[:tot.value]
 
     def start_batch(self, first: int, n: int, ibeamlet: int = -1):
         """Pipelined batch, accumulation left to the caller (see include/ompmc_b200.h)."""

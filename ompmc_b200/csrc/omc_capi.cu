@@ -76,6 +76,19 @@ struct omc_gpu_ctx {
     std::vector<int> done_q;
     bool auto_acc[2] = {false, false};
     bool pipeline_next = false, pipeline_auto = false;   // how the next omc_gpu_run_histories() body is to run (set by the callers below)
+    // multi-beamlet pass (omc_gpu_run_beamlets)
+    float *mb_grid = nullptr;
+    size_t mb_grid_elems = 0;
+    bool mb_active = false;
+    unsigned long long mb_first = 0;
+    unsigned mb_per = 0, mb_n = 0;
+    int mb_ib0 = 0;
+    double *mb_dmax = nullptr;
+    unsigned long long *mb_nnz = nullptr;
+    long long *mb_jc = nullptr, *mb_ir = nullptr;
+    double *mb_val = nullptr;
+    int mb_meta_cap = 0;
+    long long mb_col_cap = 0, mb_total = 0;
 };
 
 #define CK(call)                                                                                         \
@@ -225,10 +238,11 @@ static int wave_run(omc_gpu_handle h, bool start, long long first, long long nhi
             c.target = target;
             c.hist_next = (unsigned long long)first; c.hist_end = (unsigned long long)(first + nhist);
             c.hist_split = (unsigned long long)first; c.grid_new = (unsigned)g_new; c.old_done = 1;
-            c.n_src = (unsigned)((unsigned long long)nhist < (unsigned long long)target ? nhist : target);
+            const unsigned first_room = target / (unsigned)(P.nsplit > 1 ? P.nsplit : 1);   // (splitting multiplies the population)
+            c.n_src = (unsigned)((unsigned long long)nhist < (unsigned long long)first_room ? nhist : first_room);
             CK(cudaMemcpyAsync(h->ctl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
         } else {                                                // previous batch still in flight: it becomes "old"
-            launch_rearm(h->ctl, (unsigned long long)first, (unsigned long long)nhist, h->stream);
+            launch_rearm(h->ctl, (unsigned long long)first, (unsigned long long)nhist, (unsigned)P.nsplit, h->stream);
             old_pending = true;
         }
         h->last_ibeamlet = ibeamlet;
@@ -247,6 +261,8 @@ static int wave_run(omc_gpu_handle h, bool start, long long first, long long nhi
     L.max_cross = h->max_cross; L.electron_iters = h->electron_iters; L.ibeamlet = ibeamlet;
     L.woodcock = (h->photon_tracking == 1 && P.nsplit == 1) ? 1 : 0;
     L.max_virtual = h->max_virtual > 0 ? ((h->max_virtual + 1) & ~1) : 8;   // even: whole Philox blocks, so results do not depend on it
+    L.mb_grid = h->mb_active ? h->mb_grid : nullptr;
+    L.mb_first = h->mb_first; L.mb_per = h->mb_per; L.mb_n = h->mb_n; L.mb_ib0 = h->mb_ib0;
     WaveStreams W;
     W.s = h->stream; W.s2 = h->overlap ? h->stream2 : nullptr; W.s3 = h->stream3;
     W.fork = h->ev_fork; W.join = h->ev_join; W.fork3 = h->ev_fork3; W.join3 = h->ev_join3;
@@ -293,7 +309,8 @@ static int wave_run(omc_gpu_handle h, bool start, long long first, long long nhi
             if (exhausted && !old_pending) break;
         } else if (exhausted && s.live == 0) {
             break;
-        } else if (exhausted && s.live <= h->drain_threshold && P.nsplit == 1) {   // (split photons in flight cannot be handed over)
+        } else if (exhausted && s.live <= h->drain_threshold && P.nsplit == 1 && !h->mb_active) {
+            // (split photons in flight cannot be handed over; the drain scores into ONE fp64 grid, not per beamlet)
             drained = true;
             break;
         }
@@ -435,6 +452,7 @@ void omc_gpu_destroy(omc_gpu_handle h) {
     cudaFree(h->P.endep); cudaFree(h->P.endep32); cudaFree(h->accum); cudaFree(h->accum2);
     cudaFree(h->P.counters); cudaFree(h->P.ensrc); cudaFree(h->stack); cudaFree(h->records);
     cudaFree(h->res_dens); cudaFree(h->res_dose); cudaFree(h->res_unc);
+    cudaFree(h->mb_grid); cudaFree(h->mb_dmax); cudaFree(h->mb_nnz); cudaFree(h->mb_jc); cudaFree(h->mb_ir); cudaFree(h->mb_val);
     if (h->stream2) {
         cudaStreamDestroy(h->stream2); cudaStreamDestroy(h->stream3);
         cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_fork3); cudaEventDestroy(h->ev_join3);
@@ -869,6 +887,104 @@ int omc_gpu_accumulate_results(omc_gpu_handle h, int iout, int nhist, int nbatch
     CK(cudaMemcpyAsync(dose, h->res_dose, nreg * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(unc, h->res_unc, nreg * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int omc_gpu_run_beamlets(omc_gpu_handle h, long long first, int nhist, int nbatch, int ib0, int nb, double rel_threshold,
+                         const double *med_densities, long long *jc, long long *nnz_total) {
+    if (!h || !jc || !nnz_total || !med_densities) return 2;
+    if (!h->have_media || !h->have_geom || !h->have_source) return fail(h, "media, geometry and source must be set first");
+    if (h->source_kind != 1) return fail(h, "omc_gpu_run_beamlets needs the matRad beamlet source (omc_gpu_set_source_matrad)");
+    if (nb < 1 || ib0 < 0 || ib0 + nb > h->P.msrc.nbixels) return fail(h, "beamlet range out of bounds");
+    if (nhist < 1 || nbatch < 1) return fail(h, "history / batch counts must be positive");
+    if (h->kernel != OMC_KERNEL_WAVEFRONT) return fail(h, "omc_gpu_run_beamlets runs on the wavefront kernels (option kernel = 1)");
+    if (h->P.nsplit > 255) return fail(h, "wavefront kernels support nsplit <= 255");
+    CK(cudaSetDevice(h->device));
+    int rc = flush_all(h);
+    if (rc) return rc;
+    DevProblem &P = h->P;
+    const size_t nreg = (size_t)P.nreg, nvox = nreg - 1;
+    const size_t need = (size_t)nb * nreg;
+    if (need > h->mb_grid_elems) {
+        cudaFree(h->mb_grid);
+        h->mb_grid = nullptr; h->mb_grid_elems = 0;
+        CK(cudaMalloc((void **)&h->mb_grid, need * sizeof(float)));
+        h->mb_grid_elems = need;
+    }
+    if (nb > h->mb_meta_cap) {
+        cudaFree(h->mb_dmax); cudaFree(h->mb_nnz); cudaFree(h->mb_jc);
+        h->mb_dmax = nullptr; h->mb_nnz = nullptr; h->mb_jc = nullptr; h->mb_meta_cap = 0;
+        CK(cudaMalloc((void **)&h->mb_dmax, (size_t)nb * sizeof(double)));
+        CK(cudaMalloc((void **)&h->mb_nnz, (size_t)nb * sizeof(unsigned long long)));
+        CK(cudaMalloc((void **)&h->mb_jc, ((size_t)nb + 1) * sizeof(long long)));
+        h->mb_meta_cap = nb;
+    }
+    if (h->res_nreg != P.nreg) {                               // (density scratch shared with omc_gpu_accumulate_results)
+        cudaFree(h->res_dens); cudaFree(h->res_dose); cudaFree(h->res_unc);
+        h->res_dens = h->res_dose = h->res_unc = nullptr; h->res_nreg = -1;
+        CK(cudaMalloc((void **)&h->res_dens, (nvox ? nvox : 1) * sizeof(double)));
+        CK(cudaMalloc((void **)&h->res_dose, nreg * sizeof(double)));
+        CK(cudaMalloc((void **)&h->res_unc, nreg * sizeof(double)));
+        h->res_nreg = P.nreg;
+    }
+    CK(cudaMemcpyAsync(h->res_dens, med_densities, nvox * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->mb_grid, 0, need * sizeof(float), h->stream));
+    if (h->med_dirty) {
+        for (size_t m = 0; m < h->med_host.size(); m++) {
+            h->med_host[m].ecut = h->cut_e[m]; h->med_host[m].pcut = h->cut_p[m]; h->med_host[m].rhomax = h->rho_max[m];
+        }
+        CK(cudaMemcpyAsync((void *)P.med, h->med_host.data(), h->med_host.size() * sizeof(MedRec), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->med_dirty = false;
+    }
+    P.records = nullptr;
+    // all beamlets of the group in one pass of the wavefront kernels
+    h->mb_active = true;
+    h->mb_first = (unsigned long long)first; h->mb_per = (unsigned)nhist; h->mb_n = (unsigned)nb; h->mb_ib0 = ib0;
+    h->auto_acc[0] = false;
+    rc = wave_run(h, true, first, (long long)nhist * nb, ib0, 0);
+    if (!rc) rc = wave_run(h, false, 0, 0, -1, -1);
+    h->mb_active = false;
+    h->done_q.clear();                                          // (the two batch grids were not used)
+    if (rc) return rc;
+    // accumulateResults + threshold + column assembly, omc_matrad.c:1416-1477
+    launch_mb_scan(h->mb_grid, (long long)nreg, nb, P, h->res_dens, nhist, nbatch, rel_threshold, h->mb_dmax, h->mb_nnz, 0, h->stream);
+    launch_mb_scan(h->mb_grid, (long long)nreg, nb, P, h->res_dens, nhist, nbatch, rel_threshold, h->mb_dmax, h->mb_nnz, 1, h->stream);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    std::vector<unsigned long long> nnz((size_t)nb);
+    CK(cudaMemcpyAsync(nnz.data(), h->mb_nnz, (size_t)nb * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    jc[0] = 0;
+    for (int b = 0; b < nb; b++) jc[b + 1] = jc[b] + (long long)nnz[b];
+    const long long total = jc[nb];
+    if (total > h->mb_col_cap) {
+        cudaFree(h->mb_ir); cudaFree(h->mb_val);
+        h->mb_ir = nullptr; h->mb_val = nullptr; h->mb_col_cap = 0;
+        CK(cudaMalloc((void **)&h->mb_ir, (size_t)(total ? total : 1) * sizeof(long long)));
+        CK(cudaMalloc((void **)&h->mb_val, (size_t)(total ? total : 1) * sizeof(double)));
+        h->mb_col_cap = total;
+    }
+    CK(cudaMemcpyAsync(h->mb_jc, jc, ((size_t)nb + 1) * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    if (total > 0) {
+        launch_mb_fill(h->mb_grid, (long long)nreg, nb, P, h->res_dens, nhist, nbatch, rel_threshold, h->mb_dmax, h->mb_jc, h->mb_ir,
+                       h->mb_val, h->stream);
+        h->launches += 1;
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->mb_total = total;
+    *nnz_total = total;
+    return 0;
+}
+
+int omc_gpu_fetch_columns(omc_gpu_handle h, long long *ir, double *val) {
+    if (!h || !ir || !val) return 2;
+    CK(cudaSetDevice(h->device));
+    if (h->mb_total > 0) {
+        CK(cudaMemcpy(ir, h->mb_ir, (size_t)h->mb_total * sizeof(long long), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(val, h->mb_val, (size_t)h->mb_total * sizeof(double), cudaMemcpyDeviceToHost));
+    }
     return 0;
 }
 

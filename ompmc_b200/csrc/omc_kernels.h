@@ -76,6 +76,10 @@ struct WaveQueues {
 
 struct WaveLaunch {
     int blocks[4], max_cross, electron_iters, ibeamlet, woodcock, max_virtual;
+    float *mb_grid;                 // multi-beamlet pass (see WaveArgs), nullptr: off
+    unsigned long long mb_first;
+    unsigned mb_per, mb_n;
+    int mb_ib0;
 };
 
 void wave_blocks_per_sm(int out[4]);
@@ -96,7 +100,12 @@ struct WaveStreams {
 };
 void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, const WaveStreams &W);
 void launch_flush(float *g32, double *g64, long long n, cudaStream_t s);
+// multi-beamlet pass: per-beamlet maximum (pass 0) / count above threshold (pass 1), then ordered compaction into CSC
+void launch_mb_scan(const float *grids, long long nreg, int nb, const DevProblem &P, const double *dens, int nhist, int nbatch, double rel,
+                    double *dmax, unsigned long long *nnz, int pass, cudaStream_t s);
+void launch_mb_fill(const float *grids, long long nreg, int nb, const DevProblem &P, const double *dens, int nhist, int nbatch, double rel,
+                    const double *dmax, const long long *jc, long long *ir, double *val, cudaStream_t s);
 // start the next batch while the tail of the previous one is still in the queues (see WaveCtl::hist_split)
-void launch_rearm(WaveCtl *ctl, unsigned long long first, unsigned long long nhist, cudaStream_t s);
+void launch_rearm(WaveCtl *ctl, unsigned long long first, unsigned long long nhist, unsigned nsplit, cudaStream_t s);
 
 }  // namespace omc

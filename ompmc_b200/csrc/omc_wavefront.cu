@@ -145,20 +145,50 @@ struct Tally {
     unsigned ndep, nestep, npstep;
 };
 
+struct WaveArgs {
+    WaveCtl *ctl;
+    WaveQueues Q;
+    int max_cross, electron_iters, ibeamlet, woodcock, max_virtual;
+    // multi-beamlet pass (omc_gpu_run_beamlets): history id -> beamlet -> its own fp32 dose grid
+    float *mb_grid;                 // [mb_n][nreg], nullptr: off
+    unsigned long long mb_first;    // beamlet (mb_ib0 + k) owns history ids [mb_first + k * mb_per, + mb_per)
+    unsigned mb_per, mb_n;
+    int mb_ib0;
+};
+
 // Which of the two dose grids a particle scores into (batch pipelining, WaveCtl::hist_split), wave-uniform part
 struct BatchSel {
     unsigned long long split;
     float *g_new, *g_old;
     unsigned has_old;
-    __device__ __forceinline__ void init(const DevProblem &P, const WaveCtl *c) {
+    // multi-beamlet pass: one grid per beamlet, beamlet = (history id - mb_first) / mb_per
+    float *mb_grid;
+    unsigned long long mb_first;
+    unsigned mb_per;
+    double mb_inv;
+    size_t nreg;
+    __device__ __forceinline__ void init(const DevProblem &P, const WaveCtl *c, const WaveArgs &A) {
         split = c->hist_split; has_old = c->has_old;
         g_new = P.endep32 + (size_t)c->grid_new * P.nreg;
         g_old = P.endep32 + (size_t)(c->grid_new ^ 1u) * P.nreg;
+        mb_grid = A.mb_grid; mb_first = A.mb_first; mb_per = A.mb_per; nreg = (size_t)P.nreg;
+        mb_inv = A.mb_per ? 1.0 / (double)A.mb_per : 0.0;
     }
     __device__ __forceinline__ bool is_old(uint32_t h0, uint32_t h1) const {
         return has_old && ((((unsigned long long)h1) << 32) | h0) < split;
     }
-    __device__ __forceinline__ float *grid(bool old) const { return old ? g_old : g_new; }
+    // index of the beamlet that owns a history id (multi-beamlet pass)
+    __device__ __forceinline__ unsigned beamlet_of(uint32_t h0, uint32_t h1) const {
+        const unsigned long long x = ((((unsigned long long)h1) << 32) | h0) - mb_first;
+        unsigned q = (unsigned)(__ull2double_rz(x) * mb_inv);
+        if ((unsigned long long)(q + 1u) * mb_per <= x) q += 1u;
+        else if ((unsigned long long)q * mb_per > x) q -= 1u;
+        return q;
+    }
+    __device__ __forceinline__ float *grid(bool old, uint32_t h0, uint32_t h1) const {
+        if (mb_grid != nullptr) return mb_grid + (size_t)beamlet_of(h0, h1) * nreg;
+        return old ? g_old : g_new;
+    }
     // consumers count the previous batch's particles they meet; zero in a whole wave = that batch is complete
     __device__ __forceinline__ void count(WaveCtl *c, unsigned mask, bool old) const {
         if (!has_old) return;
@@ -190,11 +220,6 @@ __device__ __forceinline__ void deposit32(float *grid32, Tally &t, int ir, doubl
 enum { TAG_NONE = 0, TAG_COMPTON = 1, TAG_PAIR = 2, TAG_PHOTO = 3, TAG_RAYLEIGH = 4, TAG_BREMS = 5, TAG_MOLLER = 6, TAG_BHABHA = 7,
        TAG_ANNIH = 8, TAG_RANNIH = 9 };
 
-struct WaveArgs {
-    WaveCtl *ctl;
-    WaveQueues Q;
-    int max_cross, electron_iters, ibeamlet, woodcock, max_virtual;
-};
 
 // ---------------------------------------------------------------------------------------------
 // chunk P: photon free flight, photon() src/ompmc.c:1884-2067 for nsplit == 1
@@ -206,7 +231,7 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, const Batch
     q_load(A.Q.p[par], i, p, g, P, dpmfp, tag);
     const bool old = BS.is_old(g.h0, g.h1);
     BS.count(ctl, __activemask(), old);
-    float *dg = BS.grid(old);
+    float *dg = BS.grid(old, g.h0, g.h1);
     RegionRec R = load_region_w(P, p.ir);
     // uniform photon splitting, :1903-1945: the record is the ray of nsplit copies of weight wt/nsplit whose
     // interaction depths are stratified (eta'_k = eta'_0 - k/nsplit); copy `isplit` is the one in flight.
@@ -314,7 +339,7 @@ __device__ void photon_chunk_wc(const DevProblem &P, const WaveArgs &A, const Ba
     }
     const bool old = BS.is_old(g.h0, g.h1);
     BS.count(ctl, __activemask(), old);
-    float *dg = BS.grid(old);
+    float *dg = BS.grid(old, g.h0, g.h1);
     if (p.ir == 0) return;                                     // outside the phantom: howfar() discards (idisc)
     {   // cut-off test of photon() :1884 (a flight that spans several waves repeats it, harmlessly)
         double rhof; int med;
@@ -465,13 +490,15 @@ __device__ void e_interact_chunk(const DevProblem &P, const WaveArgs &A, const B
 }
 
 // chunk S: initHistory() for history ids hist_next + [i0, i0 + NT)
-__device__ void source_chunk(const DevProblem &P, const WaveArgs &A, int par, unsigned i, unsigned n, double &ensrc) {
+__device__ void source_chunk(const DevProblem &P, const WaveArgs &A, const BatchSel &BS, int par, unsigned i, unsigned n, double &ensrc) {
     if (i >= n) return;
     WaveCtl *ctl = A.ctl;
     Rng g;
-    g.seed(P.seed0, P.seed1, ctl->hist_next + i, 0u);
+    const unsigned long long hist = ctl->hist_next + i;
+    g.seed(P.seed0, P.seed1, hist, 0u);
     Part p;
-    ensrc += init_history(P, g, p, A.ibeamlet);
+    const int ibeamlet = (A.mb_grid != nullptr) ? A.mb_ib0 + (int)BS.beamlet_of((uint32_t)hist, (uint32_t)(hist >> 32)) : A.ibeamlet;
+    ensrc += init_history(P, g, p, ibeamlet);
     if (p.iq == 0) q_push(A.Q.p[par ^ 1], &ctl->n_p[par ^ 1].v, ctl, p, g, -1.0, TAG_NONE);
     else q_push_e(A.Q.e[par ^ 1], &ctl->n_e[par ^ 1].v, ctl, p, g, TAG_NONE, 0.0f, -2);
 }
@@ -874,7 +901,7 @@ __global__ void __launch_bounds__(NT, OMC_MB_ESIZE) esize_kernel(const __grid_co
     const unsigned lt = (1u << lane) - 1u;
     Tally t = {0, 0, 0};
     BatchSel BS;
-    BS.init(P, ctl);
+    BS.init(P, ctl, A);
     // warp-uniform loop: all 32 lanes stay converged through the slot reservation and the store
     for (unsigned base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
         const unsigned i = base + lane;
@@ -889,7 +916,7 @@ __global__ void __launch_bounds__(NT, OMC_MB_ESIZE) esize_kernel(const __grid_co
             const uint4 r = q.rng[i];
             g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
             old = BS.is_old(r.x, r.y);
-            cls = estep_size(P, BS.grid(old), g, p, e, t, st, rm);
+            cls = estep_size(P, BS.grid(old, r.x, r.y), g, p, e, t, st, rm);
         }
         BS.count(ctl, 0xffffffffu, old);
         // one reservation per (warp, class): lane 0 asks for the CH slots, lane 1 for the BCA slots, together
@@ -919,7 +946,7 @@ __global__ void __launch_bounds__(NT, (CLS == 1 ? OMC_MB_ECH : OMC_MB_EBCA)) edo
     const unsigned lane = threadIdx.x & 31u, stride = gridDim.x * blockDim.x, lt = (1u << lane) - 1u;
     Tally t = {0, 0, 0};
     BatchSel BS;
-    BS.init(P, ctl);
+    BS.init(P, ctl, A);
     // warp-uniform loop; one converged reservation per warp for both output queues (lane 0: E, lane 1: IE)
     for (unsigned base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
         const unsigned i = base + lane;
@@ -928,7 +955,7 @@ __global__ void __launch_bounds__(NT, (CLS == 1 ? OMC_MB_ECH : OMC_MB_EBCA)) edo
         if (i < n) {
             es_get<OMC_WAVE_F32 && OMC_CH_BLOCK_RNG>(S, (CLS == CLS_CH) ? i : 2u * S.cap - 1u - i, p, g, e, P);
             if (i + stride < n) es_prefetch(S, (CLS == CLS_CH) ? i + stride : 2u * S.cap - 1u - (i + stride));
-            st = estep_do(P, BS.grid(BS.is_old(g.h0, g.h1)), g, p, e, CLS, t, rho_new, med_new);
+            st = estep_do(P, BS.grid(BS.is_old(g.h0, g.h1), g.h0, g.h1), g, p, e, CLS, t, rho_new, med_new);
         }
         const unsigned m_e = __ballot_sync(0xffffffffu, st == 0), m_i = __ballot_sync(0xffffffffu, st > 0);
         unsigned b = 0;
@@ -965,7 +992,7 @@ __global__ void __launch_bounds__(NT, OMC_MB_MISC) misc_kernel(const __grid_cons
     Tally t = {0, 0, 0};
     double ensrc = 0.0;
     BatchSel BS;
-    BS.init(P, ctl);
+    BS.init(P, ctl, A);
     // All warps of the machine work through the classes in the same order (heaviest first), so that at any time
     // nearly every warp of an SM runs the same code: with each warp picking classes round-robin the kernel's top
     // stall was instruction fetch (ncu: stall_no_instruction 5.6 warps per issue).
@@ -982,7 +1009,7 @@ __global__ void __launch_bounds__(NT, OMC_MB_MISC) misc_kernel(const __grid_cons
             if (c == 3) {
                 if (A.woodcock) photon_chunk_wc(P, A, BS, par, i, cnt3, t);
                 else photon_chunk(P, A, BS, par, i, cnt3, t);
-            } else if (c == 2) source_chunk(P, A, par, i, cnt2, ensrc);
+            } else if (c == 2) source_chunk(P, A, BS, par, i, cnt2, ensrc);
             else if (c == 1) p_interact_chunk(P, A, BS, par, i, cnt1);
             else e_interact_chunk(P, A, BS, par, i, cnt0);
             __syncwarp();
@@ -1000,7 +1027,8 @@ __global__ void advance_kernel(const __grid_constant__ DevProblem P, WaveCtl *c)
     c->n_p[par].v = 0; c->n_e[par].v = 0; c->n_ip[par].v = 0; c->n_ie[par].v = 0; c->n_ch.v = 0; c->n_bca.v = 0;
     const unsigned live = c->n_p[nxt].v + c->n_e[nxt].v + c->n_ip[nxt].v + c->n_ie[nxt].v;
     const unsigned long long left = c->hist_end - c->hist_next;
-    const unsigned room = (live < c->target) ? c->target - live : 0u;
+    // photon splitting multiplies the particles a history puts into the queues (nsplit charged secondaries per flight)
+    const unsigned room = ((live < c->target) ? c->target - live : 0u) / (unsigned)(P.nsplit > 1 ? P.nsplit : 1);
     c->n_src = (unsigned)(left < (unsigned long long)room ? left : (unsigned long long)room);
     c->live = live;
     if (c->has_old) {                                          // nothing of the previous batch was met in this wave: it is complete
@@ -1039,6 +1067,7 @@ void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const W
     WaveArgs A;
     A.ctl = ctl; A.Q = Q; A.max_cross = L.max_cross; A.electron_iters = L.electron_iters; A.ibeamlet = L.ibeamlet;
     A.woodcock = L.woodcock; A.max_virtual = L.max_virtual;
+    A.mb_grid = L.mb_grid; A.mb_first = L.mb_first; A.mb_per = L.mb_per; A.mb_n = L.mb_n; A.mb_ib0 = L.mb_ib0;
     const bool par = (W.s2 != nullptr);
     cudaStream_t s = W.s, sm = par ? W.s2 : s, sb = par ? W.s3 : s;
     if (par) { cudaEventRecord(W.fork, s); cudaStreamWaitEvent(W.s2, W.fork, 0); }
@@ -1055,18 +1084,108 @@ void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const W
 
 // Next batch into the running pipeline: new history range, the dose grids swap roles, whatever is still alive
 // belongs to the previous batch (ids below `first`).
-__global__ void rearm_kernel(WaveCtl *c, unsigned long long first, unsigned long long nhist) {
+__global__ void rearm_kernel(WaveCtl *c, unsigned long long first, unsigned long long nhist, unsigned nsplit) {
     if (blockIdx.x || threadIdx.x) return;
     c->hist_next = first; c->hist_end = first + nhist; c->hist_split = first;
     c->grid_new ^= 1u;
     c->has_old = (c->live > 0) ? 1u : 0u;
     c->old_done = c->has_old ? 0u : 1u;
     c->old_seen.v = 0;
-    const unsigned room = (c->live < c->target) ? c->target - c->live : 0u;
+    const unsigned room = ((c->live < c->target) ? c->target - c->live : 0u) / (nsplit > 1u ? nsplit : 1u);
     c->n_src = (unsigned)(nhist < (unsigned long long)room ? nhist : (unsigned long long)room);
 }
-void launch_rearm(WaveCtl *ctl, unsigned long long first, unsigned long long nhist, cudaStream_t s) {
-    rearm_kernel<<<1, 32, 0, s>>>(ctl, first, nhist);
+void launch_rearm(WaveCtl *ctl, unsigned long long first, unsigned long long nhist, unsigned nsplit, cudaStream_t s) {
+    rearm_kernel<<<1, 32, 0, s>>>(ctl, first, nhist, nsplit);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-beamlet pass: accumulateResults(1, nhist, nbatch) + threshold + sparse column assembly of
+// omc_matrad.c:1416-1477 on the device, one block per beamlet.  dose() below = accumulateResults() for one voxel.
+// ---------------------------------------------------------------------------------------------
+struct MbGeom {
+    const double *xb, *yb, *zb, *dens;
+    int isize, jsize;
+    double inc_fluence, nbatch;
+};
+__device__ __forceinline__ double mb_dose(const float *grid, const MbGeom &G, long long v) {
+    double endep = (double)grid[v + 1];
+    endep /= G.nbatch;
+    if (endep == 0.0) return 0.0;
+    const double dens = G.dens[v];
+    if (dens < 0.044) return 0.0;
+    const int ix = (int)(v % G.isize), iy = (int)((v / G.isize) % G.jsize), iz = (int)(v / ((long long)G.isize * G.jsize));
+    double mass = (G.xb[ix + 1] - G.xb[ix]) * (G.yb[iy + 1] - G.yb[iy]) * (G.zb[iz + 1] - G.zb[iz]);
+    mass *= dens;
+    return endep * (1.602E-10 / (mass * G.inc_fluence));
+}
+// pass 1: dmax[b]; pass 2 (thresh != nullptr): nnz[b] = #{dose > rel * dmax[b]}
+__global__ void mb_scan_kernel(const float *__restrict__ grids, long long nreg, int nb, MbGeom G, double rel, double *dmax,
+                               unsigned long long *nnz, int pass) {
+    __shared__ double s_max[32];
+    __shared__ unsigned long long s_cnt[32];
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        const float *grid = grids + (size_t)b * nreg;
+        const double thresh = pass ? dmax[b] * rel : 0.0;
+        double m = 0.0;
+        unsigned long long cnt = 0;
+        for (long long v = threadIdx.x; v < nreg - 1; v += blockDim.x) {
+            const double d = mb_dose(grid, G, v);
+            if (pass) cnt += (d > thresh) ? 1ull : 0ull;
+            else m = fmax(m, d);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        if ((threadIdx.x & 31) == 0) { s_max[threadIdx.x >> 5] = m; s_cnt[threadIdx.x >> 5] = cnt; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (unsigned w = 1; w < blockDim.x / 32; w++) { m = fmax(m, s_max[w]); cnt += s_cnt[w]; }
+            if (pass) nnz[b] = cnt; else dmax[b] = m;
+        }
+        __syncthreads();
+    }
+}
+// pass 3: ordered compaction (rows ascending, as the reference's irl loop writes them)
+__global__ void mb_fill_kernel(const float *__restrict__ grids, long long nreg, int nb, MbGeom G, double rel, const double *dmax,
+                               const long long *jc, long long *ir, double *val) {
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned long long s_base;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarp = blockDim.x / 32;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        const float *grid = grids + (size_t)b * nreg;
+        const double thresh = dmax[b] * rel;
+        if (threadIdx.x == 0) s_base = (unsigned long long)jc[b];
+        __syncthreads();
+        for (long long v0 = 0; v0 < nreg - 1; v0 += blockDim.x) {
+            const long long v = v0 + threadIdx.x;
+            double d = 0.0;
+            bool keep = false;
+            if (v < nreg - 1) { d = mb_dose(grid, G, v); keep = d > thresh; }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) s_warp[warp] = (unsigned)__popc(m);
+            __syncthreads();
+            unsigned before = 0, total = 0;
+            for (unsigned w = 0; w < nwarp; w++) { const unsigned c = s_warp[w]; if (w < warp) before += c; total += c; }
+            if (keep) {
+                const unsigned long long at = s_base + before + (unsigned)__popc(m & ((1u << lane) - 1u));
+                ir[at] = v; val[at] = d;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_base += total;
+            __syncthreads();
+        }
+    }
+}
+void launch_mb_scan(const float *grids, long long nreg, int nb, const DevProblem &P, const double *dens, int nhist, int nbatch, double rel,
+                    double *dmax, unsigned long long *nnz, int pass, cudaStream_t s) {
+    MbGeom G{P.xb, P.yb, P.zb, dens, P.isize, P.jsize, (double)nhist, (double)nbatch};
+    mb_scan_kernel<<<nb < 148 * 4 ? nb : 148 * 4, 512, 0, s>>>(grids, nreg, nb, G, rel, dmax, nnz, pass);
+}
+void launch_mb_fill(const float *grids, long long nreg, int nb, const DevProblem &P, const double *dens, int nhist, int nbatch, double rel,
+                    const double *dmax, const long long *jc, long long *ir, double *val, cudaStream_t s) {
+    MbGeom G{P.xb, P.yb, P.zb, dens, P.isize, P.jsize, (double)nhist, (double)nbatch};
+    mb_fill_kernel<<<nb < 148 * 4 ? nb : 148 * 4, 512, 0, s>>>(grids, nreg, nb, G, rel, dmax, jc, ir, val);
 }
 
 void launch_flush(float *g32, double *g64, long long n, cudaStream_t s) {

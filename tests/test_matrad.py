@@ -170,3 +170,34 @@ def test_gpu_matrad_dij_wavefront_vs_lockstep(gpu):
         hot = d0 > 0.5 * d0.max()
         assert hot.sum() >= 3
         assert np.abs(d1[hot] / d0[hot] - 1.0).mean() < 0.05
+
+
+@pytest.mark.gpu
+def test_gpu_matrad_multi_beamlet_pass_vs_beamlet_loop(gpu):
+    """omc_gpu_run_beamlets: all beamlets in one pass of the wavefront kernels + accumulateResults / threshold / CSC on the
+    device, against the per-beamlet loop (same history ids per beamlet; the loop's drain makes the draws of the last few
+    particles differ, so the comparison is statistical on the dense columns and exact on the structure)."""
+    prob, ph, nb = matrad_problem(nbix=(2, 2), angles=(0.0, 120.0, 250.0))
+    gpu.load_problem(prob)
+    gpu.set_option("kernel", 1)
+    jc0, ir0, v0 = matrad.dose_influence_matrix(gpu, ph, nb, "100000", "4", 0.05)
+    jc1, ir1, v1 = matrad.dose_influence_matrix_device(gpu, ph, nb, "100000", "4", 0.05, group=5)      # 12 beamlets: groups of 5, 5, 2
+    assert len(jc0) == len(jc1) == nb + 1 and jc1[0] == 0 and jc1[-1] == len(ir1) == len(v1)
+    for b in range(nb):
+        r1 = ir1[jc1[b]:jc1[b + 1]]
+        assert (np.diff(r1) > 0).all() and r1.min() >= 0 and r1.max() < ph.nvox       # rows ascending, like the reference's loop
+        d0 = np.zeros(ph.nvox); d1 = np.zeros(ph.nvox)
+        d0[ir0[jc0[b]:jc0[b + 1]]] = v0[jc0[b]:jc0[b + 1]]
+        d1[r1] = v1[jc1[b]:jc1[b + 1]]
+        assert (v1[jc1[b]:jc1[b + 1]] > 0.05 * d1.max() * (1 - 1e-12)).all()           # threshold test of omc_matrad.c:1420-1432
+        assert abs(d0.sum() - d1.sum()) < 0.03 * d0.sum()
+        hot = d0 > 0.5 * d0.max()
+        assert hot.sum() >= 3 and np.abs(d1[hot] / d0[hot] - 1.0).mean() < 0.06
+        assert abs(len(r1) - (jc0[b + 1] - jc0[b])) <= 0.15 * (jc0[b + 1] - jc0[b]) + 3
+    # a single-beamlet group reproduces the same column as the same beamlet inside a larger group (history ids are per beamlet;
+    # no drain in either): equal to fp32 summation order
+    jcA, irA, vA = gpu.run_beamlets(3 * 100000, 100000, 4, 3, 1, 0.05, ph.med_densities)
+    dA = np.zeros(ph.nvox); dA[irA] = vA
+    dB = np.zeros(ph.nvox); dB[ir1[jc1[3]:jc1[4]]] = v1[jc1[3]:jc1[4]]
+    np.testing.assert_allclose(dA, dB, rtol=2e-3, atol=0.051 * dB.max())
+    assert abs(dA.sum() - dB.sum()) < 2e-3 * dB.sum()
