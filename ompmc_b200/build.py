@@ -68,17 +68,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 HOST_SRC = os.path.join(HERE, "host", "omc_dosxyz_b200.c")
 HOST_EXE = os.path.join(HERE, "host", "omc_dosxyz_b200")
+MATRAD_SRC = os.path.join(HERE, "host", "omc_matrad_b200.c")
+MATRAD_EXE = os.path.join(HERE, "host", "omc_matrad_b200")
+HOST_COMMON = os.path.join(HERE, "host", "omc_host_common.h")
 
 
 def build_host(force: bool = False) -> str:
-    """The plain-C host driver (batch loop + statistics + .3ddose writer) linked against the C-ABI library."""
+    """The plain-C host drivers (omc_dosxyz: batch loop + statistics + .3ddose writer; omc_matrad: beamlet loop + CSC file)
+    linked against the C-ABI library."""
     inc = os.path.join(os.path.dirname(HERE), "include")
-    if force or _stale(HOST_EXE, [HOST_SRC, LIB, os.path.join(inc, "ompmc_b200.h")]):
-        cmd = ["gcc", "-O2", "-Wall", "-o", HOST_EXE, HOST_SRC, "-I", inc, "-L", HERE, "-lompmc_b200", "-lm", "-Wl,-rpath,$ORIGIN/.."]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-            raise RuntimeError("gcc failed for host/omc_dosxyz_b200.c")
+    for src, exe in ((HOST_SRC, HOST_EXE), (MATRAD_SRC, MATRAD_EXE)):
+        if force or _stale(exe, [src, HOST_COMMON, LIB, os.path.join(inc, "ompmc_b200.h")]):
+            cmd = ["gcc", "-O2", "-Wall", "-o", exe, src, "-I", inc, "-L", HERE, "-lompmc_b200", "-lm", "-Wl,-rpath,$ORIGIN/.."]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError(f"gcc failed for {os.path.basename(src)}")
     return HOST_EXE
 
 

@@ -73,3 +73,54 @@ def test_device_accumulate_results(gpu, tmp_path):
         assert r.returncode == 0, r.stdout + r.stderr
         outs.append(open(stem + ".3ddose", "rb").read())
     assert outs[0] == outs[1]
+
+
+def _read_csc(path):
+    with open(path, "rb") as f:
+        assert f.read(8) == b"OMCCSC1\0"
+        nrows, ncols, nnz = np.fromfile(f, dtype="<i8", count=3)
+        jc = np.fromfile(f, dtype="<i8", count=ncols + 1)
+        ir = np.fromfile(f, dtype="<i8", count=nnz)
+        pr = np.fromfile(f, dtype="<f8", count=nnz)
+    return int(nrows), int(ncols), jc, ir, pr
+
+
+def test_c_matrad_driver_matches_python_device_path(gpu, tmp_path):
+    """ompmc_b200/host/omc_matrad_b200.c (plain-C replacement of omc_matrad.c's mexFunction: beamlet loop on
+    omc_gpu_run_beamlets + CSC file) against ompmc_b200.matrad.dose_influence_matrix_device: same ABI calls, same history
+    ids, so the columns agree to fp32 summation order; two "ranks" (-r/-w) together give the same matrix."""
+    from tests.test_matrad import matrad_problem
+    from ompmc_b200 import matrad
+    prob, ph, nb = matrad_problem(nbix=(2, 1), angles=(0.0, 100.0, 200.0))
+    blob = str(tmp_path / "m.blob")
+    P.save_blob(blob, prob)
+    build.build()
+    stem = str(tmp_path / "dij")
+    r = subprocess.run([build.MATRAD_EXE, "-p", blob, "-n", "60003", "-b", "3", "-t", "0.02", "-o", stem, "-g", "4"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Total number of particle histories: 60003" in r.stdout and "Histories per batch: 20001" in r.stdout
+    nrows, ncols, jc, ir, pr = _read_csc(stem + ".csc")
+    assert nrows == ph.nvox and ncols == nb and jc[0] == 0 and jc[-1] == len(ir) == len(pr)
+    gpu.load_problem(prob)
+    gpu.set_option("kernel", 1)
+    jc1, ir1, v1 = matrad.dose_influence_matrix_device(gpu, ph, nb, "60003", "3", 0.02, group=4)
+    for b in range(nb):
+        d0 = np.zeros(ph.nvox); d1 = np.zeros(ph.nvox)
+        d0[ir[jc[b]:jc[b + 1]]] = pr[jc[b]:jc[b + 1]]
+        d1[ir1[jc1[b]:jc1[b + 1]]] = v1[jc1[b]:jc1[b + 1]]
+        assert d0.max() > 0
+        np.testing.assert_allclose(d0, d1, rtol=2e-3, atol=0.021 * d1.max())     # (entries next to the threshold may flip)
+        assert abs(d0.sum() - d1.sum()) < 2e-3 * d1.sum()
+    parts = []
+    for rank in (0, 1):
+        st = str(tmp_path / f"dij{rank}")
+        r = subprocess.run([build.MATRAD_EXE, "-p", blob, "-n", "60003", "-b", "3", "-t", "0.02", "-o", st, "-r", str(rank), "-w", "2"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        parts.append(_read_csc(st + ".csc"))
+    for b in range(nb):
+        own, other = parts[b % 2], parts[1 - b % 2]
+        assert other[2][b + 1] == other[2][b]                                     # not this rank's beamlet: empty column
+        d = np.zeros(ph.nvox); d[own[3][own[2][b]:own[2][b + 1]]] = own[4][own[2][b]:own[2][b + 1]]
+        d0 = np.zeros(ph.nvox); d0[ir[jc[b]:jc[b + 1]]] = pr[jc[b]:jc[b + 1]]
+        np.testing.assert_allclose(d, d0, rtol=2e-3, atol=0.021 * d0.max())
