@@ -1,0 +1,127 @@
+"""Edge cases of the hot path through the C-ABI, both kernels: empty and one-history batches, a one-voxel phantom, a field
+that misses the phantom (every primary starts in region 0 = outside), a vacuum slab, history ids beyond 2^32, and energy
+conservation (what enters is deposited in the phantom, deposited in region 0 = "outside" by charged particles that leave
+-- score.endep has nvox + 1 entries for that reason -- or carried away by photons that leave)."""
+import numpy as np
+import pytest
+
+from ompmc_b200 import problem as P
+
+pytestmark = pytest.mark.gpu
+
+
+def water_problem(n=(5, 5, 5), voxel=(1.0, 1.0, 1.0), coll=(-1, 1, -1, 1), mono=2.0, charge=0, **kw):
+    media = P.load_blob(P.golden("media_700_water.blob"))
+    ph = P.water_phantom("H2O700ICRU", n, voxel)
+    prob = P.build_problem(media, ph, ecut=0.7, pcut=0.01, collimator=coll, ssd=100.0, charge=charge, cdfinv=None, mono_energy=mono, **kw)
+    return prob, ph
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_empty_and_single_history(gpu, kernel):
+    prob, ph = water_problem()
+    gpu.load_problem(prob)
+    gpu.set_option("kernel", kernel)
+    gpu.reset_tallies()
+    gpu.run_batch(0, 0)                                   # nothing to do: still one (empty) batch for the statistics
+    a, a2, e = gpu.get_tallies()
+    assert a.sum() == 0 and a2.sum() == 0 and e == 0 and gpu.counters()["histories"] == 0
+    gpu.run_batch(5, 1)
+    a, a2, e = gpu.get_tallies()
+    c = gpu.counters()
+    assert c["histories"] == 1 and c["errors"] == 0 and e == 2.0
+    assert 0.0 <= a.sum() <= 2.0 + 1e-9
+    gpu.set_option("kernel", 1)
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_one_voxel_phantom_and_energy_balance(gpu, kernel):
+    prob, ph = water_problem(n=(1, 1, 1), voxel=(30.0, 30.0, 30.0), coll=(-2, 2, -2, 2), mono=6.0)
+    gpu.load_problem(prob)
+    gpu.set_option("kernel", kernel)
+    gpu.reset_tallies()
+    n = 20000
+    gpu.run_histories(0, n)
+    grid = gpu.get_endep()
+    _, _, ensrc = gpu.get_tallies()
+    c = gpu.counters()
+    assert c["histories"] == n and c["errors"] == 0 and abs(ensrc - 6.0 * n) < 1e-6
+    assert grid.sum() <= ensrc * (1 + 1e-9)                # energy conservation: the rest left as photons
+    frac = grid[1] / ensrc
+    assert 0.3 < frac < 0.8, frac                          # 30 cm of water absorb a good part, not all, of a 6 MeV beam
+    assert grid[0] < 0.02 * ensrc                          # region 0 = outside: only charged particles that leave score there
+    gpu.set_option("kernel", 1)
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_field_that_misses_the_phantom(gpu, kernel):
+    prob, ph = water_problem(coll=(20, 22, 20, 22))        # collimator rectangle far outside the 5x5 cm2 surface
+    gpu.load_problem(prob)
+    gpu.set_option("kernel", kernel)
+    gpu.reset_tallies()
+    rec = gpu.run_histories(0, 3000, records=(kernel == 0))
+    if kernel == 0:
+        # the reference's initHistory() does not test for this: its voxel search ends on the last voxel of the row/column
+        # (omc_dosxyz.c:1040-1060) and the first howfar() sends the particle out through a negative step ("Warning!, negative
+        # ustep"); bug-compatible here
+        assert (rec["ir_start"] == ph.isize * ph.jsize).all(), np.unique(rec["ir_start"])
+    grid = gpu.get_endep()
+    assert grid[1:].sum() <= 1e-3 * 2.0 * 3000             # (practically) nothing reaches a voxel
+    assert gpu.counters()["histories"] == 3000
+    gpu.set_option("kernel", 1)
+
+
+def test_vacuum_slab_wavefront_vs_lockstep(gpu):
+    """Vacuum voxels (medium -1: density below nothing the media know) in the middle of the beam: photons and electrons cross
+    them without interacting in both kernels; Woodcock flight must never accept a collision there."""
+    media = P.load_blob(P.golden("media_700_water.blob"))
+    ph = P.water_phantom("H2O700ICRU", (7, 7, 12), (1.0, 1.0, 1.0))
+    prob = P.build_problem(media, ph, ecut=0.7, pcut=0.01, collimator=(-2, 2, -2, 2), ssd=100.0, charge=0, cdfinv=None, mono_energy=4.0)
+    med = prob["region_med"].copy()
+    nxy = ph.isize * ph.jsize
+    med[1 + 4 * nxy: 1 + 7 * nxy] = -1                     # slices iz = 4..6
+    prob["region_med"] = med
+    gpu.load_problem(prob)
+    res = {}
+    for kernel in (0, 1):
+        gpu.set_option("kernel", kernel)
+        gpu.reset_tallies()
+        nb, per = 8, 40000
+        for ib in range(nb):
+            gpu.run_batch(ib * per, per)
+        a, a2, _ = gpu.get_tallies()
+        m = a[1:] / nb
+        v = np.maximum(a2[1:] / nb - m * m, 0.0) / (nb - 1)
+        res[kernel] = (m.reshape(ph.ksize, -1), v.reshape(ph.ksize, -1))
+        assert gpu.counters()["errors"] == 0
+    (m0, v0), (m1, v1) = res[0], res[1]
+    assert m0[4:7].sum() == 0.0 and m1[4:7].sum() == 0.0   # no dose in vacuum
+    d0, d1 = m0.sum(axis=1), m1.sum(axis=1)
+    s = np.sqrt(v0.sum(axis=1) + v1.sum(axis=1))
+    ok = d0 > 0
+    z = (d1[ok] - d0[ok]) / s[ok]
+    assert np.abs(z).max() < 4.5 and abs(z.mean()) < 1.5, z
+    gpu.set_option("kernel", 1)
+
+
+def test_history_ids_beyond_32_bits(gpu):
+    """History ids are 64-bit (they key the RNG streams): a batch far beyond 2^32 behaves like any other and differs from
+    the batch of the same size at id 0; batch pipelining splits on the 64-bit id."""
+    prob, ph = water_problem(n=(7, 7, 10))
+    gpu.load_problem(prob)
+    gpu.set_option("kernel", 1)
+    gpu.set_option("drain_threshold", 0)                   # (the drain continues streams sequentially: particle-exact only without it)
+    big = (1 << 40) + 12345
+    grids = []
+    for first in (0, big, big):
+        gpu.reset_tallies()
+        gpu.run_histories(first, 20000)
+        grids.append(gpu.get_endep())
+        assert gpu.counters()["histories"] == 20000
+    np.testing.assert_allclose(grids[1], grids[2], rtol=2e-4, atol=1e-4 * grids[1].max())   # reproducible (fp32 summation order)
+    assert abs(grids[0].sum() - grids[1].sum()) < 0.05 * grids[0].sum() and not np.allclose(grids[0], grids[1], rtol=1e-3)
+    gpu.reset_tallies()
+    gpu.run_batch(big, 10000); gpu.run_batch(big + 10000, 10000)
+    a, a2, _ = gpu.get_tallies()
+    gpu.set_option("drain_threshold", 8192)
+    np.testing.assert_allclose(a, grids[1], rtol=3e-4, atol=2e-4 * grids[1].max())
