@@ -58,7 +58,7 @@ struct omc_gpu_ctx {
     std::vector<void *> wave_bufs;
     WaveCtl *ctl = nullptr;        // device
     WaveCtl *ctl_host = nullptr;   // pinned
-    unsigned pool_target = 1u << 22;
+    unsigned pool_target = 1u << 23;   // particles kept in flight (B200: 2 Mi 1.03e8, 4 Mi 1.07e8, 8 Mi 1.09e8 histories/s)
     unsigned pool_cap = 0, pool_cap_opt = 0;
     int electron_iters = 1, max_cross = 16, check_every = 16;
     int photon_tracking = 1;      // 0: voxel-to-voxel march as in photon(); 1: Woodcock flight when nsplit == 1
@@ -730,7 +730,8 @@ int omc_gpu_run_histories(omc_gpu_handle h, long long first, long long nhist, in
     } else {
         ibeamlet = -1;                  // omc_dosxyz source: the argument is ignored, as the reference has none
     }
-    if (nhist <= 0) return 0;
+    if (nhist < 0) return fail(h, "negative history count");
+    if (nhist == 0 && !h->pipeline_next) return 0;   // (a pipelined start registers even an empty batch: its grid is still owed)
     CK(cudaSetDevice(h->device));
     DevProblem &P = h->P;
     if (h->med_dirty) {                 // per-medium cut-offs (from the geometry) into the per-medium records
@@ -774,9 +775,11 @@ int omc_gpu_run_histories(omc_gpu_handle h, long long first, long long nhist, in
             CK(cudaMalloc((void **)&h->stack, need));
             h->stack_bytes = need;
         }
-        launch_lockstep(P, h->stack, depth, blocks, tpb, first, nhist, ibeamlet, h->inject, h->stream);
-        h->launches += 1;
-        CK(cudaGetLastError());
+        if (nhist > 0) {
+            launch_lockstep(P, h->stack, depth, blocks, tpb, first, nhist, ibeamlet, h->inject, h->stream);
+            h->launches += 1;
+            CK(cudaGetLastError());
+        }
     } else if (h->kernel == OMC_KERNEL_WAVEFRONT) {
         if (P.nsplit > 255) return fail(h, "wavefront kernels support nsplit <= 255; use the lock-step kernel beyond");
         if (h->record) return fail(h, "per-history records are a lock-step kernel feature");

@@ -72,7 +72,7 @@ def start_batch_sharded(tr, first: int, nperbatch: int, rank: int, world: int, a
     batch is still in flight; whatever batch completed meanwhile is reduced over ranks and accumulated.  Every rank
     completes batch k-1 inside its start of batch k, so the collective calls line up across ranks."""
     lo, n = shard_range(first, nperbatch, rank, world)
-    tr.start_batch(lo, max(n, 0)) if n > 0 else tr.finish_batches()
+    tr.start_batch(lo, n)            # (also when this rank's slice is empty: it still owes the batch its all-reduce)
     settle_completed(tr, world, allreduce)
 
 

@@ -23,7 +23,7 @@ def test_empty_and_single_history(gpu, kernel):
     gpu.load_problem(prob)
     gpu.set_option("kernel", kernel)
     gpu.reset_tallies()
-    gpu.run_batch(0, 0)                                   # nothing to do: still one (empty) batch for the statistics
+    gpu.run_batch(0, 0)                                   # nothing to do
     a, a2, e = gpu.get_tallies()
     assert a.sum() == 0 and a2.sum() == 0 and e == 0 and gpu.counters()["histories"] == 0
     gpu.run_batch(5, 1)

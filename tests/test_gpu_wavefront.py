@@ -144,14 +144,14 @@ def test_wavefront_scheduling_independence(gpu):
     gpu.set_option("kernel", 1)
     gpu.set_option("drain_threshold", 0)
     res = []
-    for pool, cross, every, graph in ((1 << 22, 16, 16, 1), (1 << 14, 7, 3, 0), (1 << 16, 1000, 5, 1)):
+    for pool, cross, every, graph in ((1 << 23, 16, 16, 1), (1 << 14, 7, 3, 0), (1 << 16, 1000, 5, 1)):
         gpu.set_option("pool_size", pool); gpu.set_option("max_cross", cross); gpu.set_option("check_every", every)
         gpu.set_option("max_virtual", {16: 8, 7: 3, 1000: 64}[cross])      # Woodcock flight: tentative collisions per wave
         gpu.set_option("use_graph", graph)
         gpu.reset_tallies()
         gpu.run_histories(0, 50000)
         res.append((gpu.get_endep()[1:], gpu.counters()))
-    gpu.set_option("pool_size", 1 << 22); gpu.set_option("max_cross", 16); gpu.set_option("check_every", 16); gpu.set_option("use_graph", 1)
+    gpu.set_option("pool_size", 1 << 23); gpu.set_option("max_cross", 16); gpu.set_option("check_every", 16); gpu.set_option("use_graph", 1)
     gpu.set_option("max_virtual", 8)
     g0, c0 = res[0]
     for g, c in res[1:]:
@@ -214,7 +214,7 @@ def test_batch_pipelining_matches_serial_batches(gpu):
         with pytest.raises(OmcGpuError):
             gpu.start_batch(2000, 1000)
     finally:
-        gpu.set_option("pool_size", 1 << 22); gpu.set_option("drain_threshold", 8192)
+        gpu.set_option("pool_size", 1 << 23); gpu.set_option("drain_threshold", 8192)
         gpu.reset_tallies()
     for a, b, e in ((a1, b1, e1), (a2, b2, e2)):
         assert abs(e - e0) <= 1e-9 * e0
