@@ -86,6 +86,11 @@ struct Rng {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int elec_interval(const MedRec &m, double elke) { return (int)(elke * m.eke1 + m.eke0) - 1; }
 __device__ __forceinline__ double pwl(double lvar, double c1, double c0) { return lvar * c1 + c0; }
+// one 16-byte load for a {c1, c0} coefficient pair (the records of omc_types.cuh keep every pair adjacent and 16-byte
+// aligned): a table gather costs L1 a wavefront per distinct sector and per INSTRUCTION, so halving the instructions
+// halves that (ncu: l1tex throughput of esize_kernel 73 %)
+__device__ __forceinline__ double2 ldg2(const double *pair) { return __ldg(reinterpret_cast<const double2 *>(pair)); }
+__device__ __forceinline__ double pwl2(double lvar, const double *pair) { const double2 c = ldg2(pair); return lvar * c.x + c.y; }
 
 // 32-byte sector loads through the read-only path
 __device__ __forceinline__ RegionRec load_region(const DevProblem &P, int ir) {

@@ -218,10 +218,11 @@ static __device__ __noinline__ double msdist_f(const DevProblem &P, Rng &g, cons
     int lelke = (int)(elke * (float)M.eke1 + (float)M.eke0) - 1;
     if (lelke < 0) { lelke = 0; elke = (float)((1.0 - M.eke0) / M.eke1); }
     const ElecBin *B = P.ebin + (size_t)qel * P.nmed * MXEKE + imed * MXEKE + lelke;
-    const float etap = elke * (float)__ldg(&B->eta1) + (float)__ldg(&B->eta0);
-    const float xi_corr = elke * (float)__ldg(&B->q1c1) + (float)__ldg(&B->q1c0);
-    float gamma = elke * (float)__ldg(&B->q2c1) + (float)__ldg(&B->q2c0);
-    const float ms_corr = elke * (float)__ldg(&B->blcce1) + (float)__ldg(&B->blcce0);
+    const double2 c_eta = ldg2(&B->eta1), c_q1 = ldg2(&B->q1c1), c_q2 = ldg2(&B->q2c1), c_bl = ldg2(&B->blcce1);
+    const float etap = elke * (float)c_eta.x + (float)c_eta.y;
+    const float xi_corr = elke * (float)c_q1.x + (float)c_q1.y;
+    float gamma = elke * (float)c_q2.x + (float)c_q2.y;
+    const float ms_corr = elke * (float)c_bl.x + (float)c_bl.y;
     chia2 *= etap;
     lambda = fdiv(lambda, etap * (1.0f + chia2));
     lambda *= ms_corr;
@@ -405,10 +406,11 @@ __device__ __forceinline__ double msdist_b(const DevProblem &P, Rng &g, const Pa
     int lelke = (int)(elke * (float)M.eke1 + (float)M.eke0) - 1;
     if (lelke < 0) { lelke = 0; elke = (float)((1.0 - M.eke0) / M.eke1); }
     const ElecBin *B = P.ebin + (size_t)qel * P.nmed * MXEKE + imed * MXEKE + lelke;
-    const float etap = elke * (float)__ldg(&B->eta1) + (float)__ldg(&B->eta0);
-    const float xi_corr = elke * (float)__ldg(&B->q1c1) + (float)__ldg(&B->q1c0);
-    float gamma = elke * (float)__ldg(&B->q2c1) + (float)__ldg(&B->q2c0);
-    const float ms_corr = elke * (float)__ldg(&B->blcce1) + (float)__ldg(&B->blcce0);
+    const double2 c_eta = ldg2(&B->eta1), c_q1 = ldg2(&B->q1c1), c_q2 = ldg2(&B->q2c1), c_bl = ldg2(&B->blcce1);
+    const float etap = elke * (float)c_eta.x + (float)c_eta.y;
+    const float xi_corr = elke * (float)c_q1.x + (float)c_q1.y;
+    float gamma = elke * (float)c_q2.x + (float)c_q2.y;
+    const float ms_corr = elke * (float)c_bl.x + (float)c_bl.y;
     chia2 *= etap;
     lambda = fdiv(lambda, etap * (1.0f + chia2));
     lambda *= ms_corr;
@@ -688,8 +690,9 @@ __device__ __forceinline__ double flog(double x) { return (double)__logf((float)
 static __device__ __forceinline__ double drange_m(const ElecBin *B, double ekei, double ekef, double elkei, double elkef) {
     const float fedep = fdiv((float)(ekei - ekef), (float)ekei);
     const float elktmp = 0.5f * ((float)elkei + (float)elkef + 0.25f * fedep * fedep * (1.0f + fedep * (1.0f + 0.875f * fedep)));
-    const float d1 = (float)__ldg(&B->dedx1);
-    const float dedxmid = frcp(elktmp * d1 + (float)__ldg(&B->dedx0));
+    const double2 cd = ldg2(&B->dedx1);
+    const float d1 = (float)cd.x;
+    const float dedxmid = frcp(elktmp * d1 + (float)cd.y);
     float aux = d1 * dedxmid;
     const float tf = 2.0f - fedep;
     aux = fdiv(aux * (1.0f + 2.0f * aux) * fedep * fedep, 6.0f * tf * tf);
@@ -702,8 +705,9 @@ static __device__ __noinline__ double eloss_m(const ElecBin *B0, const MedRec &M
     double de;
     double tuss = range - __ldg(&B0[lelke].range_ep) * rinv;
     if (tuss >= tustep) {
-        const float d1 = (float)__ldg(&B0[lelke].dedx1);
-        const float dedxmid = (float)elke * d1 + (float)__ldg(&B0[lelke].dedx0);
+        const double2 cd = ldg2(&B0[lelke].dedx1);
+        const float d1 = (float)cd.x;
+        const float dedxmid = (float)elke * d1 + (float)cd.y;
         const float aux = fdiv(d1, dedxmid);
         const float def = dedxmid * (float)(tustep * rhof);
         const float fedep = fdiv(def, (float)eke);
@@ -718,8 +722,9 @@ static __device__ __noinline__ double eloss_m(const ElecBin *B0, const MedRec &M
             const float elktmp = fdiv((float)(lt + 2) - (float)M.eke0, (float)M.eke1);
             const double eketmp = __ldg(&B0[lt + 1].e_array);
             tuss = (__ldg(&B0[lt + 1].range_ep) - tuss) * rinv;
-            const float d1 = (float)__ldg(&B0[lt].dedx1);
-            const float dedxmid = elktmp * d1 + (float)__ldg(&B0[lt].dedx0);
+            const double2 cd = ldg2(&B0[lt].dedx1);
+            const float d1 = (float)cd.x;
+            const float dedxmid = elktmp * d1 + (float)cd.y;
             const float aux = fdiv(d1, dedxmid);
             const float def = dedxmid * (float)(tuss * rhof);
             const float fedep = fdiv(def, (float)eketmp);

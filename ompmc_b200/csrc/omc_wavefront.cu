@@ -440,7 +440,7 @@ __device__ void p_interact_chunk(const DevProblem &P, const WaveArgs &A, const B
         const int lgle = (int)(gle * M.ge1 + M.ge0) - 1;
         const PhotBin *B = P.phot + imed * MXGE + lgle;
         p.wt *= back;
-        rayleigh(P, g2, p, pwl(gle, __ldg(&B->pmax1), __ldg(&B->pmax0)), p.e);
+        rayleigh(P, g2, p, pwl2(gle, &B->pmax1), p.e);
         q_push(pn, &ctl->n_p[par ^ 1].v, ctl, p, g2, -1.0, TAG_NONE);
     }
 }
@@ -587,9 +587,10 @@ __device__ __forceinline__ int estep_size(const DevProblem &P, float *dg, Rng &g
     const int lelke = elec_interval(M, elke);
     e.elke = elke; e.lelke = lelke;
     const ElecBin *B = B0 + lelke;
-    const double dedx0 = pwl(elke, __ldg(&B->dedx1), __ldg(&B->dedx0));
+    const double2 re = ldg2(&B->range_ep);                     // {range_ep, e_array} of this bin
+    const double dedx0 = pwl2(elke, &B->dedx1);
     double sig0;
-    if (M.sig_ismonotone[qel]) sig0 = (double)fdiv((float)pwl(elke, __ldg(&B->sig1), __ldg(&B->sig0)), (float)dedx0);
+    if (M.sig_ismonotone[qel]) sig0 = (double)fdiv((float)pwl2(elke, &B->sig1), (float)dedx0);
     else sig0 = (iq < 0) ? M.esig_e : M.psig_e;
     double tstep;
     e.total_tstep = 0.0;
@@ -606,12 +607,12 @@ __device__ __forceinline__ int estep_size(const DevProblem &P, float *dg, Rng &g
                 tstep = drange_m(B, eke, ekef, elke, elkef);
             } else {
                 const float ieke1 = frcp((float)M.eke1);
-                double ekei = __ldg(&B->e_array), elkei = (double)(((float)(lelke + 1) - (float)M.eke0) * ieke1);
+                double ekei = re.y, elkei = (double)(((float)(lelke + 1) - (float)M.eke0) * ieke1);
                 const double tuss = drange_m(B, eke, ekei, elke, elkei);
                 ekei = __ldg(&B0[lelkef + 1].e_array);
                 elkei = (double)(((float)(lelkef + 2) - (float)M.eke0) * ieke1);
                 tstep = drange_m(B0 + lelkef, ekei, ekef, elkei, elkef);
-                tstep += tuss + __ldg(&B->range_ep) - __ldg(&B0[lelkef + 1].range_ep);
+                tstep += tuss + re.x - __ldg(&B0[lelkef + 1].range_ep);
             }
         }
         e.total_tstep = tstep;
@@ -619,18 +620,18 @@ __device__ __forceinline__ int estep_size(const DevProblem &P, float *dg, Rng &g
     }
     e.sig0 = sig0;
     e.dedx = rhof * dedx0;
-    const double tmxs = pwl(elke, __ldg(&B->tmxs1), __ldg(&B->tmxs0)) * rinv;
+    const double tmxs = pwl2(elke, &B->tmxs1) * rinv;
     {
-        const double ekei = __ldg(&B->e_array), elkei = (double)fdiv((float)(lelke + 1) - (float)M.eke0, (float)M.eke1);
-        e.range = (drange_m(B, eke, ekei, elke, elkei) + __ldg(&B->range_ep)) * rinv;
+        const double ekei = re.y, elkei = (double)fdiv((float)(lelke + 1) - (float)M.eke0, (float)M.eke1);
+        e.range = (drange_m(B, eke, ekei, elke, elkei) + re.x) * rinv;
     }
     double tustep = fmin(fmin(tstep, tmxs), e.range);
     const double tperp = hownear_i(P, p);
     const float xccl = (float)(rhof * M.xcc);
     const float p2 = (float)(eke * (eke + 2.0 * RM));
     const float beta2 = fdiv(p2, p2 + RMf * RMf);
-    const float etap = (float)pwl(elke, __ldg(&B->eta1), __ldg(&B->eta0));
-    const float ms_corr = (float)pwl(elke, __ldg(&B->blcce1), __ldg(&B->blcce0));
+    const float etap = (float)pwl2(elke, &B->eta1);
+    const float ms_corr = (float)pwl2(elke, &B->blcce1);
     float blcclf = (float)(rhof * M.blcc);
     blcclf = fdiv(fdiv(blcclf, etap), 1.0f + fdiv(0.25f * etap * xccl, blcclf * p2)) * ms_corr;
     const double blccl = (double)blcclf;
@@ -643,9 +644,9 @@ __device__ __forceinline__ int estep_size(const DevProblem &P, float *dg, Rng &g
     const int lelke = elec_interval(M, elke);
     e.elke = elke; e.lelke = lelke;
     const ElecBin *B = B0 + lelke;
-    const double dedx0 = pwl(elke, __ldg(&B->dedx1), __ldg(&B->dedx0));
+    const double dedx0 = pwl2(elke, &B->dedx1);
     double sig0;
-    if (M.sig_ismonotone[qel]) sig0 = pwl(elke, __ldg(&B->sig1), __ldg(&B->sig0)) / dedx0;
+    if (M.sig_ismonotone[qel]) sig0 = pwl2(elke, &B->sig1) / dedx0;
     else sig0 = (iq < 0) ? M.esig_e : M.psig_e;
     double tstep;
     e.total_tstep = 0.0;
@@ -674,7 +675,7 @@ __device__ __forceinline__ int estep_size(const DevProblem &P, float *dg, Rng &g
     }
     e.sig0 = sig0;
     e.dedx = rhof * dedx0;
-    const double tmxs = pwl(elke, __ldg(&B->tmxs1), __ldg(&B->tmxs0)) * rinv;
+    const double tmxs = pwl2(elke, &B->tmxs1) * rinv;
     {
         const double ekei = __ldg(&B->e_array), elkei = (lelke + 1 - M.eke0) / M.eke1;
         e.range = (drange(B, eke, ekei, elke, elkei) + __ldg(&B->range_ep)) * rinv;
@@ -685,8 +686,8 @@ __device__ __forceinline__ int estep_size(const DevProblem &P, float *dg, Rng &g
     const double xccl = rhof * M.xcc;
     const double p2 = eke * (eke + 2.0 * RM);
     const double beta2 = p2 / (p2 + (RM * RM));
-    const double etap = pwl(elke, __ldg(&B->eta1), __ldg(&B->eta0));
-    const double ms_corr = pwl(elke, __ldg(&B->blcce1), __ldg(&B->blcce0));
+    const double etap = pwl2(elke, &B->eta1);
+    const double ms_corr = pwl2(elke, &B->blcce1);
     blccl = blccl / etap / (1.0 + 0.25 * etap * xccl / blccl / p2) * ms_corr;
     const double ssmfp = beta2 / blccl;
 #endif
@@ -781,7 +782,7 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, float *dg, Rng &g, 
             double chia2 = M.xcc / (4.0 * M.blcc * p2);
             const double elkems = log(ekems);
             const int lelkems = elec_interval(M, elkems);
-            chia2 *= pwl(elkems, __ldg(&B0[lelkems].eta1), __ldg(&B0[lelkems].eta0));
+            chia2 *= pwl2(elkems, &B0[lelkems].eta1);
             double costhe, sinthe;
             Frame fr;
 #if OMC_WAVE_F32 && OMC_CH_BLOCK_RNG
@@ -839,8 +840,8 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, float *dg, Rng &g, 
     if (demfp >= 1.0E-5) return 0;   // interaction point not reached (the reference burns a zero step, then resamples)
     // fictitious cross-section rejection, :5354-5372
     const ElecBin *B = B0 + lelke;
-    const double sigf = pwl(elke, __ldg(&B->sig1), __ldg(&B->sig0)) / pwl(elke, __ldg(&B->dedx1), __ldg(&B->dedx0));
-    const double br1 = pwl(elke, __ldg(&B->bra1), __ldg(&B->bra0));   // :5375-5429
+    const double sigf = pwl2(elke, &B->sig1) / pwl2(elke, &B->dedx1);
+    const double br1 = pwl2(elke, &B->bra1);   // :5375-5429
     double r;
 #if OMC_WAVE_F32 && OMC_CH_BLOCK_RNG
     if (cls == CLS_CH) {
@@ -864,7 +865,7 @@ __device__ __forceinline__ int estep_do(const DevProblem &P, float *dg, Rng &g, 
         return TAG_MOLLER;
     }
     if (r < br1) return TAG_BREMS;
-    const double pbr2 = pwl(elke, __ldg(&B->brb1), __ldg(&B->brb0));
+    const double pbr2 = pwl2(elke, &B->brb1);
     return (r < pbr2) ? TAG_BHABHA : TAG_ANNIH;
 }
 
