@@ -9,6 +9,6 @@ g = GpuTransport(0); g.load_problem(prob)
 g.set_option('kernel', 1); g.set_option('use_graph', 0); g.set_option('overlap', 0); g.set_option('pool_size', 1<<21)
 g.run_histories(0, 20000000); g.synchronize()
 PY
-ncu --metrics gpu__time_duration.sum --clock-control none -s 1000 -c 100 --csv --log-file gpurun_out/launches_r01_v4e.csv python /tmp/steady2.py > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"esize_kernel|edo_kernel|misc_kernel" -s 800 -c 4 -o gpurun_out/prof_r01_v4e python /tmp/steady2.py > gpurun_out/ncu_full10.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 1000 -c 100 --csv --log-file gpurun_out/launches_r01_v4f.csv python /tmp/steady2.py > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"esize_kernel|edo_kernel|misc_kernel" -s 800 -c 4 -o gpurun_out/prof_r01_v4f python /tmp/steady2.py > gpurun_out/ncu_full11.log 2>&1
 ls -la gpurun_out/*.ncu-rep | tail -2
