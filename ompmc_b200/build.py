@@ -71,15 +71,28 @@ HOST_EXE = os.path.join(HERE, "host", "omc_dosxyz_b200")
 MATRAD_SRC = os.path.join(HERE, "host", "omc_matrad_b200.c")
 MATRAD_EXE = os.path.join(HERE, "host", "omc_matrad_b200")
 HOST_COMMON = os.path.join(HERE, "host", "omc_host_common.h")
+TABLES_SRC = os.path.join(HERE, "host", "omc_tables.c")
+TABLES_LIB = os.path.join(HERE, "host", "libomc_tables.so")
 
 
 def build_host(force: bool = False) -> str:
     """The plain-C host drivers (omc_dosxyz: batch loop + statistics + .3ddose writer; omc_matrad: beamlet loop + CSC file)
     linked against the C-ABI library."""
     inc = os.path.join(os.path.dirname(HERE), "include")
+    hdir = os.path.join(HERE, "host")
+    deps = [HOST_COMMON, TABLES_SRC, os.path.join(hdir, "omc_tables.h"), os.path.join(hdir, "omc_host_input.h"), LIB, os.path.join(inc, "ompmc_b200.h")]
+    # host-side physics table initialisation (PEGS4 / XCOM / form factors / msnew / spinms -> omc_media_tables), also as a
+    # shared library of its own for the CPU tests; no contraction of a*b+c: the tables must equal the reference's bit for bit
+    if force or _stale(TABLES_LIB, [TABLES_SRC, os.path.join(hdir, "omc_tables.h"), os.path.join(inc, "ompmc_b200.h")]):
+        cmd = ["gcc", "-O2", "-Wall", "-ffp-contract=off", "-shared", "-fPIC", "-o", TABLES_LIB, TABLES_SRC, "-I", inc, "-lm"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("gcc failed for host/omc_tables.c")
     for src, exe in ((HOST_SRC, HOST_EXE), (MATRAD_SRC, MATRAD_EXE)):
-        if force or _stale(exe, [src, HOST_COMMON, LIB, os.path.join(inc, "ompmc_b200.h")]):
-            cmd = ["gcc", "-O2", "-Wall", "-o", exe, src, "-I", inc, "-L", HERE, "-lompmc_b200", "-lm", "-Wl,-rpath,$ORIGIN/.."]
+        if force or _stale(exe, [src] + deps):
+            extra = [TABLES_SRC, "-ffp-contract=off"] if src == HOST_SRC else []
+            cmd = ["gcc", "-O2", "-Wall", "-o", exe, src] + extra + ["-I", inc, "-I", hdir, "-L", HERE, "-lompmc_b200", "-lm", "-Wl,-rpath,$ORIGIN/.."]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 sys.stderr.write(r.stdout + r.stderr)

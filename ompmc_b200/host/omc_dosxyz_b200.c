@@ -24,6 +24,7 @@
 #include "ompmc_b200.h"
 
 #include "omc_host_common.h"
+#include "omc_host_input.h"
 
 /* ---- accumulateResults(), omc_dosxyz.c:719-799 ---------------------------------------------- */
 static void accumulate_results(const omc_geometry *g, const double *dens, double *accum, double *accum2, int iout, int nhist, int nbatch) {
@@ -95,40 +96,84 @@ static void die(const char *what) {
 }
 
 int main(int argc, char **argv) {
-    const char *pfile = NULL, *ncase = "100000", *nbatch_s = "10", *stem = "omc_b200", *seeds = "97 33";
-    int kernel = -1, device = 0;
+    const char *pfile = NULL, *ifile = NULL, *ncase = NULL, *nbatch_s = NULL, *stem = "omc_b200", *seeds = NULL;
+    int kernel = -1, device = 0, dump_only = 0;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "-p") && i + 1 < argc) pfile = argv[++i];
+        else if (!strcmp(argv[i], "-i") && i + 1 < argc) ifile = argv[++i];
         else if (!strcmp(argv[i], "-n") && i + 1 < argc) ncase = argv[++i];
         else if (!strcmp(argv[i], "-b") && i + 1 < argc) nbatch_s = argv[++i];
         else if (!strcmp(argv[i], "-o") && i + 1 < argc) stem = argv[++i];
         else if (!strcmp(argv[i], "-k") && i + 1 < argc) kernel = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-d") && i + 1 < argc) device = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-s") && i + 1 < argc) seeds = argv[++i];
+        else if (!strcmp(argv[i], "--dump-problem")) dump_only = 1;
         else {
-            printf("usage: %s -p problem.blob -n ncase -b nbatch -o out_stem [-k 0|1] [-d device] [-s \"ixx jxx\"]\n", argv[0]);
+            printf("usage: %s (-i input_stem | -p problem.blob) [-n ncase] [-b nbatch] -o out_stem [-k 0|1] [-d device] [-s \"ixx jxx\"]\n"
+                   "  -i input_stem   the reference's own input file <input_stem>.inp (phantom, PEGS4, XCOM, spectrum ... read and\n"
+                   "                  initialised here, no reference code involved), exactly like `omc_dosxyz -i input_stem -o out_stem`\n"
+                   "  -p problem.blob tables + phantom + source dumped from an initialised user code\n"
+                   "  --dump-problem  with -i: write <out_stem>.problem (every array handed to the GPU library) and exit, no GPU needed\n",
+                   argv[0]);
             return 2;
         }
     }
-    if (!pfile) { printf("Can not find the problem file (-p).\n"); return 2; }
+    if (!pfile && !ifile) { printf("Can not find the input (-i) or problem (-p) file.\n"); return 2; }
     const double tbegin = now_s();
-    blob b;
-    if (blob_read(&b, pfile) != 0) { printf("Unable to open file: %s\n", pfile); return EXIT_FAILURE; }
-
     omc_media_tables t;
     omc_geometry g;
     const double *dens;
-    host_load_media_geometry(&b, &t, &g, &dens);
-    const int gridsize = g.isize * g.jsize * g.ksize;
-
     omc_source_dosxyz s;
-    memset(&s, 0, sizeof s);
-    s.spectrum = I(&b, "src_spectrum")[0]; s.charge = I(&b, "src_charge")[0]; s.energy = F(&b, "src_energy")[0];
-    s.deltak = F(&b, "src_deltak")[0]; s.cdfinv1 = F(&b, "src_cdfinv1"); s.cdfinv2 = F(&b, "src_cdfinv2"); s.ssd = F(&b, "src_ssd")[0];
-    s.xinl = F(&b, "src_xinl")[0]; s.xinu = F(&b, "src_xinu")[0]; s.yinl = F(&b, "src_yinl")[0]; s.yinu = F(&b, "src_yinu")[0];
-    s.xsize = F(&b, "src_xsize")[0]; s.ysize = F(&b, "src_ysize")[0];
-    s.ixinl = I(&b, "src_ixinl")[0]; s.ixinu = I(&b, "src_ixinu")[0]; s.iyinl = I(&b, "src_iyinl")[0]; s.iyinu = I(&b, "src_iyinu")[0];
-    const int nsplit = I(&b, "nsplit")[0];
+    int nsplit = 1;
+    char seed_buf[384], ncase_buf[384], nbatch_buf[384];
+    if (ifile) {
+        /* the reference's main() up to the batch loop, omc_dosxyz.c:1155-1205, on our own initialisers */
+        static inp_file inp;
+        static host_phantom ph;
+        static host_regions reg;
+        static double cdfinv1[OMC_INVDIM], cdfinv2[OMC_INVDIM];
+        char path[384], folder[384], pegs[384], ffile[384], buf[384], err[512];
+        if (inp_parse(&inp, ifile)) return EXIT_FAILURE;
+        if (!inp_path(&inp, "phantom file", path) || phantom_read(&ph, path)) return EXIT_FAILURE;
+        printf("Path to phantom file : %s\n", path);
+        if (!inp_path(&inp, "pegs file", pegs) || !inp_path(&inp, "data folder", folder) || !inp_path(&inp, "pgs4form file", ffile)) return EXIT_FAILURE;
+        const char *names[OMC_MXMED];
+        for (int i = 0; i < ph.nmed; i++) names[i] = ph.names[i];
+        omc_tables *tb = omc_tables_build(folder, pegs, ffile, ph.nmed, names, err, sizeof err);
+        if (!tb) { printf("%s\n", err); return EXIT_FAILURE; }
+        t = *omc_tables_view(tb);
+        if (source_init(&s, &inp, &ph, cdfinv1, cdfinv2)) return EXIT_FAILURE;
+        if (!inp_get(&inp, "global ecut", buf)) { printf("Can not find 'global ecut' key on input file.\n"); return EXIT_FAILURE; }
+        const double ecut = atof(buf);
+        if (!inp_get(&inp, "global pcut", buf)) { printf("Can not find 'global pcut' key on input file.\n"); return EXIT_FAILURE; }
+        const double pcut = atof(buf);
+        regions_init(&reg, &ph, &t, ecut, pcut);
+        if (!inp_get(&inp, "nsplit", buf)) { printf("Can not find 'nsplit' key on input file.\n"); return EXIT_FAILURE; }
+        nsplit = atoi(buf);
+        printf(nsplit > 1 ? "Photon splitting enabled, nsplit = %d\n" : "Photon splitting disabled\n", nsplit);
+        g.isize = ph.isize; g.jsize = ph.jsize; g.ksize = ph.ksize; g.xbounds = ph.xb; g.ybounds = ph.yb; g.zbounds = ph.zb;
+        g.med = reg.med; g.rhof = reg.rhof; g.pcut = reg.pcut; g.ecut = reg.ecut;
+        dens = ph.dens;
+        if (!seeds && inp_get(&inp, "rng seeds", seed_buf)) seeds = seed_buf;
+        if (!ncase) { if (!inp_get(&inp, "ncase", ncase_buf)) { printf("Can not find 'ncase' key on input file.\n"); return EXIT_FAILURE; } ncase = ncase_buf; }
+        if (!nbatch_s) { if (!inp_get(&inp, "nbatch", nbatch_buf)) { printf("Can not find 'nbatch' key on input file.\n"); return EXIT_FAILURE; } nbatch_s = nbatch_buf; }
+        if (dump_only) return host_dump_problem(stem, &t, &g, dens, &s, nsplit) ? EXIT_FAILURE : EXIT_SUCCESS;
+    } else {
+        static blob b;
+        if (blob_read(&b, pfile) != 0) { printf("Unable to open file: %s\n", pfile); return EXIT_FAILURE; }
+        host_load_media_geometry(&b, &t, &g, &dens);
+        memset(&s, 0, sizeof s);
+        s.spectrum = I(&b, "src_spectrum")[0]; s.charge = I(&b, "src_charge")[0]; s.energy = F(&b, "src_energy")[0];
+        s.deltak = F(&b, "src_deltak")[0]; s.cdfinv1 = F(&b, "src_cdfinv1"); s.cdfinv2 = F(&b, "src_cdfinv2"); s.ssd = F(&b, "src_ssd")[0];
+        s.xinl = F(&b, "src_xinl")[0]; s.xinu = F(&b, "src_xinu")[0]; s.yinl = F(&b, "src_yinl")[0]; s.yinu = F(&b, "src_yinu")[0];
+        s.xsize = F(&b, "src_xsize")[0]; s.ysize = F(&b, "src_ysize")[0];
+        s.ixinl = I(&b, "src_ixinl")[0]; s.ixinu = I(&b, "src_ixinu")[0]; s.iyinl = I(&b, "src_iyinl")[0]; s.iyinu = I(&b, "src_iyinu")[0];
+        nsplit = I(&b, "nsplit")[0];
+    }
+    if (!ncase) ncase = "100000";
+    if (!nbatch_s) nbatch_s = "10";
+    if (!seeds) seeds = "97 33";
+    const int gridsize = g.isize * g.jsize * g.ksize;
 
     printf("Number of media in phantom : %d\n", t.nmed);
     printf("Number of voxels on each direction (X,Y,Z) : (%d, %d, %d)\n", g.isize, g.jsize, g.ksize);
