@@ -138,7 +138,7 @@ typedef struct omc_gpu_counters {
     unsigned long long deposits;       /* ausgab() calls                              */
     unsigned long long rng_draws;      /* random numbers consumed                     */
     unsigned long long errors;         /* stack/queue overflows, invalid-lambda drops */
-    unsigned long long reserved[9];
+    unsigned long long reserved[9];    /* [0..3] drain diagnostics; [4] straggler hand-overs, [5] particles handed over */
 } omc_gpu_counters;
 
 typedef struct omc_gpu_ctx *omc_gpu_handle;
@@ -161,7 +161,8 @@ int omc_gpu_set_source_dosxyz(omc_gpu_handle h, const omc_source_dosxyz *s); /* 
 int omc_gpu_set_source_matrad(omc_gpu_handle h, const omc_source_matrad *s); /* initSource(), omc_matrad.c:543 */
 int omc_gpu_set_vrt(omc_gpu_handle h, int nsplit);                         /* initVrt(), src/ompmc.c:5964 */
 int omc_gpu_set_seed(omc_gpu_handle h, int ixx, int jxx);                  /* "rng seeds", src/omc_random.c:58-82 */
-/* tuning / debug knobs: "kernel", "threads_per_block", "stack_depth", "pool_size", "record_histories" */
+/* tuning / debug knobs: "kernel", "threads_per_block", "stack_depth", "pool_size", "record_histories", "drain_threshold"
+ * (0: no drain kernel, bit-reproducible whatever the schedule), "handover" (0: no straggler hand-over between pipelined batches) */
 int omc_gpu_set_option(omc_gpu_handle h, const char *key, long long value);
 
 /* ---- the hot path ------------------------------------------------------------------------ */

@@ -306,8 +306,9 @@ class GpuTransport:
         c = Counters()
         self._ck(self.lib.omc_gpu_get_counters(self.h, C.byref(c)), "omc_gpu_get_counters")
         out = {n: int(getattr(c, n)) for n in COUNTER_NAMES}
-        if any(c.reserved):
+        if any(c.reserved[:4]):
             out["reserved"] = [int(v) for v in c.reserved[:4]]
+        out["handovers"], out["handed_over"] = int(c.reserved[4]), int(c.reserved[5])
         return out
 
     def stream_ptr(self) -> int:

@@ -55,6 +55,9 @@ struct omc_gpu_ctx {
     double cut_e[OMC_MXMED] = {0}, cut_p[OMC_MXMED] = {0}, rho_max[OMC_MXMED] = {0};
     bool cuts_uniform = false, med_dirty = false;
     WaveQueues wq{};
+    PartQueue side{};              // hand-over queue: stragglers of the previous batch on their way to drain_kernel
+    int handover = 1;              // 0: wait for the previous batch to leave the queues wave by wave
+    unsigned long long handovers = 0, handed_over = 0;
     std::vector<void *> wave_bufs;
     WaveCtl *ctl = nullptr;        // device
     WaveCtl *ctl_host = nullptr;   // pinned
@@ -175,6 +178,8 @@ static int alloc_estep_queue(omc_gpu_handle h, EStepQueue &q, unsigned cap) {
 // one is still in the queues: a particle scores into the grid of the batch its history id belongs to
 // (WaveCtl::hist_split).  h->run_grid = grid of the batch whose tail is in flight (-1: queues empty);
 // h->done_q = grids of completed batches that have not been accumulated yet (accumEndep), oldest first.
+constexpr unsigned SIDE_CAP = 65536;              // slots of the hand-over queue
+
 static int wave_prepare(omc_gpu_handle h) {
     const unsigned target = h->pool_target;
     const unsigned cap = h->pool_cap_opt ? h->pool_cap_opt : 2u * target + 65536u;
@@ -189,6 +194,7 @@ static int wave_prepare(omc_gpu_handle h) {
             if (alloc_queue(h, h->wq.ie[i], cap, false)) return 1;
         }
         if (alloc_estep_queue(h, h->wq.es, cap)) return 1;
+        if (alloc_queue(h, h->side, SIDE_CAP, false)) return 1;
         h->pool_cap = cap;
     }
     if (!h->stream2) {
@@ -218,6 +224,49 @@ static int grid_done(omc_gpu_handle h, int g) {      // fold the fp32 chunk grid
 static bool in_done(omc_gpu_handle h, int g) {
     for (int d : h->done_q) if (d == g) return true;
     return false;
+}
+
+// drain_kernel (omc_lockstep.cu) over four queues: one thread follows each queued particle and its descendants to the end,
+// scoring straight into the fp64 grid `g` of the batch they belong to
+static int drain_queues(omc_gpu_handle h, const PartQueue *const q[4], const unsigned *const cnt[4], int g) {
+    const int tpb = 128;
+    const int blocks = h->sm_count * lockstep_blocks_per_sm(tpb);
+    const int depth = 48;
+    const size_t need = (size_t)depth * blocks * tpb * sizeof(Part);
+    if (need > h->stack_bytes) {
+        cudaFree(h->stack);
+        h->stack = nullptr; h->stack_bytes = 0;
+        CK(cudaMalloc((void **)&h->stack, need));
+        h->stack_bytes = need;
+    }
+    DrainArgs D;
+    for (int k = 0; k < 4; k++) { D.q[k] = *q[k]; D.count[k] = cnt[k]; }
+    D.ticket = &h->ctl->drain_ticket.v;
+    CK(cudaMemsetAsync(&h->ctl->drain_ticket.v, 0, sizeof(unsigned), h->stream));
+    DevProblem Pd = h->P;
+    Pd.endep = h->P.endep + (size_t)g * h->P.nreg;
+    launch_drain(Pd, D, h->stack, depth, blocks, h->stream);
+    h->launches += 1;
+    return 0;
+}
+
+// Straggler hand-over (omc_wavefront.cu: handover_kernel): what is left of the previous batch leaves the queues and is
+// finished by drain_kernel, so the next batch need not wait for the last near-empty waves of that one.  Returns through
+// h->ctl_host (old_done set when nothing of the previous batch is left in the queues).
+static int hand_over_old(omc_gpu_handle h, int g_old) {
+    CK(cudaMemsetAsync(&h->ctl->n_side.v, 0, sizeof(unsigned), h->stream));
+    CK(cudaMemsetAsync(&h->ctl->side_fail, 0, sizeof(unsigned), h->stream));
+    launch_handover(h->ctl, h->wq, h->side, h->sm_count * 4, h->stream);
+    h->launches += 2;
+    CK(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const unsigned n = h->ctl_host->n_side.v < h->side.cap ? h->ctl_host->n_side.v : h->side.cap;
+    h->handovers += 1; h->handed_over += n;
+    if (h->trace) fprintf(stderr, "hand-over: %u stragglers of the previous batch to the drain kernel (%u did not fit)\n", n, h->ctl_host->side_fail);
+    if (n == 0) return 0;
+    const PartQueue *q[4] = {&h->side, &h->side, &h->side, &h->side};
+    const unsigned *cnt[4] = {&h->ctl->n_side.v, &h->ctl->zero_, &h->ctl->zero_, &h->ctl->zero_};
+    return drain_queues(h, q, cnt, g_old);
 }
 
 // start == true : inject histories [first, first+nhist) and return once all of them are started AND the previous batch
@@ -298,11 +347,17 @@ static int wave_run(omc_gpu_handle h, bool start, long long first, long long nhi
             rc = 7;
             break;
         }
+        const bool exhausted = s.hist_next >= s.hist_end && s.n_src == 0;
+        if (old_pending && !s.old_done && exhausted && h->handover && h->drain_threshold > 0 && P.nsplit == 1 && !h->mb_active &&
+            s.old_last <= (h->drain_threshold < SIDE_CAP / 2 ? h->drain_threshold : SIDE_CAP / 2)) {
+            // every history of the new batch is on its way and the previous batch is down to a few stragglers: hand them
+            // to the drain kernel instead of idling through their last waves (s refers to h->ctl_host: refreshed)
+            if (hand_over_old(h, g_old)) { rc = 1; break; }
+        }
         if (old_pending && s.old_done) {                        // the previous batch has left the queues: its grid is final
             grid_done(h, g_old);
             old_pending = false;
         }
-        const bool exhausted = s.hist_next >= s.hist_end && s.n_src == 0;
         if (start) {
             // the tail of the new batch stays in flight; it is always the NEXT call that completes a batch, even an
             // already empty one, so that every rank of a multi-GPU run sees the same sequence of completed batches
@@ -326,25 +381,9 @@ static int wave_run(omc_gpu_handle h, bool start, long long first, long long nhi
     if (drained) {
         // few particles left: one thread follows each to the end (omc_lockstep.cu: drain_kernel)
         const int par = (int)h->ctl_host->parity;
-        const int tpb = 128;
-        const int blocks = h->sm_count * lockstep_blocks_per_sm(tpb);
-        const int depth = 48;
-        const size_t need = (size_t)depth * blocks * tpb * sizeof(Part);
-        if (need > h->stack_bytes) {
-            cudaFree(h->stack);
-            h->stack = nullptr; h->stack_bytes = 0;
-            CK(cudaMalloc((void **)&h->stack, need));
-            h->stack_bytes = need;
-        }
-        DrainArgs D;
-        D.q[0] = h->wq.p[par]; D.q[1] = h->wq.e[par]; D.q[2] = h->wq.ip[par]; D.q[3] = h->wq.ie[par];
-        D.count[0] = &h->ctl->n_p[par].v; D.count[1] = &h->ctl->n_e[par].v; D.count[2] = &h->ctl->n_ip[par].v; D.count[3] = &h->ctl->n_ie[par].v;
-        D.ticket = &h->ctl->drain_ticket.v;
-        CK(cudaMemsetAsync(&h->ctl->drain_ticket.v, 0, sizeof(unsigned), h->stream));
-        DevProblem Pd = P;                                      // the drain scores straight into the fp64 grid of this batch
-        Pd.endep = P.endep + (size_t)g_old * P.nreg;
-        launch_drain(Pd, D, h->stack, depth, blocks, h->stream);
-        h->launches += 1;
+        const PartQueue *q[4] = {&h->wq.p[par], &h->wq.e[par], &h->wq.ip[par], &h->wq.ie[par]};
+        const unsigned *cnt[4] = {&h->ctl->n_p[par].v, &h->ctl->n_e[par].v, &h->ctl->n_ip[par].v, &h->ctl->n_ie[par].v};
+        if (drain_queues(h, q, cnt, g_old)) return 1;
         memset(h->ctl_host, 0, sizeof(WaveCtl));                // (status: nothing alive any more)
     }
     h->run_grid = -1;
@@ -712,6 +751,7 @@ int omc_gpu_set_option(omc_gpu_handle h, const char *key, long long value) {
     else if (k == "use_graph") h->use_graph = (int)value;
     else if (k == "overlap") h->overlap = (int)value;
     else if (k == "drain_threshold") h->drain_threshold = (unsigned)value;
+    else if (k == "handover") h->handover = (int)value;
     else if (k == "pool_cap") h->pool_cap_opt = (unsigned)value;
     else if (k == "electron_iters") h->electron_iters = (int)value;
     else if (k == "max_cross") h->max_cross = (int)value;
@@ -1019,6 +1059,7 @@ int omc_gpu_reset_tallies(omc_gpu_handle h, int which) {
         CK(cudaMemsetAsync(h->P.ensrc, 0, sizeof(double), h->stream));
         CK(cudaMemsetAsync(h->P.counters, 0, sizeof(Counters), h->stream));
         h->launches = 0;
+        h->handovers = 0; h->handed_over = 0;
     }
     CK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -1058,6 +1099,8 @@ int omc_gpu_get_counters(omc_gpu_handle h, omc_gpu_counters *out) {
     static_assert(sizeof(Counters) == sizeof(omc_gpu_counters), "counter layouts must match");
     CK(cudaMemcpy(out, h->P.counters, sizeof(Counters), cudaMemcpyDeviceToHost));
     out->kernel_launches = h->launches;
+    out->reserved[4] = h->handovers;                            // straggler hand-overs (batch pipelining) ...
+    out->reserved[5] = h->handed_over;                          // ... and the particles they moved to the drain kernel
     return 0;
 }
 

@@ -46,11 +46,14 @@ struct WaveCtl {
     PadU tk[5];                                  // chunk tickets per class (misc_kernel)
     PadU overflow, drain_ticket;
     PadU old_seen;                               // particles of the PREVIOUS batch met by the consumers of this wave
+    PadU n_side;                                 // fill count of the hand-over queue (handover_kernel)
     unsigned n_src;                              // histories injected by the current wave
     unsigned parity, target, live, waves;
     // batch pipelining: histories with id < hist_split belong to the previous batch, whose tail is still in flight
     // while this batch is injected; they score into dose grid (grid_new ^ 1), everything else into grid_new
-    unsigned has_old, old_done, grid_new, pad_;
+    unsigned has_old, old_done, grid_new;
+    unsigned old_last;                           // old_seen of the last completed wave (how many stragglers the old batch has left)
+    unsigned side_fail, zero_;                   // stragglers that did not fit into the hand-over queue (they stay in the waves); 0
     unsigned long long hist_split;
     unsigned long long hist_next, hist_end;
 };
@@ -100,6 +103,9 @@ struct WaveStreams {
 };
 void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, const WaveStreams &W);
 void launch_flush(float *g32, double *g64, long long n, cudaStream_t s);
+// Straggler hand-over (batch pipelining): move what is left of the PREVIOUS batch (history id < WaveCtl::hist_split) out of
+// the four current queues into `side` and mark the originals dead; omc_capi.cu then gives `side` to drain_kernel.
+void launch_handover(WaveCtl *ctl, const WaveQueues &Q, const PartQueue &side, int blocks, cudaStream_t s);
 // multi-beamlet pass: per-beamlet maximum (pass 0) / count above threshold (pass 1), then ordered compaction into CSC
 void launch_mb_scan(const float *grids, long long nreg, int nb, const DevProblem &P, const double *dens, int nhist, int nbatch, double rel,
                     double *dmax, unsigned long long *nnz, int pass, cudaStream_t s);

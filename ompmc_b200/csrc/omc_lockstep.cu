@@ -519,7 +519,13 @@ __global__ void __launch_bounds__(128) drain_kernel(const __grid_constant__ DevP
     c.depth = depth;
     c.nphot_steps = c.nelec_steps = 0;
     unsigned long long ndep = 0, nerr = 0;
-    for (;;) {
+    // With fewer particles than threads only every spread-th lane takes tickets, so that the particles are dealt over as many
+    // warps as possible: the per-thread shower diverges completely (lanes serialise), and the run time of the drain is the
+    // longest serialised chain of a warp.
+    unsigned spread = 1;
+    while (spread < 32u && (size_t)tot * (spread * 2u) <= nthreads) spread *= 2u;
+    const bool takes = (threadIdx.x & (spread - 1u)) == 0u;
+    for (; takes;) {
         unsigned j = atomicAdd(D.ticket, 1u);
         if (j >= tot) break;
         int k = 0;
@@ -533,6 +539,7 @@ __global__ void __launch_bounds__(128) drain_kernel(const __grid_constant__ DevP
         const int2 a = q.irq[j];
         p.ir = a.x; p.iq = (int)(short)(a.y & 0xffff);
         const int tag = a.y >> 16;
+        if (tag == 0x7fff) continue;                          // TAG_DEAD (omc_wavefront.cu): already handed over
         const uint4 r = q.rng[j];
         c.g.seed(P.seed0, P.seed1, ((unsigned long long)r.y << 32) | r.x, r.z, r.w);
         c.ndeposit = 0; c.flags = 0; c.edep_sum = 0.0;

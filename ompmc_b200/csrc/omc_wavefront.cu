@@ -218,7 +218,8 @@ __device__ __forceinline__ void deposit32(float *grid32, Tally &t, int ir, doubl
 }
 
 enum { TAG_NONE = 0, TAG_COMPTON = 1, TAG_PAIR = 2, TAG_PHOTO = 3, TAG_RAYLEIGH = 4, TAG_BREMS = 5, TAG_MOLLER = 6, TAG_BHABHA = 7,
-       TAG_ANNIH = 8, TAG_RANNIH = 9 };
+       TAG_ANNIH = 8, TAG_RANNIH = 9,
+       TAG_DEAD = 0x7fff };   // record handed over to the drain kernel (handover_kernel): consumers skip it
 
 
 // ---------------------------------------------------------------------------------------------
@@ -229,6 +230,7 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, const Batch
     WaveCtl *ctl = A.ctl;
     Part p; Rng g; double dpmfp; int tag;
     q_load(A.Q.p[par], i, p, g, P, dpmfp, tag);
+    if (tag == TAG_DEAD) return;
     const bool old = BS.is_old(g.h0, g.h1);
     BS.count(ctl, __activemask(), old);
     float *dg = BS.grid(old, g.h0, g.h1);
@@ -333,6 +335,7 @@ __device__ void photon_chunk_wc(const DevProblem &P, const WaveArgs &A, const Ba
     {
         int tag;
         q_load_part(q, i, p, tag);
+        if (tag == TAG_DEAD) return;
         entered = q.aux[i].x <= -2.0;
         const uint4 r = q.rng[i];
         g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
@@ -400,6 +403,7 @@ __device__ void p_interact_chunk(const DevProblem &P, const WaveArgs &A, const B
     const PartQueue &pn = A.Q.p[par ^ 1], &en = A.Q.e[par ^ 1];
     Part p, q; Rng g, gq; int tag;
     q_load_part(A.Q.ip[par], i, p, tag);
+    if (tag == TAG_DEAD) return;
     {
         const uint4 r = A.Q.ip[par].rng[i];
         g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
@@ -452,6 +456,7 @@ __device__ void e_interact_chunk(const DevProblem &P, const WaveArgs &A, const B
     const PartQueue &pn = A.Q.p[par ^ 1], &en = A.Q.e[par ^ 1];
     Part p, q; Rng g, gq; int tag;
     q_load_part(A.Q.ie[par], i, p, tag);
+    if (tag == TAG_DEAD) return;
     {
         const uint4 r = A.Q.ie[par].rng[i];
         g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
@@ -913,11 +918,13 @@ __global__ void __launch_bounds__(NT, OMC_MB_ESIZE) esize_kernel(const __grid_co
             int tag;
             q_load_part(q, i, p, tag);
             if (i + stride < n) q_prefetch_e(q, i + stride);
-            const int2 rm = q.rm[i];
-            const uint4 r = q.rng[i];
-            g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
-            old = BS.is_old(r.x, r.y);
-            cls = estep_size(P, BS.grid(old, r.x, r.y), g, p, e, t, st, rm);
+            if (tag != TAG_DEAD) {
+                const int2 rm = q.rm[i];
+                const uint4 r = q.rng[i];
+                g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
+                old = BS.is_old(r.x, r.y);
+                cls = estep_size(P, BS.grid(old, r.x, r.y), g, p, e, t, st, rm);
+            }
         }
         BS.count(ctl, 0xffffffffu, old);
         // one reservation per (warp, class): lane 0 asks for the CH slots, lane 1 for the BCA slots, together
@@ -1034,6 +1041,7 @@ __global__ void advance_kernel(const __grid_constant__ DevProblem P, WaveCtl *c)
     c->live = live;
     if (c->has_old) {                                          // nothing of the previous batch was met in this wave: it is complete
         if (c->old_seen.v == 0) { c->has_old = 0; c->old_done = 1; }
+        c->old_last = c->old_seen.v;
         c->old_seen.v = 0;
     }
     c->tk[0].v = c->tk[1].v = c->tk[2].v = c->tk[3].v = c->tk[4].v = 0;
@@ -1092,11 +1100,51 @@ __global__ void rearm_kernel(WaveCtl *c, unsigned long long first, unsigned long
     c->has_old = (c->live > 0) ? 1u : 0u;
     c->old_done = c->has_old ? 0u : 1u;
     c->old_seen.v = 0;
+    c->old_last = c->live;                                     // (not counted yet: the first wave of the new batch will)
     const unsigned room = ((c->live < c->target) ? c->target - c->live : 0u) / (nsplit > 1u ? nsplit : 1u);
     c->n_src = (unsigned)(nhist < (unsigned long long)room ? nhist : (unsigned long long)room);
 }
 void launch_rearm(WaveCtl *ctl, unsigned long long first, unsigned long long nhist, unsigned nsplit, cudaStream_t s) {
     rearm_kernel<<<1, 32, 0, s>>>(ctl, first, nhist, nsplit);
+}
+
+// Straggler hand-over.  Once every history of the new batch has been started, the pipeline would have to idle through the
+// last (up to ~2000) near-empty waves of the PREVIOUS batch before a third batch may be injected: only two batches can be
+// alive in the queues.  Instead the few stragglers of the previous batch are taken out of the queues here -- copied into the
+// side queue, their records marked TAG_DEAD so that the next wave's consumers skip them -- and followed to the end by
+// drain_kernel (one thread per particle, omc_lockstep.cu), which scores into the fp64 grid of that batch.  Runs between two
+// waves (the step queue is empty then), nsplit == 1 only (a split photon in flight is a ray of copies, not a particle).
+__global__ void handover_kernel(WaveCtl *c, const __grid_constant__ WaveQueues Q, const __grid_constant__ PartQueue side) {
+    const int par = (int)c->parity;
+    const unsigned long long split = c->hist_split;
+    const unsigned stride = gridDim.x * blockDim.x;
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        const PartQueue &q = (k == 0) ? Q.p[par] : (k == 1) ? Q.e[par] : (k == 2) ? Q.ip[par] : Q.ie[par];
+        const unsigned cnt = (k == 0) ? c->n_p[par].v : (k == 1) ? c->n_e[par].v : (k == 2) ? c->n_ip[par].v : c->n_ie[par].v;
+        const unsigned n = min(cnt, q.cap);
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const uint4 r = q.rng[i];
+            if (((((unsigned long long)r.y) << 32) | r.x) >= split) continue;
+            const int2 a = q.irq[i];
+            if ((a.y >> 16) == TAG_DEAD) continue;
+            const unsigned s = atomicAdd(&c->n_side.v, 1u);
+            if (s >= side.cap) { atomicAdd(&c->side_fail, 1u); continue; }     // stays in the waves (drain_kernel clamps n_side)
+            side.xy[s] = q.xy[i]; side.zu[s] = q.zu[i]; side.vw[s] = q.vw[i]; side.ew[s] = q.ew[i];
+            side.irq[s] = a; side.rng[s] = r;
+            q.irq[i] = make_int2(0, (int)TAG_DEAD << 16);
+        }
+    }
+}
+// all stragglers went over: nothing of the previous batch is left in the queues
+__global__ void handover_done_kernel(WaveCtl *c) {
+    if (blockIdx.x || threadIdx.x) return;
+    if (c->has_old && c->side_fail == 0) { c->has_old = 0; c->old_done = 1; c->old_last = 0; }
+    c->old_seen.v = 0;
+}
+void launch_handover(WaveCtl *ctl, const WaveQueues &Q, const PartQueue &side, int blocks, cudaStream_t s) {
+    handover_kernel<<<blocks, 256, 0, s>>>(ctl, Q, side);
+    handover_done_kernel<<<1, 32, 0, s>>>(ctl);
 }
 
 // ---------------------------------------------------------------------------------------------
