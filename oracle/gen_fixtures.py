@@ -34,8 +34,17 @@ sys.path.insert(0, ROOT)
 
 from ompmc_b200 import problem as P  # noqa: E402
 
-REF = "/root/reference"
+REF = os.environ.get("OMC_REFERENCE_DIR", "/root/reference")
 WORK = "/tmp/omc_fix"
+# root of the reference's input DATA files (data/, pegs4/, spectra/): the reference checkout in the build container, else the
+# copy `make -C oracle refdata` staged under the git-ignored oracle/_ref/ (travels to the GPU box)
+STAGED = os.path.join(HERE, "_ref", "refdata")
+DATA_SRC = REF if os.path.isdir(os.path.join(REF, "pegs4")) else STAGED
+DATA = os.path.join(WORK, "ref")              # short symlink: the reference reads file paths into char[128] buffers
+
+
+def have_data() -> bool:
+    return os.path.isdir(os.path.join(DATA_SRC, "pegs4"))
 GOLD = os.path.join(ROOT, "tests", "golden")
 RM = 0.5109989461
 
@@ -88,10 +97,18 @@ def write_synthetic_spinms(path: str, zmax: int = 100) -> None:
 
 def prepare_workdir() -> str:
     os.makedirs(os.path.join(WORK, "data"), exist_ok=True)
-    for fn in os.listdir(os.path.join(REF, "data")):
+    if os.path.islink(DATA) and os.readlink(DATA) != DATA_SRC:
+        os.unlink(DATA)
+    if not os.path.lexists(DATA):
+        os.symlink(DATA_SRC, DATA)
+    for fn in os.listdir(os.path.join(DATA_SRC, "data")):
         dst = os.path.join(WORK, "data", fn)
+        if fn == "spinms.data":
+            continue
+        if os.path.islink(dst) and not os.path.exists(dst):
+            os.unlink(dst)
         if not os.path.lexists(dst):
-            os.symlink(os.path.join(REF, "data", fn), dst)
+            os.symlink(os.path.join(DATA_SRC, "data", fn), dst)
     sp = os.path.join(WORK, "data", "spinms.data")
     write_synthetic_spinms(sp)
     return WORK
@@ -102,11 +119,11 @@ def write_inp(stem: str, *, phantom: str, pegs: str, spectrum: str | None, mono:
     """Same keys as ucodes/omc_dosxyz/input_file.inp."""
     lines = [f"mono energy = {mono}"]
     if spectrum:
-        lines.append(f"spectrum file = {REF}/spectra/{spectrum}")
+        lines.append(f"spectrum file = {DATA}/spectra/{spectrum}")
     lines += [f"charge = {charge}", "collimator bounds = %g %g %g %g" % tuple(coll), f"ssd = {ssd}",
               f"ncase = {ncase}", f"nbatch = {nbatch}", "rng seeds = 97 33", f"phantom file = {phantom}",
-              f"global ecut = {ecut}", f"global pcut = {pcut}", f"pegs file = {REF}/pegs4/{pegs}",
-              f"pgs4form file = {REF}/pegs4/pgs4form.dat", f"nsplit = {nsplit}", f"data folder = {WORK}/data/",
+              f"global ecut = {ecut}", f"global pcut = {pcut}", f"pegs file = {DATA}/pegs4/{pegs}",
+              f"pgs4form file = {DATA}/pegs4/pgs4form.dat", f"nsplit = {nsplit}", f"data folder = {WORK}/data/",
               f"output folder = {WORK}/"]
     with open(stem + ".inp", "w") as f:
         f.write("\n".join(lines) + "\n")

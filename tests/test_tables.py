@@ -3,7 +3,7 @@ reference itself: the physics tables built from the raw PEGS4 / XCOM / form-fact
 for bit, the tables the reference's initMediaData() produced (tests/golden/media_*.blob, dumped from the compiled reference
 by oracle/gen_fixtures.py), and an input-file run of the C driver must hand the GPU library exactly the arrays the
 reference holds in its globals before the batch loop (the golden problems).  CPU only; needs the reference's DATA files
-(/root/reference/{data,pegs4,spectra}), so it runs in the build container and is skipped on the GPU box."""
+(/root/reference/{data,pegs4,spectra}, or their copy staged under the git-ignored oracle/_ref/refdata by `make -C oracle refdata`)."""
 import ctypes as C
 import os
 import subprocess
@@ -14,7 +14,7 @@ import pytest
 from oracle import gen_fixtures as G
 from ompmc_b200 import api, build, problem as P
 
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(G.REF, "pegs4")), reason="reference data files not present")
+pytestmark = pytest.mark.skipif(not G.have_data(), reason="reference data files not present")
 
 
 @pytest.fixture(scope="module")
@@ -38,7 +38,7 @@ def workdir():
 def build_tables(lib, work, cfg):
     names = (C.c_char_p * len(cfg["media"]))(*[m.encode() for m in cfg["media"]])
     err = C.create_string_buffer(512)
-    h = lib.omc_tables_build((work + "/data/").encode(), (G.REF + "/pegs4/" + cfg["pegs"]).encode(), (G.REF + "/pegs4/pgs4form.dat").encode(),
+    h = lib.omc_tables_build((work + "/data/").encode(), (G.DATA + "/pegs4/" + cfg["pegs"]).encode(), (G.DATA + "/pegs4/pgs4form.dat").encode(),
                              len(cfg["media"]), names, err, 512)
     assert h, err.value.decode()
     return h
@@ -65,18 +65,18 @@ def test_tables_equal_the_references_bit_for_bit(tables_lib, workdir, name):
 def test_missing_medium_and_missing_file_are_reported(tables_lib, workdir):
     names = (C.c_char_p * 1)(b"NOSUCHMEDIUM")
     err = C.create_string_buffer(512)
-    args = ((workdir + "/data/").encode(), (G.REF + "/pegs4/700icru.pegs4dat").encode(), (G.REF + "/pegs4/pgs4form.dat").encode())
+    args = ((workdir + "/data/").encode(), (G.DATA + "/pegs4/700icru.pegs4dat").encode(), (G.DATA + "/pegs4/pgs4form.dat").encode())
     assert not tables_lib.omc_tables_build(*args, 1, names, err, 512) and b"NOSUCHMEDIUM" in err.value
     names = (C.c_char_p * 1)(b"H2O700ICRU")
     assert not tables_lib.omc_tables_build(b"/nonexistent/", args[1], args[2], 1, names, err, 512) and b"Unable to open" in err.value
 
 
 @pytest.mark.parametrize("key,fname", list(G.SPECTRA.items()))
-def test_spectrum_inverse_cdf(tables_lib, key, fname):
+def test_spectrum_inverse_cdf(tables_lib, workdir, key, fname):
     blob = P.load_blob(P.golden("media_700_water.blob"))
     c1 = np.zeros(1000); c2 = np.zeros(1000); emax = C.c_double(0)
     err = C.create_string_buffer(256)
-    assert tables_lib.omc_spectrum_cdfinv((G.REF + "/spectra/" + fname).encode(), c1.ctypes.data, c2.ctypes.data, C.byref(emax), err, 256) == 0
+    assert tables_lib.omc_spectrum_cdfinv((G.DATA + "/spectra/" + fname).encode(), c1.ctypes.data, c2.ctypes.data, C.byref(emax), err, 256) == 0
     assert np.array_equal(c1, blob["cdfinv1_" + key]) and np.array_equal(c2, blob["cdfinv2_" + key])
     assert emax.value >= (c1 + c2).max() > 0.0
 
