@@ -203,6 +203,14 @@ int omc_gpu_get_tallies(omc_gpu_handle h, double *accum_endep, double *accum_end
  * The device tallies are not modified. */
 int omc_gpu_accumulate_results(omc_gpu_handle h, int iout, int nhist, int nbatch, const double *med_densities, double *dose,
                                double *unc);
+/* outputResults(output_file, iout, nhist, nbatch) (omc_dosxyz.c:801-886) with BOTH halves on the device: accumulateResults()
+ * as above, then the text of the .3ddose file -- the reference's fprintf("%e ") per dose value and fprintf("%f ") per
+ * uncertainty (:862-877), byte for byte what glibc prints -- is produced by a formatting kernel and streamed through pinned
+ * buffers to `path` (the complete file name; the reference builds it from "output folder" + output_file + ".3ddose",
+ * :822-833) while the next chunk is being formatted.  At 1 mm voxels (8e7 values per block) the per-value fprintf of the
+ * reference is the wall-clock bottleneck of the output phase.  The header lines (dimensions, voxel
+ * boundaries) are written by the host with the reference's formats.  The device tallies are not modified. */
+int omc_gpu_write_3ddose(omc_gpu_handle h, const char *path, int iout, int nhist, int nbatch, const double *med_densities);
 /* The beamlet loop of omc_matrad.c:1389-1493 for beamlets [ib0, ib0+nb) in ONE pass of the wavefront kernels: all their
  * histories run concurrently (beamlet ib0+k owns history ids [first_history + k*nhist, +nhist) and its own fp32 dose
  * grid), then accumulateResults(1, nhist, nbatch) + the relDoseThreshold test + the sparse column assembly
@@ -246,6 +254,9 @@ int omc_gpu_test_particles(omc_gpu_handle h, int n, const int *iq, const double 
                            const double *wt, long long first_history, omc_history_record *records);
 /* n raw Philox draws of history `hist` as the transport sees them (double in [0,1)) */
 int omc_gpu_test_rng(omc_gpu_handle h, long long hist, int n, double *out);
+/* n host doubles through the formatting kernel of omc_gpu_write_3ddose into `path`: one block of a .3ddose file, i.e. what
+ * `for (i < n) fprintf(fp, mode ? "%f " : "%e ", values[i]); fprintf(fp, "\n");` writes (omc_dosxyz.c:859-877), byte for byte. */
+int omc_gpu_test_format(omc_gpu_handle h, int mode, long long n, const double *values, const char *path);
 
 #ifdef __cplusplus
 }

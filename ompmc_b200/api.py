@@ -89,7 +89,7 @@ EXPORTS = ["omc_gpu_create", "omc_gpu_destroy", "omc_gpu_last_error", "omc_gpu_s
            "omc_gpu_set_source_dosxyz", "omc_gpu_set_source_matrad", "omc_gpu_set_vrt", "omc_gpu_set_seed", "omc_gpu_set_option",
            "omc_gpu_run_histories", "omc_gpu_accum_batch", "omc_gpu_run_batch", "omc_gpu_start_batch", "omc_gpu_finish_batches",
            "omc_gpu_completed_batches", "omc_gpu_synchronize", "omc_gpu_get_tallies",
-           "omc_gpu_get_batch_grid", "omc_gpu_accumulate_results", "omc_gpu_run_beamlets", "omc_gpu_fetch_columns", "omc_gpu_reset_tallies", "omc_gpu_device_ptrs", "omc_gpu_stream", "omc_gpu_get_counters",
+           "omc_gpu_get_batch_grid", "omc_gpu_accumulate_results", "omc_gpu_write_3ddose", "omc_gpu_test_format", "omc_gpu_run_beamlets", "omc_gpu_fetch_columns", "omc_gpu_reset_tallies", "omc_gpu_device_ptrs", "omc_gpu_stream", "omc_gpu_get_counters",
            "omc_gpu_get_history_records", "omc_gpu_test_geometry", "omc_gpu_test_rng", "omc_gpu_test_particles",
            "omc_gpu_abi_sizeof"]
 
@@ -119,6 +119,8 @@ def load_library() -> C.CDLL:
     lib.omc_gpu_get_tallies.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.omc_gpu_get_batch_grid.argtypes = [H, C.c_void_p]
     lib.omc_gpu_accumulate_results.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.omc_gpu_write_3ddose.argtypes = [H, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.omc_gpu_test_format.argtypes = [H, C.c_int, C.c_longlong, C.c_void_p, C.c_char_p]
     lib.omc_gpu_run_beamlets.argtypes = [H, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
                                          C.POINTER(C.c_longlong)]
     lib.omc_gpu_fetch_columns.argtypes = [H, C.c_void_p, C.c_void_p]
@@ -296,6 +298,18 @@ class GpuTransport:
         self._ck(self.lib.omc_gpu_accumulate_results(self.h, int(iout), int(nhist), int(nbatch), dens.ctypes.data, dose.ctypes.data,
                                                      unc.ctypes.data), "omc_gpu_accumulate_results")
         return dose[1:], unc[1:]
+
+    def write_3ddose(self, path: str, med_densities: np.ndarray, nhist: int, nbatch: int, iout: int = 1):
+        """outputResults() (omc_dosxyz.c:801-886): accumulateResults() and the .3ddose text both produced on the device."""
+        dens = np.ascontiguousarray(med_densities, dtype=np.float64)
+        assert dens.size == self.nreg - 1
+        self._ck(self.lib.omc_gpu_write_3ddose(self.h, os.fsencode(path), int(iout), int(nhist), int(nbatch), dens.ctypes.data),
+                 "omc_gpu_write_3ddose")
+
+    def test_format(self, mode: int, values: np.ndarray, path: str):
+        """unit-test hook: `values` through the device formatter ("%e " mode 0, "%f " mode 1) into `path`."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        self._ck(self.lib.omc_gpu_test_format(self.h, int(mode), v.size, v.ctypes.data, os.fsencode(path)), "omc_gpu_test_format")
 
     def reset_tallies(self, which: int = 0):
         self._ck(self.lib.omc_gpu_reset_tallies(self.h, which), "omc_gpu_reset_tallies")

@@ -73,6 +73,8 @@ MATRAD_EXE = os.path.join(HERE, "host", "omc_matrad_b200")
 HOST_COMMON = os.path.join(HERE, "host", "omc_host_common.h")
 TABLES_SRC = os.path.join(HERE, "host", "omc_tables.c")
 TABLES_LIB = os.path.join(HERE, "host", "libomc_tables.so")
+FORMAT_SRC = os.path.join(CSRC, "omc_format_host.cc")
+FORMAT_LIB = os.path.join(HERE, "libomc_format_host.so")
 
 
 def build_host(force: bool = False) -> str:
@@ -89,6 +91,13 @@ def build_host(force: bool = False) -> str:
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("gcc failed for host/omc_tables.c")
+    # omc_format.cuh (the device's "%e " / "%f " text conversion) compiled for the host: CPU test hook
+    if force or _stale(FORMAT_LIB, [FORMAT_SRC, os.path.join(CSRC, "omc_format.cuh")]):
+        cmd = ["g++", "-O2", "-Wall", "-std=c++17", "-shared", "-fPIC", "-o", FORMAT_LIB, FORMAT_SRC]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("g++ failed for csrc/omc_format_host.cc")
     for src, exe in ((HOST_SRC, HOST_EXE), (MATRAD_SRC, MATRAD_EXE)):
         if force or _stale(exe, [src] + deps):
             extra = [TABLES_SRC, "-ffp-contract=off"] if src == HOST_SRC else []

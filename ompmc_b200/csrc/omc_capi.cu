@@ -3,6 +3,7 @@
 // Host side only: packs the reference-layout tables into the device records of omc_types.cuh,
 // owns device memory / the stream, launches the kernels.  There is NO CPU transport path in this
 // library: every entry point that does physics launches a CUDA kernel or fails.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -11,6 +12,7 @@
 #include <vector>
 
 #include "omc_kernels.h"
+#include "omc_format.cuh"
 
 using namespace omc;
 
@@ -74,6 +76,12 @@ struct omc_gpu_ctx {
     // omc_gpu_accumulate_results scratch
     double *res_dens = nullptr, *res_dose = nullptr, *res_unc = nullptr;
     int res_nreg = -1;
+    // omc_gpu_write_3ddose: power-of-ten table, two text buffers (device + pinned host), fallback lists
+    Pow10 *fmt_tab = nullptr;
+    char *fmt_dev[2] = {nullptr, nullptr}, *fmt_host[2] = {nullptr, nullptr};
+    FormatFallback *fmt_fb_dev[2] = {nullptr, nullptr}, *fmt_fb_host[2] = {nullptr, nullptr};
+    unsigned *fmt_nfb_dev = nullptr, *fmt_nfb_host = nullptr;
+    cudaEvent_t fmt_ev[2] = {nullptr, nullptr};
     // batch pipelining (see wave_run)
     int run_grid = -1, last_ibeamlet = -1;
     std::vector<int> done_q;
@@ -491,6 +499,14 @@ void omc_gpu_destroy(omc_gpu_handle h) {
     cudaFree(h->P.endep); cudaFree(h->P.endep32); cudaFree(h->accum); cudaFree(h->accum2);
     cudaFree(h->P.counters); cudaFree(h->P.ensrc); cudaFree(h->stack); cudaFree(h->records);
     cudaFree(h->res_dens); cudaFree(h->res_dose); cudaFree(h->res_unc);
+    cudaFree(h->fmt_tab); cudaFree(h->fmt_nfb_dev);
+    if (h->fmt_nfb_host) cudaFreeHost(h->fmt_nfb_host);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(h->fmt_dev[i]); cudaFree(h->fmt_fb_dev[i]);
+        if (h->fmt_host[i]) cudaFreeHost(h->fmt_host[i]);
+        if (h->fmt_fb_host[i]) cudaFreeHost(h->fmt_fb_host[i]);
+        if (h->fmt_ev[i]) cudaEventDestroy(h->fmt_ev[i]);
+    }
     cudaFree(h->mb_grid); cudaFree(h->mb_dmax); cudaFree(h->mb_nnz); cudaFree(h->mb_jc); cudaFree(h->mb_ir); cudaFree(h->mb_val);
     if (h->stream2) {
         cudaStreamDestroy(h->stream2); cudaStreamDestroy(h->stream3);
@@ -907,9 +923,8 @@ int omc_gpu_get_tallies(omc_gpu_handle h, double *accum, double *accum2, double 
     return 0;
 }
 
-int omc_gpu_accumulate_results(omc_gpu_handle h, int iout, int nhist, int nbatch, const double *med_densities, double *dose,
-                               double *unc) {
-    if (!h || !h->have_geom || !med_densities || !dose || !unc) return 2;
+// accumulateResults() on the device: leaves dose / relative uncertainty in h->res_dose / h->res_unc (indexed like the tallies)
+static int results_on_device(omc_gpu_handle h, int iout, int nhist, int nbatch, const double *med_densities) {
     if (nbatch < 2) return fail(h, "accumulateResults needs at least two batches (batch-method uncertainty)");
     if (nhist < 1) return fail(h, "accumulateResults: history count must be positive");
     int rc = omc_gpu_synchronize(h);
@@ -927,10 +942,125 @@ int omc_gpu_accumulate_results(omc_gpu_handle h, int iout, int nhist, int nbatch
     launch_results(h->P, h->accum, h->accum2, h->res_dens, iout, nhist, nbatch, h->res_dose, h->res_unc, h->stream);
     h->launches += 1;
     CK(cudaGetLastError());
+    return 0;
+}
+
+int omc_gpu_accumulate_results(omc_gpu_handle h, int iout, int nhist, int nbatch, const double *med_densities, double *dose,
+                               double *unc) {
+    if (!h || !h->have_geom || !med_densities || !dose || !unc) return 2;
+    int rc = results_on_device(h, iout, nhist, nbatch, med_densities);
+    if (rc) return rc;
+    const size_t nreg = (size_t)h->P.nreg;
     CK(cudaMemcpyAsync(dose, h->res_dose, nreg * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(unc, h->res_unc, nreg * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+// ---- outputResults() (omc_dosxyz.c:801-886): accumulateResults() + the .3ddose text, both on the device ------------------------
+static const long long FMT_CHUNK = 4ll << 20;          // values per chunk: 52 MiB of "%e " text
+static const unsigned FMT_FB_CAP = 1u << 16;           // host-formatted values per chunk before the whole chunk goes to snprintf
+
+static int format_setup(omc_gpu_handle h) {
+    if (h->fmt_tab) return 0;
+    std::vector<Pow10> tab(kPow10N);
+    build_pow10_table(tab.data());
+    CK(cudaMalloc((void **)&h->fmt_tab, sizeof(Pow10) * kPow10N));
+    CK(cudaMemcpy(h->fmt_tab, tab.data(), sizeof(Pow10) * kPow10N, cudaMemcpyHostToDevice));
+    CK(cudaMalloc((void **)&h->fmt_nfb_dev, 2 * sizeof(unsigned)));
+    CK(cudaMallocHost((void **)&h->fmt_nfb_host, 2 * sizeof(unsigned)));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaMalloc((void **)&h->fmt_dev[i], (size_t)FMT_CHUNK * kFmtEWidth));
+        CK(cudaMallocHost((void **)&h->fmt_host[i], (size_t)FMT_CHUNK * kFmtEWidth));
+        CK(cudaMalloc((void **)&h->fmt_fb_dev[i], sizeof(FormatFallback) * FMT_FB_CAP));
+        CK(cudaMallocHost((void **)&h->fmt_fb_host[i], sizeof(FormatFallback) * FMT_FB_CAP));
+        CK(cudaEventCreateWithFlags(&h->fmt_ev[i], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+// one block of the file: n values of src (device) as text; chunk c+1 is formatted and copied while chunk c is written
+static int format_block(omc_gpu_handle h, FILE *fp, const double *src, long long n, int mode) {
+    const int W = mode == 0 ? kFmtEWidth : kFmtFWidth;
+    const char *spec = mode == 0 ? "%e " : "%f ";
+    const long long nchunk = (n + FMT_CHUNK - 1) / FMT_CHUNK;
+    auto issue = [&](long long c) -> int {
+        const int b = (int)(c & 1);
+        const long long lo = c * FMT_CHUNK, cnt = std::min(FMT_CHUNK, n - lo);
+        CK(cudaMemsetAsync(h->fmt_nfb_dev + b, 0, sizeof(unsigned), h->stream));
+        launch_format(mode, src + lo, cnt, h->fmt_tab, h->fmt_dev[b], h->fmt_fb_dev[b], h->fmt_nfb_dev + b, FMT_FB_CAP, h->stream);
+        h->launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h->fmt_host[b], h->fmt_dev[b], (size_t)cnt * W, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->fmt_nfb_host + b, h->fmt_nfb_dev + b, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->fmt_fb_host[b], h->fmt_fb_dev[b], sizeof(FormatFallback) * FMT_FB_CAP, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->fmt_ev[b], h->stream));
+        return 0;
+    };
+    if (nchunk > 0 && issue(0)) return 1;
+    std::vector<double> raw;
+    char one[512];
+    for (long long c = 0; c < nchunk; c++) {
+        const int b = (int)(c & 1);
+        const long long lo = c * FMT_CHUNK, cnt = std::min(FMT_CHUNK, n - lo);
+        CK(cudaEventSynchronize(h->fmt_ev[b]));
+        if (c + 1 < nchunk && issue(c + 1)) return 1;          // the other buffer: formatted + copied while this one is written
+        const unsigned nfb = h->fmt_nfb_host[b];
+        const char *text = h->fmt_host[b];
+        bool ok = true;
+        if (nfb == 0) {
+            ok = fwrite(text, 1, (size_t)cnt * W, fp) == (size_t)cnt * W;
+        } else if (nfb <= FMT_FB_CAP) {                         // splice the host-formatted values in, in index order
+            FormatFallback *fb = h->fmt_fb_host[b];
+            std::sort(fb, fb + nfb, [](const FormatFallback &x, const FormatFallback &y) { return x.index < y.index; });
+            long long at = 0;
+            for (unsigned k = 0; k < nfb && ok; k++) {
+                const long long i = (long long)fb[k].index;
+                ok = fwrite(text + at * W, 1, (size_t)(i - at) * W, fp) == (size_t)(i - at) * W;
+                const int len = snprintf(one, sizeof one, spec, fb[k].value);
+                ok = ok && fwrite(one, 1, (size_t)len, fp) == (size_t)len;
+                at = i + 1;
+            }
+            ok = ok && fwrite(text + at * W, 1, (size_t)(cnt - at) * W, fp) == (size_t)(cnt - at) * W;
+        } else {                                                // (pathological grid, e.g. all NaN) the reference's loop for this chunk
+            raw.resize((size_t)cnt);
+            CK(cudaMemcpy(raw.data(), src + lo, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost));
+            for (long long i = 0; i < cnt && ok; i++) ok = fprintf(fp, spec, raw[(size_t)i]) > 0;
+        }
+        if (!ok) return fail(h, "omc_gpu_write_3ddose: write failed");
+    }
+    return fputc('\n', fp) == EOF ? fail(h, "omc_gpu_write_3ddose: write failed") : 0;
+}
+
+int omc_gpu_write_3ddose(omc_gpu_handle h, const char *path, int iout, int nhist, int nbatch, const double *med_densities) {
+    if (!h || !path || !h->have_geom || !med_densities) return 2;
+    CK(cudaSetDevice(h->device));
+    int rc = results_on_device(h, iout, nhist, nbatch, med_densities);
+    if (rc) return rc;
+    if (format_setup(h)) return 1;
+    const DevProblem &P = h->P;
+    std::vector<double> xb(P.isize + 1), yb(P.jsize + 1), zb(P.ksize + 1);
+    CK(cudaMemcpyAsync(xb.data(), P.xb, xb.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(yb.data(), P.yb, yb.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(zb.data(), P.zb, zb.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    FILE *fp = fopen(path, "w");
+    if (!fp) { h->err = std::string("Unable to open file: ") + path; return 2; }
+    static const size_t IOBUF = 8u << 20;
+    std::vector<char> iobuf(IOBUF);
+    setvbuf(fp, iobuf.data(), _IOFBF, IOBUF);
+    fprintf(fp, "%5d%5d%5d\n", P.isize, P.jsize, P.ksize);
+    for (double v : xb) fprintf(fp, "%f ", v);
+    fprintf(fp, "\n");
+    for (double v : yb) fprintf(fp, "%f ", v);
+    fprintf(fp, "\n");
+    for (double v : zb) fprintf(fp, "%f ", v);
+    fprintf(fp, "\n");
+    const long long nvox = (long long)P.nreg - 1;
+    rc = format_block(h, fp, h->res_dose + 1, nvox, 0);
+    if (!rc) rc = format_block(h, fp, h->res_unc + 1, nvox, 1);
+    if (fclose(fp) != 0 && !rc) rc = fail(h, "omc_gpu_write_3ddose: write failed");
+    return rc;
 }
 
 int omc_gpu_run_beamlets(omc_gpu_handle h, long long first, int nhist, int nbatch, int ib0, int nb, double rel_threshold,
@@ -1174,6 +1304,21 @@ int omc_gpu_test_rng(omc_gpu_handle h, long long hist, int n, double *out) {
     CK(cudaMemcpy(out, d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
     cudaFree(d);
     return 0;
+}
+
+int omc_gpu_test_format(omc_gpu_handle h, int mode, long long n, const double *values, const char *path) {
+    if (!h || !values || !path || n < 0 || (mode != 0 && mode != 1)) return 2;
+    CK(cudaSetDevice(h->device));
+    if (format_setup(h)) return 1;
+    double *d = nullptr;
+    CK(cudaMalloc((void **)&d, (size_t)(n ? n : 1) * sizeof(double)));
+    CK(cudaMemcpy(d, values, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    FILE *fp = fopen(path, "w");
+    if (!fp) { cudaFree(d); h->err = std::string("Unable to open file: ") + path; return 2; }
+    int rc = format_block(h, fp, d, n, mode);
+    if (fclose(fp) != 0 && !rc) rc = fail(h, "omc_gpu_test_format: write failed");
+    cudaFree(d);
+    return rc;
 }
 
 }  // extern "C"

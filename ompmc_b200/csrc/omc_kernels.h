@@ -111,6 +111,15 @@ void launch_mb_scan(const float *grids, long long nreg, int nb, const DevProblem
                     double *dmax, unsigned long long *nnz, int pass, cudaStream_t s);
 void launch_mb_fill(const float *grids, long long nreg, int nb, const DevProblem &P, const double *dens, int nhist, int nbatch, double rel,
                     const double *dmax, const long long *jc, long long *ir, double *val, cudaStream_t s);
+// .3ddose text on the device (omc_format.cuh): mode 0 = "%e " (13 bytes per value), 1 = "%f " (9 bytes); values the device does
+// not certify go to fb[0..*nfb) (capped at fb_cap, *nfb keeps counting) for the host to format
+struct Pow10;
+struct FormatFallback {
+    unsigned long long index;
+    double value;
+};
+void launch_format(int mode, const double *src, long long n, const Pow10 *tab, char *out, FormatFallback *fb, unsigned *nfb, unsigned fb_cap,
+                   cudaStream_t stream);
 // start the next batch while the tail of the previous one is still in the queues (see WaveCtl::hist_split)
 void launch_rearm(WaveCtl *ctl, unsigned long long first, unsigned long long nhist, unsigned nsplit, cudaStream_t s);
 

@@ -7,6 +7,7 @@
 // Compiled with -fmad=false so that a*b+c rounds twice as it does in the reference's x86-64 build.
 #include "omc_physics.cuh"
 #include "omc_kernels.h"
+#include "omc_format.cuh"
 
 namespace omc {
 
@@ -692,6 +693,52 @@ void launch_results(const DevProblem &P, const double *accum, const double *accu
     if (blocks < 1) blocks = 1;
     results_kernel<<<blocks, 256, 0, stream>>>(accum, accum2, dens, P.xb, P.yb, P.zb, P.isize, P.jsize, P.ksize, iout, (double)nhist,
                                                (double)nbatch, dose, unc);
+}
+
+// ---- .3ddose text on the device (outputResults(), omc_dosxyz.c:841-879) -------------------------------------------
+// One thread formats one value with omc_format.cuh ("%e " = 13 bytes, "%f " = 9 bytes, glibc-exact); a block stages its 256
+// records in shared memory and stores them as 16-byte words (256 * 13 and 256 * 9 are multiples of 16, the output buffer is
+// 256-byte aligned).  Values the device does not certify (rounding ties, negative / non-finite numbers, other widths) are
+// appended to `fb` for the host to format with snprintf; their slot in the text is left as written here (spaces).
+template <int MODE>
+__global__ void __launch_bounds__(256) format_kernel(const double *__restrict__ src, long long n, const Pow10 *__restrict__ tab,
+                                                     char *__restrict__ out, FormatFallback *__restrict__ fb, unsigned *__restrict__ nfb,
+                                                     unsigned fb_cap) {
+    constexpr int W = MODE == 0 ? kFmtEWidth : kFmtFWidth;
+    __shared__ __align__(16) char sh[256 * W];
+    const long long nblk = (n + 255) / 256;
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const long long i = blk * 256 + threadIdx.x;
+        if (i < n) {
+            const double v = src[i];
+            char *o = sh + threadIdx.x * W;
+            const int bad = MODE == 0 ? fmt_e(v, tab, o) : fmt_f(v, o);
+            if (bad) {
+                for (int c = 0; c < W; c++) o[c] = ' ';
+                const unsigned slot = atomicAdd(nfb, 1u);
+                if (slot < fb_cap) { fb[slot].index = (unsigned long long)i; fb[slot].value = v; }
+            }
+        }
+        __syncthreads();
+        const long long base = blk * 256 * W;
+        const long long cnt = (n - blk * 256 < 256 ? n - blk * 256 : 256) * W;
+        if (cnt == 256 * W) {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(sh);
+            uint4 *o4 = reinterpret_cast<uint4 *>(out + base);
+            for (int w = threadIdx.x; w < 256 * W / 16; w += 256) o4[w] = s4[w];
+        } else {
+            for (long long c = threadIdx.x; c < cnt; c += 256) out[base + c] = sh[c];
+        }
+        __syncthreads();
+    }
+}
+void launch_format(int mode, const double *src, long long n, const Pow10 *tab, char *out, FormatFallback *fb, unsigned *nfb, unsigned fb_cap,
+                   cudaStream_t stream) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    if (mode == 0) format_kernel<0><<<(int)blocks, 256, 0, stream>>>(src, n, tab, out, fb, nfb, fb_cap);
+    else format_kernel<1><<<(int)blocks, 256, 0, stream>>>(src, n, tab, out, fb, nfb, fb_cap);
 }
 
 }  // namespace omc

@@ -216,12 +216,21 @@ int main(int argc, char **argv) {
     printf("Fraction of incident energy deposited in the phantom: %5.4f\n", etot / ensrc);
     /* accumulateResults(iout = 1, nperbatch, nbatch), omc_dosxyz.c:1281-1282: on the device by default (the tallies are
      * resident there); OMC_HOST_RESULTS=1 runs the host restatement above instead -- same numbers, bit for bit */
-    if (getenv("OMC_HOST_RESULTS") && atoi(getenv("OMC_HOST_RESULTS")) == 1) {
+    const int host_results = getenv("OMC_HOST_RESULTS") ? atoi(getenv("OMC_HOST_RESULTS")) : 0;
+    const double t2 = now_s();
+    if (host_results == 1) {                /* host restatement of both halves of outputResults() */
         accumulate_results(&g, dens, accum, accum2, 1, nperbatch, nbatch);
-    } else if (omc_gpu_accumulate_results(gpu, 1, nperbatch, nbatch, dens, accum, accum2)) {
-        die("omc_gpu_accumulate_results");
+        if (write_3ddose(stem, &g, accum, accum2)) return EXIT_FAILURE;
+    } else if (host_results == 2) {         /* statistics on the device, the reference's fprintf loop on the host */
+        if (omc_gpu_accumulate_results(gpu, 1, nperbatch, nbatch, dens, accum, accum2)) die("omc_gpu_accumulate_results");
+        if (write_3ddose(stem, &g, accum, accum2)) return EXIT_FAILURE;
+    } else {                                /* default: statistics AND the text of the file on the device */
+        char *fn = malloc(strlen(stem) + 16);
+        sprintf(fn, "%s.3ddose", stem);
+        if (omc_gpu_write_3ddose(gpu, fn, 1, nperbatch, nbatch, dens)) die("omc_gpu_write_3ddose");
+        free(fn);
     }
-    if (write_3ddose(stem, &g, accum, accum2)) return EXIT_FAILURE;
+    printf("Output written in %8.3f seconds\n", now_s() - t2);
     omc_gpu_destroy(gpu);
     printf("Total execution time : %8.5f seconds\n", now_s() - tbegin);
     return EXIT_SUCCESS;

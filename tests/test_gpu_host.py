@@ -66,13 +66,13 @@ def test_device_accumulate_results(gpu, tmp_path):
     blob = str(tmp_path / "p.blob")
     P.save_blob(blob, prob)
     outs = []
-    for host in ("0", "1"):
+    for host in ("0", "1", "2"):      # 0: statistics + .3ddose text on the device; 1: both on the host; 2: device statistics, host fprintf
         stem = str(tmp_path / ("out" + host))
         r = subprocess.run([build.HOST_EXE, "-p", blob, "-n", "20000", "-b", "5", "-o", stem, "-k", "0"], capture_output=True, text=True,
                            env=dict(os.environ, OMC_HOST_RESULTS=host))
         assert r.returncode == 0, r.stdout + r.stderr
         outs.append(open(stem + ".3ddose", "rb").read())
-    assert outs[0] == outs[1]
+    assert outs[0] == outs[1] == outs[2]
 
 
 def _read_csc(path):
