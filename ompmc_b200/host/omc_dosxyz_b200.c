@@ -224,6 +224,18 @@ int main(int argc, char **argv) {
     } else if (host_results == 2) {         /* statistics on the device, the reference's fprintf loop on the host */
         if (omc_gpu_accumulate_results(gpu, 1, nperbatch, nbatch, dens, accum, accum2)) die("omc_gpu_accumulate_results");
         if (write_3ddose(stem, &g, accum, accum2)) return EXIT_FAILURE;
+    } else if (host_results == 3) {         /* probe: both writers on the SAME tallies -> <stem>.3ddose (device) and <stem>_host.3ddose */
+        char *fn = malloc(strlen(stem) + 32);
+        sprintf(fn, "%s.3ddose", stem);
+        double ta = now_s();
+        if (omc_gpu_write_3ddose(gpu, fn, 1, nperbatch, nbatch, dens)) die("omc_gpu_write_3ddose");
+        printf("Device writer: %8.3f seconds\n", now_s() - ta);
+        ta = now_s();
+        if (omc_gpu_accumulate_results(gpu, 1, nperbatch, nbatch, dens, accum, accum2)) die("omc_gpu_accumulate_results");
+        sprintf(fn, "%s_host", stem);
+        if (write_3ddose(fn, &g, accum, accum2)) return EXIT_FAILURE;
+        printf("Host writer: %8.3f seconds\n", now_s() - ta);
+        free(fn);
     } else {                                /* default: statistics AND the text of the file on the device */
         char *fn = malloc(strlen(stem) + 16);
         sprintf(fn, "%s.3ddose", stem);
