@@ -162,7 +162,7 @@ int omc_gpu_set_source_matrad(omc_gpu_handle h, const omc_source_matrad *s); /* 
 int omc_gpu_set_vrt(omc_gpu_handle h, int nsplit);                         /* initVrt(), src/ompmc.c:5964 */
 int omc_gpu_set_seed(omc_gpu_handle h, int ixx, int jxx);                  /* "rng seeds", src/omc_random.c:58-82 */
 /* tuning / debug knobs: "kernel", "threads_per_block", "stack_depth", "pool_size", "record_histories", "drain_threshold"
- * (0: no drain kernel, bit-reproducible whatever the schedule), "handover" (0: no straggler hand-over between pipelined batches) */
+ * (0: no drain kernel, bit-reproducible whatever the schedule), "handover" (1: hand the last stragglers of the previous pipelined batch to the drain kernel; default 0, measured slower) */
 int omc_gpu_set_option(omc_gpu_handle h, const char *key, long long value);
 
 /* ---- the hot path ------------------------------------------------------------------------ */

@@ -26,4 +26,4 @@ for per, nb in ((1000000, 20), (4000000, 10), (16777216, 6), (67108864, 4)):
         n = nb * per
         print('per', per, 'nb', nb, 'handover', ho, 'ms/batch %.1f' % (ms / nb), '%.4g hist/s' % (n / ms * 1e3), 'launches', c['kernel_launches'],
               'handovers', c['handovers'], 'handed_over', c['handed_over'], 'edep/h %.6f' % (a[1:].sum() / n), 'errors', c['errors'], flush=True)
-g.set_option('handover', 1)
+g.set_option('handover', 0)

@@ -246,7 +246,7 @@ def test_straggler_handover_between_pipelined_batches(gpu, pool):
             a, a2, e = gpu.get_tallies()
             out[ho] = (a[1:], a2[1:], e, gpu.counters())
     finally:
-        gpu.set_option("pool_size", 1 << 23); gpu.set_option("handover", 1)
+        gpu.set_option("pool_size", 1 << 23); gpu.set_option("handover", 0)
         gpu.reset_tallies()
     (a0, b0, e0, c0), (a1, b1, e1, c1) = out[0], out[1]
     assert c0["handovers"] == 0 and c0["handed_over"] == 0
