@@ -12,7 +12,7 @@
  * accumulateResults(1, nhist, nbatch) normalises it).
  *
  * usage: omc_matrad_b200 -p problem.blob -n nHistories -b nbatch -t relDoseThreshold -o out_stem [-g group] [-d device]
- *        [-r rank -w world]   (beamlets rank, rank+world, ... only: one process per GPU, columns of the others left empty)
+ *        [-r rank -w world]   (one process per GPU: this rank's groups of consecutive beamlets only, columns of the others left empty)
  * There is no CPU transport here: without a CUDA device the program exits with the library's error.
  */
 #include <math.h>
@@ -104,12 +104,18 @@ int main(int argc, char **argv) {
     long long *ncol = calloc((size_t)nbeamlets, sizeof(long long));
     long long **cir = calloc((size_t)nbeamlets, sizeof(long long *));
     double **cval = calloc((size_t)nbeamlets, sizeof(double *));
+    if (group < 1) group = 1;
     long long *gjc = malloc(((size_t)group + 1) * sizeof(long long));
     const double t0 = now_s();
     long long done = 0;
-    for (int b0 = rank; b0 < nbeamlets;) {
-        /* world == 1: `group` consecutive beamlets per pass; several ranks: beamlets are dealt round-robin, one per pass */
-        const int nb = (world == 1) ? ((nbeamlets - b0 < group) ? nbeamlets - b0 : group) : 1;
+    /* Sharding plan (same as ompmc_b200.matrad.beamlet_groups): contiguous groups of at most `group` beamlets -- one pass of the
+     * wavefront kernels each, which pays the tail of its longest particle lineages once per GROUP, so a rank owns whole groups --
+     * as many groups as a multiple of `world`, dealt round-robin. */
+    const int ngroups = world * ((nbeamlets + world * group - 1) / (world * group));
+    const int gsize = ngroups > 0 ? (nbeamlets + ngroups - 1) / ngroups : 1;
+    for (int b0 = 0; b0 < nbeamlets; b0 += gsize) {
+        if ((b0 / gsize) % world != rank) continue;
+        const int nb = (nbeamlets - b0 < gsize) ? nbeamlets - b0 : gsize;
         long long tot = 0;
         if (omc_gpu_run_beamlets(gpu, (long long)b0 * nhist, nhist, nbatch, b0, nb, rel, dens, gjc, &tot)) die("omc_gpu_run_beamlets");
         long long *ir = malloc((size_t)(tot ? tot : 1) * sizeof(long long));
@@ -125,7 +131,6 @@ int main(int argc, char **argv) {
         }
         free(ir); free(val);
         done += nb;
-        b0 += (world == 1) ? nb : world;
     }
     const double t1 = now_s();
     for (int b2 = 0; b2 < nbeamlets; b2++) jc[b2 + 1] = jc[b2] + ncol[b2];

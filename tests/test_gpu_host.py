@@ -118,8 +118,10 @@ def test_c_matrad_driver_matches_python_device_path(gpu, tmp_path):
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stdout + r.stderr
         parts.append(_read_csc(st + ".csc"))
+    owner = {b0 + k: r for b0, n, r in matrad.beamlet_groups(nb, 2, 64) for k in range(n)}     # whole groups per rank
+    assert sorted(set(owner.values())) == [0, 1]
     for b in range(nb):
-        own, other = parts[b % 2], parts[1 - b % 2]
+        own, other = parts[owner[b]], parts[1 - owner[b]]
         assert other[2][b + 1] == other[2][b]                                     # not this rank's beamlet: empty column
         d = np.zeros(ph.nvox); d[own[3][own[2][b]:own[2][b + 1]]] = own[4][own[2][b]:own[2][b + 1]]
         d0 = np.zeros(ph.nvox); d0[ir[jc[b]:jc[b + 1]]] = pr[jc[b]:jc[b + 1]]

@@ -201,3 +201,17 @@ def test_gpu_matrad_multi_beamlet_pass_vs_beamlet_loop(gpu):
     dB = np.zeros(ph.nvox); dB[ir1[jc1[3]:jc1[4]]] = v1[jc1[3]:jc1[4]]
     np.testing.assert_allclose(dA, dB, rtol=2e-3, atol=0.051 * dB.max())
     assert abs(dA.sum() - dB.sum()) < 2e-3 * dB.sum()
+
+
+def test_beamlet_group_plan_covers_every_beamlet_once_and_balances_ranks():
+    """Sharding plan of the multi-beamlet pass (matrad.beamlet_groups; omc_matrad_b200.c computes the same): whole groups of
+    consecutive beamlets per rank, every beamlet exactly once, groups no larger than asked, ranks balanced to one group size,
+    ragged and degenerate cases (fewer beamlets than ranks, none at all)."""
+    for n, world, group in ((320, 2, 64), (320, 1, 64), (6, 2, 64), (6, 2, 4), (1, 2, 64), (3, 8, 64), (0, 2, 64), (129, 2, 64), (320, 8, 64), (7, 3, 1)):
+        plan = matrad.beamlet_groups(n, world, group)
+        assert [b for b0, c, r in plan for b in range(b0, b0 + c)] == list(range(n))
+        assert all(0 < c <= group and 0 <= r < world for _, c, r in plan)
+        per = [sum(c for _, c, r in plan if r == k) for k in range(world)]
+        if n:
+            assert max(per) - min(per) <= max(c for _, c, _ in plan)
+        assert [r for _, _, r in plan] == [j % world for j in range(len(plan))]
