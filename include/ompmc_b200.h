@@ -217,9 +217,15 @@ int omc_gpu_write_3ddose(omc_gpu_handle h, const char *path, int iout, int nhist
  * (omc_matrad.c:1416-1477) run on the device.  nbatch only enters as the reference's normalisation: the
  * batch-method uncertainty is never exported by omc_matrad (Q12), so no batch structure is kept.  jc[nb+1] receives
  * the column starts (jc[0] = 0), *nnz_total their sum; rows (irl-1, ascending) and values of all columns stay on the
- * device until omc_gpu_fetch_columns(ir[nnz_total], val[nnz_total]).  Needs nb * nreg * 4 bytes of device memory. */
+ * device until omc_gpu_fetch_columns(ir[nnz_total], val[nnz_total]).  Needs nb * nreg * 4 bytes of device memory.  A pass pays
+ * the ramp-up and the tail of its longest particle lineages once whatever its size, but its dose atomics spread over nb grids:
+ * measured on B200 (PROSTATE at 3 mm, 12 MB per grid, 320 beamlets x 1e6 histories) 64 beamlets per pass run 7.3-7.9e7
+ * histories/s, all 320 in one pass 6.5e7, one per pass 1.2e7 -- hence OMC_BEAMLETS_PER_PASS. */
 int omc_gpu_run_beamlets(omc_gpu_handle h, long long first_history, int nhist, int nbatch, int ib0, int nb, double rel_threshold,
                          const double *med_densities, long long *jc, long long *nnz_total);
+/* default pass size of the drivers, and the HBM budget that caps it for large grids (1 mm voxels: 0.33 GB per beamlet) */
+#define OMC_BEAMLETS_PER_PASS 64
+#define OMC_BEAMLET_GRID_BUDGET (64.0 * 1073741824.0)
 int omc_gpu_fetch_columns(omc_gpu_handle h, long long *ir, double *val);
 /* score.endep of the running batch, [nreg] fp64 (before accum_batch) */
 int omc_gpu_get_batch_grid(omc_gpu_handle h, double *endep);

@@ -20,6 +20,7 @@ import numpy as np
 from . import problem as P
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+BEAMLETS_PER_PASS, BEAMLET_GRID_BUDGET = 64, 64 * 1073741824        # OMC_BEAMLETS_PER_PASS, OMC_BEAMLET_GRID_BUDGET of the header
 LIB_PATH = os.path.join(HERE, "libompmc_b200.so")
 
 KERNEL_LOCKSTEP, KERNEL_WAVEFRONT = 0, 1
@@ -263,6 +264,11 @@ class GpuTransport:
         ir = np.zeros(max(tot.value, 1), dtype=np.int64); val = np.zeros(max(tot.value, 1))
         self._ck(self.lib.omc_gpu_fetch_columns(self.h, ir.ctypes.data, val.ctypes.data), "omc_gpu_fetch_columns")
         return jc, ir[:tot.value], val[:tot.value]
+
+    def beamlet_capacity(self) -> int:
+        """default beamlets per run_beamlets() pass: OMC_BEAMLETS_PER_PASS, fewer when their fp32 dose grids exceed
+        OMC_BEAMLET_GRID_BUDGET (include/ompmc_b200.h, with the measurement behind the 64)"""
+        return max(1, min(BEAMLETS_PER_PASS, int(BEAMLET_GRID_BUDGET // (self.nreg * 4))))
 
     def start_batch(self, first: int, n: int, ibeamlet: int = -1):
         """Pipelined batch, accumulation left to the caller (see include/ompmc_b200.h)."""

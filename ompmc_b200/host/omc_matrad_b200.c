@@ -11,7 +11,7 @@
  * int64 jc[ncols+1], int64 ir[nnz] (voxel index irl-1, ascending inside a column), double pr[nnz] (Gy per history as
  * accumulateResults(1, nhist, nbatch) normalises it).
  *
- * usage: omc_matrad_b200 -p problem.blob -n nHistories -b nbatch -t relDoseThreshold -o out_stem [-g group] [-d device]
+ * usage: omc_matrad_b200 -p problem.blob -n nHistories -b nbatch -t relDoseThreshold -o out_stem [-g beamlets per pass, default 64] [-d device]
  *        [-r rank -w world]   (one process per GPU: this rank's groups of consecutive beamlets only, columns of the others left empty)
  * There is no CPU transport here: without a CUDA device the program exits with the library's error.
  */
@@ -35,7 +35,7 @@ static uint64_t count_of(const blob *b, const char *name) { return blob_find(b, 
 int main(int argc, char **argv) {
     const char *pfile = NULL, *ncase = "100000", *nbatch_s = "10", *stem = "omc_matrad_b200", *seeds = "97 33";
     double rel = 1.0e-3;
-    int device = 0, group = 64, rank = 0, world = 1;
+    int device = 0, group = 0, rank = 0, world = 1;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "-p") && i + 1 < argc) pfile = argv[++i];
         else if (!strcmp(argv[i], "-n") && i + 1 < argc) ncase = argv[++i];
@@ -48,13 +48,12 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[i], "-w") && i + 1 < argc) world = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-s") && i + 1 < argc) seeds = argv[++i];
         else {
-            printf("usage: %s -p problem.blob -n nHistories -b nbatch -t relDoseThreshold -o out_stem [-g group] [-d device] [-r rank -w world]\n",
+            printf("usage: %s -p problem.blob -n nHistories -b nbatch -t relDoseThreshold -o out_stem [-g beamlets per pass, default 64] [-d device] [-r rank -w world]\n",
                    argv[0]);
             return 2;
         }
     }
     if (!pfile) { printf("Can not find the problem file (-p).\n"); return 2; }
-    if (group < 1) group = 1;
     if (world < 1 || rank < 0 || rank >= world) { printf("rank/world out of range.\n"); return 2; }
     const double tbegin = now_s();
     blob b;
@@ -104,9 +103,16 @@ int main(int argc, char **argv) {
     long long *ncol = calloc((size_t)nbeamlets, sizeof(long long));
     long long **cir = calloc((size_t)nbeamlets, sizeof(long long *));
     double **cval = calloc((size_t)nbeamlets, sizeof(double *));
-    if (group < 1) group = 1;
+    if (group < 1) {            /* default: 64 beamlets per pass, fewer when their dose grids would not fit the HBM budget */
+        long long capn = (long long)(OMC_BEAMLET_GRID_BUDGET / ((double)(nvox + 1) * 4.0));
+        group = capn > OMC_BEAMLETS_PER_PASS ? OMC_BEAMLETS_PER_PASS : (int)capn;
+        if (group < 1) group = 1;
+    }
+    if (group > nbeamlets) group = nbeamlets > 0 ? nbeamlets : 1;
+    printf("Beamlets per pass: up to %d\n", group);
     long long *gjc = malloc(((size_t)group + 1) * sizeof(long long));
     const double t0 = now_s();
+    printf("Execution time up to this point : %8.2f seconds\n", t0 - tbegin);
     long long done = 0;
     /* Sharding plan (same as ompmc_b200.matrad.beamlet_groups): contiguous groups of at most `group` beamlets -- one pass of the
      * wavefront kernels each, which pays the tail of its longest particle lineages once per GROUP, so a rank owns whole groups --

@@ -76,7 +76,7 @@ def beamlet_groups(nbeamlets: int, world: int = 1, group: int = 64):
 
 
 def dose_influence_matrix_device(tr, ph: P.Phantom, nbeamlets: int, ncase, nbatch, rel_threshold: float, rank: int = 0, world: int = 1,
-                                 gather=None, first_history: int = 0, group: int = 64):
+                                 gather=None, first_history: int = 0, group: int | None = None):
     """Same matrix as dose_influence_matrix() built the B200 way (north_star: "each GPU builds its slice of the sparse
     dose-influence matrix"): the beamlets of a rank are run `group` at a time in ONE pass of the wavefront kernels
     (omc_gpu_run_beamlets: history id -> beamlet -> its own dose grid; no per-batch tail per beamlet), and
@@ -84,6 +84,8 @@ def dose_influence_matrix_device(tr, ph: P.Phantom, nbeamlets: int, ncase, nbatc
     [first_history + b*nhist, +nhist), so up to scheduling-independent statistics this is the per-beamlet loop's result."""
     nhist, nb, nper = P.batch_plan(ncase, nbatch)
     mine = {}
+    if group is None:               # 64 per pass unless the grids would not fit (api.beamlet_capacity)
+        group = tr.beamlet_capacity()
     for b0, n, owner in beamlet_groups(nbeamlets, world, group):
         if owner != rank:
             continue
@@ -113,7 +115,7 @@ def gather_columns_torch(mine: dict, group=None) -> dict:
 
 
 def dose_influence_matrix_device(tr, ph: P.Phantom, nbeamlets: int, ncase, nbatch, rel_threshold: float, rank: int = 0, world: int = 1,
-                                 gather=None, first_history: int = 0, group: int = 64):
+                                 gather=None, first_history: int = 0, group: int | None = None):
     """Same matrix as dose_influence_matrix() built the B200 way (north_star: "each GPU builds its slice of the sparse
     dose-influence matrix"): the beamlets of a rank are run `group` at a time in ONE pass of the wavefront kernels
     (omc_gpu_run_beamlets: history id -> beamlet -> its own dose grid; no per-batch tail per beamlet), and

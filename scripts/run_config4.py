@@ -14,7 +14,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
-from ompmc_b200 import build, problem as P  # noqa: E402
+from ompmc_b200 import build, matrad, problem as P  # noqa: E402
 
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 ny = int(sys.argv[2]) if len(sys.argv) > 2 else 8
@@ -47,20 +47,22 @@ except Exception:
     ngpu = 1
 rows = []
 single = None
-for world in [n for n in (1, 2, 4, 8) if n <= ngpu]:
+for world, group in [(n, 64) for n in (1, 2, 4, 8) if n <= ngpu] + [(1, 320), (1, 1)][:int(os.environ.get('C4_SWEEP', '0')) * 2]:
     t0 = time.time()
     procs = [subprocess.Popen([build.MATRAD_EXE, "-p", "/tmp/c4/m.blob", "-n", str(nhist), "-b", "10", "-t", "0.001", "-o", f"/tmp/c4/w{world}r{r}",
-                               "-g", "64", "-d", str(r), "-r", str(r), "-w", str(world)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                               "-g", str(group), "-d", str(r), "-r", str(r), "-w", str(world)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
              for r in range(world)]
     outs = [p.communicate()[0] for p in procs]
     dt = time.time() - t0
     assert all(p.returncode == 0 for p in procs), outs[0][-1500:]
     parts = [read_csc(f"/tmp/c4/w{world}r{r}.csc") for r in range(world)]
-    cols = [parts[b % world] for b in range(nb)]
+    owner = {b0 + k: r for b0, n, r in matrad.beamlet_groups(nb, world, group if group else 1 << 16) for k in range(n)}
+    cols = [parts[owner[b]] for b in range(nb)]
     nnz = sum(int(c[2][b + 1] - c[2][b]) for b, c in enumerate(cols))
-    row = {"config": "config4_prostate_matrad", "gpus": world, "beamlets": nb, "histories_per_beamlet": nhist, "wall_s": round(dt, 3),
+    row = {"config": "config4_prostate_matrad", "gpus": world, "beamlets_per_pass": group, "beamlets": nb, "histories_per_beamlet": nhist, "wall_s": round(dt, 3),
            "beamlets_per_s": nb / dt, "hist_per_s": nb * nhist / dt, "nnz": nnz, "nvox": ph.nvox}
-    if world == 1:
+    row["per_rank"] = [[ln.strip() for ln in o.splitlines() if ln.startswith(("Beamlets computed", "Beamlets per pass", "Total execution time", "Execution time up"))] for o in outs]
+    if single is None:
         single = cols
     else:                                     # same history ids per beamlet whatever the rank count: columns agree to fp32 summation order
         worst = 0.0

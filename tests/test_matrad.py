@@ -181,7 +181,7 @@ def test_gpu_matrad_multi_beamlet_pass_vs_beamlet_loop(gpu):
     gpu.load_problem(prob)
     gpu.set_option("kernel", 1)
     jc0, ir0, v0 = matrad.dose_influence_matrix(gpu, ph, nb, "100000", "4", 0.05)
-    jc1, ir1, v1 = matrad.dose_influence_matrix_device(gpu, ph, nb, "100000", "4", 0.05, group=5)      # 12 beamlets: groups of 5, 5, 2
+    jc1, ir1, v1 = matrad.dose_influence_matrix_device(gpu, ph, nb, "100000", "4", 0.05, group=5)      # 12 beamlets in passes of at most 5: 4, 4, 4
     assert len(jc0) == len(jc1) == nb + 1 and jc1[0] == 0 and jc1[-1] == len(ir1) == len(v1)
     for b in range(nb):
         r1 = ir1[jc1[b]:jc1[b + 1]]
