@@ -79,7 +79,6 @@ def _read_csc(path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU minutes were spent: first run on a device pending")
 def test_reference_matrad_user_code_on_the_gpu_library(gpu):
     cmd, prob, ph, nb, blob, stem = dropin_cmd()
     build.build()
