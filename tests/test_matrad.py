@@ -57,6 +57,23 @@ class _OracleAsTransport:
     def get_tallies(self):
         return self.o.get_accum()
 
+    def beamlet_capacity(self):
+        return 64
+
+    def run_beamlets(self, first, nhist, nbatch, ib0, nb, rel_threshold, med_densities, ph=None):
+        """CPU stand-in of omc_gpu_run_beamlets(): beamlet ib0+k owns history ids [first + k*nhist, +nhist); (jc, ir, val)."""
+        ph = ph or self.ph
+        nper = nhist // nbatch
+        jc, irs, vals = [0], [], []
+        for k in range(nb):
+            self.reset_tallies(0)
+            for ib in range(nbatch):
+                self.run_batch(first + k * nhist + ib * nper, nper, ib0 + k)
+            a, a2, _ = self.get_tallies()
+            rows, v = matrad.beamlet_column(ph, a, a2, nhist, nbatch, rel_threshold)
+            irs.append(rows); vals.append(v); jc.append(jc[-1] + len(rows))
+        return np.asarray(jc, dtype=np.int64), np.concatenate(irs), np.concatenate(vals)
+
     def reset_tallies(self, which=0):
         if which == 0:
             self.o.reset_score()
@@ -103,8 +120,12 @@ dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 prob, ph, nb = matrad_problem(nbix=(2, 1), angles=(0.0, 90.0, 180.0))
 orc = OracleTransport(); orc.set_num_threads(1); orc.load_problem(prob); orc.set_rng("philox")
-jc, ir, val = matrad.dose_influence_matrix(_OracleAsTransport(orc), ph, nb, "600", "3", 0.02, rank, world, matrad.gather_columns_torch)
-np.savez(%(out)r + f".{rank}.npz", jc=jc, ir=ir, val=val)
+tr = _OracleAsTransport(orc); tr.ph = ph
+jc, ir, val = matrad.dose_influence_matrix(tr, ph, nb, "600", "3", 0.02, rank, world, matrad.gather_columns_torch)
+# the multi-beamlet flow: whole groups of consecutive beamlets per rank (6 beamlets in passes of 2 -> groups 0,2 on rank 0, 1 on rank 1)
+jd, id_, vd = matrad.dose_influence_matrix_device(tr, ph, nb, "600", "3", 0.02, rank, world, matrad.gather_columns_torch, group=2)
+assert [g for g in matrad.beamlet_groups(nb, world, 2) if g[2] == rank]
+np.savez(%(out)r + f".{rank}.npz", jc=jc, ir=ir, val=val, jd=jd, id=id_, vd=vd)
 dist.destroy_process_group()
 """
 
@@ -126,6 +147,10 @@ def test_beamlets_sharded_over_two_ranks(tmp_path, oracle_lib):
         np.testing.assert_array_equal(z["jc"], jc)
         np.testing.assert_array_equal(z["ir"], ir)
         np.testing.assert_allclose(z["val"], val, rtol=1e-12)
+        # grouped sharding of the multi-beamlet flow: same history ids per beamlet -> the same matrix
+        np.testing.assert_array_equal(z["jd"], jc)
+        np.testing.assert_array_equal(z["id"], ir)
+        np.testing.assert_allclose(z["vd"], val, rtol=1e-12)
 
 
 @pytest.mark.gpu
