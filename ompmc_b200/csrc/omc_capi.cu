@@ -78,6 +78,7 @@ struct omc_gpu_ctx {
     int res_nreg = -1;
     // omc_gpu_write_3ddose: power-of-ten table, two text buffers (device + pinned host), fallback lists
     Pow10 *fmt_tab = nullptr;
+    bool fmt_ready = false;
     char *fmt_dev[2] = {nullptr, nullptr}, *fmt_host[2] = {nullptr, nullptr};
     FormatFallback *fmt_fb_dev[2] = {nullptr, nullptr}, *fmt_fb_host[2] = {nullptr, nullptr};
     unsigned *fmt_nfb_dev = nullptr, *fmt_nfb_host = nullptr;
@@ -962,20 +963,22 @@ static const long long FMT_CHUNK = 4ll << 20;          // values per chunk: 52 M
 static const unsigned FMT_FB_CAP = 1u << 16;           // host-formatted values per chunk before the whole chunk goes to snprintf
 
 static int format_setup(omc_gpu_handle h) {
-    if (h->fmt_tab) return 0;
+    if (h->fmt_ready) return 0;
     std::vector<Pow10> tab(kPow10N);
     build_pow10_table(tab.data());
-    CK(cudaMalloc((void **)&h->fmt_tab, sizeof(Pow10) * kPow10N));
+    if (!h->fmt_tab) CK(cudaMalloc((void **)&h->fmt_tab, sizeof(Pow10) * kPow10N));
     CK(cudaMemcpy(h->fmt_tab, tab.data(), sizeof(Pow10) * kPow10N, cudaMemcpyHostToDevice));
-    CK(cudaMalloc((void **)&h->fmt_nfb_dev, 2 * sizeof(unsigned)));
-    CK(cudaMallocHost((void **)&h->fmt_nfb_host, 2 * sizeof(unsigned)));
+    // (a failed allocation leaves fmt_ready false: the next call retries only what is still missing)
+    if (!h->fmt_nfb_dev) CK(cudaMalloc((void **)&h->fmt_nfb_dev, 2 * sizeof(unsigned)));
+    if (!h->fmt_nfb_host) CK(cudaMallocHost((void **)&h->fmt_nfb_host, 2 * sizeof(unsigned)));
     for (int i = 0; i < 2; i++) {
-        CK(cudaMalloc((void **)&h->fmt_dev[i], (size_t)FMT_CHUNK * kFmtEWidth));
-        CK(cudaMallocHost((void **)&h->fmt_host[i], (size_t)FMT_CHUNK * kFmtEWidth));
-        CK(cudaMalloc((void **)&h->fmt_fb_dev[i], sizeof(FormatFallback) * FMT_FB_CAP));
-        CK(cudaMallocHost((void **)&h->fmt_fb_host[i], sizeof(FormatFallback) * FMT_FB_CAP));
-        CK(cudaEventCreateWithFlags(&h->fmt_ev[i], cudaEventDisableTiming));
+        if (!h->fmt_dev[i]) CK(cudaMalloc((void **)&h->fmt_dev[i], (size_t)FMT_CHUNK * kFmtEWidth));
+        if (!h->fmt_host[i]) CK(cudaMallocHost((void **)&h->fmt_host[i], (size_t)FMT_CHUNK * kFmtEWidth));
+        if (!h->fmt_fb_dev[i]) CK(cudaMalloc((void **)&h->fmt_fb_dev[i], sizeof(FormatFallback) * FMT_FB_CAP));
+        if (!h->fmt_fb_host[i]) CK(cudaMallocHost((void **)&h->fmt_fb_host[i], sizeof(FormatFallback) * FMT_FB_CAP));
+        if (!h->fmt_ev[i]) CK(cudaEventCreateWithFlags(&h->fmt_ev[i], cudaEventDisableTiming));
     }
+    h->fmt_ready = true;
     return 0;
 }
 
