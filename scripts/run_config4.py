@@ -2,7 +2,8 @@
 """BASELINE config 4 at treatment-plan scale through the plain-C matRad driver (ompmc_b200/host/omc_matrad_b200.c): PROSTATE-like
 phantom, 5 gantry angles x (nx x ny) bixels of 5 mm, nHistories per beamlet, relDoseThreshold 1e-3; one process per GPU
 (-r rank -w world -d device), beamlets dealt round-robin; the per-rank CSC files are merged in beamlet order and compared with
-the single-GPU matrix.  usage: python scripts/run_config4.py [nx=8] [ny=8] [histories_per_beamlet=1000000]"""
+the single-GPU matrix.  VERIFICATION / MEASUREMENT SCRIPT (not product code; like tests/ it may use the test infrastructure under oracle/).
+usage: python scripts/run_config4.py [nx=8] [ny=8] [histories_per_beamlet=1000000]"""
 import json
 import os
 import subprocess

@@ -5,7 +5,8 @@ data files) to a .3ddose file on one B200, twice per config:
   dropin  oracle/_ref/omc_dosxyz_dropin -i     (the reference's own user code + init code, batch loop on libompmc_b200.so)
 Both hand the device the same problem and the same history ids, so the two dose files must agree to the summation order of
 the fp32 dose atomics.  Phantoms are the synthetic stand-ins of bench.py (the reference checkout lacks its .egsphant files),
-spinms.data the synthetic one of oracle/gen_fixtures.py.  usage: python scripts/run_configs.py [scale=1.0]"""
+spinms.data the synthetic one of oracle/gen_fixtures.py.  VERIFICATION / MEASUREMENT SCRIPT (not product code; like tests/ it may use the test infrastructure under oracle/).
+usage: python scripts/run_configs.py [scale=1.0]"""
 import json
 import os
 import re

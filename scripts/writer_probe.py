@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Output phase of BASELINE config 5 (up-sampled PROSTATE grid): outputResults() with the statistics and the .3ddose text on the
 device (omc_gpu_write_3ddose) against the reference's per-value fprintf loop on the host (plain-C driver, OMC_HOST_RESULTS=3:
-both writers on the same tallies); the two files must be byte-identical.  usage: python scripts/writer_probe.py [factor=2] [histories=2e6]"""
+both writers on the same tallies); the two files must be byte-identical.  VERIFICATION / MEASUREMENT SCRIPT (not product code; like tests/ it may use the test infrastructure under oracle/).
+usage: python scripts/writer_probe.py [factor=2] [histories=2e6]"""
 import json
 import os
 import subprocess
