@@ -15,6 +15,13 @@ namespace omc {
 
 constexpr float RMf = (float)OMC_RM;
 
+// EXPERIMENT (default off, not yet measured): the azimuth of selectAzimuthalAngle() (src/ompmc.c:101-122) drawn directly as
+// (cos, sin)(2 pi u) instead of the reference's box rejection -- same uniform distribution, no retry loop (the loop runs at 11 of 32
+// lanes in the condensed-history kernel and costs a Philox block per retry round), one random word per angle instead of two.
+#ifndef OMC_AZIMUTH_SINCOS
+#define OMC_AZIMUTH_SINCOS 0
+#endif
+
 __device__ __forceinline__ float nextf(Rng &g) {           // 24-bit lattice in [0,1), like RANMAR's
     if (g.pos >= 4u) g.refill();
     const uint32_t w = g.pos == 0u ? g.b0 : (g.pos == 1u ? g.b1 : (g.pos == 2u ? g.b2 : g.b3));
@@ -373,6 +380,13 @@ __device__ __forceinline__ void sscat_b(const DevProblem &P, Rng &g, int imed, i
     }
     cost = 1.0f - x;
     sint = sqrtf(x * (2.0f - x));
+#if OMC_AZIMUTH_SINCOS
+    {
+        uint32_t wu, wr;
+        ps.next(g, wu, wr);
+        __sincosf(6.2831853f * u24(wu), &sphi, &cphi);
+    }
+#else
     for (;;) {
         uint32_t wu, wr;
         ps.next(g, wu, wr);
@@ -383,6 +397,7 @@ __device__ __forceinline__ void sscat_b(const DevProblem &P, Rng &g, int imed, i
             break;
         }
     }
+#endif
 }
 
 __device__ __forceinline__ double msdist_b(const DevProblem &P, Rng &g, const Part &p, int imed, int qel, double rhof_d, double de_d,
@@ -519,6 +534,13 @@ __device__ __forceinline__ double msdist_b(const DevProblem &P, Rng &g, const Pa
     }
     // both azimuths, selectAzimuthalAngle() :101-122, from one block per round
     float cphi1 = 1.0f, sphi1 = 0.0f, cphi2 = 1.0f, sphi2 = 0.0f;
+#if OMC_AZIMUTH_SINCOS
+    {
+        const uint4 ba = g.block();
+        __sincosf(6.2831853f * u24(ba.x), &sphi1, &cphi1);
+        __sincosf(6.2831853f * u24(ba.y), &sphi2, &cphi2);
+    }
+#else
     {
         bool ok1 = false, ok2 = false;
         do {
@@ -533,6 +555,7 @@ __device__ __forceinline__ double msdist_b(const DevProblem &P, Rng &g, const Pa
             }
         } while (!(ok1 && ok2));
     }
+#endif
     const float u2 = sint2 * cphi2, v2 = sint2 * sphi2;
     float u2p = w1 * u2 + sint1 * w2;
     float us = u2p * cphi1 - v2 * sphi1, vs = u2p * sphi1 + v2 * cphi1, ws = w1 * w2 - sint1 * u2;
