@@ -158,6 +158,12 @@ int main(int argc, char **argv) {
         if (!ncase) { if (!inp_get(&inp, "ncase", ncase_buf)) { printf("Can not find 'ncase' key on input file.\n"); return EXIT_FAILURE; } ncase = ncase_buf; }
         if (!nbatch_s) { if (!inp_get(&inp, "nbatch", nbatch_buf)) { printf("Can not find 'nbatch' key on input file.\n"); return EXIT_FAILURE; } nbatch_s = nbatch_buf; }
         if (dump_only) return host_dump_problem(stem, &t, &g, dens, &s, nsplit) ? EXIT_FAILURE : EXIT_SUCCESS;
+        /* outputResults() writes "output folder" + output_file + ".3ddose" (omc_dosxyz.c:822-833): a relative -o name goes there */
+        static char out_stem[800];
+        if (stem[0] != '/' && inp_path(&inp, "output folder", folder)) {
+            snprintf(out_stem, sizeof out_stem, "%s%s", folder, stem);
+            stem = out_stem;
+        }
     } else {
         static blob b;
         if (blob_read(&b, pfile) != 0) { printf("Unable to open file: %s\n", pfile); return EXIT_FAILURE; }
