@@ -336,7 +336,8 @@ def main() -> None:
     e2e_value = e2e_steps * H * world / (e2e_ms * 1e-3)
     peak, peak_kind = measured_peaks()
     line = {"metric": "histories/s", "value": value, "unit": "histories/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "mixed f64/f32" if kernel == 1 else "f64",
             "data": "synthetic",
             "config": {"workload": args.workload, "desc": w["desc"], "hist_per_step_per_gpu": H, "nsplit": args.nsplit,
                        "kernel": {0: "lockstep", 1: "wavefront"}[kernel], "rng": "philox4x32-10 per history",

@@ -258,6 +258,30 @@ int omc_gpu_test_geometry(omc_gpu_handle h, int n, const double *xyzuvw /* [6*n]
  */
 int omc_gpu_test_particles(omc_gpu_handle h, int n, const int *iq, const double *e, const double *xyzuvw, const int *ir,
                            const double *wt, long long first_history, omc_history_record *records);
+/*
+ * The samplers of the PRODUCTION (wavefront) kernels on explicit inputs, one thread per record, record i drawing from the
+ * Philox stream of history first_history + i.  `in` and `out` hold n records of 8 doubles.  These are the mixed-precision /
+ * block-draw re-implementations (csrc/omc_physics_f32.cuh, omc_wavefront.cu) of the reference functions cited per sampler;
+ * tests/test_gpu_production_samplers.py compares them with the reference's own functions on the same inputs.
+ *   OMC_SAMPLER_DRANGE   computeDrange()  src/ompmc.c:3979-4014   in {imed, iq, ekei, ekef (same PWL bin)}   out {path length}
+ *   OMC_SAMPLER_ELOSS    computeEloss()   :4016-4108 + the range of electron() :4905-4918
+ *                                         in {imed, iq, rhof, eke, tustep / range}                            out {range, de}
+ *   OMC_SAMPLER_MSDIST   msdist() + mscat() + spinRejection()  :3787-3976, :3606-3785, :3097-3168
+ *                                         in {imed, iq, rhof, eke, tustep / range, u, v, w}   out {ustep, dx, dy, dz, uf, vf, wf, de}
+ *   OMC_SAMPLER_SSCAT    sscat() + selectAzimuthalAngle()  :3170-3199, :101-122
+ *                                         in {imed, qel, chia2, elke, beta2}                 out {cos, sin, cos(phi), sin(phi)}
+ *   OMC_SAMPLER_COMPTON  compton()        :1670-1783   in {e, u, v, w}        out {e_photon, u, v, w, e_electron (total), u, v, w}
+ *   OMC_SAMPLER_MOLLER   moller()         :4359-4435   in {imed, e, u, v, w}  out {e1, u1, v1, w1, e2 (0: none created), u2, v2, w2}
+ *   OMC_SAMPLER_WOODCOCK photon free flight :1951-2019 (Woodcock tracking instead of the voxel march)
+ *                                         in {e, x, y, z, u, v, w}  out {1 = interaction site / 0 = left the phantom, x, y, z, ir, tentative collisions}
+ *   OMC_SAMPLER_ESTEP    step-size phase of electron() :4694-4967
+ *                                         in {iq, e (total), x, y, z, ir}  out {class (1 CH, 2 BCA, 0 below cut-off), tustep, tperp, range,
+ *                                                                               total_tstep, demfp, blccl, ssmfp}
+ */
+enum { OMC_SAMPLER_DRANGE = 0, OMC_SAMPLER_ELOSS = 1, OMC_SAMPLER_MSDIST = 2, OMC_SAMPLER_SSCAT = 3, OMC_SAMPLER_COMPTON = 4,
+       OMC_SAMPLER_MOLLER = 5, OMC_SAMPLER_WOODCOCK = 6, OMC_SAMPLER_ESTEP = 7 };
+int omc_gpu_test_samplers(omc_gpu_handle h, int which, int n, const double *in /* [8*n] */, long long first_history,
+                          double *out /* [8*n] */);
 /* n raw Philox draws of history `hist` as the transport sees them (double in [0,1)) */
 int omc_gpu_test_rng(omc_gpu_handle h, long long hist, int n, double *out);
 /* n host doubles through the formatting kernel of omc_gpu_write_3ddose into `path`: one block of a .3ddose file, i.e. what

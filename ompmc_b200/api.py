@@ -91,7 +91,7 @@ EXPORTS = ["omc_gpu_create", "omc_gpu_destroy", "omc_gpu_last_error", "omc_gpu_s
            "omc_gpu_run_histories", "omc_gpu_accum_batch", "omc_gpu_run_batch", "omc_gpu_start_batch", "omc_gpu_finish_batches",
            "omc_gpu_completed_batches", "omc_gpu_synchronize", "omc_gpu_get_tallies",
            "omc_gpu_get_batch_grid", "omc_gpu_accumulate_results", "omc_gpu_write_3ddose", "omc_gpu_test_format", "omc_gpu_run_beamlets", "omc_gpu_fetch_columns", "omc_gpu_reset_tallies", "omc_gpu_device_ptrs", "omc_gpu_stream", "omc_gpu_get_counters",
-           "omc_gpu_get_history_records", "omc_gpu_test_geometry", "omc_gpu_test_rng", "omc_gpu_test_particles",
+           "omc_gpu_get_history_records", "omc_gpu_test_geometry", "omc_gpu_test_rng", "omc_gpu_test_particles", "omc_gpu_test_samplers",
            "omc_gpu_abi_sizeof"]
 
 
@@ -134,6 +134,7 @@ def load_library() -> C.CDLL:
     lib.omc_gpu_test_rng.argtypes = [H, C.c_longlong, C.c_int, C.c_void_p]
     lib.omc_gpu_abi_sizeof.argtypes = [C.c_int]
     lib.omc_gpu_test_particles.argtypes = [H, C.c_int] + [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]
+    lib.omc_gpu_test_samplers.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]
     return lib
 
 
@@ -357,6 +358,17 @@ class GpuTransport:
         self._ck(self.lib.omc_gpu_test_particles(self.h, n, iq.ctypes.data, e.ctypes.data, xyzuvw.ctypes.data, ir.ctypes.data,
                                                  wt.ctypes.data, first_history, rec.ctypes.data), "omc_gpu_test_particles")
         return rec
+
+    def test_samplers(self, which: int, inputs, first_history: int = 0) -> np.ndarray:
+        """One sampler of the PRODUCTION kernels on explicit inputs (OMC_SAMPLER_* of include/ompmc_b200.h): n records of up to
+        8 doubles in -> n records of 8 doubles out, record i drawing from the Philox stream of history first_history + i."""
+        inputs = np.asarray(inputs, dtype=np.float64)
+        a = np.zeros((len(inputs), 8))
+        a[:, :inputs.shape[1]] = inputs
+        out = np.zeros_like(a)
+        self._ck(self.lib.omc_gpu_test_samplers(self.h, int(which), len(a), a.ctypes.data, int(first_history), out.ctypes.data),
+                 "omc_gpu_test_samplers")
+        return out
 
     def test_rng(self, hist: int, n: int) -> np.ndarray:
         out = np.zeros(n)

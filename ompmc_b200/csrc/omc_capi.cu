@@ -1296,6 +1296,33 @@ int omc_gpu_test_particles(omc_gpu_handle h, int n, const int *iq, const double 
     return rc;
 }
 
+int omc_gpu_test_samplers(omc_gpu_handle h, int which, int n, const double *in, long long first_history, double *out) {
+    if (!h || !in || !out || n <= 0) return 2;
+    if (which < 0 || which > OMC_SAMPLER_ESTEP) return fail(h, "unknown sampler");
+    if (!h->have_media || !h->have_geom) return fail(h, "media and geometry must be set first");
+    CK(cudaSetDevice(h->device));
+    if (h->med_dirty) {
+        for (size_t m = 0; m < h->med_host.size(); m++) {
+            h->med_host[m].ecut = h->cut_e[m]; h->med_host[m].pcut = h->cut_p[m]; h->med_host[m].rhomax = h->rho_max[m];
+        }
+        CK(cudaMemcpyAsync((void *)h->P.med, h->med_host.data(), h->med_host.size() * sizeof(MedRec), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->med_dirty = false;
+    }
+    double *din = nullptr, *dout = nullptr;
+    CK(cudaMalloc((void **)&din, (size_t)8 * n * sizeof(double)));
+    CK(cudaMalloc((void **)&dout, (size_t)8 * n * sizeof(double)));
+    CK(cudaMemcpy(din, in, (size_t)8 * n * sizeof(double), cudaMemcpyHostToDevice));
+    launch_test_samplers(h->P, which, n, din, (unsigned long long)first_history, dout, h->stream);
+    h->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, (size_t)8 * n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(din); cudaFree(dout);
+    if (e != cudaSuccess) { h->err = std::string("omc_gpu_test_samplers: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+
 int omc_gpu_test_rng(omc_gpu_handle h, long long hist, int n, double *out) {
     if (!h || !out || n <= 0) return 2;
     CK(cudaSetDevice(h->device));

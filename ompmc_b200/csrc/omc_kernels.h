@@ -102,6 +102,8 @@ struct WaveStreams {
     cudaEvent_t fork, join, fork3, join3;
 };
 void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, const WaveStreams &W);
+// unit-test hook: one production sampler on explicit inputs (omc_gpu_test_samplers)
+void launch_test_samplers(const DevProblem &P, int which, int n, const double *in, unsigned long long first, double *out, cudaStream_t s);
 void launch_flush(float *g32, double *g64, long long n, cudaStream_t s);
 // Straggler hand-over (batch pipelining): move what is left of the PREVIOUS batch (history id < WaveCtl::hist_split) out of
 // the four current queues into `side` and mark the originals dead; omc_capi.cu then gives `side` to drain_kernel.

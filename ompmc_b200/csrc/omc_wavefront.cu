@@ -326,12 +326,59 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, const Batch
 // voxel-to-voxel march (photon() src/ompmc.c:1951-2019: mean free paths accumulated over the voxels crossed),
 // but a flight costs a few voxel look-ups instead of one per voxel crossed, and there is no dependent chain of
 // voxel-record loads.  Draws are consumed in whole Philox blocks: {distance, accept} x 2 per block.
+// One Woodcock flight of at most max_virtual tentative collisions.  Returns 1 = real collision at p (p.ir = its voxel),
+// 0 = flight unfinished (p = last tentative site), -1 = the photon left the phantom.  `entered`: has been seen inside the box.
+__device__ __forceinline__ int woodcock_flight(const DevProblem &P, Rng &g, Part &p, bool &entered, int max_virtual, unsigned &npstep) {
+    const double gle = log(p.e);
+    double smaj = 0.0;
+    for (int m = 0; m < P.nmed; m++) {
+        const double rmax = P.med[m].rhomax;
+        if (rmax > 0.0) smaj = fmax(smaj, rmax * phot_sig0(P, m, gle));
+    }
+    if (!(smaj > 0.0)) return -1;                              // vacuum everywhere: the photon leaves
+    const double imaj = 1.0 / smaj;
+    const double x0 = __ldg(P.xb), x1 = __ldg(P.xb + P.isize), y0 = __ldg(P.yb), y1 = __ldg(P.yb + P.jsize),
+                 z0 = __ldg(P.zb), z1 = __ldg(P.zb + P.ksize);
+    int medc = -2;
+    double sigc = 0.0;
+    uint4 b = make_uint4(0u, 0u, 0u, 0u);
+    for (int k = 0; k < max_virtual; k++) {
+        if (!(k & 1)) b = g.block();
+        const uint32_t w0 = (k & 1) ? b.z : b.x, w1 = (k & 1) ? b.w : b.y;
+        const float r = ((float)(w0 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const double s = (double)(-__logf(r)) * imaj;
+        p.x += s * p.u; p.y += s * p.v; p.z += s * p.w;
+        npstep++;
+        if (p.x >= x0 && p.x < x1 && p.y >= y0 && p.y < y1 && p.z >= z0 && p.z < z1) {
+            entered = true;
+        } else {
+            if (entered) return -1;                            // left the phantom
+            // Not inside yet: a source particle sitting exactly on a max face, or one that the matRad source
+            // clamped with the wrong bound (omc_matrad.c:1225, SURVEY Q13: p.z = ybounds[0]).  The reference keeps
+            // such a particle in the voxel layer it was assigned to until it crosses a plane; the clamped
+            // look-up below does the same.  It is discarded if it moves away from the box.
+            if ((p.x < x0 && p.u <= 0.0) || (p.x >= x1 && p.u >= 0.0) || (p.y < y0 && p.v <= 0.0) || (p.y >= y1 && p.v >= 0.0) ||
+                (p.z < z0 && p.w <= 0.0) || (p.z >= z1 && p.w >= 0.0)) return -1;
+        }
+        const int ix = find_bin(P.xb, P.isize, p.x, P.inv_dx, P.uniform_x != 0);
+        const int iy = find_bin(P.yb, P.jsize, p.y, P.inv_dy, P.uniform_y != 0);
+        const int iz = find_bin(P.zb, P.ksize, p.z, P.inv_dz, P.uniform_z != 0);
+        p.ir = 1 + ix + iy * P.isize + iz * P.ijmax;
+        double rhof; int med;
+        load_region_rm(P, p.ir, rhof, med);
+        if (med < 0) continue;
+        if (med != medc) { sigc = phot_sig0(P, med, gle); medc = med; }
+        if ((double)w1 * (1.0 / 4294967296.0) * smaj < sigc * rhof) return 1;
+    }
+    return 0;
+}
+
 __device__ void photon_chunk_wc(const DevProblem &P, const WaveArgs &A, const BatchSel &BS, int par, unsigned i, unsigned n, Tally &t) {
     if (i >= n) return;
     WaveCtl *ctl = A.ctl;
     const PartQueue &q = A.Q.p[par];
     Part p; Rng g;
-    bool entered;                                              // has been seen inside the phantom box (see below)
+    bool entered;                                              // has been seen inside the phantom box (see woodcock_flight)
     {
         int tag;
         q_load_part(q, i, p, tag);
@@ -350,49 +397,9 @@ __device__ void photon_chunk_wc(const DevProblem &P, const WaveArgs &A, const Ba
         const double pcut = (P.reg8 != nullptr) ? (med >= 0 ? P.med[med].pcut : 0.0) : load_region(P, p.ir).pcut;
         if (p.e <= pcut || p.wt == 0) { deposit32(dg, t, p.ir, p.wt * p.e); return; }
     }
-    const double gle = log(p.e);
-    double smaj = 0.0;
-    for (int m = 0; m < P.nmed; m++) {
-        const double rmax = P.med[m].rhomax;
-        if (rmax > 0.0) smaj = fmax(smaj, rmax * phot_sig0(P, m, gle));
-    }
-    if (!(smaj > 0.0)) return;                                 // vacuum everywhere: the photon leaves
-    const double imaj = 1.0 / smaj;
-    const double x0 = __ldg(P.xb), x1 = __ldg(P.xb + P.isize), y0 = __ldg(P.yb), y1 = __ldg(P.yb + P.jsize),
-                 z0 = __ldg(P.zb), z1 = __ldg(P.zb + P.ksize);
-    int medc = -2;
-    double sigc = 0.0;
-    bool hit = false;
-    uint4 b = make_uint4(0u, 0u, 0u, 0u);
-    for (int k = 0; k < A.max_virtual; k++) {
-        if (!(k & 1)) b = g.block();
-        const uint32_t w0 = (k & 1) ? b.z : b.x, w1 = (k & 1) ? b.w : b.y;
-        const float r = ((float)(w0 >> 8) + 0.5f) * (1.0f / 16777216.0f);
-        const double s = (double)(-__logf(r)) * imaj;
-        p.x += s * p.u; p.y += s * p.v; p.z += s * p.w;
-        t.npstep++;
-        if (p.x >= x0 && p.x < x1 && p.y >= y0 && p.y < y1 && p.z >= z0 && p.z < z1) {
-            entered = true;
-        } else {
-            if (entered) return;                               // left the phantom
-            // Not inside yet: a source particle sitting exactly on a max face, or one that the matRad source
-            // clamped with the wrong bound (omc_matrad.c:1225, SURVEY Q13: p.z = ybounds[0]).  The reference keeps
-            // such a particle in the voxel layer it was assigned to until it crosses a plane; the clamped
-            // look-up below does the same.  It is discarded if it moves away from the box.
-            if ((p.x < x0 && p.u <= 0.0) || (p.x >= x1 && p.u >= 0.0) || (p.y < y0 && p.v <= 0.0) || (p.y >= y1 && p.v >= 0.0) ||
-                (p.z < z0 && p.w <= 0.0) || (p.z >= z1 && p.w >= 0.0)) return;
-        }
-        const int ix = find_bin(P.xb, P.isize, p.x, P.inv_dx, P.uniform_x != 0);
-        const int iy = find_bin(P.yb, P.jsize, p.y, P.inv_dy, P.uniform_y != 0);
-        const int iz = find_bin(P.zb, P.ksize, p.z, P.inv_dz, P.uniform_z != 0);
-        p.ir = 1 + ix + iy * P.isize + iz * P.ijmax;
-        double rhof; int med;
-        load_region_rm(P, p.ir, rhof, med);
-        if (med < 0) continue;
-        if (med != medc) { sigc = phot_sig0(P, med, gle); medc = med; }
-        if ((double)w1 * (1.0 / 4294967296.0) * smaj < sigc * rhof) { hit = true; break; }
-    }
-    if (hit) q_push(A.Q.ip[par ^ 1], &ctl->n_ip[par ^ 1].v, ctl, p, g, -1.0, TAG_NONE | 16);
+    const int st = woodcock_flight(P, g, p, entered, A.max_virtual, t.npstep);
+    if (st < 0) return;
+    if (st > 0) q_push(A.Q.ip[par ^ 1], &ctl->n_ip[par ^ 1].v, ctl, p, g, -1.0, TAG_NONE | 16);
     else q_push(A.Q.p[par ^ 1], &ctl->n_p[par ^ 1].v, ctl, p, g, entered ? -2.0 : -1.0, TAG_NONE);
 }
 
@@ -1235,6 +1242,91 @@ void launch_mb_fill(const float *grids, long long nreg, int nb, const DevProblem
                     const double *dmax, const long long *jc, long long *ir, double *val, cudaStream_t s) {
     MbGeom G{P.xb, P.yb, P.zb, dens, P.isize, P.jsize, (double)nhist, (double)nbatch};
     mb_fill_kernel<<<nb < 148 * 4 ? nb : 148 * 4, 512, 0, s>>>(grids, nreg, nb, G, rel, dmax, jc, ir, val);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Unit-test hook (omc_gpu_test_samplers, include/ompmc_b200.h): ONE production sampler per launch on explicit inputs,
+// one thread per record of 8 doubles, random numbers from the Philox stream of history first + i consumed exactly as the
+// transport kernels consume them.  Nothing here is used by the transport path.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double test_range(const DevProblem &P, const ElecBin *B0, const MedRec &M, double eke, double rinv, double &elke, int &lelke) {
+    elke = flog(eke);                                          // as estep_size()
+    lelke = elec_interval(M, elke);
+    const ElecBin *B = B0 + lelke;
+    const double2 re = ldg2(&B->range_ep);
+    const double elkei = (double)fdiv((float)(lelke + 1) - (float)M.eke0, (float)M.eke1);
+    return (drange_m(B, eke, re.y, elke, elkei) + re.x) * rinv;
+}
+
+__global__ void test_sampler_kernel(const __grid_constant__ DevProblem P, int which, int n, const double *__restrict__ in,
+                                    unsigned long long first, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *a = in + 8 * (size_t)i;
+    double *o = out + 8 * (size_t)i;
+    for (int k = 0; k < 8; k++) o[k] = 0.0;
+    Rng g;
+    const unsigned long long hist = first + (unsigned long long)i;
+    g.seed_blocks(P.seed0, P.seed1, (uint32_t)hist, (uint32_t)(hist >> 32), 0u, 0u);
+    if (which == OMC_SAMPLER_DRANGE) {
+        const int imed = (int)a[0], qel = (1 + (int)a[1]) / 2;
+        const MedRec &M = P.med[imed];
+        const ElecBin *B0 = P.ebin + (size_t)qel * P.nmed * MXEKE + imed * MXEKE;
+        const double elkei = flog(a[2]), elkef = flog(a[3]);
+        o[0] = drange_m(B0 + elec_interval(M, elkei), a[2], a[3], elkei, elkef);
+    } else if (which == OMC_SAMPLER_ELOSS || which == OMC_SAMPLER_MSDIST) {
+        const int imed = (int)a[0], iq = (int)a[1], qel = (1 + iq) / 2;
+        const MedRec &M = P.med[imed];
+        const ElecBin *B0 = P.ebin + (size_t)qel * P.nmed * MXEKE + imed * MXEKE;
+        const double rhof = a[2], eke = a[3], rinv = 1.0 / rhof;
+        double elke; int lelke;
+        const double range = test_range(P, B0, M, eke, rinv, elke, lelke);
+        const double tustep = a[4] * range;
+        const double de = eloss_m(B0, M, rhof, rinv, tustep, range, eke, elke, lelke);
+        if (which == OMC_SAMPLER_ELOSS) { o[0] = range; o[1] = de; return; }
+        Part p;
+        p.x = p.y = p.z = 0.0; p.u = a[5]; p.v = a[6]; p.w = a[7]; p.e = eke + RM; p.wt = 1.0; p.ir = 1; p.iq = iq;
+        double xf, yf, zf, uf, vf, wf;
+        uint32_t w_rfict;
+        o[0] = msdist_b(P, g, p, imed, qel, rhof, de, tustep, eke, xf, yf, zf, uf, vf, wf, w_rfict);
+        o[1] = xf; o[2] = yf; o[3] = zf; o[4] = uf; o[5] = vf; o[6] = wf; o[7] = de;
+    } else if (which == OMC_SAMPLER_SSCAT) {
+        const uint4 g0 = g.block();
+        float cf, sf, cphi, sphi;
+        sscat_b(P, g, (int)a[0], (int)a[1], (float)a[2], (float)a[3], (float)a[4], g0.y, cf, sf, cphi, sphi);
+        o[0] = (double)cf; o[1] = (double)sf; o[2] = (double)cphi; o[3] = (double)sphi;
+    } else if (which == OMC_SAMPLER_COMPTON || which == OMC_SAMPLER_MOLLER) {
+        const int off = (which == OMC_SAMPLER_MOLLER) ? 1 : 0;
+        Part p, q;
+        p.x = p.y = p.z = 0.0; p.e = a[off]; p.u = a[off + 1]; p.v = a[off + 2]; p.w = a[off + 3]; p.wt = 1.0; p.ir = 1;
+        p.iq = off ? -1 : 0;
+        q = p; q.e = 0.0;
+        if (which == OMC_SAMPLER_COMPTON) compton_b(g, p, q);
+        else if (!moller_b(P, g, p, q, (int)a[0])) q.e = 0.0;
+        o[0] = p.e; o[1] = p.u; o[2] = p.v; o[3] = p.w; o[4] = q.e; o[5] = q.u; o[6] = q.v; o[7] = q.w;
+    } else if (which == OMC_SAMPLER_WOODCOCK) {
+        Part p;
+        p.e = a[0]; p.x = a[1]; p.y = a[2]; p.z = a[3]; p.u = a[4]; p.v = a[5]; p.w = a[6]; p.wt = 1.0; p.iq = 0;
+        p.ir = 1 + find_bin(P.xb, P.isize, p.x, P.inv_dx, P.uniform_x != 0) + find_bin(P.yb, P.jsize, p.y, P.inv_dy, P.uniform_y != 0) * P.isize +
+               find_bin(P.zb, P.ksize, p.z, P.inv_dz, P.uniform_z != 0) * P.ijmax;
+        bool entered = false;
+        unsigned nv = 0;
+        int st = 0;
+        for (int k = 0; k < 100000 && st == 0; k++) st = woodcock_flight(P, g, p, entered, 8, nv);
+        o[0] = (st > 0) ? 1.0 : 0.0; o[1] = p.x; o[2] = p.y; o[3] = p.z; o[4] = (double)p.ir; o[5] = (double)nv;
+    } else if (which == OMC_SAMPLER_ESTEP) {
+        Part p;
+        p.iq = (int)a[0]; p.e = a[1]; p.x = a[2]; p.y = a[3]; p.z = a[4]; p.ir = (int)a[5]; p.u = 0.0; p.v = 0.0; p.w = 1.0; p.wt = 0.0;
+        EStep e;
+        e.total_tstep = e.range = e.tustep = e.tperp = e.demfp = e.blccl = e.ssmfp = 0.0;
+        Tally t = {0, 0, 0};
+        int st = 0;
+        const int cls = estep_size(P, P.endep32, g, p, e, t, st, make_int2(0, -2));    // (weight 0: a cut-off deposit adds nothing)
+        o[0] = (double)cls; o[1] = e.tustep; o[2] = e.tperp; o[3] = e.range; o[4] = e.total_tstep; o[5] = e.demfp; o[6] = e.blccl; o[7] = e.ssmfp;
+    }
+}
+void launch_test_samplers(const DevProblem &P, int which, int n, const double *in, unsigned long long first, double *out, cudaStream_t s) {
+    test_sampler_kernel<<<(n + 127) / 128, 128, 0, s>>>(P, which, n, in, first, out);
 }
 
 void launch_flush(float *g32, double *g64, long long n, cudaStream_t s) {

@@ -100,49 +100,3 @@ def dose_influence_matrix_device(tr, ph: P.Phantom, nbeamlets: int, ncase, nbatc
         irs.append(r); vals.append(v)
         jc[b + 1] = jc[b] + len(r)
     return jc, (np.concatenate(irs) if irs else np.zeros(0, np.int64)), (np.concatenate(vals) if vals else np.zeros(0))
-
-
-def gather_columns_torch(mine: dict, group=None) -> dict:
-    """all_gather_object of the per-rank column dicts (host-side gather)."""
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    parts = [None] * world
-    dist.all_gather_object(parts, mine, group=group)
-    out = {}
-    for p in parts:
-        out.update(p)
-    return out
-
-
-def dose_influence_matrix_device(tr, ph: P.Phantom, nbeamlets: int, ncase, nbatch, rel_threshold: float, rank: int = 0, world: int = 1,
-                                 gather=None, first_history: int = 0, group: int | None = None):
-    """Same matrix as dose_influence_matrix() built the B200 way (north_star: "each GPU builds its slice of the sparse
-    dose-influence matrix"): the beamlets of a rank are run `group` at a time in ONE pass of the wavefront kernels
-    (omc_gpu_run_beamlets: history id -> beamlet -> its own dose grid; no per-batch tail per beamlet), and
-    accumulateResults + threshold + column assembly run on the device.  Beamlet b keeps the history ids
-    [first_history + b*nhist, +nhist), so up to scheduling-independent statistics this is the per-beamlet loop's result."""
-    nhist, nb, nper = P.batch_plan(ncase, nbatch)
-    mine = {}
-    my = list(range(rank, nbeamlets, world))
-    # contiguous runs of beamlet indices (world == 1: everything; otherwise singletons dealt round-robin, grouped by stride)
-    i = 0
-    while i < len(my):
-        if world == 1:
-            chunk = my[i:i + group]
-            jc, ir, val = tr.run_beamlets(first_history + chunk[0] * nhist, nhist, nb, chunk[0], len(chunk), rel_threshold, ph.med_densities)
-            for k, b in enumerate(chunk):
-                mine[b] = (ir[jc[k]:jc[k + 1]].copy(), val[jc[k]:jc[k + 1]].copy())
-            i += len(chunk)
-        else:
-            b = my[i]
-            jc, ir, val = tr.run_beamlets(first_history + b * nhist, nhist, nb, b, 1, rel_threshold, ph.med_densities)
-            mine[b] = (ir, val)
-            i += 1
-    cols = mine if gather is None or world == 1 else gather(mine)
-    jc = np.zeros(nbeamlets + 1, dtype=np.int64)
-    irs, vals = [], []
-    for b in range(nbeamlets):
-        r, v = cols[b]
-        irs.append(r); vals.append(v)
-        jc[b + 1] = jc[b] + len(r)
-    return jc, (np.concatenate(irs) if irs else np.zeros(0, np.int64)), (np.concatenate(vals) if vals else np.zeros(0))

@@ -56,6 +56,11 @@ class _CpuTransport:
         f("test_geometry").argtypes = [C.c_int] + [C.c_void_p] * 7
         f("test_rng").argtypes = [C.c_longlong, C.c_int, C.c_void_p]
         f("run_particle").argtypes = [C.c_longlong, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+        f("test_samplers").argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]
+        try:
+            f("test_photon_tau").argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        except AttributeError:      # the matRad build of the reference harness has no dosxyz geometry hook
+            pass
 
     def _f(self, name):
         return getattr(self.lib, self.prefix + name)
@@ -139,6 +144,26 @@ class _CpuTransport:
         out = np.zeros(n)
         self._f("test_rng")(hist, n, out.ctypes.data)
         return out
+
+    def test_samplers(self, which: int, inputs, first: int = 0) -> np.ndarray:
+        """One sampler function on explicit inputs: n records of 8 doubles in -> n records of 8 doubles out
+        (OMC_SAMPLER_* of include/ompmc_b200.h), record i drawing from the Philox stream of history first + i."""
+        a = np.zeros((len(inputs), 8))
+        inputs = np.asarray(inputs, dtype=np.float64)
+        a[:, :inputs.shape[1]] = inputs
+        out = np.zeros_like(a)
+        self._f("test_samplers")(int(which), len(a), a.ctypes.data, int(first), out.ctypes.data)
+        return out
+
+    def test_photon_tau(self, e, xyzuvw, s) -> tuple[np.ndarray, np.ndarray]:
+        """Optical depth of straight photon paths of length s (photon() src/ompmc.c:1951-2019) and the region at their end."""
+        xyzuvw = np.asarray(xyzuvw, dtype=np.float64).reshape(-1, 6)
+        n = len(xyzuvw)
+        a = np.zeros((n, 8))
+        a[:, 0] = e; a[:, 1:7] = xyzuvw; a[:, 7] = s
+        out = np.zeros((n, 2))
+        self._f("test_photon_tau")(n, a.ctypes.data, out.ctypes.data)
+        return out[:, 0], out[:, 1].astype(np.int64)
 
     def run_particle(self, hist: int, iq: int, e: float, xyzuvw, ir: int, wt: float = 1.0):
         xyzuvw = np.ascontiguousarray(xyzuvw, dtype=np.float64)

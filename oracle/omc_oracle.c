@@ -1708,3 +1708,108 @@ void orc_run_particle(long long hist, int iq, double e, const double *q, int ir,
         rec->edep = c->edep_sum;
     }
 }
+
+/* ---- unit hooks: the restated samplers on explicit inputs (same contract as ref_test_samplers() of ref_harness.c and
+ * omc_gpu_test_samplers() of the C-ABI; draws one by one from the Philox stream of history first + i) -------------------- */
+static double orc_range(int imed, int iq, double eke, double rhof, double *elke_out, int *lelke_out) {
+    /* electron() src/ompmc.c:4905-4918 */
+    const omc_media_tables *T = &PB.T;
+    int qel = (1 + iq) / 2;
+    double elke = log(eke);
+    int lelke = pwlf_interval(imed, elke, T->eke1, T->eke0) - 1;
+    double ekei = T->e_array[imed * MXEKE + lelke];
+    double elkei = (lelke + 1 - T->eke0[imed]) / T->eke1[imed];
+    double range = drange(imed, iq, lelke, eke, ekei, elke, elkei);
+    range += T->range_ep[(size_t)qel * T->nmed * MXEKE + (size_t)imed * MXEKE + lelke];
+    *elke_out = elke; *lelke_out = lelke;
+    return range / rhof;
+}
+
+void orc_test_samplers(int which, int n, const double *in, long long first, double *out) {
+    const omc_media_tables *T = &PB.T;
+    ctx_setup();
+    hist_ctx *c = &g_ctx[0];
+    int mode = g_rng_mode;
+    for (int i = 0; i < n; i++) {
+        const double *a = in + 8 * (size_t)i;
+        double *o = out + 8 * (size_t)i;
+        for (int k = 0; k < 8; k++) o[k] = 0.0;
+        g_rng_mode = 1;
+        begin_history(c, first + i);
+        g_rng_mode = mode;
+        c->np = 0; c->npold = 0;
+        part *p = &c->stk[0];
+        p->x = p->y = p->z = 0.0; p->wt = 1.0; p->ir = 1; p->iq = 0; p->e = 1.0; p->u = p->v = 0.0; p->w = 1.0;
+        if (which == OMC_SAMPLER_DRANGE) {
+            int imed = (int)a[0], iq = (int)a[1];
+            double elkei = log(a[2]), elkef = log(a[3]);
+            int lelke = pwlf_interval(imed, elkei, T->eke1, T->eke0) - 1;
+            o[0] = drange(imed, iq, lelke, a[2], a[3], elkei, elkef);
+        } else if (which == OMC_SAMPLER_ELOSS || which == OMC_SAMPLER_MSDIST) {
+            int imed = (int)a[0], iq = (int)a[1], lelke;
+            double rhof = a[2], eke = a[3], elke;
+            double range = orc_range(imed, iq, eke, rhof, &elke, &lelke);
+            double tustep = a[4] * range;
+            double de = eloss(imed, iq, rhof, tustep, range, eke, elke, lelke);
+            if (which == OMC_SAMPLER_ELOSS) { o[0] = range; o[1] = de; continue; }
+            p->iq = iq; p->e = eke + RM; p->u = a[5]; p->v = a[6]; p->w = a[7];
+            o[0] = msdist(c, p, imed, iq, rhof, de, tustep, eke, &o[1], &o[2], &o[3], &o[4], &o[5], &o[6]);
+            o[7] = de;
+        } else if (which == OMC_SAMPLER_SSCAT) {
+            sscat(c, (int)a[0], (int)a[1], a[2], a[3], a[4], &o[0], &o[1]);
+            azimuth(c, &o[2], &o[3]);
+        } else if (which == OMC_SAMPLER_COMPTON) {
+            p->iq = 0; p->e = a[0]; p->u = a[1]; p->v = a[2]; p->w = a[3];
+            compton(c);
+            for (int k = 0; k <= c->np; k++) {
+                int off = (c->stk[k].iq == 0) ? 0 : 4;
+                o[off] = c->stk[k].e; o[off + 1] = c->stk[k].u; o[off + 2] = c->stk[k].v; o[off + 3] = c->stk[k].w;
+            }
+        } else if (which == OMC_SAMPLER_MOLLER) {
+            int imed = (int)a[0], ir = -1;
+            for (int r = 1; r < PB.nreg; r++) if (PB.G.med[r] == imed) { ir = r; break; }
+            if (ir < 0) continue;
+            p->ir = ir; p->iq = -1; p->e = a[1]; p->u = a[2]; p->v = a[3]; p->w = a[4];
+            moller(c);
+            int hi = 0, lo = -1;
+            if (c->np == 1) { hi = (c->stk[0].e >= c->stk[1].e) ? 0 : 1; lo = 1 - hi; }
+            o[0] = c->stk[hi].e; o[1] = c->stk[hi].u; o[2] = c->stk[hi].v; o[3] = c->stk[hi].w;
+            if (lo >= 0) { o[4] = c->stk[lo].e; o[5] = c->stk[lo].u; o[6] = c->stk[lo].v; o[7] = c->stk[lo].w; }
+        }
+    }
+}
+
+/* optical depth of a straight photon path: the transport loop of photon() src/ompmc.c:1951-2019 without the mean-free-path
+ * budget (see ref_test_photon_tau() in ref_harness.c).  in {e, x, y, z, u, v, w, s} -> out {tau, region at the end} */
+void orc_test_photon_tau(int n, const double *in, double *out) {
+    const omc_media_tables *T = &PB.T;
+    const omc_geometry *G = &PB.G;
+    for (int i = 0; i < n; i++) {
+        const double *a = in + 8 * (size_t)i;
+        double gle = log(a[0]), left = a[7], tau = 0.0;
+        int ix = 0, iy = 0, iz = 0;
+        while (ix < G->isize - 1 && G->xbounds[ix + 1] <= a[1]) ix++;
+        while (iy < G->jsize - 1 && G->ybounds[iy + 1] <= a[2]) iy++;
+        while (iz < G->ksize - 1 && G->zbounds[iz + 1] <= a[3]) iz++;
+        part p = {0, 1 + ix + iy * G->isize + iz * G->isize * G->jsize, a[0], a[1], a[2], a[3], a[4], a[5], a[6], 1.0};
+        while (left > 0.0) {
+            int imed = G->med[p.ir];
+            double sig = 0.0;
+            if (imed != -1) {
+                int lgle = pwlf_interval(imed, gle, T->ge1, T->ge0) - 1;
+                double gmfp = pwlf_eval(imed * MXGE + lgle, gle, T->gmfp1, T->gmfp0) / G->rhof[p.ir];
+                gmfp *= pwlf_eval(imed * MXGE + lgle, gle, T->cohe1, T->cohe0);
+                sig = 1.0 / gmfp;
+            }
+            int idisc = 0, irnew = p.ir;
+            double ustep = left;
+            howfar(&p, &idisc, &irnew, &ustep);
+            if (idisc > 0) { p.ir = 0; break; }
+            p.x += ustep * p.u; p.y += ustep * p.v; p.z += ustep * p.w;
+            tau += ustep * sig;
+            left -= ustep;
+            if (irnew != p.ir) { p.ir = irnew; if (irnew == 0) break; }
+        }
+        out[2 * i] = tau; out[2 * i + 1] = (double)p.ir;
+    }
+}

@@ -441,3 +441,120 @@ void ref_run_particle(long long hist, int iq, double e, const double *xyzuvw, in
     }
     g_rng_mode = mode;
 }
+
+/* ---- unit hooks: the reference's OWN sampler functions on explicit inputs ------------------ */
+/*
+ * Counterpart of omc_gpu_test_samplers() (include/ompmc_b200.h): record i = 8 doubles in, 8 doubles out, random
+ * numbers from the Philox stream of history first + i drawn one by one as the reference draws them.  Every number
+ * comes out of the unmodified functions of src/ompmc.c; this wrapper only sets the top of the stack.
+ */
+static double ref_range(int imed, int iq, double eke, double rhof, double *elke_out, int *lelke_out) {
+    /* electron() src/ompmc.c:4905-4918 */
+    int qel = (1 + iq) / 2;
+    double elke = log(eke);
+    int lelke = pwlfInterval(imed, elke, electron_data.eke1, electron_data.eke0) - 1;
+    double ekei = electron_data.e_array[imed * MXEKE + lelke];
+    double elkei = (lelke + 1 - electron_data.eke0[imed]) / electron_data.eke1[imed];
+    double range = computeDrange(imed, iq, lelke, eke, ekei, elke, elkei);
+    range += electron_data.range_ep[qel * media.nmed * MXEKE + imed * MXEKE + lelke];
+    *elke_out = elke; *lelke_out = lelke;
+    return range / rhof;
+}
+
+void ref_test_samplers(int which, int n, const double *in, long long first, double *out) {
+    int mode = g_rng_mode;
+    g_rng_mode = 1;
+    for (int i = 0; i < n; i++) {
+        const double *a = in + 8 * (size_t)i;
+        double *o = out + 8 * (size_t)i;
+        for (int k = 0; k < 8; k++) o[k] = 0.0;
+        omc_philox_seed(&g_philox, g_seed0, g_seed1, (uint64_t)(first + i), 0);
+        stack.np = 0; stack.npold = 0;
+        stack.x[0] = stack.y[0] = stack.z[0] = 0.0; stack.wt[0] = 1.0; stack.ir[0] = 1; stack.dnear[0] = 0.0;
+        if (which == OMC_SAMPLER_DRANGE) {
+            int imed = (int)a[0], iq = (int)a[1];
+            double elkei = log(a[2]), elkef = log(a[3]);
+            int lelke = pwlfInterval(imed, elkei, electron_data.eke1, electron_data.eke0) - 1;
+            o[0] = computeDrange(imed, iq, lelke, a[2], a[3], elkei, elkef);
+        } else if (which == OMC_SAMPLER_ELOSS || which == OMC_SAMPLER_MSDIST) {
+            int imed = (int)a[0], iq = (int)a[1], lelke;
+            double rhof = a[2], eke = a[3], elke;
+            double range = ref_range(imed, iq, eke, rhof, &elke, &lelke);
+            double tustep = a[4] * range;
+            double de = computeEloss(imed, iq, 1, rhof, tustep, range, eke, elke, lelke);
+            if (which == OMC_SAMPLER_ELOSS) { o[0] = range; o[1] = de; continue; }
+            stack.iq[0] = iq; stack.e[0] = eke + RM;
+            stack.u[0] = a[5]; stack.v[0] = a[6]; stack.w[0] = a[7];
+            o[0] = msdist(imed, iq, rhof, de, tustep, eke, &o[1], &o[2], &o[3], &o[4], &o[5], &o[6]);
+            o[7] = de;
+        } else if (which == OMC_SAMPLER_SSCAT) {
+            double cphi, sphi;
+            sscat((int)a[0], (int)a[1], a[2], a[3], a[4], &o[0], &o[1]);
+            selectAzimuthalAngle(&cphi, &sphi);
+            o[2] = cphi; o[3] = sphi;
+        } else if (which == OMC_SAMPLER_COMPTON) {
+            stack.iq[0] = 0; stack.e[0] = a[0]; stack.u[0] = a[1]; stack.v[0] = a[2]; stack.w[0] = a[3];
+            compton();
+            /* the reference leaves the scattered photon and the electron on the stack (order not relied upon) */
+            for (int k = 0; k <= stack.np; k++) {
+                int off = (stack.iq[k] == 0) ? 0 : 4;
+                o[off] = stack.e[k]; o[off + 1] = stack.u[k]; o[off + 2] = stack.v[k]; o[off + 3] = stack.w[k];
+            }
+        } else if (which == OMC_SAMPLER_MOLLER) {
+            /* moller() reads the medium from region.med[stack.ir]: find a region filled with it */
+            int imed = (int)a[0], ir = -1, nreg = ref_nreg();
+            for (int r = 1; r < nreg; r++) if (region.med[r] == imed) { ir = r; break; }
+            if (ir < 0) continue;
+            stack.ir[0] = ir; stack.iq[0] = -1; stack.e[0] = a[1]; stack.u[0] = a[2]; stack.v[0] = a[3]; stack.w[0] = a[4];
+            moller();
+            /* higher-energy electron first, as the production sampler reports them */
+            int hi = 0, lo = -1;
+            if (stack.np == 1) { hi = (stack.e[0] >= stack.e[1]) ? 0 : 1; lo = 1 - hi; }
+            o[0] = stack.e[hi]; o[1] = stack.u[hi]; o[2] = stack.v[hi]; o[3] = stack.w[hi];
+            if (lo >= 0) { o[4] = stack.e[lo]; o[5] = stack.u[lo]; o[6] = stack.v[lo]; o[7] = stack.w[lo]; }
+        }
+    }
+    g_rng_mode = mode;
+}
+
+#ifndef OMC_REF_MATRAD
+/*
+ * Optical depth of the straight photon path of length s from (x,y,z) along (u,v,w): the transport loop of photon()
+ * src/ompmc.c:1951-2019 (the reference's howfar(), its gmfp / Rayleigh-correction tables and density scaling) with the
+ * mean-free-path budget left out.  in: n records {e, x, y, z, u, v, w, s}; out: n records {tau, region at the end (0 = outside)}.
+ * Checker of the Woodcock photon flight of the production kernels: the interaction depth must be exponential in tau.
+ */
+void ref_test_photon_tau(int n, const double *in, double *out) {
+    for (int i = 0; i < n; i++) {
+        const double *a = in + 8 * (size_t)i;
+        double gle = log(a[0]), left = a[7], tau = 0.0;
+        int ix = 0, iy = 0, iz = 0;
+        while (ix < geometry.isize - 1 && geometry.xbounds[ix + 1] <= a[1]) ix++;
+        while (iy < geometry.jsize - 1 && geometry.ybounds[iy + 1] <= a[2]) iy++;
+        while (iz < geometry.ksize - 1 && geometry.zbounds[iz + 1] <= a[3]) iz++;
+        int irl = 1 + ix + iy * geometry.isize + iz * geometry.isize * geometry.jsize;
+        stack.np = 0;
+        stack.x[0] = a[1]; stack.y[0] = a[2]; stack.z[0] = a[3]; stack.u[0] = a[4]; stack.v[0] = a[5]; stack.w[0] = a[6];
+        stack.ir[0] = irl; stack.iq[0] = 0; stack.e[0] = a[0]; stack.wt[0] = 1.0;
+        while (left > 0.0) {
+            int imed = region.med[irl];
+            double sig = 0.0;
+            if (imed != -1) {
+                int lgle = pwlfInterval(imed, gle, photon_data.ge1, photon_data.ge0) - 1;
+                double gmfp = pwlfEval(imed * MXGE + lgle, gle, photon_data.gmfp1, photon_data.gmfp0) / region.rhof[irl];
+                gmfp *= pwlfEval(imed * MXGE + lgle, gle, photon_data.cohe1, photon_data.cohe0);
+                sig = 1.0 / gmfp;
+            }
+            int idisc = 0, irnew = irl;
+            double ustep = left;
+            howfar(&idisc, &irnew, &ustep);
+            if (idisc > 0) { irl = 0; break; }
+            stack.x[0] += ustep * stack.u[0]; stack.y[0] += ustep * stack.v[0]; stack.z[0] += ustep * stack.w[0];
+            tau += ustep * sig;
+            left -= ustep;
+            if (irnew != irl) { irl = irnew; stack.ir[0] = irl; if (irl == 0) break; }
+        }
+        out[2 * i] = tau; out[2 * i + 1] = (double)irl;
+    }
+}
+#endif

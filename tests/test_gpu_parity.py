@@ -1,0 +1,81 @@
+"""Statistical parity of the PRODUCTION kernels (wavefront: Woodcock flight, mixed-precision samplers, block-wise RNG, fp32
+dose grid) against the UNMODIFIED reference, inside the driver-run GPU suite.
+
+tests/golden/parity_<case>.npz hold the batch statistics of the reference's own OpenMP build (RANMAR, its own batch loop,
+omc_dosxyz.c:1237-1263) on scaled-down BASELINE configurations -- same physics and physical extent, coarser voxels
+(oracle/parity_cases.py; written by oracle/gen_parity_fixtures.py, which needs /root/reference).  The CUDA side runs the same
+problems through the C-ABI with GPU_MULT times the histories (it costs seconds) so that the gamma evaluation sees mostly the
+reference's noise.  north_star acceptance criteria, each an assert:
+
+  * voxels with dose > 20 % of Dmax agree within the combined batch-method uncertainty: the z-scores have no offset
+    (|mean z| < 0.1, i.e. a bias below 0.1 sigma ~ 0.03 % of the local dose), the width of a Student-t with ~40 batches a side
+    (0.9 < std z < 1.15), >= 93 % of the voxels within 2 sigma and >= 99 % within 3 sigma;
+  * total deposited energy per history equal within 3 sigma (batch-to-batch scatter of both sides);
+  * gamma(1 % of Dmax, 1 mm) pass rate >= 99 % at the grid's NATIVE resolution, voxels above 10 % of Dmax;
+  * integer bookkeeping exact: history count, no overflow.
+All statements are relative to the reference run with the synthetic spinms.data of oracle/gen_fixtures.py.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.parity_cases import CASES, build_case, fixture_path
+from tests.parity_tools import batch_stats, dose_grid, gamma_pass
+
+pytestmark = pytest.mark.gpu
+
+GPU_MULT = {"water250kv": 8, "water6mv": 8, "tg119_6mv": 8, "prostate6mv": 8, "water_inp_ns20": 5}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_production_kernels_vs_reference_batch_statistics(gpu, case):
+    path = fixture_path(case)
+    if not os.path.exists(path):
+        pytest.fail(f"{path} is missing: run oracle/gen_parity_fixtures.py where /root/reference exists and commit the file")
+    z = np.load(path)
+    info = json.loads(str(z["info"]))
+    mr, vr = z["mean"].astype(np.float64), z["var"].astype(np.float64)
+    prob, ph, c = build_case(case)
+    assert info["grid"] == [ph.isize, ph.jsize, ph.ksize] and info["nsplit"] == c["nsplit"]
+    nb, per, mult = info["nbatch"], info["hist_per_batch"], GPU_MULT[case]
+    gpu.load_problem(prob)
+    gpu.set_option("kernel", 1)
+    gpu.reset_tallies()
+    totals = np.zeros(nb)
+    for ib in range(nb):
+        gpu.run_histories(ib * per * mult, per * mult)
+        totals[ib] = gpu.get_endep()[1:].sum() / mult
+        gpu.accum_batch()
+    a, a2, ensrc = gpu.get_tallies()
+    cnt = gpu.counters()
+    assert cnt["histories"] == nb * per * mult and cnt["errors"] == 0                 # integer bookkeeping
+    mg, vg = batch_stats(a / mult, a2 / mult ** 2, nb)                                  # per reference-sized batch
+    # source energy per history: the same spectrum sampling on both sides
+    assert abs(ensrc / (nb * per * mult) - float(z["ensrc"]) / (nb * per)) < 2e-3 * float(z["ensrc"]) / (nb * per)
+
+    sel = (mr > 0.2 * mr.max()) & (vr + vg > 0)
+    zs = (mg[sel] - mr[sel]) / np.sqrt(vr[sel] + vg[sel])
+    rep = {"case": case, "voxels": int(sel.sum()), "z_mean": float(zs.mean()), "z_std": float(zs.std()),
+           "within_2sigma": float((np.abs(zs) < 2).mean()), "within_3sigma": float((np.abs(zs) < 3).mean()),
+           "ref_rel_sigma": float(np.sqrt(vr[sel]).mean() / mr[sel].mean()), "gpu_rel_sigma": float(np.sqrt(vg[sel]).mean() / mg[sel].mean())}
+    # total deposited energy per reference-sized batch
+    tr = z["totals"]
+    se = np.sqrt(tr.var(ddof=1) / nb + totals.var(ddof=1) / nb)
+    rep["total_energy_ratio"] = float(totals.mean() / tr.mean())
+    rep["total_energy_z"] = float((totals.mean() - tr.mean()) / se)
+    spacing = tuple(10.0 * float(np.diff(b)[0]) for b in (ph.xbounds, ph.ybounds, ph.zbounds))
+    gp, ng, gmax = gamma_pass(dose_grid(mr, ph), dose_grid(mg, ph), spacing)
+    rep.update(gamma_1pct_1mm_pass=gp, gamma_voxels=ng, gamma_max=gmax, gamma_grid_mm=list(spacing))
+    print("PARITY", json.dumps(rep))
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, f"parity_{case}.json"), "w") as f:
+            json.dump(rep, f, indent=1)
+
+    assert abs(rep["z_mean"]) < 0.1, rep
+    assert 0.9 < rep["z_std"] < 1.15, rep
+    assert rep["within_2sigma"] >= 0.93 and rep["within_3sigma"] >= 0.99, rep
+    assert abs(rep["total_energy_z"]) <= 3.0, rep
+    assert gp >= 0.99, rep

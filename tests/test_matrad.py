@@ -240,3 +240,37 @@ def test_beamlet_group_plan_covers_every_beamlet_once_and_balances_ranks():
         if n:
             assert max(per) - min(per) <= max(c for _, c, _ in plan)
         assert [r for _, _, r in plan] == [j % world for j in range(len(plan))]
+
+
+class _RecordingTransport:
+    """Stands in for GpuTransport.run_beamlets(): records the passes and returns one non-zero per beamlet (row = beamlet)."""
+
+    def __init__(self, capacity):
+        self.capacity, self.calls = capacity, []
+
+    def beamlet_capacity(self):
+        return self.capacity
+
+    def run_beamlets(self, first, nhist, nbatch, ib0, nb, rel, dens):
+        self.calls.append((first, nhist, ib0, nb))
+        return np.arange(nb + 1, dtype=np.int64), np.arange(ib0, ib0 + nb, dtype=np.int64), np.full(nb, 1.0)
+
+
+def test_device_matrix_default_group_and_call_pattern():
+    """dose_influence_matrix_device() without `group` takes the pass size from the transport (a stale second
+    definition evaluated my[i:i+None]); with two ranks each owns whole groups of consecutive beamlets, one pass per group."""
+    ph = P.tissue_phantom((6, 6, 6), (1.0, 1.0, 1.0))
+    tr = _RecordingTransport(capacity=4)
+    jc, ir, val = matrad.dose_influence_matrix_device(tr, ph, 10, "1000", "2", 0.01)
+    assert [c[2:] for c in tr.calls] == [(0, 4), (4, 4), (8, 2)]
+    assert [c[0] for c in tr.calls] == [0, 4 * 1000, 8 * 1000] and all(c[1] == 1000 for c in tr.calls)
+    assert np.array_equal(jc, np.arange(11)) and np.array_equal(ir, np.arange(10))
+    plan = matrad.beamlet_groups(10, 2, 4)
+    for rank in (0, 1):
+        tr = _RecordingTransport(capacity=4)
+        merged = {}
+        matrad.dose_influence_matrix_device(tr, ph, 10, "1000", "2", 0.01, rank, 2, gather=lambda mine: merged.update(mine) or
+                                            {b: (np.zeros(0, np.int64), np.zeros(0)) for b in range(10)})
+        assert [(c[2], c[3]) for c in tr.calls] == [(b0, n) for b0, n, owner in plan if owner == rank]
+        assert len(tr.calls) == 2                                # whole groups: 10 beamlets = 4 passes over 2 ranks, not 5 + 5
+        assert sorted(merged) == [b for b0, n, owner in plan if owner == rank for b in range(b0, b0 + n)]
