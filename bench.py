@@ -9,7 +9,8 @@ missing from the reference checkout), 183x183x90 voxels of 3 mm, 4 media of 700i
 var_6MV.spectrum point source at SSD 90 cm, 10x10 cm2 field, ECUT 0.700 / PCUT 0.010, nsplit 1.
 A "step" is one statistical batch = one pass {initHistory(); shower();} x H + accumEndep()
 (omc_dosxyz.c:1237-1263) with H = --hist-per-step histories PER GPU (weak scaling); with N > 1 ranks
-the batch grid is summed over ranks by NCCL before accumEndep() (ompmc_b200/dist.py).
+the batch grid is summed over ranks by NCCL inside the library before accumEndep()
+(omc_gpu_comm_init, include/ompmc_b200.h).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
   torchrun --nproc-per-node N ... bench.py --gpus N ...        (one rank per GPU)
@@ -213,7 +214,6 @@ def main() -> None:
     import torch
     import torch.distributed as dist
     from ompmc_b200 import build as builder
-    from ompmc_b200 import dist as odist
     from ompmc_b200.api import GpuTransport, DEFAULT_KERNEL
 
     rank = int(os.environ.get("RANK", "0"))
@@ -240,7 +240,13 @@ def main() -> None:
     H = args.hist_per_step
     stream = torch.cuda.ExternalStream(tr.stream_ptr(), device=f"cuda:{local}")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")      # > 126 MB L2
-    allreduce = odist.allreduce_gpu_grid if world > 1 else None
+    if world > 1:
+        # NCCL inside the library (include/ompmc_b200.h, multi-GPU): rank 0 makes the unique id, torch.distributed only carries
+        # its 128 bytes to the other ranks.  From here on run_batch() shards every batch over the ranks and sums the completed
+        # batch grids on a side stream before accumEndep(); torch takes no part in the data path.
+        box = [tr.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        tr.comm_init(rank, world, box[0])
 
     def barrier():
         torch.cuda.synchronize()
@@ -249,15 +255,15 @@ def main() -> None:
         torch.cuda.synchronize()
 
     def step(i: int):
-        # batch i = history ids [i*H*world, (i+1)*H*world), rank r takes its contiguous slice.  Batches are pipelined
-        # (ompmc_b200/dist.py): batch i is started while the tail of batch i-1 is still in flight; i-1 is then
-        # summed over ranks and accumulated.
+        # batch i = history ids [i*H*world, (i+1)*H*world); the library gives rank r its contiguous slice.  Batches are
+        # pipelined: batch i is started while the tail of batch i-1 is still in flight; i-1 is then summed over the ranks
+        # and accumulated on the side stream.
         with torch.cuda.stream(stream):
             flush.zero_()                                     # L2 flush between timed iterations
-        odist.start_batch_sharded(tr, i * H * world, H * world, rank, world, allreduce)
+        tr.run_batch(i * H * world, H * world)
 
     def finish():
-        odist.finish_batches_sharded(tr, rank, world, allreduce)
+        tr.synchronize()
 
     for i in range(args.warmup):
         step(i)
@@ -285,7 +291,7 @@ def main() -> None:
     nk = max(2, min(args.steps, 4))
     ka.record(stream)
     for i in range(nk):                                        # same pipelined batches, no L2 flush: the launch group of the roofline
-        odist.start_batch_sharded(tr, (args.warmup + args.steps + i) * H * world, H * world, rank, world, allreduce)
+        tr.run_batch((args.warmup + args.steps + i) * H * world, H * world)
     finish()
     kb.record(stream)
     torch.cuda.synchronize()
@@ -317,8 +323,8 @@ def main() -> None:
     for i in range(e2e_steps):
         tr.load_problem(e2e_prob)                              # H2D of tables + geometry + source (host arrays)
         tr.set_option("kernel", kernel)
-        odist.run_batch_sharded(tr, (1000 + i) * H * world, H * world, rank, world, allreduce)
-        tr.get_tallies()                                       # D2H of accum_endep / accum_endep2
+        tr.run_batch((1000 + i) * H * world, H * world)
+        tr.get_tallies()                                       # D2H of accum_endep / accum_endep2 (completes the batch first)
     barrier()
     e2e_s = time.perf_counter() - t0
 

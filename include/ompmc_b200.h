@@ -138,7 +138,7 @@ typedef struct omc_gpu_counters {
     unsigned long long deposits;       /* ausgab() calls                              */
     unsigned long long rng_draws;      /* random numbers consumed                     */
     unsigned long long errors;         /* stack/queue overflows, invalid-lambda drops */
-    unsigned long long reserved[9];    /* [0..3] drain diagnostics; [4] straggler hand-overs, [5] particles handed over */
+    unsigned long long reserved[9];    /* [0..3] drain diagnostics */
 } omc_gpu_counters;
 
 typedef struct omc_gpu_ctx *omc_gpu_handle;
@@ -162,7 +162,7 @@ int omc_gpu_set_source_matrad(omc_gpu_handle h, const omc_source_matrad *s); /* 
 int omc_gpu_set_vrt(omc_gpu_handle h, int nsplit);                         /* initVrt(), src/ompmc.c:5964 */
 int omc_gpu_set_seed(omc_gpu_handle h, int ixx, int jxx);                  /* "rng seeds", src/omc_random.c:58-82 */
 /* tuning / debug knobs: "kernel", "threads_per_block", "stack_depth", "pool_size", "record_histories", "drain_threshold"
- * (0: no drain kernel, bit-reproducible whatever the schedule), "handover" (1: hand the last stragglers of the previous pipelined batch to the drain kernel; default 0, measured slower) */
+ * (0: no drain kernel, bit-reproducible whatever the schedule) */
 int omc_gpu_set_option(omc_gpu_handle h, const char *key, long long value);
 
 /* ---- the hot path ------------------------------------------------------------------------ */
@@ -179,7 +179,10 @@ int omc_gpu_accum_batch(omc_gpu_handle h);
  * With the wavefront kernels consecutive calls are PIPELINED: the call returns when all its histories have been
  * started and every earlier batch is complete and accumulated; the tail of this batch keeps running underneath the
  * next call (each particle scores into the grid of the batch its history id belongs to) and is completed and
- * accumulated by the next call or by whichever call reads results (get_tallies, accumulate_results, synchronize...). */
+ * accumulated by the next call or by whichever call reads results (get_tallies, accumulate_results, synchronize...).
+ * Pipelining attributes a particle in flight to its batch by its history id, so consecutive batches overlap only when
+ * their id ranges ASCEND (first_history >= the end of the previous range, as in the reference's loop, where batch k owns
+ * ids [k * nperbatch, (k+1) * nperbatch)); a call whose range starts lower first completes the batch in flight. */
 int omc_gpu_run_batch(omc_gpu_handle h, long long first_history, long long nhist, int ibeamlet);
 /* The same pipelining with the accumulation left to the caller (multi-GPU: the batch grid is summed over ranks before
  * accumEndep() squares it): start_batch returns when its histories are all started and the PREVIOUS started batch is
@@ -238,6 +241,63 @@ void *omc_gpu_stream(omc_gpu_handle h);
 int omc_gpu_get_counters(omc_gpu_handle h, omc_gpu_counters *c);
 /* debug: copy per-history records of the last run_histories (needs option record_histories=1) */
 int omc_gpu_get_history_records(omc_gpu_handle h, omc_history_record *out, long long n);
+
+/* ---- multi-GPU: histories shard, the only exchange is the sum of a completed batch grid ---------------- */
+/*
+ * The reference parallelises the history loop of ONE batch over an OpenMP team that shares score.endep
+ * (omc_dosxyz.c:1184-1191, :1252-1259, :690-691).  Here the team is a set of GPUs joined by an NCCL communicator that lives
+ * INSIDE the library (NCCL is resolved with dlopen at the first call; single-GPU use needs none):
+ *
+ *   one process per GPU (MPI-style launchers, torchrun):   rank 0 calls omc_gpu_comm_unique_id(id) and hands the 128 bytes
+ *       to the other ranks by whatever means the launcher offers; every rank calls omc_gpu_comm_init(h, rank, world, id).
+ *   one process, several GPUs (a plain C user code):        omc_gpu_multi_* below does exactly that with one host thread
+ *       per device.
+ *
+ * With a communicator, omc_gpu_run_batch() / omc_gpu_start_batch() take the batch's WHOLE id range on every rank and
+ * transport this rank's contiguous slice of it (history id -> RNG stream: the result does not depend on the rank count
+ * beyond fp64 summation order); omc_gpu_accum_batch() -- explicit, or owed by omc_gpu_run_batch() -- sums the completed batch
+ * grid over the ranks (ncclAllReduce, fp64) BEFORE accumEndep() squares it, so accum / accum2 on every rank are those of a
+ * single-GPU run of the same batches.  Both run on a side stream behind an event: the transport stream starts the next
+ * batch at once and waits for them only when that dose grid is needed again, one batch later.  Every rank must issue the
+ * same sequence of batch calls.  score.ensrc and the work counters stay per rank (omc_gpu_comm_sum adds host values up).
+ */
+int omc_gpu_comm_unique_id(char *id128 /* [128] out */);
+int omc_gpu_comm_init(omc_gpu_handle h, int rank, int world, const char *id128);   /* world == 1: drops the communicator */
+int omc_gpu_comm_rank(omc_gpu_handle h);
+int omc_gpu_comm_size(omc_gpu_handle h);
+int omc_gpu_comm_sum(omc_gpu_handle h, double *values, int n);   /* in-place sum of n host doubles over the ranks (collective) */
+
+/* One handle over several GPUs of this node for a single-process user code: the batch loop of omc_dosxyz.c:1237-1263 with
+ * `omc_gpu_multi_run_batch(m, ibatch*nperbatch, nperbatch, -1)` in place of the OpenMP loop + accumEndep(), and the beamlet
+ * loop of omc_matrad.c:1389-1493 with omc_gpu_multi_run_beamlets().  Setters broadcast the problem to every device; results
+ * come from device 0 (every device holds the same statistics), ensrc and the counters are summed. */
+typedef struct omc_gpu_multi_ctx *omc_gpu_multi;
+int  omc_gpu_multi_create(omc_gpu_multi *m, int ndev /* <= 0: all visible */, const int *device_ids /* NULL: 0..ndev-1 */);
+void omc_gpu_multi_destroy(omc_gpu_multi m);
+int  omc_gpu_multi_size(omc_gpu_multi m);
+omc_gpu_handle omc_gpu_multi_device(omc_gpu_multi m, int i);
+const char *omc_gpu_multi_last_error(omc_gpu_multi m);
+int omc_gpu_multi_set_media(omc_gpu_multi m, const omc_media_tables *t);
+int omc_gpu_multi_set_geometry(omc_gpu_multi m, const omc_geometry *g);
+int omc_gpu_multi_set_source_dosxyz(omc_gpu_multi m, const omc_source_dosxyz *s);
+int omc_gpu_multi_set_source_matrad(omc_gpu_multi m, const omc_source_matrad *s);
+int omc_gpu_multi_set_vrt(omc_gpu_multi m, int nsplit);
+int omc_gpu_multi_set_seed(omc_gpu_multi m, int ixx, int jxx);
+int omc_gpu_multi_set_option(omc_gpu_multi m, const char *key, long long value);
+int omc_gpu_multi_reset_tallies(omc_gpu_multi m, int which);
+int omc_gpu_multi_run_batch(omc_gpu_multi m, long long first_history, long long nhist, int ibeamlet);
+int omc_gpu_multi_synchronize(omc_gpu_multi m);
+int omc_gpu_multi_get_tallies(omc_gpu_multi m, double *accum_endep, double *accum_endep2, double *ensrc);
+int omc_gpu_multi_accumulate_results(omc_gpu_multi m, int iout, int nhist, int nbatch, const double *med_densities, double *dose,
+                                     double *unc);
+int omc_gpu_multi_write_3ddose(omc_gpu_multi m, const char *path, int iout, int nhist, int nbatch, const double *med_densities);
+int omc_gpu_multi_get_counters(omc_gpu_multi m, omc_gpu_counters *c);
+/* omc_gpu_run_beamlets() over the devices: passes of `per_pass` consecutive beamlets (<= 0: OMC_BEAMLETS_PER_PASS), pass p on
+ * device p % ndev, the column slices gathered in beamlet order as the reference's loop appends them (omc_matrad.c:1416-1477);
+ * beamlet ib0 + k owns history ids [first_history + k*nhist, +nhist) whatever the device count. */
+int omc_gpu_multi_run_beamlets(omc_gpu_multi m, long long first_history, int nhist, int nbatch, int ib0, int nb, int per_pass,
+                               double rel_threshold, const double *med_densities, long long *jc /* [nb+1] */, long long *nnz_total);
+int omc_gpu_multi_fetch_columns(omc_gpu_multi m, long long *ir, double *val);
 
 /* sizeof() of the structs above as this library was compiled (0 media, 1 geometry, 2 source_dosxyz,
  * 3 source_matrad, 4 history_record, 5 counters): lets a foreign-language binding check its layout */

@@ -21,7 +21,8 @@ from . import problem as P
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 BEAMLETS_PER_PASS, BEAMLET_GRID_BUDGET = 64, 64 * 1073741824        # OMC_BEAMLETS_PER_PASS, OMC_BEAMLET_GRID_BUDGET of the header
-LIB_PATH = os.path.join(HERE, "libompmc_b200.so")
+# (OMPMC_B200_LIB: an A/B build of the same library for the measurement scripts, e.g. built with OMC_NVCC_FLAGS; never a fallback)
+LIB_PATH = os.environ.get("OMPMC_B200_LIB") or os.path.join(HERE, "libompmc_b200.so")
 
 KERNEL_LOCKSTEP, KERNEL_WAVEFRONT = 0, 1
 DEFAULT_KERNEL = KERNEL_WAVEFRONT    # production default used by bench.py (nsplit == 1)
@@ -92,7 +93,13 @@ EXPORTS = ["omc_gpu_create", "omc_gpu_destroy", "omc_gpu_last_error", "omc_gpu_s
            "omc_gpu_completed_batches", "omc_gpu_synchronize", "omc_gpu_get_tallies",
            "omc_gpu_get_batch_grid", "omc_gpu_accumulate_results", "omc_gpu_write_3ddose", "omc_gpu_test_format", "omc_gpu_run_beamlets", "omc_gpu_fetch_columns", "omc_gpu_reset_tallies", "omc_gpu_device_ptrs", "omc_gpu_stream", "omc_gpu_get_counters",
            "omc_gpu_get_history_records", "omc_gpu_test_geometry", "omc_gpu_test_rng", "omc_gpu_test_particles", "omc_gpu_test_samplers",
-           "omc_gpu_abi_sizeof"]
+           "omc_gpu_abi_sizeof",
+           "omc_gpu_comm_unique_id", "omc_gpu_comm_init", "omc_gpu_comm_rank", "omc_gpu_comm_size", "omc_gpu_comm_sum",
+           "omc_gpu_multi_create", "omc_gpu_multi_destroy", "omc_gpu_multi_size", "omc_gpu_multi_device", "omc_gpu_multi_last_error",
+           "omc_gpu_multi_set_media", "omc_gpu_multi_set_geometry", "omc_gpu_multi_set_source_dosxyz", "omc_gpu_multi_set_source_matrad",
+           "omc_gpu_multi_set_vrt", "omc_gpu_multi_set_seed", "omc_gpu_multi_set_option", "omc_gpu_multi_reset_tallies",
+           "omc_gpu_multi_run_batch", "omc_gpu_multi_synchronize", "omc_gpu_multi_get_tallies", "omc_gpu_multi_accumulate_results",
+           "omc_gpu_multi_write_3ddose", "omc_gpu_multi_get_counters", "omc_gpu_multi_run_beamlets", "omc_gpu_multi_fetch_columns"]
 
 
 def load_library() -> C.CDLL:
@@ -135,7 +142,58 @@ def load_library() -> C.CDLL:
     lib.omc_gpu_abi_sizeof.argtypes = [C.c_int]
     lib.omc_gpu_test_particles.argtypes = [H, C.c_int] + [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]
     lib.omc_gpu_test_samplers.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]
+    # multi-GPU
+    lib.omc_gpu_comm_unique_id.argtypes = [C.c_char_p]
+    lib.omc_gpu_comm_init.argtypes = [H, C.c_int, C.c_int, C.c_char_p]
+    lib.omc_gpu_comm_rank.argtypes = [H]; lib.omc_gpu_comm_size.argtypes = [H]
+    lib.omc_gpu_comm_sum.argtypes = [H, C.c_void_p, C.c_int]
+    lib.omc_gpu_multi_create.argtypes = [C.POINTER(H), C.c_int, C.c_void_p]
+    lib.omc_gpu_multi_destroy.argtypes = [H]; lib.omc_gpu_multi_destroy.restype = None
+    lib.omc_gpu_multi_size.argtypes = [H]
+    lib.omc_gpu_multi_device.argtypes = [H, C.c_int]; lib.omc_gpu_multi_device.restype = C.c_void_p
+    lib.omc_gpu_multi_last_error.argtypes = [H]; lib.omc_gpu_multi_last_error.restype = C.c_char_p
+    lib.omc_gpu_multi_set_media.argtypes = [H, C.POINTER(MediaTables)]
+    lib.omc_gpu_multi_set_geometry.argtypes = [H, C.POINTER(Geometry)]
+    lib.omc_gpu_multi_set_source_dosxyz.argtypes = [H, C.POINTER(SourceDosxyz)]
+    lib.omc_gpu_multi_set_source_matrad.argtypes = [H, C.POINTER(SourceMatrad)]
+    lib.omc_gpu_multi_set_vrt.argtypes = [H, C.c_int]
+    lib.omc_gpu_multi_set_seed.argtypes = [H, C.c_int, C.c_int]
+    lib.omc_gpu_multi_set_option.argtypes = [H, C.c_char_p, C.c_longlong]
+    lib.omc_gpu_multi_reset_tallies.argtypes = [H, C.c_int]
+    lib.omc_gpu_multi_run_batch.argtypes = [H, C.c_longlong, C.c_longlong, C.c_int]
+    lib.omc_gpu_multi_synchronize.argtypes = [H]
+    lib.omc_gpu_multi_get_tallies.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.omc_gpu_multi_accumulate_results.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.omc_gpu_multi_write_3ddose.argtypes = [H, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.omc_gpu_multi_get_counters.argtypes = [H, C.POINTER(Counters)]
+    lib.omc_gpu_multi_run_beamlets.argtypes = [H, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
+                                               C.c_void_p, C.POINTER(C.c_longlong)]
+    lib.omc_gpu_multi_fetch_columns.argtypes = [H, C.c_void_p, C.c_void_p]
     return lib
+
+
+_NCCL_PRELOADED = False
+
+
+def preload_nccl() -> None:
+    """Map the NCCL that PyTorch bundles BEFORE the library resolves NCCL with dlopen("libnccl.so.2") (csrc/omc_nccl.h): a
+    Python process must hold one copy of NCCL, and torch's libtorch_cuda.so needs the symbols of its own (newer) one -- were the
+    system library mapped first under the same SONAME, a later `import torch` would fail.  Plain C user codes have no such
+    constraint and get the system NCCL."""
+    global _NCCL_PRELOADED
+    if _NCCL_PRELOADED:
+        return
+    _NCCL_PRELOADED = True
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (spec.submodule_search_locations if spec else []):
+            path = os.path.join(root, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                C.CDLL(path, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass
 
 
 def _f64(a):
@@ -148,6 +206,52 @@ def _i32(a):
 
 class OmcGpuError(RuntimeError):
     pass
+
+
+def problem_structs(prob: dict):
+    """The C structs of include/ompmc_b200.h over the arrays of a problem dict: (media, geometry, source, keep-alive list)."""
+    keep = []
+
+    def pd(name):
+        a = _f64(prob[name]); keep.append(a)
+        return a.ctypes.data_as(PD)
+
+    def pi(name):
+        a = _i32(prob[name]); keep.append(a)
+        return a.ctypes.data_as(PI)
+    mt = MediaTables()
+    mt.nmed = int(prob["nmed"][0])
+    for name, typ in MediaTables._fields_[1:]:
+        if typ is PD:
+            setattr(mt, name, pd(name))
+        elif typ is PI:
+            setattr(mt, name, pi(name))
+        else:
+            setattr(mt, name, float(prob[name][0]))
+    g = Geometry()
+    g.isize, g.jsize, g.ksize = int(prob["isize"][0]), int(prob["jsize"][0]), int(prob["ksize"][0])
+    g.xbounds, g.ybounds, g.zbounds = pd("xbounds"), pd("ybounds"), pd("zbounds")
+    g.med, g.rhof, g.pcut, g.ecut = pi("region_med"), pd("region_rhof"), pd("region_pcut"), pd("region_ecut")
+    if "mr_nbeamlets" in prob:                     # matRad beamlet source (omc_matrad.c)
+        m = SourceMatrad()
+        m.spectrum, m.charge = int(prob["src_spectrum"][0]), int(prob["src_charge"][0])
+        m.energy, m.deltak = float(prob["src_energy"][0]), float(prob["src_deltak"][0])
+        m.cdfinv1, m.cdfinv2 = pd("src_cdfinv1"), pd("src_cdfinv2")
+        m.nbixels, m.nbeams = int(prob["mr_nbeamlets"][0]), len(prob["mr_xsource"])
+        m.ibeam = pi("mr_ibeam")
+        for k in ["xsource", "ysource", "zsource", "xcorner", "ycorner", "zcorner", "xside1", "yside1", "zside1",
+                  "xside2", "yside2", "zside2"]:
+            setattr(m, k, pd("mr_" + k))
+        return mt, g, m, keep
+    s = SourceDosxyz()
+    s.spectrum, s.charge = int(prob["src_spectrum"][0]), int(prob["src_charge"][0])
+    s.energy, s.deltak = float(prob["src_energy"][0]), float(prob["src_deltak"][0])
+    s.cdfinv1, s.cdfinv2 = pd("src_cdfinv1"), pd("src_cdfinv2")
+    for k in ["ssd", "xinl", "xinu", "yinl", "yinu", "xsize", "ysize"]:
+        setattr(s, k, float(prob["src_" + k][0]))
+    for k in ["ixinl", "ixinu", "iyinl", "iyinu"]:
+        setattr(s, k, int(prob["src_" + k][0]))
+    return mt, g, s, keep
 
 
 class GpuTransport:
@@ -179,55 +283,18 @@ class GpuTransport:
             raise OmcGpuError(f"{what} failed (rc={rc}): {self.lib.omc_gpu_last_error(self.h).decode()}")
 
     # -- problem upload ----------------------------------------------------------------------
+    _PFX = "omc_gpu_"
+
     def load_problem(self, prob: dict, seeds=(97, 33)):
-        keep = []
-
-        def pd(name):
-            a = _f64(prob[name]); keep.append(a)
-            return a.ctypes.data_as(PD)
-
-        def pi(name):
-            a = _i32(prob[name]); keep.append(a)
-            return a.ctypes.data_as(PI)
-        mt = MediaTables()
-        mt.nmed = int(prob["nmed"][0])
-        for name, typ in MediaTables._fields_[1:]:
-            if typ is PD:
-                setattr(mt, name, pd(name))
-            elif typ is PI:
-                setattr(mt, name, pi(name))
-            else:
-                setattr(mt, name, float(prob[name][0]))
-        self._ck(self.lib.omc_gpu_set_media(self.h, C.byref(mt)), "omc_gpu_set_media")
-        g = Geometry()
-        g.isize, g.jsize, g.ksize = int(prob["isize"][0]), int(prob["jsize"][0]), int(prob["ksize"][0])
-        g.xbounds, g.ybounds, g.zbounds = pd("xbounds"), pd("ybounds"), pd("zbounds")
-        g.med, g.rhof, g.pcut, g.ecut = pi("region_med"), pd("region_rhof"), pd("region_pcut"), pd("region_ecut")
-        self._ck(self.lib.omc_gpu_set_geometry(self.h, C.byref(g)), "omc_gpu_set_geometry")
+        mt, g, src, keep = problem_structs(prob)
+        f = lambda name: getattr(self.lib, self._PFX + name)         # noqa: E731
+        self._ck(f("set_media")(self.h, C.byref(mt)), self._PFX + "set_media")
+        self._ck(f("set_geometry")(self.h, C.byref(g)), self._PFX + "set_geometry")
         self.nreg = g.isize * g.jsize * g.ksize + 1
-        if "mr_nbeamlets" in prob:                     # matRad beamlet source (omc_matrad.c)
-            m = SourceMatrad()
-            m.spectrum, m.charge = int(prob["src_spectrum"][0]), int(prob["src_charge"][0])
-            m.energy, m.deltak = float(prob["src_energy"][0]), float(prob["src_deltak"][0])
-            m.cdfinv1, m.cdfinv2 = pd("src_cdfinv1"), pd("src_cdfinv2")
-            m.nbixels, m.nbeams = int(prob["mr_nbeamlets"][0]), len(prob["mr_xsource"])
-            m.ibeam = pi("mr_ibeam")
-            for k in ["xsource", "ysource", "zsource", "xcorner", "ycorner", "zcorner", "xside1", "yside1", "zside1",
-                      "xside2", "yside2", "zside2"]:
-                setattr(m, k, pd("mr_" + k))
-            self._ck(self.lib.omc_gpu_set_source_matrad(self.h, C.byref(m)), "omc_gpu_set_source_matrad")
-        else:
-            s = SourceDosxyz()
-            s.spectrum, s.charge = int(prob["src_spectrum"][0]), int(prob["src_charge"][0])
-            s.energy, s.deltak = float(prob["src_energy"][0]), float(prob["src_deltak"][0])
-            s.cdfinv1, s.cdfinv2 = pd("src_cdfinv1"), pd("src_cdfinv2")
-            for k in ["ssd", "xinl", "xinu", "yinl", "yinu", "xsize", "ysize"]:
-                setattr(s, k, float(prob["src_" + k][0]))
-            for k in ["ixinl", "ixinu", "iyinl", "iyinu"]:
-                setattr(s, k, int(prob["src_" + k][0]))
-            self._ck(self.lib.omc_gpu_set_source_dosxyz(self.h, C.byref(s)), "omc_gpu_set_source_dosxyz")
-        self._ck(self.lib.omc_gpu_set_vrt(self.h, int(prob["nsplit"][0])), "omc_gpu_set_vrt")
-        self._ck(self.lib.omc_gpu_set_seed(self.h, int(seeds[0]), int(seeds[1])), "omc_gpu_set_seed")
+        kind = "set_source_matrad" if isinstance(src, SourceMatrad) else "set_source_dosxyz"
+        self._ck(f(kind)(self.h, C.byref(src)), self._PFX + kind)
+        self._ck(f("set_vrt")(self.h, int(prob["nsplit"][0])), self._PFX + "set_vrt")
+        self._ck(f("set_seed")(self.h, int(seeds[0]), int(seeds[1])), self._PFX + "set_seed")
         del keep   # arrays were copied to the device by the set_* calls
 
     def set_option(self, key: str, value: int):
@@ -329,7 +396,6 @@ class GpuTransport:
         out = {n: int(getattr(c, n)) for n in COUNTER_NAMES}
         if any(c.reserved[:4]):
             out["reserved"] = [int(v) for v in c.reserved[:4]]
-        out["handovers"], out["handed_over"] = int(c.reserved[4]), int(c.reserved[5])
         return out
 
     def stream_ptr(self) -> int:
@@ -374,3 +440,95 @@ class GpuTransport:
         out = np.zeros(n)
         self._ck(self.lib.omc_gpu_test_rng(self.h, hist, n, out.ctypes.data), "omc_gpu_test_rng")
         return out
+
+    # -- multi-GPU: NCCL inside the library (one process per GPU) ------------------------------
+    def comm_unique_id(self) -> bytes:
+        preload_nccl()
+        buf = C.create_string_buffer(128)
+        rc = self.lib.omc_gpu_comm_unique_id(buf)
+        if rc != 0:
+            raise OmcGpuError(f"omc_gpu_comm_unique_id failed rc={rc}: NCCL not available")
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, uid: bytes):
+        assert len(uid) == 128
+        preload_nccl()
+        self._ck(self.lib.omc_gpu_comm_init(self.h, int(rank), int(world), uid), "omc_gpu_comm_init")
+
+    def comm_sum(self, values) -> np.ndarray:
+        v = np.ascontiguousarray(values, dtype=np.float64).copy()
+        self._ck(self.lib.omc_gpu_comm_sum(self.h, v.ctypes.data, v.size), "omc_gpu_comm_sum")
+        return v
+
+
+class MultiGpuTransport(GpuTransport):
+    """``omc_gpu_multi``: several GPUs of this node behind one handle in ONE process (one host thread per device inside the
+    library, NCCL between the devices); same calls as GpuTransport for the batch loop and the results."""
+    _PFX = "omc_gpu_multi_"
+
+    def __init__(self, ndev: int = 0, device_ids=None):
+        self.lib = load_library()
+        preload_nccl()
+        self.h = C.c_void_p()
+        ids = None if device_ids is None else _i32(device_ids)
+        rc = self.lib.omc_gpu_multi_create(C.byref(self.h), int(ndev if ids is None else len(ids)), None if ids is None else ids.ctypes.data)
+        if rc != 0:
+            raise OmcGpuError(f"omc_gpu_multi_create failed rc={rc}: CUDA devices (and NCCL for more than one) required")
+        self.ndev = int(self.lib.omc_gpu_multi_size(self.h))
+        self.device = 0
+        self.nreg = 0
+
+    def close(self):
+        if self.h:
+            self.lib.omc_gpu_multi_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def _ck(self, rc: int, what: str):
+        if rc != 0:
+            raise OmcGpuError(f"{what} failed (rc={rc}): {self.lib.omc_gpu_multi_last_error(self.h).decode()}")
+
+    def set_option(self, key: str, value: int):
+        self._ck(self.lib.omc_gpu_multi_set_option(self.h, key.encode(), int(value)), f"omc_gpu_multi_set_option({key})")
+
+    def run_batch(self, first: int, n: int, ibeamlet: int = -1):
+        self._ck(self.lib.omc_gpu_multi_run_batch(self.h, first, n, ibeamlet), "omc_gpu_multi_run_batch")
+
+    def synchronize(self):
+        self._ck(self.lib.omc_gpu_multi_synchronize(self.h), "omc_gpu_multi_synchronize")
+
+    def reset_tallies(self, which: int = 0):
+        self._ck(self.lib.omc_gpu_multi_reset_tallies(self.h, which), "omc_gpu_multi_reset_tallies")
+
+    def get_tallies(self):
+        a = np.zeros(self.nreg); a2 = np.zeros(self.nreg); e = C.c_double(0.0)
+        self._ck(self.lib.omc_gpu_multi_get_tallies(self.h, a.ctypes.data, a2.ctypes.data, C.addressof(e)), "omc_gpu_multi_get_tallies")
+        return a, a2, e.value
+
+    def accumulate_results(self, med_densities: np.ndarray, nhist: int, nbatch: int, iout: int = 1):
+        dens = np.ascontiguousarray(med_densities, dtype=np.float64)
+        dose = np.zeros(self.nreg); unc = np.zeros(self.nreg)
+        self._ck(self.lib.omc_gpu_multi_accumulate_results(self.h, int(iout), int(nhist), int(nbatch), dens.ctypes.data, dose.ctypes.data,
+                                                           unc.ctypes.data), "omc_gpu_multi_accumulate_results")
+        return dose[1:], unc[1:]
+
+    def write_3ddose(self, path: str, med_densities: np.ndarray, nhist: int, nbatch: int, iout: int = 1):
+        dens = np.ascontiguousarray(med_densities, dtype=np.float64)
+        self._ck(self.lib.omc_gpu_multi_write_3ddose(self.h, os.fsencode(path), int(iout), int(nhist), int(nbatch), dens.ctypes.data),
+                 "omc_gpu_multi_write_3ddose")
+
+    def counters(self) -> dict:
+        c = Counters()
+        self._ck(self.lib.omc_gpu_multi_get_counters(self.h, C.byref(c)), "omc_gpu_multi_get_counters")
+        return {n: int(getattr(c, n)) for n in COUNTER_NAMES}
+
+    def run_beamlets(self, first: int, nhist: int, nbatch: int, ib0: int, nb: int, rel_threshold: float, med_densities: np.ndarray,
+                     per_pass: int = 0):
+        dens = np.ascontiguousarray(med_densities, dtype=np.float64)
+        jc = np.zeros(nb + 1, dtype=np.int64)
+        tot = C.c_longlong(0)
+        self._ck(self.lib.omc_gpu_multi_run_beamlets(self.h, int(first), int(nhist), int(nbatch), int(ib0), int(nb), int(per_pass),
+                                                     float(rel_threshold), dens.ctypes.data, jc.ctypes.data, C.byref(tot)),
+                 "omc_gpu_multi_run_beamlets")
+        ir = np.zeros(max(tot.value, 1), dtype=np.int64); val = np.zeros(max(tot.value, 1))
+        self._ck(self.lib.omc_gpu_multi_fetch_columns(self.h, ir.ctypes.data, val.ctypes.data), "omc_gpu_multi_fetch_columns")
+        return jc, ir[:tot.value], val[:tot.value]

@@ -19,6 +19,7 @@ SOURCES = {
     "omc_lockstep.cu": ["-fmad=false"],
     "omc_wavefront.cu": [],
     "omc_capi.cu": [],
+    "omc_multi.cu": [],
 }
 
 
@@ -34,6 +35,27 @@ def _stale(target: str, deps: list[str]) -> bool:
         return True
     t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_variant(tag: str, flags: list[str]) -> str:
+    """An A/B build of the library with extra nvcc flags -> ompmc_b200/libompmc_b200_<tag>.so (measurement scripts select it with
+    OMPMC_B200_LIB); objects go to build/<tag>/."""
+    objdir = os.path.join(HERE, "build", tag)
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    for src, extra in SOURCES.items():
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        r = subprocess.run([nvcc()] + ARCH + COMMON + extra + flags + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError(f"nvcc failed for {src} ({tag})")
+    lib = os.path.join(HERE, f"libompmc_b200_{tag}.so")
+    r = subprocess.run([nvcc()] + ARCH + ["-shared", "-o", lib] + objs + ["-ldl", "-lpthread"], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    return lib
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -57,7 +79,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {src}")
     if force or _stale(LIB, objs):
-        cmd = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs
+        cmd = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl", "-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
@@ -110,4 +132,8 @@ def build_host(force: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:         # build.py --variant TAG -DFOO=1 ...
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

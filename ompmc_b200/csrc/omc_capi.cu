@@ -13,6 +13,7 @@
 
 #include "omc_kernels.h"
 #include "omc_format.cuh"
+#include "omc_nccl.h"
 
 using namespace omc;
 
@@ -57,19 +58,29 @@ struct omc_gpu_ctx {
     double cut_e[OMC_MXMED] = {0}, cut_p[OMC_MXMED] = {0}, rho_max[OMC_MXMED] = {0};
     bool cuts_uniform = false, med_dirty = false;
     WaveQueues wq{};
-    PartQueue side{};              // hand-over queue: stragglers of the previous batch on their way to drain_kernel
-    int handover = 0;              // 1: hand the stragglers of the previous batch to the drain kernel (measured 3-30 % slower: off)
-    unsigned long long handovers = 0, handed_over = 0;
     std::vector<void *> wave_bufs;
     WaveCtl *ctl = nullptr;        // device
-    WaveCtl *ctl_host = nullptr;   // pinned
+    WaveCtl *ctl_host = nullptr;   // pinned: the latest status examined by the host loop
+    WaveCtl *ctl_slot[2] = {nullptr, nullptr};   // pinned: status read-backs in flight (the host loop looks one group ahead)
+    cudaEvent_t ev_stat[2] = {nullptr, nullptr};
+    // the `check_every` waves captured as a CUDA graph, kept across calls while the launch parameters do not change
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    std::vector<char> graph_key;
+    // multi-GPU (omc_gpu_comm_init): completed batch grids are summed over the ranks on a side stream, off the transport stream
+    nccl_comm_t comm = nullptr;
+    int rank = 0, world = 1;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    bool grid_wait[2] = {false, false};          // grid g may be scored into only after ev_free[g]
+    unsigned long long reduces = 0;
     unsigned pool_target = 1u << 23;   // particles kept in flight (B200: 2 Mi 1.03e8, 4 Mi 1.07e8, 8 Mi 1.09e8 histories/s)
     unsigned pool_cap = 0, pool_cap_opt = 0;
-    int electron_iters = 1, max_cross = 16, check_every = 16;
+    int max_cross = 16, check_every = 16;
     int photon_tracking = 1;      // 0: voxel-to-voxel march as in photon(); 1: Woodcock flight when nsplit == 1
     int max_virtual = 8;          // Woodcock: tentative collisions per photon per wave
     unsigned long long waves = 0;
-    int trace = 0, use_graph = 1, overlap = 1, source_kind = 0;
+    int trace = 0, use_graph = 1, overlap = 1, source_kind = 0, lookahead = 1;
     cudaStream_t stream2 = nullptr, stream3 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork3 = nullptr, ev_join3 = nullptr;
     unsigned drain_threshold = 8192;     // measured on B200 (16M-history call): 0 -> 183.5 ms, 8 Ki -> 182.4, 32 Ki -> 193.9, 128 Ki -> 223.5
@@ -85,6 +96,7 @@ struct omc_gpu_ctx {
     cudaEvent_t fmt_ev[2] = {nullptr, nullptr};
     // batch pipelining (see wave_run)
     int run_grid = -1, last_ibeamlet = -1;
+    long long hist_hi = 0;         // end of the history-id range of the batch in flight (pipelining needs ascending ids)
     std::vector<int> done_q;
     bool auto_acc[2] = {false, false};
     bool pipeline_next = false, pipeline_auto = false;   // how the next omc_gpu_run_histories() body is to run (set by the callers below)
@@ -145,11 +157,13 @@ static void free_pool(std::vector<void *> &pool) {
 
 static int alloc_queue(omc_gpu_handle h, PartQueue &q, unsigned cap, bool photons, bool electrons = false) {
     q.cap = cap;
-    double2 **f[4] = {&q.xy, &q.zu, &q.vw, &q.ew};
+    double2 **f[2] = {&q.xy, &q.ze};
     for (auto pp : f) {
         CK(cudaMalloc((void **)pp, (size_t)cap * sizeof(double2)));
         h->wave_bufs.push_back(*pp);
     }
+    CK(cudaMalloc((void **)&q.dw, (size_t)cap * sizeof(float4)));
+    h->wave_bufs.push_back(q.dw);
     q.aux = nullptr;
     if (photons) {
         CK(cudaMalloc((void **)&q.aux, (size_t)cap * sizeof(double2)));
@@ -169,12 +183,16 @@ static int alloc_queue(omc_gpu_handle h, PartQueue &q, unsigned cap, bool photon
 
 static int alloc_estep_queue(omc_gpu_handle h, EStepQueue &q, unsigned cap) {
     q.cap = cap;                                  // per step class; both classes share arrays of 2 * cap slots
-    for (int i = 0; i < 6; i++) {
+    for (int i = 0; i < 3; i++) {
         CK(cudaMalloc((void **)&q.v[i], (size_t)2 * cap * sizeof(double2)));
         h->wave_bufs.push_back(q.v[i]);
     }
+    CK(cudaMalloc((void **)&q.d, (size_t)2 * cap * sizeof(float4)));
+    h->wave_bufs.push_back(q.d);
     CK(cudaMalloc((void **)&q.f, (size_t)2 * cap * sizeof(float4)));
     h->wave_bufs.push_back(q.f);
+    CK(cudaMalloc((void **)&q.t, (size_t)2 * cap * sizeof(float2)));
+    h->wave_bufs.push_back(q.t);
     CK(cudaMalloc((void **)&q.m, (size_t)2 * cap * sizeof(uint4)));
     h->wave_bufs.push_back(q.m);
     CK(cudaMalloc((void **)&q.rng, (size_t)2 * cap * sizeof(uint4)));
@@ -187,8 +205,6 @@ static int alloc_estep_queue(omc_gpu_handle h, EStepQueue &q, unsigned cap) {
 // one is still in the queues: a particle scores into the grid of the batch its history id belongs to
 // (WaveCtl::hist_split).  h->run_grid = grid of the batch whose tail is in flight (-1: queues empty);
 // h->done_q = grids of completed batches that have not been accumulated yet (accumEndep), oldest first.
-constexpr unsigned SIDE_CAP = 65536;              // slots of the hand-over queue
-
 static int wave_prepare(omc_gpu_handle h) {
     const unsigned target = h->pool_target;
     const unsigned cap = h->pool_cap_opt ? h->pool_cap_opt : 2u * target + 65536u;
@@ -203,7 +219,6 @@ static int wave_prepare(omc_gpu_handle h) {
             if (alloc_queue(h, h->wq.ie[i], cap, false)) return 1;
         }
         if (alloc_estep_queue(h, h->wq.es, cap)) return 1;
-        if (alloc_queue(h, h->side, SIDE_CAP, false)) return 1;
         h->pool_cap = cap;
     }
     if (!h->stream2) {
@@ -218,6 +233,10 @@ static int wave_prepare(omc_gpu_handle h) {
         CK(cudaMalloc((void **)&h->ctl, sizeof(WaveCtl)));
         CK(cudaMallocHost((void **)&h->ctl_host, sizeof(WaveCtl)));
         memset(h->ctl_host, 0, sizeof(WaveCtl));
+        for (int i = 0; i < 2; i++) {
+            CK(cudaMallocHost((void **)&h->ctl_slot[i], sizeof(WaveCtl)));
+            CK(cudaEventCreateWithFlags(&h->ev_stat[i], cudaEventDisableTiming));
+        }
     }
     return 0;
 }
@@ -259,23 +278,10 @@ static int drain_queues(omc_gpu_handle h, const PartQueue *const q[4], const uns
     return 0;
 }
 
-// Straggler hand-over (omc_wavefront.cu: handover_kernel): what is left of the previous batch leaves the queues and is
-// finished by drain_kernel, so the next batch need not wait for the last near-empty waves of that one.  Returns through
-// h->ctl_host (old_done set when nothing of the previous batch is left in the queues).
-static int hand_over_old(omc_gpu_handle h, int g_old) {
-    CK(cudaMemsetAsync(&h->ctl->n_side.v, 0, sizeof(unsigned), h->stream));
-    CK(cudaMemsetAsync(&h->ctl->side_fail, 0, sizeof(unsigned), h->stream));
-    launch_handover(h->ctl, h->wq, h->side, h->sm_count * 4, h->stream);
-    h->launches += 2;
-    CK(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    const unsigned n = h->ctl_host->n_side.v < h->side.cap ? h->ctl_host->n_side.v : h->side.cap;
-    h->handovers += 1; h->handed_over += n;
-    if (h->trace) fprintf(stderr, "hand-over: %u stragglers of the previous batch to the drain kernel (%u did not fit)\n", n, h->ctl_host->side_fail);
-    if (n == 0) return 0;
-    const PartQueue *q[4] = {&h->side, &h->side, &h->side, &h->side};
-    const unsigned *cnt[4] = {&h->ctl->n_side.v, &h->ctl->zero_, &h->ctl->zero_, &h->ctl->zero_};
-    return drain_queues(h, q, cnt, g_old);
+static void drop_graph(omc_gpu_handle h) {
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+    h->graph_key.clear();
 }
 
 // start == true : inject histories [first, first+nhist) and return once all of them are started AND the previous batch
@@ -290,6 +296,10 @@ static int wave_run(omc_gpu_handle h, bool start, long long first, long long nhi
     int g_old = h->run_grid;
     bool old_pending = false;
     if (start) {
+        if (h->grid_wait[g_new]) {                              // the grid's previous batch is still being summed over the ranks
+            CK(cudaStreamWaitEvent(h->stream, h->ev_free[g_new], 0));
+            h->grid_wait[g_new] = false;
+        }
         if (g_old < 0) {                                        // empty pipeline
             WaveCtl c;
             memset(&c, 0, sizeof c);
@@ -299,6 +309,7 @@ static int wave_run(omc_gpu_handle h, bool start, long long first, long long nhi
             const unsigned first_room = target / (unsigned)(P.nsplit > 1 ? P.nsplit : 1);   // (splitting multiplies the population)
             c.n_src = (unsigned)((unsigned long long)nhist < (unsigned long long)first_room ? nhist : first_room);
             CK(cudaMemcpyAsync(h->ctl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaStreamSynchronize(h->stream));               // (c is a stack object)
         } else {                                                // previous batch still in flight: it becomes "old"
             launch_rearm(h->ctl, (unsigned long long)first, (unsigned long long)nhist, (unsigned)P.nsplit, h->stream);
             old_pending = true;
@@ -313,10 +324,11 @@ static int wave_run(omc_gpu_handle h, bool start, long long first, long long nhi
         ibeamlet = h->last_ibeamlet;
     }
     WaveLaunch L;
+    memset(&L, 0, sizeof L);
     int occ[4];
     wave_blocks_per_sm(occ);
     for (int i = 0; i < 4; i++) L.blocks[i] = h->max_blocks > 0 ? h->max_blocks : h->sm_count * occ[i];
-    L.max_cross = h->max_cross; L.electron_iters = h->electron_iters; L.ibeamlet = ibeamlet;
+    L.max_cross = h->max_cross; L.ibeamlet = ibeamlet;
     L.woodcock = (h->photon_tracking == 1 && P.nsplit == 1) ? 1 : 0;
     L.max_virtual = h->max_virtual > 0 ? ((h->max_virtual + 1) & ~1) : 8;   // even: whole Philox blocks, so results do not depend on it
     L.mb_grid = h->mb_active ? h->mb_grid : nullptr;
@@ -325,76 +337,113 @@ static int wave_run(omc_gpu_handle h, bool start, long long first, long long nhi
     W.s = h->stream; W.s2 = h->overlap ? h->stream2 : nullptr; W.s3 = h->stream3;
     W.fork = h->ev_fork; W.join = h->ev_join; W.fork3 = h->ev_fork3; W.join3 = h->ev_join3;
     const int every = h->check_every > 0 ? h->check_every : 1;
-    // `every` waves are captured once into a CUDA graph (all launch parameters are wave-invariant: cur/next
-    // parity lives in WaveCtl on the device), so the host issues one graph launch per `every` waves
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t gexec = nullptr;
+    // `every` waves are captured once into a CUDA graph (all launch parameters are wave-invariant: cur/next parity lives
+    // in WaveCtl on the device), so the host issues one graph launch per `every` waves.  The instantiated graph is kept
+    // across calls for as long as nothing that the kernels receive by value changes (problem, queues, launch shape).
     if (h->use_graph) {
-        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        for (int k = 0; k < every; k++) launch_wave(P, h->ctl, h->wq, L, W);
-        CK(cudaStreamEndCapture(h->stream, &graph));
-        CK(cudaGraphInstantiate(&gexec, graph, 0));
+        std::vector<char> key(sizeof(DevProblem) + sizeof(WaveLaunch) + sizeof(WaveQueues) + 2 * sizeof(int));
+        char *k = key.data();
+        memcpy(k, &P, sizeof(DevProblem)); k += sizeof(DevProblem);
+        memcpy(k, &L, sizeof(WaveLaunch)); k += sizeof(WaveLaunch);
+        memcpy(k, &h->wq, sizeof(WaveQueues)); k += sizeof(WaveQueues);
+        memcpy(k, &every, sizeof(int)); k += sizeof(int);
+        memcpy(k, &h->overlap, sizeof(int));
+        if (!h->gexec || key != h->graph_key) {
+            drop_graph(h);
+            CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            for (int i = 0; i < every; i++) launch_wave(P, h->ctl, h->wq, L, W);
+            CK(cudaStreamEndCapture(h->stream, &h->graph));
+            CK(cudaGraphInstantiate(&h->gexec, h->graph, 0));
+            h->graph_key = key;
+        }
+    } else {
+        drop_graph(h);
     }
     int rc = 0;
-    bool drained = false;
-    for (unsigned long long wave = 0;; wave += every) {
-        if (gexec) {
-            CK(cudaGraphLaunch(gexec, h->stream));
+    bool drained = false, done = false;
+    // The host looks ONE group of waves ahead while the pool is busy: group k+1 is enqueued before the status read-back of
+    // group k is examined, so the device never idles for the host's wake-up + launch latency (it did, once per 16 waves,
+    // and with 8 ranks on one socket that showed as rank skew).  Every decision below is monotone in the status (a batch
+    // that was complete stays complete), so acting one group late only appends waves over queues that are emptier.
+    // Near the end (few particles alive) the look-ahead is dropped: the extra group would be pure latency there.
+    int issued = 0, examined = 0;
+    bool ahead = false;
+    for (unsigned long long wave = 0; !done; wave += every) {
+        const int slot = issued & 1;
+        if (h->gexec) {
+            CK(cudaGraphLaunch(h->gexec, h->stream));
         } else {
-            for (int k = 0; k < every; k++) launch_wave(P, h->ctl, h->wq, L, W);
+            for (int i = 0; i < every; i++) launch_wave(P, h->ctl, h->wq, L, W);
         }
         h->launches += 5ull * every;
         h->waves += every;
-        CK(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        const WaveCtl &s = *h->ctl_host;
-        if (h->trace)
-            fprintf(stderr, "wave %llu live %u n_src %u P %u E %u IP %u IE %u hist_next %llu old %u/%u\n", wave + every, s.live, s.n_src,
-                    s.n_p[s.parity].v, s.n_e[s.parity].v, s.n_ip[s.parity].v, s.n_ie[s.parity].v, s.hist_next, s.has_old, s.old_done);
-        if (s.overflow.v) {
-            h->err = "particle queue overflow on the device: increase option pool_size";
-            rc = 7;
-            break;
+        // Fold the fp32 chunk grids into the fp64 batch grids every few checks, not only when a batch completes: with 1e8
+        // histories per batch a hot voxel's fp32 sum reaches 1e4 MeV, where one ulp is 1e-3 MeV.  (Between two graph launches
+        // nothing else runs on this stream, so the plain read-add-zero of flush_kernel is safe.)
+        if (!h->mb_active && ((wave / every) & 3ull) == 3ull) {
+            const int gs[2] = {start ? g_new : g_old, (start && old_pending) ? g_old : -1};
+            for (int g : gs)
+                if (g >= 0) {
+                    const size_t off = (size_t)g * P.nreg;
+                    launch_flush(P.endep32 + off, P.endep + off, P.nreg, h->stream);
+                    h->launches += 1;
+                }
         }
-        const bool exhausted = s.hist_next >= s.hist_end && s.n_src == 0;
-        if (old_pending && !s.old_done && exhausted && h->handover && h->drain_threshold > 0 && P.nsplit == 1 && !h->mb_active &&
-            s.old_last <= (h->drain_threshold < SIDE_CAP / 2 ? h->drain_threshold : SIDE_CAP / 2)) {
-            // every history of the new batch is on its way and the previous batch is down to a few stragglers: hand them
-            // to the drain kernel instead of idling through their last waves (s refers to h->ctl_host: refreshed)
-            if (hand_over_old(h, g_old)) { rc = 1; break; }
+        CK(cudaMemcpyAsync(h->ctl_slot[slot], h->ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->ev_stat[slot], h->stream));
+        issued += 1;
+        while (!done && issued - examined > (ahead ? 1 : 0)) {
+            const int es = examined & 1;
+            CK(cudaEventSynchronize(h->ev_stat[es]));
+            memcpy(h->ctl_host, h->ctl_slot[es], sizeof(WaveCtl));
+            examined += 1;
+            const WaveCtl &s = *h->ctl_host;
+            if (h->trace)
+                fprintf(stderr, "wave %llu live %u n_src %u P %u E %u IP %u IE %u hist_next %llu old %u/%u\n",
+                        (unsigned long long)examined * every, s.live, s.n_src, s.n_p[s.parity].v, s.n_e[s.parity].v, s.n_ip[s.parity].v,
+                        s.n_ie[s.parity].v, s.hist_next, s.has_old, s.old_done);
+            if (s.overflow.v) {
+                h->err = "particle queue overflow on the device: increase option pool_size";
+                rc = 7; done = true;
+                break;
+            }
+            const bool exhausted = s.hist_next >= s.hist_end && s.n_src == 0;
+            ahead = h->lookahead && !exhausted && s.live > (1u << 18);
+            if (old_pending && s.old_done) {                    // the previous batch has left the queues: its grid is final
+                grid_done(h, g_old);
+                old_pending = false;
+            }
+            if (start) {
+                // the tail of the new batch stays in flight; it is always the NEXT call that completes a batch, even an
+                // already empty one, so that every rank of a multi-GPU run sees the same sequence of completed batches
+                if (exhausted && !old_pending) done = true;
+            } else if (exhausted && s.live == 0) {
+                done = true;
+            } else if (exhausted && s.live <= h->drain_threshold && P.nsplit == 1 && !h->mb_active) {
+                // (split photons in flight cannot be handed over; the drain scores into ONE fp64 grid, not per beamlet)
+                drained = true; done = true;
+            }
         }
-        if (old_pending && s.old_done) {                        // the previous batch has left the queues: its grid is final
-            grid_done(h, g_old);
-            old_pending = false;
-        }
-        if (start) {
-            // the tail of the new batch stays in flight; it is always the NEXT call that completes a batch, even an
-            // already empty one, so that every rank of a multi-GPU run sees the same sequence of completed batches
-            if (exhausted && !old_pending) break;
-        } else if (exhausted && s.live == 0) {
-            break;
-        } else if (exhausted && s.live <= h->drain_threshold && P.nsplit == 1 && !h->mb_active) {
-            // (split photons in flight cannot be handed over; the drain scores into ONE fp64 grid, not per beamlet)
-            drained = true;
-            break;
-        }
-        if (wave > 50000000ull) { rc = fail(h, "wavefront did not terminate"); break; }
+        if (!done && wave > 50000000ull) { rc = fail(h, "wavefront did not terminate"); break; }
     }
-    if (gexec) { cudaGraphExecDestroy(gexec); cudaGraphDestroy(graph); }
+    if (issued > examined) {                                    // a group was still in flight: its status is the current one
+        CK(cudaEventSynchronize(h->ev_stat[(issued - 1) & 1]));
+        memcpy(h->ctl_host, h->ctl_slot[(issued - 1) & 1], sizeof(WaveCtl));
+    }
     if (rc) { h->run_grid = -1; return rc; }
     if (start) {
         h->run_grid = g_new;
         CK(cudaGetLastError());
         return 0;
     }
-    if (drained) {
+    if (drained && h->ctl_host->live > 0) {
         // few particles left: one thread follows each to the end (omc_lockstep.cu: drain_kernel)
         const int par = (int)h->ctl_host->parity;
         const PartQueue *q[4] = {&h->wq.p[par], &h->wq.e[par], &h->wq.ip[par], &h->wq.ie[par]};
         const unsigned *cnt[4] = {&h->ctl->n_p[par].v, &h->ctl->n_e[par].v, &h->ctl->n_ip[par].v, &h->ctl->n_ie[par].v};
         if (drain_queues(h, q, cnt, g_old)) return 1;
-        memset(h->ctl_host, 0, sizeof(WaveCtl));                // (status: nothing alive any more)
     }
+    memset(h->ctl_host, 0, sizeof(WaveCtl));                    // (status: nothing alive any more)
     h->run_grid = -1;
     grid_done(h, g_old);
     CK(cudaGetLastError());
@@ -409,7 +458,11 @@ static int free_grid(omc_gpu_handle h) {
 }
 
 // accumEndep() of every completed batch that is waiting for it (oldest first); `only_auto`: just those started by
-// omc_gpu_run_batch(), which owes them an accumulation
+// omc_gpu_run_batch(), which owes them an accumulation.  With a communicator (omc_gpu_comm_init) the completed grid is first
+// summed over the ranks -- before accumEndep() squares it, so the statistics are those of a single-GPU run -- and both steps
+// run on the SIDE stream, ordered after the grid's final fold by an event: the transport stream goes on with the next batch
+// and only waits (ev_free) when this grid is needed again, one whole batch later.  A rank that finishes its slice early no
+// longer holds the others' waves behind its collective.
 static int accum_done(omc_gpu_handle h, bool only_auto) {
     std::vector<int> keep;
     bool took = false;
@@ -417,7 +470,18 @@ static int accum_done(omc_gpu_handle h, bool only_auto) {
         if ((only_auto && !h->auto_acc[g]) || (!only_auto && took)) { keep.push_back(g); continue; }   // explicit call: the oldest one only
         took = true;
         const size_t off = (size_t)g * h->P.nreg;
-        launch_accum(h->P.endep + off, h->accum, h->accum2, h->P.nreg, h->stream);
+        if (h->comm) {
+            CK(cudaEventRecord(h->ev_done[g], h->stream));
+            CK(cudaStreamWaitEvent(h->side, h->ev_done[g], 0));
+            const int e = nccl_api().AllReduce(h->P.endep + off, h->P.endep + off, (size_t)h->P.nreg, NCCL_FLOAT64, NCCL_SUM, h->comm, h->side);
+            if (e) { h->err = std::string("ncclAllReduce: ") + nccl_api().GetErrorString(e); return 1; }
+            launch_accum(h->P.endep + off, h->accum, h->accum2, h->P.nreg, h->side);
+            CK(cudaEventRecord(h->ev_free[g], h->side));
+            h->grid_wait[g] = true;
+            h->reduces += 1;
+        } else {
+            launch_accum(h->P.endep + off, h->accum, h->accum2, h->P.nreg, h->stream);
+        }
         h->launches += 1;
         h->auto_acc[g] = false;
     }
@@ -446,12 +510,20 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
         if (!h->done_q.empty()) { g = h->done_q.back(); h->done_q.pop_back(); }
         else g = 0;
     } else {
+        // A particle in flight is attributed to the previous or to the new batch by `history id < first` (WaveCtl::hist_split):
+        // a batch that re-uses or lowers ids cannot share the queues with the tail of the previous one -- complete that first.
+        if (h->run_grid >= 0 && first < h->hist_hi) {
+            int rc = wave_run(h, false, 0, 0, -1, -1);
+            if (rc) return rc;
+            if (auto_acc && (rc = accum_done(h, true))) return rc;
+        }
         g = free_grid(h);
         if (g < 0) return fail(h, "two batches are waiting for omc_gpu_accum_batch(): accumulate before starting another one");
     }
     h->auto_acc[g] = auto_acc;
     int rc = wave_run(h, true, first, nhist, ibeamlet, g);
     if (rc) return rc;
+    h->hist_hi = first + nhist;
     if (!pipelined) rc = wave_run(h, false, 0, 0, -1, -1);
     return rc;
 }
@@ -495,8 +567,18 @@ void omc_gpu_destroy(omc_gpu_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     h->media_bufs.clear(); h->geom_bufs.clear(); h->source_bufs.clear(); free_pool(h->wave_bufs);
+    drop_graph(h);
+    if (h->comm) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
+    if (h->side) {
+        cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side);
+        for (int i = 0; i < 2; i++) { cudaEventDestroy(h->ev_done[i]); cudaEventDestroy(h->ev_free[i]); }
+    }
     cudaFree(h->ctl);
     if (h->ctl_host) cudaFreeHost(h->ctl_host);
+    for (int i = 0; i < 2; i++) {
+        if (h->ctl_slot[i]) cudaFreeHost(h->ctl_slot[i]);
+        if (h->ev_stat[i]) cudaEventDestroy(h->ev_stat[i]);
+    }
     cudaFree(h->P.endep); cudaFree(h->P.endep32); cudaFree(h->accum); cudaFree(h->accum2);
     cudaFree(h->P.counters); cudaFree(h->P.ensrc); cudaFree(h->stack); cudaFree(h->records);
     cudaFree(h->res_dens); cudaFree(h->res_dose); cudaFree(h->res_unc);
@@ -768,13 +850,12 @@ int omc_gpu_set_option(omc_gpu_handle h, const char *key, long long value) {
     else if (k == "use_graph") h->use_graph = (int)value;
     else if (k == "overlap") h->overlap = (int)value;
     else if (k == "drain_threshold") h->drain_threshold = (unsigned)value;
-    else if (k == "handover") h->handover = (int)value;
     else if (k == "pool_cap") h->pool_cap_opt = (unsigned)value;
-    else if (k == "electron_iters") h->electron_iters = (int)value;
     else if (k == "max_cross") h->max_cross = (int)value;
     else if (k == "photon_tracking") h->photon_tracking = (int)value;
     else if (k == "max_virtual") h->max_virtual = (int)value;
     else if (k == "check_every") h->check_every = (int)value;
+    else if (k == "lookahead") h->lookahead = (int)value;
     else return fail(h, "unknown option");
     return 0;
 }
@@ -832,6 +913,7 @@ int omc_gpu_run_histories(omc_gpu_handle h, long long first, long long nhist, in
             CK(cudaMalloc((void **)&h->stack, need));
             h->stack_bytes = need;
         }
+        if (h->grid_wait[0]) { CK(cudaStreamWaitEvent(h->stream, h->ev_free[0], 0)); h->grid_wait[0] = false; }
         if (nhist > 0) {
             launch_lockstep(P, h->stack, depth, blocks, tpb, first, nhist, ibeamlet, h->inject, h->stream);
             h->launches += 1;
@@ -864,8 +946,17 @@ int omc_gpu_accum_batch(omc_gpu_handle h) {
     return accum_done(h, false);
 }
 
+// this rank's contiguous slice of the batch's history ids (the first nhist % world ranks get one more)
+static void shard_range(omc_gpu_handle h, long long &first, long long &nhist) {
+    if (h->world <= 1) return;
+    const long long base = nhist / h->world, extra = nhist % h->world, r = h->rank;
+    first += r * base + (r < extra ? r : extra);
+    nhist = base + (r < extra ? 1 : 0);
+}
+
 int omc_gpu_start_batch(omc_gpu_handle h, long long first, long long nhist, int ibeamlet) {
     if (!h) return 2;
+    shard_range(h, first, nhist);
     const bool wave = (h->kernel == OMC_KERNEL_WAVEFRONT) && !h->record;
     h->pipeline_next = wave; h->pipeline_auto = false;
     int rc = omc_gpu_run_histories(h, first, nhist, ibeamlet);
@@ -887,6 +978,7 @@ int omc_gpu_run_batch(omc_gpu_handle h, long long first, long long nhist, int ib
     // pipelined with the wavefront kernels: on return the histories are all started and every EARLIER batch is
     // accumulated; this batch is completed and accumulated by the next call or by whatever reads results
     const bool wave = (h->kernel == OMC_KERNEL_WAVEFRONT) && !h->record;
+    shard_range(h, first, nhist);
     h->pipeline_next = wave; h->pipeline_auto = true;
     int rc = omc_gpu_run_histories(h, first, nhist, ibeamlet);
     h->pipeline_next = false; h->pipeline_auto = false;
@@ -903,6 +995,7 @@ int omc_gpu_synchronize(omc_gpu_handle h) {
         if (rc) return rc;
     }
     CK(cudaStreamSynchronize(h->stream));
+    if (h->side) CK(cudaStreamSynchronize(h->side));
     Counters c;
     CK(cudaMemcpy(&c, h->P.counters, sizeof c, cudaMemcpyDeviceToHost));
     if (c.errors) {
@@ -926,7 +1019,8 @@ int omc_gpu_get_tallies(omc_gpu_handle h, double *accum, double *accum2, double 
 
 // accumulateResults() on the device: leaves dose / relative uncertainty in h->res_dose / h->res_unc (indexed like the tallies)
 static int results_on_device(omc_gpu_handle h, int iout, int nhist, int nbatch, const double *med_densities) {
-    if (nbatch < 2) return fail(h, "accumulateResults needs at least two batches (batch-method uncertainty)");
+    // (nbatch == 1 is accepted as the reference accepts it: its division by nbatch - 1 leaves NaN uncertainties in the file)
+    if (nbatch < 1) return fail(h, "accumulateResults: batch count must be positive");
     if (nhist < 1) return fail(h, "accumulateResults: history count must be positive");
     int rc = omc_gpu_synchronize(h);
     if (rc) return rc;
@@ -967,7 +1061,8 @@ static int format_setup(omc_gpu_handle h) {
     std::vector<Pow10> tab(kPow10N);
     build_pow10_table(tab.data());
     if (!h->fmt_tab) CK(cudaMalloc((void **)&h->fmt_tab, sizeof(Pow10) * kPow10N));
-    CK(cudaMemcpy(h->fmt_tab, tab.data(), sizeof(Pow10) * kPow10N, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(h->fmt_tab, tab.data(), sizeof(Pow10) * kPow10N, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     // (a failed allocation leaves fmt_ready false: the next call retries only what is still missing)
     if (!h->fmt_nfb_dev) CK(cudaMalloc((void **)&h->fmt_nfb_dev, 2 * sizeof(unsigned)));
     if (!h->fmt_nfb_host) CK(cudaMallocHost((void **)&h->fmt_nfb_host, 2 * sizeof(unsigned)));
@@ -1177,8 +1272,10 @@ int omc_gpu_reset_tallies(omc_gpu_handle h, int which) {
     if (!h || !h->have_geom) return 2;
     CK(cudaSetDevice(h->device));
     const size_t n = (size_t)h->P.nreg;
+    if (h->side) CK(cudaStreamSynchronize(h->side));
     if (which == 0) {                       // everything starts over: particles still in flight are dropped with their grids
         h->run_grid = -1; h->done_q.clear(); h->auto_acc[0] = h->auto_acc[1] = false;
+        h->grid_wait[0] = h->grid_wait[1] = false;
         if (h->ctl_host) memset(h->ctl_host, 0, sizeof(WaveCtl));
     } else {                                // omc_matrad.c:1482 zeroes accum_endep between beamlets: settle what is owed first
         int rc = flush_all(h);
@@ -1192,7 +1289,6 @@ int omc_gpu_reset_tallies(omc_gpu_handle h, int which) {
         CK(cudaMemsetAsync(h->P.ensrc, 0, sizeof(double), h->stream));
         CK(cudaMemsetAsync(h->P.counters, 0, sizeof(Counters), h->stream));
         h->launches = 0;
-        h->handovers = 0; h->handed_over = 0;
     }
     CK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -1204,6 +1300,61 @@ int omc_gpu_device_ptrs(omc_gpu_handle h, void **endep, void **accum, void **acc
     if (accum) *accum = h->accum;
     if (accum2) *accum2 = h->accum2;
     if (nreg) *nreg = h->P.nreg;
+    return 0;
+}
+
+// ---- multi-GPU: NCCL inside the library ------------------------------------------------------------------------
+int omc_gpu_comm_unique_id(char *id128) {
+    if (!id128) return 2;
+    NcclApi &N = nccl_api();
+    if (!N.ok) { fprintf(stderr, "ompmc_b200: %s\n", N.err.c_str()); return 8; }
+    nccl_uid id;
+    if (N.GetUniqueId(&id)) return 8;
+    memcpy(id128, id.internal, 128);
+    return 0;
+}
+
+int omc_gpu_comm_init(omc_gpu_handle h, int rank, int world, const char *id128) {
+    if (!h || !id128) return 2;
+    if (world < 1 || rank < 0 || rank >= world) return fail(h, "omc_gpu_comm_init: rank / world out of range");
+    if (h->run_grid >= 0 || !h->done_q.empty()) return fail(h, "omc_gpu_comm_init: batches are in flight");
+    CK(cudaSetDevice(h->device));
+    if (h->comm) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
+    h->rank = rank; h->world = world;
+    if (world == 1) return 0;
+    NcclApi &N = nccl_api();
+    if (!N.ok) { h->err = N.err; return 8; }
+    nccl_uid id;
+    memcpy(id.internal, id128, 128);
+    const int e = N.CommInitRank(&h->comm, world, id, rank);
+    if (e) { h->comm = nullptr; h->world = 1; h->rank = 0; h->err = std::string("ncclCommInitRank: ") + N.GetErrorString(e); return 8; }
+    if (!h->side) {
+        CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
+        }
+    }
+    return 0;
+}
+
+int omc_gpu_comm_rank(omc_gpu_handle h) { return h ? h->rank : -1; }
+int omc_gpu_comm_size(omc_gpu_handle h) { return h ? h->world : -1; }
+
+int omc_gpu_comm_sum(omc_gpu_handle h, double *values, int n) {
+    if (!h || !values || n < 1) return 2;
+    if (!h->comm) return 0;
+    CK(cudaSetDevice(h->device));
+    double *d = nullptr;
+    CK(cudaMalloc((void **)&d, (size_t)n * sizeof(double)));
+    cudaError_t ce = cudaMemcpyAsync(d, values, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    int e = 0;
+    if (ce == cudaSuccess) e = nccl_api().AllReduce(d, d, (size_t)n, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
+    if (ce == cudaSuccess && !e) ce = cudaMemcpyAsync(values, d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (ce == cudaSuccess && !e) ce = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e) { h->err = std::string("ncclAllReduce: ") + nccl_api().GetErrorString(e); return 8; }
+    if (ce != cudaSuccess) { h->err = std::string("omc_gpu_comm_sum: ") + cudaGetErrorString(ce); return 1; }
     return 0;
 }
 
@@ -1232,8 +1383,6 @@ int omc_gpu_get_counters(omc_gpu_handle h, omc_gpu_counters *out) {
     static_assert(sizeof(Counters) == sizeof(omc_gpu_counters), "counter layouts must match");
     CK(cudaMemcpy(out, h->P.counters, sizeof(Counters), cudaMemcpyDeviceToHost));
     out->kernel_launches = h->launches;
-    out->reserved[4] = h->handovers;                            // straggler hand-overs (batch pipelining) ...
-    out->reserved[5] = h->handed_over;                          // ... and the particles they moved to the drain kernel
     return 0;
 }
 
@@ -1257,9 +1406,9 @@ int omc_gpu_test_geometry(omc_gpu_handle h, int n, const double *xyzuvw, const i
     CK(cudaMalloc((void **)&duo, (size_t)n * sizeof(double)));    CK(cudaMalloc((void **)&dtp, (size_t)n * sizeof(double)));
     CK(cudaMalloc((void **)&dir, (size_t)n * sizeof(int)));       CK(cudaMalloc((void **)&did, (size_t)n * sizeof(int)));
     CK(cudaMalloc((void **)&dirn, (size_t)n * sizeof(int)));
-    CK(cudaMemcpy(dq, xyzuvw, (size_t)6 * n * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dus, ustep_in, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dir, ir, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(dq, xyzuvw, (size_t)6 * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dus, ustep_in, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dir, ir, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     launch_test_geometry(h->P, n, dq, dir, dus, did, dirn, duo, dtp, h->stream);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
@@ -1286,7 +1435,7 @@ int omc_gpu_test_particles(omc_gpu_handle h, int n, const int *iq, const double 
     }
     Part *dev = nullptr;
     CK(cudaMalloc((void **)&dev, (size_t)n * sizeof(Part)));
-    CK(cudaMemcpy(dev, host.data(), (size_t)n * sizeof(Part), cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(dev, host.data(), (size_t)n * sizeof(Part), cudaMemcpyHostToDevice, h->stream));
     const int kernel = h->kernel, record = h->record;
     h->kernel = OMC_KERNEL_LOCKSTEP; h->record = 1; h->inject = dev;
     int rc = omc_gpu_run_histories(h, first_history, n, -1);
@@ -1298,7 +1447,7 @@ int omc_gpu_test_particles(omc_gpu_handle h, int n, const int *iq, const double 
 
 int omc_gpu_test_samplers(omc_gpu_handle h, int which, int n, const double *in, long long first_history, double *out) {
     if (!h || !in || !out || n <= 0) return 2;
-    if (which < 0 || which > OMC_SAMPLER_ESTEP) return fail(h, "unknown sampler");
+    if (which < 0 || (which & 0xff) > OMC_SAMPLER_ESTEP || (which >> 8) > 2) return fail(h, "unknown sampler");
     if (!h->have_media || !h->have_geom) return fail(h, "media and geometry must be set first");
     CK(cudaSetDevice(h->device));
     if (h->med_dirty) {
@@ -1312,12 +1461,14 @@ int omc_gpu_test_samplers(omc_gpu_handle h, int which, int n, const double *in, 
     double *din = nullptr, *dout = nullptr;
     CK(cudaMalloc((void **)&din, (size_t)8 * n * sizeof(double)));
     CK(cudaMalloc((void **)&dout, (size_t)8 * n * sizeof(double)));
-    CK(cudaMemcpy(din, in, (size_t)8 * n * sizeof(double), cudaMemcpyHostToDevice));
+    // (on the context's stream: a cudaMemcpy on the legacy stream may return while its DMA from the staging buffer is still
+    // running, and h->stream is a non-blocking stream that would not wait for it)
+    CK(cudaMemcpyAsync(din, in, (size_t)8 * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     launch_test_samplers(h->P, which, n, din, (unsigned long long)first_history, dout, h->stream);
     h->launches += 1;
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, (size_t)8 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    if (e == cudaSuccess) e = cudaMemcpy(out, dout, (size_t)8 * n * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(din); cudaFree(dout);
     if (e != cudaSuccess) { h->err = std::string("omc_gpu_test_samplers: ") + cudaGetErrorString(e); return 1; }
     return 0;
@@ -1342,7 +1493,7 @@ int omc_gpu_test_format(omc_gpu_handle h, int mode, long long n, const double *v
     if (format_setup(h)) return 1;
     double *d = nullptr;
     CK(cudaMalloc((void **)&d, (size_t)(n ? n : 1) * sizeof(double)));
-    CK(cudaMemcpy(d, values, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(d, values, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     FILE *fp = fopen(path, "w");
     if (!fp) { cudaFree(d); h->err = std::string("Unable to open file: ") + path; return 2; }
     int rc = format_block(h, fp, d, n, mode);

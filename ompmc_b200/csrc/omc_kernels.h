@@ -17,19 +17,23 @@ void launch_results(const DevProblem &P, const double *accum, const double *accu
 
 
 // ---- omc_wavefront.cu ---------------------------------------------------------------------------
-// One particle queue in HBM, structure-of-arrays with 16-byte lanes (one 128-bit access per warp and field pair):
-// {x,y} {z,u} {v,w} {e,wt}; irq = {ir, iq | tag << 16}; rng = {hist_lo, hist_hi, stream, draws consumed}.
+// One particle queue in HBM, structure-of-arrays with 16-byte lanes (one 128-bit access per warp and lane):
+//   xy = {x, y}   ze = {z, e}   (fp64: positions and energies)        dw = {u, v, w, wt} (fp32: direction cosines and weight)
+//   irq = {ir, iq | tag << 16}   rng = {hist_lo, hist_hi, stream, draws consumed}
+// 72 bytes per particle (the first layout kept direction and weight in fp64: 88).  Directions leave the samplers in fp32
+// precision anyway (omc_physics_f32.cuh) or are rounded once per interaction; weights are 1, 1/nsplit or nsplit/nsplit.
 // Photon queues only (aux != nullptr): aux = {mfp left (-1: not sampled yet; Woodcock flight: -1 / -2 = not yet / already
 // inside the phantom box), eta' of the running split copy}; for photons in flight tag = isplit | i_survive << 8.
 struct PartQueue {
-    double2 *xy, *zu, *vw, *ew;
+    double2 *xy, *ze;
+    float4 *dw;
     double2 *aux;
     int2 *rm;        // electron queues only (else nullptr): voxel record {float rhof, int med} of region ir, med = -2: not known
     int2 *irq;
     uint4 *rng;
     unsigned cap;
 };
-constexpr size_t PART_QUEUE_BYTES_PER_SLOT = 4 * sizeof(double2) + sizeof(int2) + sizeof(uint4);   // + 16 for photon queues
+constexpr size_t PART_QUEUE_BYTES_PER_SLOT = 2 * sizeof(double2) + sizeof(float4) + sizeof(int2) + sizeof(uint4);   // + 16 photons, + 8 electrons
 
 constexpr int WAVE_THREADS = 128;   // threads per block == particles per chunk
 
@@ -46,31 +50,35 @@ struct WaveCtl {
     PadU tk[5];                                  // chunk tickets per class (misc_kernel)
     PadU overflow, drain_ticket;
     PadU old_seen;                               // particles of the PREVIOUS batch met by the consumers of this wave
-    PadU n_side;                                 // fill count of the hand-over queue (handover_kernel)
     unsigned n_src;                              // histories injected by the current wave
     unsigned parity, target, live, waves;
     // batch pipelining: histories with id < hist_split belong to the previous batch, whose tail is still in flight
     // while this batch is injected; they score into dose grid (grid_new ^ 1), everything else into grid_new
     unsigned has_old, old_done, grid_new;
     unsigned old_last;                           // old_seen of the last completed wave (how many stragglers the old batch has left)
-    unsigned side_fail, zero_;                   // stragglers that did not fit into the hand-over queue (they stay in the waves); 0
     unsigned long long hist_split;
     unsigned long long hist_next, hist_end;
 };
 
-// electrons between "step size known" and "step taken", 144 bytes in nine 16-byte lanes:
-//   v[0..5] = {x,y} {z,u} {v,w} {e,total_tstep} {range,tustep} {tperp, (float wt, float elke)}
-//   f = {demfp, sig0, rhof, dedx} (fp32: these are fp32-born or only enter ratios)
-//   m = {float blccl, float ssmfp, ir, iq+1 | (imed+1) << 2 | lelke << 16};  rng as in PartQueue
+// electrons between "step size known" and "step taken", 120 bytes (seven 16-byte lanes + one 8-byte lane):
+//   v[0..2] = {x,y} {z,e} {tustep,range}                       fp64
+//   d = {u, v, w, wt}   f = {demfp, sig0, rhof, dedx}          fp32 (fp32-born, or only enter ratios)
+//   m = {float blccl, float ssmfp, ir, iq+1 | (imed+1) << 2 | flags << 6 | lelke << 16}
+//   t = {float tperp (rounded down), float elke}               rng as in PartQueue
+// flags replace the fp64 total_tstep of electron() :4787-4830, which the step only needs for its test "was this step the
+// whole distance to the next interaction" (:5290): bit 0 = yes if the step is taken in full, bit 1 = yes whatever the step.
+// (The first layouts: 21 doubles + 2 x 16 B = 200 B, then nine 16-byte lanes = 144 B.)
 // ONE set of arrays of 2*cap slots holds both step classes: condensed-history steps fill slots 0, 1, 2, ... and
 // boundary-crossing steps 2*cap-1, 2*cap-2, ..., so esize_kernel stores with a single converged code path.
 struct EStepQueue {
-    double2 *v[6];
-    float4 *f;
+    double2 *v[3];
+    float4 *d, *f;
     uint4 *m;
+    float2 *t;
     uint4 *rng;
     unsigned cap;                                // per class
 };
+constexpr size_t ESTEP_QUEUE_BYTES_PER_SLOT = 3 * sizeof(double2) + 2 * sizeof(float4) + 2 * sizeof(uint4) + sizeof(float2);
 
 struct WaveQueues {
     PartQueue p[2], e[2], ip[2], ie[2];
@@ -78,7 +86,7 @@ struct WaveQueues {
 };
 
 struct WaveLaunch {
-    int blocks[4], max_cross, electron_iters, ibeamlet, woodcock, max_virtual;
+    int blocks[4], max_cross, ibeamlet, woodcock, max_virtual;
     float *mb_grid;                 // multi-beamlet pass (see WaveArgs), nullptr: off
     unsigned long long mb_first;
     unsigned mb_per, mb_n;
@@ -105,9 +113,6 @@ void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const W
 // unit-test hook: one production sampler on explicit inputs (omc_gpu_test_samplers)
 void launch_test_samplers(const DevProblem &P, int which, int n, const double *in, unsigned long long first, double *out, cudaStream_t s);
 void launch_flush(float *g32, double *g64, long long n, cudaStream_t s);
-// Straggler hand-over (batch pipelining): move what is left of the PREVIOUS batch (history id < WaveCtl::hist_split) out of
-// the four current queues into `side` and mark the originals dead; omc_capi.cu then gives `side` to drain_kernel.
-void launch_handover(WaveCtl *ctl, const WaveQueues &Q, const PartQueue &side, int blocks, cudaStream_t s);
 // multi-beamlet pass: per-beamlet maximum (pass 0) / count above threshold (pass 1), then ordered compaction into CSC
 void launch_mb_scan(const float *grids, long long nreg, int nb, const DevProblem &P, const double *dens, int nhist, int nbatch, double rel,
                     double *dmax, unsigned long long *nnz, int pass, cudaStream_t s);

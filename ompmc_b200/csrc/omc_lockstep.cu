@@ -534,13 +534,13 @@ __global__ void __launch_bounds__(128) drain_kernel(const __grid_constant__ DevP
         const PartQueue &q = D.q[k];
         Part p, s2;
         {
-            const double2 xy = q.xy[j], zu = q.zu[j], vw = q.vw[j], ew = q.ew[j];
-            p.x = xy.x; p.y = xy.y; p.z = zu.x; p.u = zu.y; p.v = vw.x; p.w = vw.y; p.e = ew.x; p.wt = ew.y;
+            const double2 xy = q.xy[j], ze = q.ze[j];
+            const float4 dw = q.dw[j];
+            p.x = xy.x; p.y = xy.y; p.z = ze.x; p.e = ze.y; p.u = (double)dw.x; p.v = (double)dw.y; p.w = (double)dw.z; p.wt = (double)dw.w;
         }
         const int2 a = q.irq[j];
         p.ir = a.x; p.iq = (int)(short)(a.y & 0xffff);
         const int tag = a.y >> 16;
-        if (tag == 0x7fff) continue;                          // TAG_DEAD (omc_wavefront.cu): already handed over
         const uint4 r = q.rng[j];
         c.g.seed(P.seed0, P.seed1, ((unsigned long long)r.y << 32) | r.x, r.z, r.w);
         c.ndeposit = 0; c.flags = 0; c.edep_sum = 0.0;

@@ -1093,9 +1093,12 @@ OMC_FN double init_history_matrad(const DevProblem &P, Rng &g, Part &p, int ib) 
     if (p.z < zlo) p.z = ylo + tiny;                               // Q13
     if (p.z > zhi) p.z = zhi - tiny;
     int ix = 0, iy = 0, iz = 0;
-    while (__ldg(P.xb + ix + 1) < p.x) ix++;
-    while (__ldg(P.yb + iy + 1) < p.y) iy++;
-    while (__ldg(P.zb + iz + 1) < p.z) iz++;
+    // (omc_matrad.c:1233-1246 searches without an upper bound; with the Q13 clamp a z above zbounds[ksize] would walk past the
+    // array -- on the device that is an illegal address for the whole context -- so the searches stop at the last voxel;
+    // identical for every particle inside the grid)
+    while (ix < P.isize - 1 && __ldg(P.xb + ix + 1) < p.x) ix++;
+    while (iy < P.jsize - 1 && __ldg(P.yb + iy + 1) < p.y) iy++;
+    while (iz < P.ksize - 1 && __ldg(P.zb + iz + 1) < p.z) iz++;
     p.ir = 1 + ix + iy * P.isize + iz * P.ijmax;
     p.wt = 1.0;
     return ein;

@@ -21,6 +21,10 @@ constexpr float RMf = (float)OMC_RM;
 #ifndef OMC_AZIMUTH_SINCOS
 #define OMC_AZIMUTH_SINCOS 0
 #endif
+// 1: condensed-history step with the packed three-block draw plan, one trial loop for both polar angles and sincos azimuths
+#ifndef OMC_CH_PACKED
+#define OMC_CH_PACKED 0
+#endif
 
 __device__ __forceinline__ float nextf(Rng &g) {           // 24-bit lattice in [0,1), like RANMAR's
     if (g.pos >= 4u) g.refill();
@@ -464,6 +468,103 @@ __device__ __forceinline__ double msdist_b(const DevProblem &P, Rng &g, const Pa
     const MsEntryF *tab = P.ms_f + (mi * OMC_MS_NQ + mj) * OMC_MS_NU;
     const float *row = spin_row(P, imed, qel, elke, beta2, xi, u16lo(g1.y), u16hi(g1.y));
 
+#if OMC_CH_PACKED
+    // Packed draw plan (see the header comment of this section): G2 = {second (u, r) pair, azimuth 1, azimuth 2} is always drawn,
+    // so a step whose two polar angles are both accepted at their first trial -- the common case -- costs three blocks in all.
+    // The two polar angles are sampled by ONE loop over trials (trial t serves whichever pass the lane is at), not by one
+    // rejection loop per pass: a warp iterates max_lanes(trials_0 + trials_1) times instead of max(trials_0) + max(trials_1),
+    // and since every lane in the loop consumes exactly one pair per iteration, the lanes that need a fresh block need it in
+    // the same iteration.
+    const uint4 g2 = g.block();
+    float w1 = 1.0f, sint1 = 0.0f, w2 = 1.0f, sint2 = 0.0f;
+    int reg0 = 2, reg1 = 2;
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+        // regime of mscat(): 0 no scattering (or Q7), 1 single scattering, 2 table, 3 plural scattering (lambda <= 1)
+        const float sprob = u24(pass ? g0.y : g0.x);
+        int r = 2;
+        if (lambda <= 13.8f) {
+            if (sprob < explambda) r = 0;
+            else if (sprob < (1.0f + lambda) * explambda) r = 1;
+            else if (lambda <= 1.0f) r = 3;
+        } else if (!(lambda <= 1.0E5f)) {
+            r = 0;
+        }
+        if (pass == 0) reg0 = r; else reg1 = r;
+    }
+    if (reg0 == 3 || reg1 == 3) {                          // :3652-3682, rare in a condensed-history step: its own blocks
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+            if ((pass ? reg1 : reg0) != 3) continue;
+            const float sprob = u24(pass ? g0.y : g0.x);
+            float c = 1.0f, sv = 0.0f;
+            int icount = 0;
+            float wprob = explambda, wsum = explambda;
+            do {
+                icount += 1;
+                if (icount > 20) break;
+                wprob = wprob * lambda / (float)icount;
+                wsum = wsum + wprob;
+                float x;
+                uint4 bb;
+                for (;;) {
+                    bb = g.block();                            // {u, r, phi, -}
+                    const float u = u24(bb.x);
+                    x = fdiv(2.0f * chia2 * u, 1.0f - u + chia2);
+                    if (!(u24(bb.y) > spin_rej_row(row, x))) break;
+                }
+                const float cosz = 1.0f - x;
+                float sinz = x * (2.0f - x);
+                if (sinz > 1.0E-20f) {
+                    sinz = sqrtf(sinz);
+                    const float phi = u24(bb.z) * 6.2831853f;
+                    c = c * cosz - sv * sinz * __cosf(phi);
+                    sv = sqrtf(fmaxf(0.0f, (1.0f - c) * (1.0f + c)));
+                }
+            } while (wsum <= sprob);
+            if (pass == 0) { w1 = c; sint1 = sv; } else { w2 = c; sint2 = sv; }
+            if (pass == 0) reg0 = 0; else reg1 = 0;
+        }
+    }
+    {
+        int pass = (reg0 != 0) ? 0 : ((reg1 != 0) ? 1 : 2);
+        uint4 bx = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+        for (int t = 0; pass < 2; t++) {
+            uint32_t wu, wr;
+            if (t == 0) { wu = g1.z; wr = g1.w; }
+            else if (t == 1) { wu = g2.x; wr = g2.y; }
+            else {
+                if (!(t & 1)) bx = g.block();
+                wu = (t & 1) ? bx.z : bx.x; wr = (t & 1) ? bx.w : bx.y;
+            }
+            const float u = u24(wu);
+            float x;
+            if ((pass ? reg1 : reg0) == 1) {
+                x = fdiv(2.0f * chia2 * u, 1.0f - u + chia2);
+            } else {
+                float ak = u * 31.0f;
+                int k = (int)ak;
+                ak -= (float)k;
+                const float4 t0 = __ldg(reinterpret_cast<const float4 *>(tab + k));   // {ums, wms, ims, fms}
+                if (ak > t0.y) k = __float_as_int(t0.z);
+                const float um = __ldg(&tab[k].ums);
+                x = fdiv(omega2 * um, 1.0f + 0.5f * omega2 - um);
+                if (x > 1.99999f) x = 1.99999f;
+            }
+            if (!(u24(wr) > spin_rej_row(row, x))) {
+                const float c = 1.0f - x, sv = sqrtf(x * (2.0f - x));
+                if (pass == 0) { w1 = c; sint1 = sv; pass = (reg1 != 0) ? 1 : 2; }
+                else { w2 = c; sint2 = sv; pass = 2; }
+            }
+        }
+    }
+    // both azimuths: selectAzimuthalAngle() :101-122 draws a uniform azimuth by box rejection; (cos, sin)(2 pi u) is the same
+    // distribution without the loop
+    float cphi1, sphi1, cphi2, sphi2;
+    __sincosf(6.2831853f * u24(g2.z), &sphi1, &cphi1);
+    __sincosf(6.2831853f * u24(g2.w), &sphi2, &cphi2);
+#else
     PairSrc ps;
     ps.a0 = g1.z; ps.a1 = g1.w; ps.have = 1; ps.nb = 2;
     float w1 = 1.0f, sint1 = 0.0f, w2 = 1.0f, sint2 = 0.0f;
@@ -555,6 +656,7 @@ __device__ __forceinline__ double msdist_b(const DevProblem &P, Rng &g, const Pa
             }
         } while (!(ok1 && ok2));
     }
+#endif
 #endif
     const float u2 = sint2 * cphi2, v2 = sint2 * sphi2;
     float u2p = w1 * u2 + sint1 * w2;

@@ -4,15 +4,15 @@
 // event of its class, with one kernel per event class so that ALL warps on the machine run the same,
 // instruction-cache-sized code at the same time:
 //
-//   misc_kernel     persistent, typed 128-particle chunks pulled from tickets:
+//   misc_kernel       persistent; every WARP pulls typed 32-particle chunks from per-class tickets, classes in a fixed order:
 //        P   photon flight       P[cur]  -> P[next] (flight unfinished) | IP[next] (at an interaction site)
 //        IP  photon interaction  IP[cur] -> P[next], E[next]            Compton / pair / photo / Rayleigh
 //        IE  e+- interaction     IE[cur] -> E[next], P[next]            brems / Moller / Bhabha / annihilation
 //        S   source              initHistory() for new history ids -> P[next] or E[next]
-//   esize_kernel    E[cur] -> CH | BCA      cut-off test, distance to the next interaction, step-size limits
-//   ech_kernel      CH  -> E[next] | IE[next]   condensed-history step (PRESTA-II msdist)
-//   ebca_kernel     BCA -> E[next] | IE[next]   boundary-crossing / single-scattering step
-//   advance_kernel  swaps cur/next, sizes the next injection so that `pool_size` particles stay in flight
+//   esize_kernel      E[cur] -> step queue, class CH | BCA   cut-off test, distance to the next interaction, step-size limits
+//   edo_kernel<CH>    CH  -> E[next] | IE[next]   condensed-history step (PRESTA-II msdist)
+//   edo_kernel<BCA>   BCA -> E[next] | IE[next]   boundary-crossing / single-scattering step
+//   advance_kernel    swaps cur/next, sizes the next injection so that `pool_size` particles stay in flight
 //
 // (interaction queues are consumed one wave after they were filled).  Sorting electrons into the CH and
 // BCA queues after the step size is known matters because those two long paths otherwise split every warp.
@@ -67,9 +67,10 @@ constexpr int NT = WAVE_THREADS;   // threads per block == particles per chunk
 // ---- queues ----------------------------------------------------------------------------------
 __device__ __forceinline__ void q_load_part(const PartQueue &q, unsigned i, Part &p, int &tag) {
     const int2 a = q.irq[i];                                   // first: a voxel-record load usually depends on it
-    const double2 xy = q.xy[i], zu = q.zu[i], vw = q.vw[i], ew = q.ew[i];
+    const double2 xy = q.xy[i], ze = q.ze[i];
+    const float4 dw = q.dw[i];
     p.ir = a.x; p.iq = (int)(short)(a.y & 0xffff); tag = a.y >> 16;
-    p.x = xy.x; p.y = xy.y; p.z = zu.x; p.u = zu.y; p.v = vw.x; p.w = vw.y; p.e = ew.x; p.wt = ew.y;
+    p.x = xy.x; p.y = xy.y; p.z = ze.x; p.e = ze.y; p.u = (double)dw.x; p.v = (double)dw.y; p.w = (double)dw.z; p.wt = (double)dw.w;
 }
 
 __device__ __forceinline__ void q_load(const PartQueue &q, unsigned i, Part &p, Rng &g, const DevProblem &P, double &aux, int &tag) {
@@ -81,8 +82,8 @@ __device__ __forceinline__ void q_load(const PartQueue &q, unsigned i, Part &p, 
 
 __device__ __forceinline__ void q_store(const PartQueue &q, unsigned i, const Part &p, const Rng &g, double aux, int tag,
                                         double aux2 = 0.0) {
-    q.xy[i] = make_double2(p.x, p.y); q.zu[i] = make_double2(p.z, p.u); q.vw[i] = make_double2(p.v, p.w);
-    q.ew[i] = make_double2(p.e, p.wt);
+    q.xy[i] = make_double2(p.x, p.y); q.ze[i] = make_double2(p.z, p.e);
+    q.dw[i] = make_float4((float)p.u, (float)p.v, (float)p.w, (float)p.wt);
     if (q.aux) q.aux[i] = make_double2(aux, aux2);             // photon queues only
     q.irq[i] = make_int2(p.ir, (p.iq & 0xffff) | (tag << 16));
     q.rng[i] = make_uint4(g.h0, g.h1, g.stream, g.ndraws());
@@ -95,13 +96,13 @@ __device__ __forceinline__ void prefetch_l1(const void *p) {
 }
 // the record of slot i of a particle queue / of the step queue (what the next grid-stride iteration will load)
 __device__ __forceinline__ void q_prefetch_e(const PartQueue &q, unsigned i) {
-    prefetch_l1(q.irq + i); prefetch_l1(q.rm + i); prefetch_l1(q.xy + i); prefetch_l1(q.zu + i); prefetch_l1(q.vw + i);
-    prefetch_l1(q.ew + i); prefetch_l1(q.rng + i);
+    prefetch_l1(q.irq + i); prefetch_l1(q.rm + i); prefetch_l1(q.xy + i); prefetch_l1(q.ze + i); prefetch_l1(q.dw + i);
+    prefetch_l1(q.rng + i);
 }
 __device__ __forceinline__ void es_prefetch(const EStepQueue &S, unsigned s) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) prefetch_l1(S.v[k] + s);
-    prefetch_l1(S.f + s); prefetch_l1(S.m + s); prefetch_l1(S.rng + s);
+    for (int k = 0; k < 3; k++) prefetch_l1(S.v[k] + s);
+    prefetch_l1(S.d + s); prefetch_l1(S.f + s); prefetch_l1(S.m + s); prefetch_l1(S.t + s); prefetch_l1(S.rng + s);
 }
 
 // warp-aggregated slot reservation: one atomic per (warp, queue) instead of one per lane
@@ -148,7 +149,7 @@ struct Tally {
 struct WaveArgs {
     WaveCtl *ctl;
     WaveQueues Q;
-    int max_cross, electron_iters, ibeamlet, woodcock, max_virtual;
+    int max_cross, ibeamlet, woodcock, max_virtual;
     // multi-beamlet pass (omc_gpu_run_beamlets): history id -> beamlet -> its own fp32 dose grid
     float *mb_grid;                 // [mb_n][nreg], nullptr: off
     unsigned long long mb_first;    // beamlet (mb_ib0 + k) owns history ids [mb_first + k * mb_per, + mb_per)
@@ -218,8 +219,7 @@ __device__ __forceinline__ void deposit32(float *grid32, Tally &t, int ir, doubl
 }
 
 enum { TAG_NONE = 0, TAG_COMPTON = 1, TAG_PAIR = 2, TAG_PHOTO = 3, TAG_RAYLEIGH = 4, TAG_BREMS = 5, TAG_MOLLER = 6, TAG_BHABHA = 7,
-       TAG_ANNIH = 8, TAG_RANNIH = 9,
-       TAG_DEAD = 0x7fff };   // record handed over to the drain kernel (handover_kernel): consumers skip it
+       TAG_ANNIH = 8, TAG_RANNIH = 9 };
 
 
 // ---------------------------------------------------------------------------------------------
@@ -230,7 +230,6 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, const Batch
     WaveCtl *ctl = A.ctl;
     Part p; Rng g; double dpmfp; int tag;
     q_load(A.Q.p[par], i, p, g, P, dpmfp, tag);
-    if (tag == TAG_DEAD) return;
     const bool old = BS.is_old(g.h0, g.h1);
     BS.count(ctl, __activemask(), old);
     float *dg = BS.grid(old, g.h0, g.h1);
@@ -382,8 +381,7 @@ __device__ void photon_chunk_wc(const DevProblem &P, const WaveArgs &A, const Ba
     {
         int tag;
         q_load_part(q, i, p, tag);
-        if (tag == TAG_DEAD) return;
-        entered = q.aux[i].x <= -2.0;
+            entered = q.aux[i].x <= -2.0;
         const uint4 r = q.rng[i];
         g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
     }
@@ -410,7 +408,6 @@ __device__ void p_interact_chunk(const DevProblem &P, const WaveArgs &A, const B
     const PartQueue &pn = A.Q.p[par ^ 1], &en = A.Q.e[par ^ 1];
     Part p, q; Rng g, gq; int tag;
     q_load_part(A.Q.ip[par], i, p, tag);
-    if (tag == TAG_DEAD) return;
     {
         const uint4 r = A.Q.ip[par].rng[i];
         g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
@@ -463,7 +460,6 @@ __device__ void e_interact_chunk(const DevProblem &P, const WaveArgs &A, const B
     const PartQueue &pn = A.Q.p[par ^ 1], &en = A.Q.e[par ^ 1];
     Part p, q; Rng g, gq; int tag;
     q_load_part(A.Q.ie[par], i, p, tag);
-    if (tag == TAG_DEAD) return;
     {
         const uint4 r = A.Q.ie[par].rng[i];
         g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
@@ -533,26 +529,33 @@ __device__ __forceinline__ double region_ecut(const DevProblem &P, int ir, int i
     return load_region(P, ir).ecut;
 }
 __device__ __forceinline__ void es_put(const EStepQueue &S, unsigned s, const Part &p, const Rng &g, const EStep &e) {
-    S.v[0][s] = make_double2(p.x, p.y); S.v[1][s] = make_double2(p.z, p.u); S.v[2][s] = make_double2(p.v, p.w);
-    S.v[3][s] = make_double2(p.e, e.total_tstep); S.v[4][s] = make_double2(e.range, e.tustep);
-    S.v[5][s] = make_double2(e.tperp, __hiloint2double(__float_as_int((float)e.elke), __float_as_int((float)p.wt)));
+    // "the step reaches the interaction point", electron() :5290 (total_tstep - tvstep * rhof < 1e-9), decided here where
+    // total_tstep lives: for the full step tustep, and for any step at all (total_tstep itself below the tolerance)
+    const unsigned flags = ((e.total_tstep - e.tustep * e.rhof < 1.0E-9) ? 1u : 0u) | ((e.total_tstep < 1.0E-9) ? 2u : 0u);
+    S.v[0][s] = make_double2(p.x, p.y); S.v[1][s] = make_double2(p.z, p.e); S.v[2][s] = make_double2(e.tustep, e.range);
+    S.d[s] = make_float4((float)p.u, (float)p.v, (float)p.w, (float)p.wt);
     S.f[s] = make_float4((float)e.demfp, (float)e.sig0, (float)e.rhof, (float)e.dedx);
     S.m[s] = make_uint4((unsigned)__float_as_int((float)e.blccl), (unsigned)__float_as_int((float)e.ssmfp), (unsigned)p.ir,
-                        (unsigned)(p.iq + 1) | ((unsigned)(e.imed + 1) << 2) | ((unsigned)e.lelke << 16));
+                        (unsigned)(p.iq + 1) | ((unsigned)(e.imed + 1) << 2) | (flags << 6) | ((unsigned)e.lelke << 16));
+    S.t[s] = make_float2(__double2float_rd(e.tperp), (float)e.elke);
     S.rng[s] = make_uint4(g.h0, g.h1, g.stream, g.ndraws());
 }
 template <bool BLOCKS>
 __device__ __forceinline__ void es_get(const EStepQueue &S, unsigned s, Part &p, Rng &g, EStep &e, const DevProblem &P) {
     const uint4 m = S.m[s];
-    const double2 v0 = S.v[0][s], v1 = S.v[1][s], v2 = S.v[2][s], v3 = S.v[3][s], v4 = S.v[4][s], v5 = S.v[5][s];
-    const float4 f = S.f[s];
+    const double2 v0 = S.v[0][s], v1 = S.v[1][s], v2 = S.v[2][s];
+    const float4 d = S.d[s], f = S.f[s];
+    const float2 t = S.t[s];
     const uint4 r = S.rng[s];
     p.ir = (int)m.z; p.iq = (int)(m.w & 3u) - 1; e.imed = (int)((m.w >> 2) & 15u) - 1; e.lelke = (int)m.w >> 16;
-    p.x = v0.x; p.y = v0.y; p.z = v1.x; p.u = v1.y; p.v = v2.x; p.w = v2.y; p.e = v3.x;
-    e.total_tstep = v3.y; e.range = v4.x; e.tustep = v4.y; e.tperp = v5.x;
-    p.wt = (double)__int_as_float(__double2loint(v5.y)); e.elke = (double)__int_as_float(__double2hiint(v5.y));
+    p.x = v0.x; p.y = v0.y; p.z = v1.x; p.e = v1.y; e.tustep = v2.x; e.range = v2.y;
+    p.u = (double)d.x; p.v = (double)d.y; p.w = (double)d.z; p.wt = (double)d.w;
+    e.tperp = (double)t.x; e.elke = (double)t.y;
     e.demfp = (double)f.x; e.sig0 = (double)f.y; e.rhof = (double)f.z; e.dedx = (double)f.w;
     e.blccl = (double)__int_as_float((int)m.x); e.ssmfp = (double)__int_as_float((int)m.y);
+    // a stand-in that makes the :5290 test of estep_do() come out as the flags say (see es_put)
+    const unsigned flags = (m.w >> 6) & 3u;
+    e.total_tstep = (flags & 2u) ? 0.0 : ((flags & 1u) ? e.tustep * e.rhof : 1.0E30);
     e.eke = p.e - RM;
     e.ecut = region_ecut(P, p.ir, e.imed);
     if (BLOCKS) g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
@@ -925,7 +928,7 @@ __global__ void __launch_bounds__(NT, OMC_MB_ESIZE) esize_kernel(const __grid_co
             int tag;
             q_load_part(q, i, p, tag);
             if (i + stride < n) q_prefetch_e(q, i + stride);
-            if (tag != TAG_DEAD) {
+            {
                 const int2 rm = q.rm[i];
                 const uint4 r = q.rng[i];
                 g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
@@ -1081,7 +1084,7 @@ void wave_blocks_per_sm(int out[4]) {
 // kernels after esize_kernel (forked and joined with events; under stream capture this becomes a fork/join graph).
 void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const WaveLaunch &L, const WaveStreams &W) {
     WaveArgs A;
-    A.ctl = ctl; A.Q = Q; A.max_cross = L.max_cross; A.electron_iters = L.electron_iters; A.ibeamlet = L.ibeamlet;
+    A.ctl = ctl; A.Q = Q; A.max_cross = L.max_cross; A.ibeamlet = L.ibeamlet;
     A.woodcock = L.woodcock; A.max_virtual = L.max_virtual;
     A.mb_grid = L.mb_grid; A.mb_first = L.mb_first; A.mb_per = L.mb_per; A.mb_n = L.mb_n; A.mb_ib0 = L.mb_ib0;
     const bool par = (W.s2 != nullptr);
@@ -1113,45 +1116,6 @@ __global__ void rearm_kernel(WaveCtl *c, unsigned long long first, unsigned long
 }
 void launch_rearm(WaveCtl *ctl, unsigned long long first, unsigned long long nhist, unsigned nsplit, cudaStream_t s) {
     rearm_kernel<<<1, 32, 0, s>>>(ctl, first, nhist, nsplit);
-}
-
-// Straggler hand-over.  Once every history of the new batch has been started, the pipeline would have to idle through the
-// last (up to ~2000) near-empty waves of the PREVIOUS batch before a third batch may be injected: only two batches can be
-// alive in the queues.  Instead the few stragglers of the previous batch are taken out of the queues here -- copied into the
-// side queue, their records marked TAG_DEAD so that the next wave's consumers skip them -- and followed to the end by
-// drain_kernel (one thread per particle, omc_lockstep.cu), which scores into the fp64 grid of that batch.  Runs between two
-// waves (the step queue is empty then), nsplit == 1 only (a split photon in flight is a ray of copies, not a particle).
-__global__ void handover_kernel(WaveCtl *c, const __grid_constant__ WaveQueues Q, const __grid_constant__ PartQueue side) {
-    const int par = (int)c->parity;
-    const unsigned long long split = c->hist_split;
-    const unsigned stride = gridDim.x * blockDim.x;
-#pragma unroll 1
-    for (int k = 0; k < 4; k++) {
-        const PartQueue &q = (k == 0) ? Q.p[par] : (k == 1) ? Q.e[par] : (k == 2) ? Q.ip[par] : Q.ie[par];
-        const unsigned cnt = (k == 0) ? c->n_p[par].v : (k == 1) ? c->n_e[par].v : (k == 2) ? c->n_ip[par].v : c->n_ie[par].v;
-        const unsigned n = min(cnt, q.cap);
-        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-            const uint4 r = q.rng[i];
-            if (((((unsigned long long)r.y) << 32) | r.x) >= split) continue;
-            const int2 a = q.irq[i];
-            if ((a.y >> 16) == TAG_DEAD) continue;
-            const unsigned s = atomicAdd(&c->n_side.v, 1u);
-            if (s >= side.cap) { atomicAdd(&c->side_fail, 1u); continue; }     // stays in the waves (drain_kernel clamps n_side)
-            side.xy[s] = q.xy[i]; side.zu[s] = q.zu[i]; side.vw[s] = q.vw[i]; side.ew[s] = q.ew[i];
-            side.irq[s] = a; side.rng[s] = r;
-            q.irq[i] = make_int2(0, (int)TAG_DEAD << 16);
-        }
-    }
-}
-// all stragglers went over: nothing of the previous batch is left in the queues
-__global__ void handover_done_kernel(WaveCtl *c) {
-    if (blockIdx.x || threadIdx.x) return;
-    if (c->has_old && c->side_fail == 0) { c->has_old = 0; c->old_done = 1; c->old_last = 0; }
-    c->old_seen.v = 0;
-}
-void launch_handover(WaveCtl *ctl, const WaveQueues &Q, const PartQueue &side, int blocks, cudaStream_t s) {
-    handover_kernel<<<blocks, 256, 0, s>>>(ctl, Q, side);
-    handover_done_kernel<<<1, 32, 0, s>>>(ctl);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1258,10 +1222,14 @@ __device__ __forceinline__ double test_range(const DevProblem &P, const ElecBin 
     return (drange_m(B, eke, re.y, elke, elkei) + re.x) * rinv;
 }
 
-__global__ void test_sampler_kernel(const __grid_constant__ DevProblem P, int which, int n, const double *__restrict__ in,
+__global__ void test_sampler_kernel(const __grid_constant__ DevProblem P, int which_v, int n, const double *__restrict__ in,
                                     unsigned long long first, double *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    // bits 8.. of the sampler id select a variant of the condensed-history step: 0 = the production one (msdist_b, block draws),
+    // 1 = msdist_f (fp32, word-by-word draws), 2 = the fp64 msdist of the lock-step kernel -- to tell precision effects from
+    // restructuring effects when a distribution test fails
+    const int which = which_v & 0xff, variant = which_v >> 8;
     const double *a = in + 8 * (size_t)i;
     double *o = out + 8 * (size_t)i;
     for (int k = 0; k < 8; k++) o[k] = 0.0;
@@ -1288,7 +1256,14 @@ __global__ void test_sampler_kernel(const __grid_constant__ DevProblem P, int wh
         p.x = p.y = p.z = 0.0; p.u = a[5]; p.v = a[6]; p.w = a[7]; p.e = eke + RM; p.wt = 1.0; p.ir = 1; p.iq = iq;
         double xf, yf, zf, uf, vf, wf;
         uint32_t w_rfict;
-        o[0] = msdist_b(P, g, p, imed, qel, rhof, de, tustep, eke, xf, yf, zf, uf, vf, wf, w_rfict);
+        if (variant == 0) {
+            o[0] = msdist_b(P, g, p, imed, qel, rhof, de, tustep, eke, xf, yf, zf, uf, vf, wf, w_rfict);
+        } else {
+            Rng g2;
+            g2.seed(P.seed0, P.seed1, hist, 0u);
+            o[0] = (variant == 1) ? msdist_f(P, g2, p, imed, qel, rhof, de, tustep, eke, xf, yf, zf, uf, vf, wf)
+                                  : msdist<true>(P, g2, p, imed, qel, rhof, de, tustep, eke, xf, yf, zf, uf, vf, wf);
+        }
         o[1] = xf; o[2] = yf; o[3] = zf; o[4] = uf; o[5] = vf; o[6] = wf; o[7] = de;
     } else if (which == OMC_SAMPLER_SSCAT) {
         const uint4 g0 = g.block();

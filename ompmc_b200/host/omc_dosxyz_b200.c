@@ -11,7 +11,7 @@
  * is read from a problem blob (format: "OMCBLOB1", see ompmc_b200/problem.py save_blob/load_blob).  A maintainer
  * who links the reference's own init code instead follows INTEGRATION.md; the calls below are the same.
  *
- * usage: omc_dosxyz_b200 -p problem.blob -n ncase -b nbatch -o out_stem [-k 0|1] [-d device] [-s "ixx jxx"]
+ * usage: omc_dosxyz_b200 -p problem.blob -n ncase -b nbatch -o out_stem [-k 0|1] [-d device | -g ngpu] [-s "ixx jxx"]
  * There is no CPU transport here: without a CUDA device the program exits with the library's error.
  */
 #include <math.h>
@@ -89,15 +89,15 @@ static double now_s(void) {
     return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
 }
 
-static omc_gpu_handle gpu;
+static omc_gpu_multi gpu;       /* one handle over -g N devices (default 1) */
 static void die(const char *what) {
-    printf("%s: %s\n", what, omc_gpu_last_error(gpu));
+    printf("%s: %s\n", what, omc_gpu_multi_last_error(gpu));
     exit(EXIT_FAILURE);
 }
 
 int main(int argc, char **argv) {
-    const char *pfile = NULL, *ifile = NULL, *ncase = NULL, *nbatch_s = NULL, *stem = "omc_b200", *seeds = NULL;
-    int kernel = -1, device = 0, dump_only = 0;
+    const char *pfile = NULL, *ifile = NULL, *ncase = NULL, *nbatch_s = NULL, *stem = "omc_b200", *seeds = NULL, *voxel = NULL;
+    int kernel = -1, device = 0, dump_only = 0, ngpu = getenv("OMC_GPUS") ? atoi(getenv("OMC_GPUS")) : 1;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "-p") && i + 1 < argc) pfile = argv[++i];
         else if (!strcmp(argv[i], "-i") && i + 1 < argc) ifile = argv[++i];
@@ -106,12 +106,16 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[i], "-o") && i + 1 < argc) stem = argv[++i];
         else if (!strcmp(argv[i], "-k") && i + 1 < argc) kernel = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-d") && i + 1 < argc) device = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-g") && i + 1 < argc) ngpu = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-s") && i + 1 < argc) seeds = argv[++i];
+        else if (!strcmp(argv[i], "-v") && i + 1 < argc) voxel = argv[++i];
         else if (!strcmp(argv[i], "--dump-problem")) dump_only = 1;
         else {
-            printf("usage: %s (-i input_stem | -p problem.blob) [-n ncase] [-b nbatch] -o out_stem [-k 0|1] [-d device] [-s \"ixx jxx\"]\n"
+            printf("usage: %s (-i input_stem | -p problem.blob) [-n ncase] [-b nbatch] -o out_stem [-k 0|1] [-d device | -g ngpu] [-s \"ixx jxx\"]\n"
+                   "  -g ngpu         GPUs of this node to spread every batch over (default 1, or OMC_GPUS); -d picks the device when ngpu = 1\n"
                    "  -i input_stem   the reference's own input file <input_stem>.inp (phantom, PEGS4, XCOM, spectrum ... read and\n"
                    "                  initialised here, no reference code involved), exactly like `omc_dosxyz -i input_stem -o out_stem`\n"
+                   "  -v \"dx dy dz\"   with -i: resample the phantom to voxels of about this size in cm (any ratio; mass-conserving), BASELINE config 5\n"
                    "  -p problem.blob tables + phantom + source dumped from an initialised user code\n"
                    "  --dump-problem  with -i: write <out_stem>.problem (every array handed to the GPU library) and exit, no GPU needed\n",
                    argv[0]);
@@ -136,6 +140,13 @@ int main(int argc, char **argv) {
         if (inp_parse(&inp, ifile)) return EXIT_FAILURE;
         if (!inp_path(&inp, "phantom file", path) || phantom_read(&ph, path)) return EXIT_FAILURE;
         printf("Path to phantom file : %s\n", path);
+        if (voxel) {                                             /* config 5: the same phantom on a finer (or coarser) grid */
+            double vx = 0, vy = 0, vz = 0;
+            static host_phantom fine;
+            if (sscanf(voxel, "%lf %lf %lf", &vx, &vy, &vz) != 3 || phantom_resample(&ph, vx, vy, vz, &fine)) { printf("Bad -v voxel sizes.\n"); return EXIT_FAILURE; }
+            printf("Phantom resampled from (%d, %d, %d) to (%d, %d, %d) voxels\n", ph.isize, ph.jsize, ph.ksize, fine.isize, fine.jsize, fine.ksize);
+            ph = fine;
+        }
         if (!inp_path(&inp, "pegs file", pegs) || !inp_path(&inp, "data folder", folder) || !inp_path(&inp, "pgs4form file", ffile)) return EXIT_FAILURE;
         const char *names[OMC_MXMED];
         for (int i = 0; i < ph.nmed; i++) names[i] = ph.names[i];
@@ -183,16 +194,20 @@ int main(int argc, char **argv) {
 
     printf("Number of media in phantom : %d\n", t.nmed);
     printf("Number of voxels on each direction (X,Y,Z) : (%d, %d, %d)\n", g.isize, g.jsize, g.ksize);
-    if (omc_gpu_create(&gpu, device)) { printf("No CUDA device: this program has no CPU transport path.\n"); return EXIT_FAILURE; }
-    if (omc_gpu_set_media(gpu, &t)) die("omc_gpu_set_media");
-    if (omc_gpu_set_geometry(gpu, &g)) die("omc_gpu_set_geometry");
-    if (omc_gpu_set_source_dosxyz(gpu, &s)) die("omc_gpu_set_source_dosxyz");
-    if (omc_gpu_set_vrt(gpu, nsplit)) die("omc_gpu_set_vrt");
+    if (omc_gpu_multi_create(&gpu, ngpu > 1 ? ngpu : 1, ngpu > 1 ? NULL : &device)) {
+        printf("No CUDA device (or no NCCL for %d of them): this program has no CPU transport path.\n", ngpu);
+        return EXIT_FAILURE;
+    }
+    printf("GPUs: %d\n", omc_gpu_multi_size(gpu));
+    if (omc_gpu_multi_set_media(gpu, &t)) die("omc_gpu_multi_set_media");
+    if (omc_gpu_multi_set_geometry(gpu, &g)) die("omc_gpu_multi_set_geometry");
+    if (omc_gpu_multi_set_source_dosxyz(gpu, &s)) die("omc_gpu_multi_set_source_dosxyz");
+    if (omc_gpu_multi_set_vrt(gpu, nsplit)) die("omc_gpu_multi_set_vrt");
     int ixx = 97, jxx = 33;
     sscanf(seeds, "%d %d", &ixx, &jxx);
-    omc_gpu_set_seed(gpu, ixx, jxx);
+    omc_gpu_multi_set_seed(gpu, ixx, jxx);
     if (kernel < 0) kernel = nsplit > 255 ? OMC_KERNEL_LOCKSTEP : OMC_KERNEL_WAVEFRONT;
-    if (omc_gpu_set_option(gpu, "kernel", kernel)) die("omc_gpu_set_option");
+    if (omc_gpu_multi_set_option(gpu, "kernel", kernel)) die("omc_gpu_multi_set_option");
 
     /* batch bookkeeping exactly as omc_dosxyz.c:1207-1225 */
     int nhist = atoi(ncase), nbatch = atoi(nbatch_s);
@@ -209,10 +224,10 @@ int main(int argc, char **argv) {
     for (int ibatch = 0; ibatch < nbatch; ibatch++) {
         if (ibatch == 0) printf("%-10s\t%-15s\n", "Batch #", "Elapsed time");
         printf("%-10d\t%-15.2f\n", ibatch, now_s() - tbegin);
-        if (omc_gpu_run_batch(gpu, (long long)ibatch * nperbatch, nperbatch, -1)) die("omc_gpu_run_batch");
+        if (omc_gpu_multi_run_batch(gpu, (long long)ibatch * nperbatch, nperbatch, -1)) die("omc_gpu_multi_run_batch");
     }
     double *accum = malloc(((size_t)gridsize + 1) * sizeof(double)), *accum2 = malloc(((size_t)gridsize + 1) * sizeof(double)), ensrc = 0.0;
-    if (omc_gpu_get_tallies(gpu, accum, accum2, &ensrc)) die("omc_gpu_get_tallies");
+    if (omc_gpu_multi_get_tallies(gpu, accum, accum2, &ensrc)) die("omc_gpu_multi_get_tallies");
     const double t1 = now_s();
     printf("Simulation finished\n");
     printf("Execution time up to this point : %8.2f seconds\n", t1 - tbegin);
@@ -228,16 +243,16 @@ int main(int argc, char **argv) {
         accumulate_results(&g, dens, accum, accum2, 1, nperbatch, nbatch);
         if (write_3ddose(stem, &g, accum, accum2)) return EXIT_FAILURE;
     } else if (host_results == 2) {         /* statistics on the device, the reference's fprintf loop on the host */
-        if (omc_gpu_accumulate_results(gpu, 1, nperbatch, nbatch, dens, accum, accum2)) die("omc_gpu_accumulate_results");
+        if (omc_gpu_multi_accumulate_results(gpu, 1, nperbatch, nbatch, dens, accum, accum2)) die("omc_gpu_multi_accumulate_results");
         if (write_3ddose(stem, &g, accum, accum2)) return EXIT_FAILURE;
     } else if (host_results == 3) {         /* probe: both writers on the SAME tallies -> <stem>.3ddose (device) and <stem>_host.3ddose */
         char *fn = malloc(strlen(stem) + 32);
         sprintf(fn, "%s.3ddose", stem);
         double ta = now_s();
-        if (omc_gpu_write_3ddose(gpu, fn, 1, nperbatch, nbatch, dens)) die("omc_gpu_write_3ddose");
+        if (omc_gpu_multi_write_3ddose(gpu, fn, 1, nperbatch, nbatch, dens)) die("omc_gpu_multi_write_3ddose");
         printf("Device writer: %8.3f seconds\n", now_s() - ta);
         ta = now_s();
-        if (omc_gpu_accumulate_results(gpu, 1, nperbatch, nbatch, dens, accum, accum2)) die("omc_gpu_accumulate_results");
+        if (omc_gpu_multi_accumulate_results(gpu, 1, nperbatch, nbatch, dens, accum, accum2)) die("omc_gpu_multi_accumulate_results");
         sprintf(fn, "%s_host", stem);
         if (write_3ddose(fn, &g, accum, accum2)) return EXIT_FAILURE;
         printf("Host writer: %8.3f seconds\n", now_s() - ta);
@@ -245,11 +260,11 @@ int main(int argc, char **argv) {
     } else {                                /* default: statistics AND the text of the file on the device */
         char *fn = malloc(strlen(stem) + 16);
         sprintf(fn, "%s.3ddose", stem);
-        if (omc_gpu_write_3ddose(gpu, fn, 1, nperbatch, nbatch, dens)) die("omc_gpu_write_3ddose");
+        if (omc_gpu_multi_write_3ddose(gpu, fn, 1, nperbatch, nbatch, dens)) die("omc_gpu_multi_write_3ddose");
         free(fn);
     }
     printf("Output written in %8.3f seconds\n", now_s() - t2);
-    omc_gpu_destroy(gpu);
+    omc_gpu_multi_destroy(gpu);
     printf("Total execution time : %8.5f seconds\n", now_s() - tbegin);
     return EXIT_SUCCESS;
 }

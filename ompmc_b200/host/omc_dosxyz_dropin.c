@@ -10,12 +10,12 @@
  * is what SURVEY.md 8b names as the boundary:
  *
  *     omc_dosxyz.c:1252-1262   #pragma omp parallel for ... { initHistory(); shower(); }  accumEndep();
- *  -> omc_gpu_run_batch(gpu, first_history, nperbatch, -1)
+ *  -> omc_gpu_multi_run_batch(gpu, first_history, nperbatch, -1)
  *
  * The main() below restates the control flow of omc_dosxyz.c:1072-1307 (options -i/-o, init order, batch plan by atoi,
  * printed lines) around that call.  There is no CPU fallback: without a CUDA device the program stops with the library's
  * message and EXIT_FAILURE, the reference's error behaviour.  Extra option (not in the reference): -k 0|1 selects the
- * lock-step parity kernel or the wavefront kernels (default: wavefront, lock-step when nsplit > 255).
+ * lock-step parity kernel or the wavefront kernels (default: wavefront, lock-step when nsplit > 255); -g N (or OMC_GPUS=N) the number of GPUs.
  */
 #define main omc_dosxyz_reference_main
 #include OMC_REF_DOSXYZ_C
@@ -23,16 +23,16 @@
 
 #include "ompmc_b200.h"
 
-static omc_gpu_handle gpu;
+static omc_gpu_multi gpu;                     /* one handle over `ngpu` devices (-g N / OMC_GPUS; default 1) */
 
 static void die(const char *what) {           /* the reference's error behaviour: printf + exit */
-    printf("%s: %s\n", what, gpu ? omc_gpu_last_error(gpu) : "no CUDA device / library not usable");
+    printf("%s: %s\n", what, gpu ? omc_gpu_multi_last_error(gpu) : "no CUDA device / library not usable");
     exit(EXIT_FAILURE);
 }
 
 /* hand the reference's initialised globals (borrowed pointers) to the device; INTEGRATION.md, gpu_upload() */
-static void gpu_upload(int kernel) {
-    if (omc_gpu_create(&gpu, 0)) { gpu = NULL; die("omc_gpu_create"); }
+static void gpu_upload(int kernel, int ngpu) {
+    if (omc_gpu_multi_create(&gpu, ngpu, NULL)) { gpu = NULL; die("omc_gpu_multi_create"); }
 
     omc_media_tables t;
     memset(&t, 0, sizeof t);
@@ -62,39 +62,40 @@ static void gpu_upload(int kernel) {
     t.ims = mscat_data.ims_array; t.dllambi = mscat_data.dllambi; t.dqmsi = mscat_data.dqmsi;
     t.pegs_ap = pegs_data.ap; t.pegs_ae = pegs_data.ae; t.pegs_te = pegs_data.te;
     t.pegs_thmoll = pegs_data.thmoll; t.pegs_rho = pegs_data.rho; t.pegs_meke = pegs_data.meke;
-    if (omc_gpu_set_media(gpu, &t)) die("omc_gpu_set_media");
+    if (omc_gpu_multi_set_media(gpu, &t)) die("omc_gpu_multi_set_media");
 
     omc_geometry g = { geometry.isize, geometry.jsize, geometry.ksize,
                        geometry.xbounds, geometry.ybounds, geometry.zbounds,
                        region.med, region.rhof, region.pcut, region.ecut };
-    if (omc_gpu_set_geometry(gpu, &g)) die("omc_gpu_set_geometry");
+    if (omc_gpu_multi_set_geometry(gpu, &g)) die("omc_gpu_multi_set_geometry");
 
     omc_source_dosxyz s = { source.spectrum, source.charge, source.energy, source.deltak,
                             source.cdfinv1, source.cdfinv2, source.ssd,
                             source.xinl, source.xinu, source.yinl, source.yinu, source.xsize, source.ysize,
                             source.ixinl, source.ixinu, source.iyinl, source.iyinu };
-    if (omc_gpu_set_source_dosxyz(gpu, &s)) die("omc_gpu_set_source_dosxyz");
-    if (omc_gpu_set_vrt(gpu, vrt.nsplit)) die("omc_gpu_set_vrt");
+    if (omc_gpu_multi_set_source_dosxyz(gpu, &s)) die("omc_gpu_multi_set_source_dosxyz");
+    if (omc_gpu_multi_set_vrt(gpu, vrt.nsplit)) die("omc_gpu_multi_set_vrt");
 
     char buffer[BUFFER_SIZE];
     int ixx = 1802, jxx = 9373;               /* defaults of initRandom(), src/omc_random.c:64-82 */
     if (getInputValue(buffer, "rng seeds") == 1) sscanf(buffer, "%d %d", &ixx, &jxx);
-    if (omc_gpu_set_seed(gpu, ixx, jxx)) die("omc_gpu_set_seed");
+    if (omc_gpu_multi_set_seed(gpu, ixx, jxx)) die("omc_gpu_multi_set_seed");
     if (kernel < 0) kernel = vrt.nsplit > 255 ? OMC_KERNEL_LOCKSTEP : OMC_KERNEL_WAVEFRONT;
-    if (omc_gpu_set_option(gpu, "kernel", kernel)) die("omc_gpu_set_option");
+    if (omc_gpu_multi_set_option(gpu, "kernel", kernel)) die("omc_gpu_multi_set_option");
 }
 
 int main(int argc, char **argv) {
     double tbegin = omc_get_time();
     char *input_file = NULL, *output_file = NULL;
-    int kernel = -1;
+    int kernel = -1, ngpu = getenv("OMC_GPUS") ? atoi(getenv("OMC_GPUS")) : 1;
     for (int i = 1; i < argc; i++) {
         if ((!strcmp(argv[i], "-i") || !strcmp(argv[i], "--input")) && i + 1 < argc) input_file = argv[++i];
+        else if (!strcmp(argv[i], "-g") && i + 1 < argc) ngpu = atoi(argv[++i]);
         else if ((!strcmp(argv[i], "-o") || !strcmp(argv[i], "--output")) && i + 1 < argc) output_file = argv[++i];
         else if (!strcmp(argv[i], "-k") && i + 1 < argc) kernel = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--verbose")) verbose_flag = 1;
         else if (!strcmp(argv[i], "--brief")) verbose_flag = 0;
-        else { printf("usage: %s -i <input stem> -o <output stem> [-k 0|1] [--verbose]\n", argv[0]); exit(EXIT_FAILURE); }
+        else { printf("usage: %s -i <input stem> -o <output stem> [-k 0|1] [-g ngpu] [--verbose]\n", argv[0]); exit(EXIT_FAILURE); }
     }
     if (!input_file || !output_file) { printf("usage: %s -i <input stem> -o <output stem>\n", argv[0]); exit(EXIT_FAILURE); }
 
@@ -121,17 +122,18 @@ int main(int argc, char **argv) {
     printf("Number of statistical batches: %d\n", nbatch);
     printf("Histories per batch: %d\n", nperbatch);
 
-    gpu_upload(kernel);
+    gpu_upload(kernel, ngpu);
+    printf("GPUs: %d\n", omc_gpu_multi_size(gpu));
     printf("Execution time up to this point : %8.2f seconds\n", omc_get_time() - tbegin);
 
     double tloop = omc_get_time();
     for (int ibatch = 0; ibatch < nbatch; ibatch++) {
         printf("%-10d\t%-15.2f\n", ibatch, omc_get_time() - tbegin);
         /* == { initHistory(); shower(); } x nperbatch + accumEndep()   (omc_dosxyz.c:1252-1262) */
-        if (omc_gpu_run_batch(gpu, (long long)ibatch * nperbatch, nperbatch, -1)) die("omc_gpu_run_batch");
+        if (omc_gpu_multi_run_batch(gpu, (long long)ibatch * nperbatch, nperbatch, -1)) die("omc_gpu_multi_run_batch");
     }
     /* the tallies accumEndep() would have left in the reference's struct Score (omc_dosxyz.c:696-717) */
-    if (omc_gpu_get_tallies(gpu, score.accum_endep, score.accum_endep2, &score.ensrc)) die("omc_gpu_get_tallies");
+    if (omc_gpu_multi_get_tallies(gpu, score.accum_endep, score.accum_endep2, &score.ensrc)) die("omc_gpu_multi_get_tallies");
     printf("Simulation finished\n");
     printf("Execution time up to this point : %8.2f seconds\n", omc_get_time() - tbegin);
     printf("Batch loop: %.6f seconds, %.4e histories/s\n", omc_get_time() - tloop, nhist / (omc_get_time() - tloop));
@@ -146,7 +148,7 @@ int main(int argc, char **argv) {
     /* unchanged reference code from here: accumulateResults() + the .3ddose writer (omc_dosxyz.c:719-886, :1281-1282) */
     outputResults(output_file, 1, nperbatch, nbatch);
 
-    omc_gpu_destroy(gpu);
+    omc_gpu_multi_destroy(gpu);
     cleanPhantom(); cleanPhoton(); cleanRayleigh(); cleanPair(); cleanElectron(); cleanMscat(); cleanSpin();
     cleanRegions(); cleanScore(); cleanSource();
     printf("Total execution time : %8.5f seconds\n", omc_get_time() - tbegin);

@@ -112,6 +112,85 @@ static int phantom_read(host_phantom *p, const char *path) {
     return 0;
 }
 
+/* ---- resampling (BASELINE config 5: the PROSTATE grid "up-sampled 3 mm -> 2 mm / 1 mm") ---------------------------------------
+ * The reference has no resampler: its users prepare the finer .egsphant outside.  This one keeps the physical
+ * extent of the phantom and cuts every axis into round(extent / size) equal voxels of (about) the requested size -- any
+ * ratio, not only integer splits.  A new voxel takes the VOLUME-weighted mean density of the old voxels it overlaps and the
+ * medium that fills most of its volume (ties: the lowest medium index; 0 = vacuum competes like a medium), so that mass is
+ * conserved exactly and an integer split reproduces the material map voxel for voxel.  Same rule, same arithmetic order as
+ * ompmc_b200.problem.resample_phantom_to(). */
+typedef struct { int n; int *lo, *cnt; double *w; } axis_overlap;   /* new cell i overlaps old cells lo[i] .. lo[i]+cnt[i]-1 with lengths w[off..] */
+
+static double *axis_resample(const double *b, int n, double size, int *n_out) {
+    const double ext = b[n] - b[0];
+    int m = (int)floor(ext / size + 0.5);
+    if (m < 1) m = 1;
+    double *out = malloc(((size_t)m + 1) * sizeof(double));
+    for (int i = 0; i <= m; i++) out[i] = b[0] + ext * (double)i / (double)m;
+    out[m] = b[n];
+    *n_out = m;
+    return out;
+}
+
+static int phantom_resample(const host_phantom *src, double sx, double sy, double sz, host_phantom *dst) {
+    if (!(sx > 0.0 && sy > 0.0 && sz > 0.0)) { printf("Voxel sizes must be positive.\n"); return 1; }
+    *dst = *src;
+    dst->xb = axis_resample(src->xb, src->isize, sx, &dst->isize);
+    dst->yb = axis_resample(src->yb, src->jsize, sy, &dst->jsize);
+    dst->zb = axis_resample(src->zb, src->ksize, sz, &dst->ksize);
+    const size_t nvox = (size_t)dst->isize * dst->jsize * dst->ksize;
+    if (nvox + 1 > 2147483647u) { printf("Resampled grid has too many voxels.\n"); return 1; }
+    dst->med = malloc(nvox * sizeof(int));
+    dst->dens = malloc(nvox * sizeof(double));
+    /* per axis: first old cell and overlap lengths of every new cell */
+    const double *ob[3] = {src->xb, src->yb, src->zb}, *nb[3] = {dst->xb, dst->yb, dst->zb};
+    const int on[3] = {src->isize, src->jsize, src->ksize}, nn[3] = {dst->isize, dst->jsize, dst->ksize};
+    int *first[3], *count[3];
+    double **len[3];
+    for (int a = 0; a < 3; a++) {
+        first[a] = malloc((size_t)nn[a] * sizeof(int)); count[a] = malloc((size_t)nn[a] * sizeof(int));
+        len[a] = malloc((size_t)nn[a] * sizeof(double *));
+        int j = 0;
+        for (int i = 0; i < nn[a]; i++) {
+            const double lo = nb[a][i], hi = nb[a][i + 1];
+            while (j < on[a] - 1 && ob[a][j + 1] <= lo) j++;
+            int k = j, c = 0;
+            double *w = malloc((size_t)on[a] * sizeof(double));
+            while (k < on[a] && ob[a][k] < hi) {
+                const double l = (ob[a][k + 1] < hi ? ob[a][k + 1] : hi) - (ob[a][k] > lo ? ob[a][k] : lo);
+                w[c++] = l > 0.0 ? l : 0.0;
+                k++;
+            }
+            first[a][i] = j; count[a][i] = c;
+            len[a][i] = realloc(w, (size_t)(c > 0 ? c : 1) * sizeof(double));
+        }
+    }
+    for (int kz = 0; kz < nn[2]; kz++)
+        for (int jy = 0; jy < nn[1]; jy++)
+            for (int ix = 0; ix < nn[0]; ix++) {
+                double vol[OMC_MXMED + 1] = {0.0}, mass = 0.0, vtot = 0.0;
+                for (int c = 0; c < count[2][kz]; c++)
+                    for (int b = 0; b < count[1][jy]; b++)
+                        for (int a = 0; a < count[0][ix]; a++) {
+                            const size_t o = (size_t)(first[0][ix] + a) + (size_t)(first[1][jy] + b) * on[0] + (size_t)(first[2][kz] + c) * on[0] * on[1];
+                            const double v = len[0][ix][a] * len[1][jy][b] * len[2][kz][c];
+                            vol[src->med[o]] += v;
+                            mass += v * src->dens[o];
+                            vtot += v;
+                        }
+                int best = 0;
+                for (int m = 1; m <= src->nmed; m++) if (vol[m] > vol[best]) best = m;
+                const size_t d = (size_t)ix + (size_t)jy * nn[0] + (size_t)kz * nn[0] * nn[1];
+                dst->med[d] = best;
+                dst->dens[d] = vtot > 0.0 ? mass / vtot : 0.0;
+            }
+    for (int a = 0; a < 3; a++) {
+        for (int i = 0; i < nn[a]; i++) free(len[a][i]);
+        free(len[a]); free(first[a]); free(count[a]);
+    }
+    return 0;
+}
+
 /* ---- regions ------------------------------------------------------------------------------------------------------- */
 typedef struct { int *med; double *rhof, *pcut, *ecut; } host_regions;
 

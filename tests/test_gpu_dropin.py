@@ -42,7 +42,7 @@ def test_dropin_fails_loudly_without_a_device():
         pytest.skip("a CUDA device is present")
     work, stem, ph = write_case("golden_water700_6MV", 1000, 10)
     r = subprocess.run([DROPIN, "-i", stem, "-o", "dropin_nogpu"], capture_output=True, text=True)
-    assert r.returncode != 0 and "Histories per batch: 100" in r.stdout and "omc_gpu_create" in r.stdout
+    assert r.returncode != 0 and "Histories per batch: 100" in r.stdout and "omc_gpu_multi_create" in r.stdout
     assert not os.path.exists(os.path.join(work, "dropin_nogpu.3ddose"))
 
 

@@ -1,0 +1,118 @@
+"""Multi-GPU inside the C library (include/ompmc_b200.h, "multi-GPU"): NCCL communicator per handle, history ids of a batch
+sharded over the ranks by omc_gpu_run_batch(), completed batch grids summed on a side stream BEFORE accumEndep() squares
+them (the statistics must be those of a single-GPU run of the same batches), one handle over several devices for
+single-process C user codes (omc_gpu_multi_*), the reference's own omc_dosxyz user code on it (-g N).
+
+The driver's GPU box has one device: the world-size-2 cases skip there and are run with `gpurun --gpus 2`
+(scripts/gpu_multi.sh; result committed under profiles/)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from ompmc_b200 import build, problem as P
+from tests.test_gpu_wavefront import CASES, make_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def ndev():
+    import torch
+    return torch.cuda.device_count()
+
+
+def run_batches(tr, nb, per):
+    tr.set_option("kernel", 1)
+    tr.reset_tallies()
+    for ib in range(nb):
+        tr.run_batch(ib * per, per)
+    a, a2, e = tr.get_tallies()
+    return a[1:], a2[1:], e, tr.counters()
+
+
+def same_statistics(ref, got, nb):
+    (a0, b0, e0, c0), (a1, b1, e1, c1) = ref, got
+    assert c1["histories"] == c0["histories"] and c1["errors"] == 0
+    assert abs(e1 - e0) <= 1e-9 * e0                                    # the same source particles, summed in another order
+    # (the last few particles of a run are finished by the drain kernel on continued random streams: work counts agree closely,
+    # not exactly, when the batches are cut differently)
+    assert abs(c1["deposits"] - c0["deposits"]) <= 2e-3 * c0["deposits"]
+    assert abs(c1["electron_steps"] - c0["electron_steps"]) <= 2e-3 * c0["electron_steps"]
+    # history id -> RNG stream: every history is the same whichever device ran it; only the fp32 atomics order differs
+    np.testing.assert_allclose(a1, a0, rtol=3e-4, atol=1e-4 * a0.max())
+    np.testing.assert_allclose(b1, b0, rtol=6e-4, atol=1e-4 * b0.max())
+
+
+def test_one_device_behind_the_multi_handle(gpu):
+    from ompmc_b200.api import MultiGpuTransport
+    prob, ph = make_problem(CASES[1][1])
+    gpu.load_problem(prob)
+    ref = run_batches(gpu, 4, 50000)
+    m = MultiGpuTransport(ndev=1)
+    try:
+        assert m.ndev == 1
+        m.load_problem(prob)
+        got = run_batches(m, 4, 50000)
+    finally:
+        m.close()
+    same_statistics(ref, got, 4)
+
+
+def test_communicator_of_one_is_a_no_op(gpu):
+    prob, ph = make_problem(CASES[0][1])
+    gpu.load_problem(prob)
+    ref = run_batches(gpu, 3, 20000)
+    gpu.comm_init(0, 1, gpu.comm_unique_id())
+    got = run_batches(gpu, 3, 20000)
+    same_statistics(ref, got, 3)
+    assert np.array_equal(gpu.comm_sum([1.5, 2.0]), [1.5, 2.0])
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_batches_sharded_over_devices_equal_one_device(gpu, n):
+    if ndev() < n:
+        pytest.skip(f"needs {n} GPUs")
+    from ompmc_b200.api import MultiGpuTransport
+    prob, ph = make_problem(CASES[1][1])
+    gpu.load_problem(prob)
+    nb, per = 6, 200001                                                 # (not divisible by the device count: ragged slices)
+    ref = run_batches(gpu, nb, per)
+    m = MultiGpuTransport(ndev=n)
+    try:
+        m.load_problem(prob)
+        got = run_batches(m, nb, per)
+        # the statistics live on every device: device 1's copy equals device 0's bit for bit (same all-reduced grids)
+        dose, unc = m.accumulate_results(ph.med_densities, per, nb)
+    finally:
+        m.close()
+    same_statistics(ref, got, nb)
+    d0, u0 = gpu.accumulate_results(ph.med_densities, per, nb)
+    np.testing.assert_allclose(dose, d0, rtol=3e-4, atol=1e-4 * d0.max())
+    sel = d0 > 0.2 * d0.max()
+    # batch-method uncertainty: squares were taken AFTER the sum over devices, so it matches the single-device one (a per-device
+    # accumEndep() would give sqrt(n) times less)
+    np.testing.assert_allclose(unc[sel], u0[sel], rtol=0.05)
+
+
+def test_reference_user_code_on_two_gpus(gpu):
+    """The reference's own omc_dosxyz.c with its batch loop on the library, -g 2 against -g 1 (omc_dosxyz.c:1237-1263 replaced)."""
+    from tests.test_gpu_dropin import DROPIN, write_case
+    from oracle import gen_fixtures as G
+    if ndev() < 2:
+        pytest.skip("needs 2 GPUs")
+    if not (os.path.exists(DROPIN) and G.have_data()):
+        pytest.skip("oracle/_ref/omc_dosxyz_dropin not built")
+    work, stem, ph = write_case("golden_tissue4_6MV", 800008, 8)
+    build.build()
+    out = {}
+    for g in (1, 2):
+        r = subprocess.run([DROPIN, "-i", stem, "-o", f"dropin_g{g}", "-g", str(g)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-500:]
+        assert f"GPUs: {g}" in r.stdout
+        out[g] = P.read_3ddose(os.path.join(work, f"dropin_g{g}.3ddose"))
+    (dims1, _, dose1, unc1), (dims2, _, dose2, unc2) = out[1], out[2]
+    assert dims1 == dims2
+    np.testing.assert_allclose(dose2, dose1, rtol=5e-4, atol=5e-4 * dose1.max())
+    sel = dose1 > 0.2 * dose1.max()
+    np.testing.assert_allclose(unc2[sel], unc1[sel], rtol=0.05, atol=2e-3)

@@ -52,8 +52,15 @@ def test_production_kernels_vs_reference_batch_statistics(gpu, case):
     cnt = gpu.counters()
     assert cnt["histories"] == nb * per * mult and cnt["errors"] == 0                 # integer bookkeeping
     mg, vg = batch_stats(a / mult, a2 / mult ** 2, nb)                                  # per reference-sized batch
-    # source energy per history: the same spectrum sampling on both sides
-    assert abs(ensrc / (nb * per * mult) - float(z["ensrc"]) / (nb * per)) < 2e-3 * float(z["ensrc"]) / (nb * per)
+    # Source energy per history: initHistory() draws ein = cdfinv1[k] + r * cdfinv2[k] with k uniform (omc_dosxyz.c:975-983), whose
+    # exact mean is mean(cdfinv1 + cdfinv2 / 2).  The reference's own score.ensrc is NOT usable as the yardstick: it is a shared
+    # global incremented without atomics inside the OpenMP loop (omc_dosxyz.c:1002, SURVEY 4: "racy"), so it loses updates and
+    # can only come out low (by 0.2-0.7 % with 8 threads in the committed files).
+    e_exact = float(np.mean(prob["src_cdfinv1"] + 0.5 * prob["src_cdfinv2"]))
+    e_gpu = ensrc / (nb * per * mult)
+    assert abs(e_gpu - e_exact) < 3e-4 * e_exact, (e_gpu, e_exact)
+    e_ref = float(z["ensrc"]) / (nb * per)
+    assert e_ref <= e_exact * (1 + 3e-4) and e_ref > 0.97 * e_exact, (e_ref, e_exact)
 
     sel = (mr > 0.2 * mr.max()) & (vr + vg > 0)
     zs = (mg[sel] - mr[sel]) / np.sqrt(vr[sel] + vg[sel])

@@ -224,45 +224,6 @@ def test_batch_pipelining_matches_serial_batches(gpu):
     assert c1["deposits"] == c0["deposits"] and c1["electron_steps"] == c0["electron_steps"]
 
 
-@pytest.mark.parametrize("pool", [1 << 15, 1 << 23])
-def test_straggler_handover_between_pipelined_batches(gpu, pool):
-    """Batch pipelining with the drain on: once the histories of batch k are all started, what is left of batch k-1 is taken
-    out of the queues and finished by the drain kernel (handover_kernel), scoring into the grid of batch k-1.  Against the
-    same batches without hand-over: same histories and source energy exactly, and -- as only the few handed-over lineages
-    continue on other random sub-streams -- accum AND accum2 (a particle scored into the wrong batch would show there)
-    nearly identical voxel by voxel."""
-    prob, ph = make_problem(CASES[1][1])
-    gpu.load_problem(prob)
-    gpu.set_option("kernel", 1)
-    nb, per = 8, 60000
-    out = {}
-    try:
-        gpu.set_option("pool_size", pool)
-        for ho in (0, 1):
-            gpu.set_option("handover", ho)
-            gpu.reset_tallies()
-            for ib in range(nb):
-                gpu.run_batch(ib * per, per)
-            a, a2, e = gpu.get_tallies()
-            out[ho] = (a[1:], a2[1:], e, gpu.counters())
-    finally:
-        gpu.set_option("pool_size", 1 << 23); gpu.set_option("handover", 0)
-        gpu.reset_tallies()
-    (a0, b0, e0, c0), (a1, b1, e1, c1) = out[0], out[1]
-    assert c0["handovers"] == 0 and c0["handed_over"] == 0
-    assert c1["handovers"] >= nb // 2 and 0 < c1["handed_over"] <= c1["handovers"] * 8192
-    assert c0["errors"] == 0 and c1["errors"] == 0
-    assert c1["histories"] == c0["histories"] == nb * per
-    assert abs(e1 - e0) <= 1e-9 * e0
-    assert abs(a1.sum() - a0.sum()) < 2e-3 * a0.sum() and abs(b1.sum() - b0.sum()) < 4e-3 * b0.sum()
-    # voxel-wise: the two runs share all but the handed-over lineages, so they differ by much less than their own noise
-    mean0, mean1 = a0 / nb, a1 / nb
-    var0 = np.maximum(b0 / nb - mean0 * mean0, 0.0) / (nb - 1)
-    sel = (mean0 > 0.2 * mean0.max()) & (var0 > 0)
-    z = (mean1[sel] - mean0[sel]) / np.sqrt(var0[sel])
-    assert sel.sum() >= 20 and np.abs(z).max() < 4.0 and z.std() < 0.8
-
-
 def test_wavefront_rejects_unsupported(gpu):
     prob, ph = make_problem(dict(CASES[0][1], nsplit=300))
     gpu.load_problem(prob)

@@ -120,3 +120,39 @@ def test_input_parser_follows_the_reference(tmp_path):
                            "nbatch = 9", "phantom file = /no such / file .egsphant", ""]))
     r = subprocess.run([build.HOST_EXE, "-i", stem, "-o", stem, "--dump-problem"], capture_output=True, text=True)
     assert r.returncode != 0 and "Unable to open file: /nosuch/file.egsphant" in r.stdout
+
+
+@pytest.mark.parametrize("voxel", [(0.2, 0.2, 0.2), (0.1, 0.1, 0.1), (0.45, 0.3, 0.25)])
+def test_phantom_resampler_any_ratio(workdir, voxel):
+    """BASELINE config 5: `omc_dosxyz_b200 -i <stem> -v "dx dy dz" --dump-problem` resamples the .egsphant to any
+    voxel size -- 3 mm -> 2 mm is not an integer split -- keeping the extent, conserving mass exactly (volume-weighted densities),
+    medium by largest overlap; identical to the numpy mirror problem.resample_phantom_to(); a 3 -> 1 mm split copies the map."""
+    name = "golden_tissue4_6MV"
+    cfg = G.GOLDEN_RUNS[name]
+    ph = P.tissue_phantom((21, 19, 11), (0.3, 0.3, 0.3), "prostate")
+    ppath = os.path.join(workdir, "resample_src.egsphant")
+    P.write_egsphant(ppath, ph)
+    ph = P.read_egsphant(ppath)                      # (the densities as the file's text holds them)
+    stem = os.path.join(workdir, "resample_%g" % voxel[0])
+    mcfg = G.MEDIA_SETS[cfg["mset"]]
+    G.write_inp(stem, phantom=ppath, pegs=mcfg["pegs"], spectrum=G.SPECTRA[cfg["spectrum"]], mono=cfg["mono"], charge=cfg["charge"],
+                coll=cfg["coll"], ssd=cfg["ssd"], ecut=mcfg["ecut"], pcut=0.01, nsplit=1)
+    build.build()
+    r = subprocess.run([build.HOST_EXE, "-i", stem, "-o", stem, "-v", "%g %g %g" % voxel, "--dump-problem"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-500:]
+    mine = P.load_blob(stem + ".problem")
+    want = P.resample_phantom_to(ph, voxel)
+    assert (int(mine["isize"][0]), int(mine["jsize"][0]), int(mine["ksize"][0])) == (want.isize, want.jsize, want.ksize)
+    np.testing.assert_allclose(mine["xbounds"], want.xbounds, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(mine["zbounds"], want.zbounds, rtol=0, atol=1e-12)
+    assert np.array_equal(mine["region_med"][1:], want.med_indices - 1)
+    np.testing.assert_allclose(mine["med_densities"], want.med_densities, rtol=1e-9)
+    # mass conservation
+    def mass(p):
+        vol = np.multiply.outer(np.diff(p.zbounds), np.multiply.outer(np.diff(p.ybounds), np.diff(p.xbounds))).reshape(-1)
+        return float((vol * p.med_densities).sum())
+    assert abs(mass(want) - mass(ph)) < 1e-10 * mass(ph)
+    if voxel == (0.1, 0.1, 0.1):                     # integer split: the material map is copied voxel for voxel
+        split = P.resample_phantom(ph, (3, 3, 3))
+        assert np.array_equal(split.med_indices, want.med_indices)
+        np.testing.assert_allclose(split.med_densities, want.med_densities, rtol=1e-9)
