@@ -191,13 +191,180 @@ def run_reference_arm(args) -> None:
 
 
 # ---------------------------------------------------------------------------------------------
+# BASELINE config 4: omc_matrad dose-influence matrix, beamlets sharded over the GPUs
+MATRAD_DESC = ("omc_matrad: PROSTATE-like 183x183x90 @3mm, 4 media 700icru, var_6MV, 5 gantry angles x 25x25 bixels of 5 mm (3125 beamlets), "
+               "relDoseThreshold 1e-3, 64 beamlets per pass")
+MATRAD_PASS = 64
+
+
+def build_matrad_workload():
+    w = WORKLOADS["prostate6mv"]
+    media = P.load_blob(P.golden(w["media"]))
+    ph = w["phantom"]()
+    bl = P.matrad_beamlets(ph, gantry_deg=(0.0, 72.0, 144.0, 216.0, 288.0), nbix=(25, 25), bixel_cm=0.5)
+    prob = P.build_problem_matrad(media, ph, bl, ecut=0.7, pcut=0.01, cdfinv=(media["cdfinv1_var_6MV"], media["cdfinv2_var_6MV"]))
+    return prob, ph, int(bl["mr_nbeamlets"][0])
+
+
+def run_matrad(args) -> None:
+    """One step = one pass of omc_gpu_run_beamlets() per GPU: 64 beamlets x --hist-per-beamlet histories through the wavefront
+    kernels, accumulateResults + threshold + CSC columns on the device (omc_matrad.c:1389-1477).  Step i gives rank r the
+    beamlets [64 (i world + r), +64) (weak scaling: 64 beamlets per GPU per step); beamlet b always owns history ids
+    [b nhist, (b+1) nhist).  `value` times the passes with the columns left on the device; `e2e` adds what a user of the plugin
+    pays: fetching every pass's columns to the host and the in-library gather of all ranks' columns into the complete matrix."""
+    import torch
+    import torch.distributed as dist
+    from ompmc_b200 import build as builder
+    from ompmc_b200.api import GpuTransport
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    if rank == 0:
+        builder.build()
+    if world > 1:
+        dist.barrier()
+    prob, ph, nbeam = build_matrad_workload()
+    nh, nbatch, rel = args.hist_per_beamlet, 10, 1.0e-3
+    need = MATRAD_PASS * args.steps * world
+    if need > nbeam:
+        raise SystemExit(f"bench.py: {args.steps} steps x {world} GPUs x {MATRAD_PASS} beamlets exceed the plan's {nbeam} beamlets")
+    tr = GpuTransport(local)
+    tr.load_problem(prob)
+    tr.set_option("kernel", 1)
+    if world > 1:
+        box = [tr.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        tr.comm_init(rank, world, box[0])
+    stream = torch.cuda.ExternalStream(tr.stream_ptr(), device=f"cuda:{local}")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_pass(i: int, fetch: bool):
+        b0 = MATRAD_PASS * (i * world + rank)
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        return b0, tr.run_beamlets(b0 * nh, nh, nbatch, b0, MATRAD_PASS, rel, ph.med_densities, fetch=fetch)
+
+    for i in range(args.warmup):
+        one_pass(i % max(args.steps, 1), False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = tr.counters()["kernel_launches"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for i in range(args.steps):
+        one_pass(i, False)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = tr.counters()["kernel_launches"] - l0
+    # end to end: every pass's columns to the host, then the complete matrix on every rank
+    barrier()
+    t0 = time.perf_counter()
+    mine = {}
+    d2h = 0
+    for i in range(args.steps):
+        b0, (jc, ir, val) = one_pass(i, True)
+        d2h += ir.nbytes + val.nbytes + jc.nbytes
+        for k in range(MATRAD_PASS):
+            mine[b0 + k] = (ir[jc[k]:jc[k + 1]], val[jc[k]:jc[k + 1]])
+    nb_total = MATRAD_PASS * args.steps * world
+    jc_all, ir_all, val_all = tr.comm_gather_columns(nb_total, mine)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = (float(x) for x in times.tolist())
+    if rank == 0:
+        total_hist = args.steps * MATRAD_PASS * nh * world
+        peak, peak_kind = measured_peaks()
+        line = {"metric": "histories/s", "value": total_hist / (ms * 1e-3), "unit": "histories/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "mixed f64/f32", "data": "synthetic",
+                "config": {"workload": "matrad_prostate", "desc": MATRAD_DESC, "beamlets_per_step_per_gpu": MATRAD_PASS, "hist_per_beamlet": nh,
+                           "beamlets_total": nb_total, "kernel": "wavefront", "l2": "256 MiB buffer written between steps (L2 flush)"},
+                "clocks": clocks, "gpu_launches": int(launches), "beamlets_per_s": args.steps * MATRAD_PASS * world / (ms * 1e-3),
+                "e2e": {"value": total_hist / (e2e_ms * 1e-3), "unit": "histories/s", "beamlets_per_s": nb_total / (e2e_ms * 1e-3),
+                        "h2d_bytes_per_step": int(ph.nvox * 8), "d2h_bytes_per_step": int(d2h / max(args.steps, 1)),
+                        "steps": args.steps, "gather": "omc_gpu_comm_gather_columns (NCCL inside the library)" if world > 1 else "single rank"},
+                "matrix": {"rows": int(ph.nvox), "cols": int(nb_total), "nnz": int(jc_all[-1]),
+                           "checksum": float(val_all.sum()), "row_checksum": int(ir_all.sum())}}
+        work = json.load(open(os.path.join(ROOT, "profiles", "work_counts.json"))).get("prostate6mv")
+        if work:
+            balg = alg_bytes_per_history(work)
+            achieved = balg * MATRAD_PASS * nh / (ms / args.steps * 1e-3) / 1e9
+            line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                                "peak_kind": peak_kind, "alg_bytes_per_history": balg,
+                                "note": "per-history work counts of the prostate6mv dosxyz workload (same phantom, spectrum and cut-offs)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_matrad_reference_arm(args) -> None:
+    """The unmodified reference on the host cores for the same beamlets: initHistory(ibeamlet) + shower() of omc_matrad.c through
+    the reference harness, a bounded number of histories per beamlet."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    prob, ph, nbeam = build_matrad_workload()
+    from oracle import cpudrv
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    with quiet_stdout():
+        if not cpudrv.have_ref(omp=True, matrad=True):
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libompmc_ref_matrad_omp.so not built (needs /root/reference)"}))
+            return
+        tr, kind = cpudrv.RefTransport(omp=True, matrad=True), "reference"
+        tr.set_num_threads(ncores)
+        tr.load_problem(prob)
+        tr.set_rng("ranmar")
+        cores = tr.num_threads()
+        nper = 20000
+        t0 = time.perf_counter()
+        done = 0
+        for i in range(args.warmup + args.steps):
+            if i == args.warmup:
+                t0 = time.perf_counter(); done = 0
+            for b in range(8):                                   # eight beamlets of the step's pass, nper histories each
+                bb = (MATRAD_PASS * i + 8 * b) % nbeam
+                tr.set_beamlet(bb)
+                tr.run_histories(bb * args.hist_per_beamlet, nper)
+                done += nper
+        dt = time.perf_counter() - t0
+    value = done / dt
+    line = {"impl": "reference", "metric": "histories/s", "value": value, "unit": "histories/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "matrad_prostate", "desc": MATRAD_DESC, "hist_per_step": 8 * nper},
+            "cpu_baseline": {"value": value, "unit": "histories/s", "cores": cores, "kind": kind,
+                             "sample": f"{args.steps} steps x 8 beamlets x {nper} histories, RANMAR, schedule(dynamic)"},
+            "e2e": {"value": value, "unit": "histories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="prostate6mv", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="prostate6mv", choices=list(WORKLOADS) + ["matrad_prostate"])
+    ap.add_argument("--hist-per-beamlet", type=int, default=1_000_000, help="matrad_prostate: nHistories of every beamlet")
+    ap.add_argument("--voxel-mm", type=float, default=0.0, help="BASELINE config 5: resample the phantom to this voxel size (2 or 1)")
     # one step = one statistical batch; 1 % sigma above half Dmax needs ~6e8 histories on this workload = 10 batches of ~6e7
     ap.add_argument("--hist-per-step", type=int, default=1 << 26, help="histories per step PER GPU")
     ap.add_argument("--kernel", type=int, default=-1, help="-1 production default, 0 lock-step, 1 wavefront")
@@ -208,7 +375,13 @@ def main() -> None:
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
-        run_reference_arm(args)
+        if args.workload == "matrad_prostate":
+            run_matrad_reference_arm(args)
+        else:
+            run_reference_arm(args)
+        return
+    if args.workload == "matrad_prostate":
+        run_matrad(args)
         return
 
     import torch

@@ -266,6 +266,12 @@ int omc_gpu_comm_init(omc_gpu_handle h, int rank, int world, const char *id128);
 int omc_gpu_comm_rank(omc_gpu_handle h);
 int omc_gpu_comm_size(omc_gpu_handle h);
 int omc_gpu_comm_sum(omc_gpu_handle h, double *values, int n);   /* in-place sum of n host doubles over the ranks (collective) */
+/* omc_matrad with one process per GPU: the columns each rank computed (omc_gpu_run_beamlets / omc_gpu_fetch_columns) -> the
+ * complete sparse matrix on every rank, in beamlet order as omc_matrad.c:1416-1477 appends them.  jc[nb_total+1] = global
+ * column starts (per-beamlet counts summed with omc_gpu_comm_sum), mine[b] != 0 marks this rank's beamlets, ir_mine / val_mine
+ * hold their rows and values concatenated in beamlet order.  Collective. */
+int omc_gpu_comm_gather_columns(omc_gpu_handle h, int nb_total, const long long *jc, const unsigned char *mine, const long long *ir_mine,
+                                const double *val_mine, long long *ir_out /* [jc[nb_total]] */, double *val_out);
 
 /* One handle over several GPUs of this node for a single-process user code: the batch loop of omc_dosxyz.c:1237-1263 with
  * `omc_gpu_multi_run_batch(m, ibatch*nperbatch, nperbatch, -1)` in place of the OpenMP loop + accumEndep(), and the beamlet

@@ -94,7 +94,7 @@ EXPORTS = ["omc_gpu_create", "omc_gpu_destroy", "omc_gpu_last_error", "omc_gpu_s
            "omc_gpu_get_batch_grid", "omc_gpu_accumulate_results", "omc_gpu_write_3ddose", "omc_gpu_test_format", "omc_gpu_run_beamlets", "omc_gpu_fetch_columns", "omc_gpu_reset_tallies", "omc_gpu_device_ptrs", "omc_gpu_stream", "omc_gpu_get_counters",
            "omc_gpu_get_history_records", "omc_gpu_test_geometry", "omc_gpu_test_rng", "omc_gpu_test_particles", "omc_gpu_test_samplers",
            "omc_gpu_abi_sizeof",
-           "omc_gpu_comm_unique_id", "omc_gpu_comm_init", "omc_gpu_comm_rank", "omc_gpu_comm_size", "omc_gpu_comm_sum",
+           "omc_gpu_comm_unique_id", "omc_gpu_comm_init", "omc_gpu_comm_rank", "omc_gpu_comm_size", "omc_gpu_comm_sum", "omc_gpu_comm_gather_columns",
            "omc_gpu_multi_create", "omc_gpu_multi_destroy", "omc_gpu_multi_size", "omc_gpu_multi_device", "omc_gpu_multi_last_error",
            "omc_gpu_multi_set_media", "omc_gpu_multi_set_geometry", "omc_gpu_multi_set_source_dosxyz", "omc_gpu_multi_set_source_matrad",
            "omc_gpu_multi_set_vrt", "omc_gpu_multi_set_seed", "omc_gpu_multi_set_option", "omc_gpu_multi_reset_tallies",
@@ -147,6 +147,7 @@ def load_library() -> C.CDLL:
     lib.omc_gpu_comm_init.argtypes = [H, C.c_int, C.c_int, C.c_char_p]
     lib.omc_gpu_comm_rank.argtypes = [H]; lib.omc_gpu_comm_size.argtypes = [H]
     lib.omc_gpu_comm_sum.argtypes = [H, C.c_void_p, C.c_int]
+    lib.omc_gpu_comm_gather_columns.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.omc_gpu_multi_create.argtypes = [C.POINTER(H), C.c_int, C.c_void_p]
     lib.omc_gpu_multi_destroy.argtypes = [H]; lib.omc_gpu_multi_destroy.restype = None
     lib.omc_gpu_multi_size.argtypes = [H]
@@ -321,14 +322,18 @@ class GpuTransport:
     def run_batch(self, first: int, n: int, ibeamlet: int = -1):
         self._ck(self.lib.omc_gpu_run_batch(self.h, first, n, ibeamlet), "omc_gpu_run_batch")
 
-    def run_beamlets(self, first: int, nhist: int, nbatch: int, ib0: int, nb: int, rel_threshold: float, med_densities: np.ndarray):
-        """Beamlets [ib0, ib0+nb) in one pass + device-side column assembly: (jc[nb+1], ir[nnz], val[nnz])."""
+    def run_beamlets(self, first: int, nhist: int, nbatch: int, ib0: int, nb: int, rel_threshold: float, med_densities: np.ndarray,
+                     fetch: bool = True):
+        """Beamlets [ib0, ib0+nb) in one pass + device-side column assembly: (jc[nb+1], ir[nnz], val[nnz]); fetch=False leaves
+        rows and values on the device (jc only)."""
         dens = np.ascontiguousarray(med_densities, dtype=np.float64)
         assert dens.size == self.nreg - 1
         jc = np.zeros(nb + 1, dtype=np.int64)
         tot = C.c_longlong(0)
         self._ck(self.lib.omc_gpu_run_beamlets(self.h, int(first), int(nhist), int(nbatch), int(ib0), int(nb), float(rel_threshold),
                                                dens.ctypes.data, jc.ctypes.data, C.byref(tot)), "omc_gpu_run_beamlets")
+        if not fetch:
+            return jc, None, None
         ir = np.zeros(max(tot.value, 1), dtype=np.int64); val = np.zeros(max(tot.value, 1))
         self._ck(self.lib.omc_gpu_fetch_columns(self.h, ir.ctypes.data, val.ctypes.data), "omc_gpu_fetch_columns")
         return jc, ir[:tot.value], val[:tot.value]
@@ -454,6 +459,25 @@ class GpuTransport:
         assert len(uid) == 128
         preload_nccl()
         self._ck(self.lib.omc_gpu_comm_init(self.h, int(rank), int(world), uid), "omc_gpu_comm_init")
+
+    def comm_gather_columns(self, nbeamlets: int, mine: dict):
+        """{beamlet: (rows, values)} of this rank -> (jc, ir, val) of the complete matrix on every rank (collective)."""
+        cnt = np.zeros(nbeamlets)
+        for b, (r, _) in mine.items():
+            cnt[b] = len(r)
+        cnt = self.comm_sum(cnt)
+        jc = np.zeros(nbeamlets + 1, dtype=np.int64)
+        jc[1:] = np.cumsum(cnt.astype(np.int64))
+        flag = np.zeros(nbeamlets, dtype=np.uint8)
+        flag[list(mine)] = 1
+        order = sorted(mine)
+        ir_m = np.ascontiguousarray(np.concatenate([mine[b][0] for b in order]) if order else np.zeros(0), dtype=np.int64)
+        val_m = np.ascontiguousarray(np.concatenate([mine[b][1] for b in order]) if order else np.zeros(0), dtype=np.float64)
+        tot = int(jc[-1])
+        ir = np.zeros(max(tot, 1), dtype=np.int64); val = np.zeros(max(tot, 1))
+        self._ck(self.lib.omc_gpu_comm_gather_columns(self.h, int(nbeamlets), jc.ctypes.data, flag.ctypes.data, ir_m.ctypes.data,
+                                                      val_m.ctypes.data, ir.ctypes.data, val.ctypes.data), "omc_gpu_comm_gather_columns")
+        return jc, ir[:tot], val[:tot]
 
     def comm_sum(self, values) -> np.ndarray:
         v = np.ascontiguousarray(values, dtype=np.float64).copy()

@@ -1358,6 +1358,34 @@ int omc_gpu_comm_sum(omc_gpu_handle h, double *values, int n) {
     return 0;
 }
 
+// Sparse columns of the beamlets this rank computed -> the complete matrix on every rank, in beamlet order (what the
+// reference's loop builds column by column, omc_matrad.c:1416-1477).  jc[nb_total + 1] = global column starts (from the
+// per-beamlet counts, summed over the ranks with omc_gpu_comm_sum); mine[b] != 0 marks this rank's beamlets, whose rows and
+// values are passed concatenated in beamlet order.  One all-reduce of zero-padded arrays over NVLink (rows travel as exact
+// doubles): the matrix is a few tens of MB, the exchange is noise next to the transport.
+int omc_gpu_comm_gather_columns(omc_gpu_handle h, int nb_total, const long long *jc, const unsigned char *mine, const long long *ir_mine,
+                                const double *val_mine, long long *ir_out, double *val_out) {
+    if (!h || !jc || !mine || !ir_out || !val_out || nb_total < 1) return 2;
+    const long long total = jc[nb_total];
+    if (total <= 0) return 0;
+    if (2 * total > 2147483647LL) return fail(h, "omc_gpu_comm_gather_columns: more than 2^30 non-zeros");
+    std::vector<double> buf((size_t)2 * total, 0.0);           // [rows as doubles | values]
+    long long at = 0;
+    for (int b = 0; b < nb_total; b++) {
+        if (!mine[b]) continue;
+        const long long n = jc[b + 1] - jc[b];
+        for (long long k = 0; k < n; k++) {
+            buf[(size_t)(jc[b] + k)] = (double)ir_mine[at + k];
+            buf[(size_t)(total + jc[b] + k)] = val_mine[at + k];
+        }
+        at += n;
+    }
+    const int rc = omc_gpu_comm_sum(h, buf.data(), (int)(2 * total));
+    if (rc) return rc;
+    for (long long k = 0; k < total; k++) { ir_out[k] = (long long)buf[(size_t)k]; val_out[k] = buf[(size_t)(total + k)]; }
+    return 0;
+}
+
 int omc_gpu_abi_sizeof(int what) {
     switch (what) {
         case 0: return (int)sizeof(omc_media_tables);

@@ -15,17 +15,6 @@ namespace omc {
 
 constexpr float RMf = (float)OMC_RM;
 
-// EXPERIMENT (default off, not yet measured): the azimuth of selectAzimuthalAngle() (src/ompmc.c:101-122) drawn directly as
-// (cos, sin)(2 pi u) instead of the reference's box rejection -- same uniform distribution, no retry loop (the loop runs at 11 of 32
-// lanes in the condensed-history kernel and costs a Philox block per retry round), one random word per angle instead of two.
-#ifndef OMC_AZIMUTH_SINCOS
-#define OMC_AZIMUTH_SINCOS 0
-#endif
-// 1: condensed-history step with the packed three-block draw plan, one trial loop for both polar angles and sincos azimuths
-#ifndef OMC_CH_PACKED
-#define OMC_CH_PACKED 0
-#endif
-
 __device__ __forceinline__ float nextf(Rng &g) {           // 24-bit lattice in [0,1), like RANMAR's
     if (g.pos >= 4u) g.refill();
     const uint32_t w = g.pos == 0u ? g.b0 : (g.pos == 1u ? g.b1 : (g.pos == 2u ? g.b2 : g.b3));
@@ -306,7 +295,11 @@ static __device__ __noinline__ double msdist_f(const DevProblem &P, Rng &g, cons
 // 16-bit halves of two words; the dead interpolation draw of mscat (Q1) is not generated.
 //   block G0 = {sprob pass 0, sprob pass 1, eta of msdist, rfict of the caller's sigma-ratio test}
 //   block G1 = {ms i|j rounding, spin i|j rounding, first (u, r) pair}
-//   further (u, r) pairs two per block; both azimuths from one block {x1, y1, x2, y2} per round
+//   block G2 = {second (u, r) pair, azimuth 1, azimuth 2}          -> three blocks for the common step (was ~5)
+//   further (u, r) pairs, only after a rejection, two per block
+// The azimuths are (cos, sin)(2 pi u) instead of selectAzimuthalAngle()'s box rejection (:101-122): same uniform distribution,
+// no retry loop (it ran at 11 of 32 lanes and cost a block per round).  Measured on B200 (prostate6mv, 4e7-history call):
+// box-rejection azimuths 1.106e8, sincos 1.155e8, packed plan + one trial loop for both polar angles 1.205e8 histories/s.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float u24(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
 __device__ __forceinline__ float u16lo(uint32_t w) { return (float)(w & 0xffffu) * (1.0f / 65536.0f); }
@@ -384,24 +377,11 @@ __device__ __forceinline__ void sscat_b(const DevProblem &P, Rng &g, int imed, i
     }
     cost = 1.0f - x;
     sint = sqrtf(x * (2.0f - x));
-#if OMC_AZIMUTH_SINCOS
-    {
+    {   // selectAzimuthalAngle() :101-122 draws a uniform azimuth by box rejection; (cos, sin)(2 pi u) is the same distribution
         uint32_t wu, wr;
         ps.next(g, wu, wr);
         __sincosf(6.2831853f * u24(wu), &sphi, &cphi);
     }
-#else
-    for (;;) {
-        uint32_t wu, wr;
-        ps.next(g, wu, wr);
-        const float xx = 2.0f * u24(wu) - 1.0f, y = u24(wr), x2 = xx * xx, y2 = y * y, r2 = x2 + y2;
-        if (r2 <= 1.0f && r2 > 0.0f) {
-            const float ir2 = frcp(r2);
-            cphi = (x2 - y2) * ir2; sphi = 2.0f * xx * y * ir2;
-            break;
-        }
-    }
-#endif
 }
 
 __device__ __forceinline__ double msdist_b(const DevProblem &P, Rng &g, const Part &p, int imed, int qel, double rhof_d, double de_d,
@@ -468,7 +448,6 @@ __device__ __forceinline__ double msdist_b(const DevProblem &P, Rng &g, const Pa
     const MsEntryF *tab = P.ms_f + (mi * OMC_MS_NQ + mj) * OMC_MS_NU;
     const float *row = spin_row(P, imed, qel, elke, beta2, xi, u16lo(g1.y), u16hi(g1.y));
 
-#if OMC_CH_PACKED
     // Packed draw plan (see the header comment of this section): G2 = {second (u, r) pair, azimuth 1, azimuth 2} is always drawn,
     // so a step whose two polar angles are both accepted at their first trial -- the common case -- costs three blocks in all.
     // The two polar angles are sampled by ONE loop over trials (trial t serves whichever pass the lane is at), not by one
@@ -564,100 +543,6 @@ __device__ __forceinline__ double msdist_b(const DevProblem &P, Rng &g, const Pa
     float cphi1, sphi1, cphi2, sphi2;
     __sincosf(6.2831853f * u24(g2.z), &sphi1, &cphi1);
     __sincosf(6.2831853f * u24(g2.w), &sphi2, &cphi2);
-#else
-    PairSrc ps;
-    ps.a0 = g1.z; ps.a1 = g1.w; ps.have = 1; ps.nb = 2;
-    float w1 = 1.0f, sint1 = 0.0f, w2 = 1.0f, sint2 = 0.0f;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; pass++) {
-        const float sprob = u24(pass ? g0.y : g0.x);
-        float c = 1.0f, sv = 0.0f;
-        // regime of mscat(): 0 no scattering (or Q7), 1 single scattering, 2 table, 3 plural scattering (lambda <= 1)
-        int regime = 2;
-        if (lambda <= 13.8f) {
-            if (sprob < explambda) regime = 0;
-            else if (sprob < (1.0f + lambda) * explambda) regime = 1;
-            else if (lambda <= 1.0f) regime = 3;
-        } else if (!(lambda <= 1.0E5f)) {
-            regime = 0;
-        }
-        if (regime == 1 || regime == 2) {
-            float x;
-            for (;;) {
-                uint32_t wu, wr;
-                ps.next(g, wu, wr);
-                const float u = u24(wu);
-                if (regime == 1) {
-                    x = fdiv(2.0f * chia2 * u, 1.0f - u + chia2);
-                } else {
-                    float ak = u * 31.0f;
-                    int k = (int)ak;
-                    ak -= (float)k;
-                    const float4 t0 = __ldg(reinterpret_cast<const float4 *>(tab + k));   // {ums, wms, ims, fms}
-                    if (ak > t0.y) k = __float_as_int(t0.z);
-                    const float um = __ldg(&tab[k].ums);
-                    x = fdiv(omega2 * um, 1.0f + 0.5f * omega2 - um);
-                    if (x > 1.99999f) x = 1.99999f;
-                }
-                if (!(u24(wr) > spin_rej_row(row, x))) break;
-            }
-            c = 1.0f - x;
-            sv = sqrtf(x * (2.0f - x));
-        } else if (regime == 3) {                              // :3652-3682, rare in a condensed-history step
-            int icount = 0;
-            float wprob = explambda, wsum = explambda;
-            do {
-                icount += 1;
-                if (icount > 20) break;
-                wprob = wprob * lambda / (float)icount;
-                wsum = wsum + wprob;
-                float x;
-                for (;;) {
-                    uint32_t wu, wr;
-                    ps.next(g, wu, wr);
-                    const float u = u24(wu);
-                    x = fdiv(2.0f * chia2 * u, 1.0f - u + chia2);
-                    if (!(u24(wr) > spin_rej_row(row, x))) break;
-                }
-                const float cosz = 1.0f - x;
-                float sinz = x * (2.0f - x);
-                if (sinz > 1.0E-20f) {
-                    sinz = sqrtf(sinz);
-                    uint32_t wu, wr;
-                    ps.next(g, wu, wr);
-                    const float phi = u24(wu) * 6.2831853f;
-                    c = c * cosz - sv * sinz * __cosf(phi);
-                    sv = sqrtf(fmaxf(0.0f, (1.0f - c) * (1.0f + c)));
-                }
-            } while (wsum <= sprob);
-        }
-        if (pass == 0) { w1 = c; sint1 = sv; } else { w2 = c; sint2 = sv; }
-    }
-    // both azimuths, selectAzimuthalAngle() :101-122, from one block per round
-    float cphi1 = 1.0f, sphi1 = 0.0f, cphi2 = 1.0f, sphi2 = 0.0f;
-#if OMC_AZIMUTH_SINCOS
-    {
-        const uint4 ba = g.block();
-        __sincosf(6.2831853f * u24(ba.x), &sphi1, &cphi1);
-        __sincosf(6.2831853f * u24(ba.y), &sphi2, &cphi2);
-    }
-#else
-    {
-        bool ok1 = false, ok2 = false;
-        do {
-            const uint4 ba = g.block();
-            if (!ok1) {
-                const float x = 2.0f * u24(ba.x) - 1.0f, y = u24(ba.y), x2 = x * x, y2 = y * y, r2 = x2 + y2;
-                if (r2 <= 1.0f && r2 > 0.0f) { const float ir2 = frcp(r2); cphi1 = (x2 - y2) * ir2; sphi1 = 2.0f * x * y * ir2; ok1 = true; }
-            }
-            if (!ok2) {
-                const float x = 2.0f * u24(ba.z) - 1.0f, y = u24(ba.w), x2 = x * x, y2 = y * y, r2 = x2 + y2;
-                if (r2 <= 1.0f && r2 > 0.0f) { const float ir2 = frcp(r2); cphi2 = (x2 - y2) * ir2; sphi2 = 2.0f * x * y * ir2; ok2 = true; }
-            }
-        } while (!(ok1 && ok2));
-    }
-#endif
-#endif
     const float u2 = sint2 * cphi2, v2 = sint2 * sphi2;
     float u2p = w1 * u2 + sint1 * w2;
     float us = u2p * cphi1 - v2 * sphi1, vs = u2p * sphi1 + v2 * cphi1, ws = w1 * w2 - sint1 * u2;

@@ -46,15 +46,16 @@
 #define OMC_WARP_AGGREGATE_DOSE 0
 #endif
 // minimum resident blocks per SM asked of ptxas for each kernel (register cap 65536 / (128 * n)); measured on
-// B200: (5,6,6,6) 4.93e7 hist/s, (4,4,3,4) 4.30e7, (8,6,5,8) 4.90e7 -- latency hiding needs >= 20 warps/SM
+// B200, v3 kernels: (5,6,6,6) 4.93e7 hist/s, (4,4,3,4) 4.30e7, (8,6,5,8) 4.90e7 -- latency hiding needs >= 20 warps/SM;
+// round-2 kernels (slim records, packed draw plan): (5,5,5,6) 1.243e8, (6,6,6,6) 1.303e8 (80 registers everywhere)
 #ifndef OMC_MB_MISC
-#define OMC_MB_MISC 5
+#define OMC_MB_MISC 6
 #endif
 #ifndef OMC_MB_ESIZE
-#define OMC_MB_ESIZE 5
+#define OMC_MB_ESIZE 6
 #endif
 #ifndef OMC_MB_ECH
-#define OMC_MB_ECH 5
+#define OMC_MB_ECH 6
 #endif
 #ifndef OMC_MB_EBCA
 #define OMC_MB_EBCA 6
@@ -1045,8 +1046,12 @@ __global__ void advance_kernel(const __grid_constant__ DevProblem P, WaveCtl *c)
     c->n_p[par].v = 0; c->n_e[par].v = 0; c->n_ip[par].v = 0; c->n_ie[par].v = 0; c->n_ch.v = 0; c->n_bca.v = 0;
     const unsigned live = c->n_p[nxt].v + c->n_e[nxt].v + c->n_ip[nxt].v + c->n_ie[nxt].v;
     const unsigned long long left = c->hist_end - c->hist_next;
-    // photon splitting multiplies the particles a history puts into the queues (nsplit charged secondaries per flight)
-    const unsigned room = ((live < c->target) ? c->target - live : 0u) / (unsigned)(P.nsplit > 1 ? P.nsplit : 1);
+    // photon splitting multiplies the particles a history puts into the queues: a photon record in flight is a ray that will
+    // still release up to nsplit interaction sites over its next waves, so it counts as nsplit particles when the next
+    // injection is sized (counting it as one let the population overshoot the queue capacity at nsplit = 20)
+    const unsigned ns = (unsigned)(P.nsplit > 1 ? P.nsplit : 1);
+    const unsigned long long load = (unsigned long long)live + (unsigned long long)(ns - 1u) * c->n_p[nxt].v;
+    const unsigned room = (unsigned)(((load < c->target) ? c->target - load : 0ull) / ns);
     c->n_src = (unsigned)(left < (unsigned long long)room ? left : (unsigned long long)room);
     c->live = live;
     if (c->has_old) {                                          // nothing of the previous batch was met in this wave: it is complete
@@ -1111,7 +1116,9 @@ __global__ void rearm_kernel(WaveCtl *c, unsigned long long first, unsigned long
     c->old_done = c->has_old ? 0u : 1u;
     c->old_seen.v = 0;
     c->old_last = c->live;                                     // (not counted yet: the first wave of the new batch will)
-    const unsigned room = ((c->live < c->target) ? c->target - c->live : 0u) / (nsplit > 1u ? nsplit : 1u);
+    const unsigned ns = nsplit > 1u ? nsplit : 1u;                // (a split ray in flight counts as nsplit particles, see advance_kernel)
+    const unsigned long long load = (unsigned long long)c->live + (unsigned long long)(ns - 1u) * c->n_p[c->parity].v;
+    const unsigned room = (unsigned)(((load < c->target) ? c->target - load : 0ull) / ns);
     c->n_src = (unsigned)(nhist < (unsigned long long)room ? nhist : (unsigned long long)room);
 }
 void launch_rearm(WaveCtl *ctl, unsigned long long first, unsigned long long nhist, unsigned nsplit, cudaStream_t s) {

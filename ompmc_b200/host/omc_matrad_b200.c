@@ -13,6 +13,8 @@
  *
  * usage: omc_matrad_b200 -p problem.blob -n nHistories -b nbatch -t relDoseThreshold -o out_stem [-g beamlets per pass, default 64] [-d device]
  *        [-r rank -w world]   (one process per GPU: this rank's groups of consecutive beamlets only, columns of the others left empty)
+ *        [-G ngpu]            (ONE process over ngpu GPUs of the node, or OMC_GPUS: omc_gpu_multi_run_beamlets() deals whole passes to the
+ *                              devices and gathers the column slices in beamlet order -- the complete matrix in one file)
  * There is no CPU transport here: without a CUDA device the program exits with the library's error.
  */
 #include <math.h>
@@ -35,7 +37,7 @@ static uint64_t count_of(const blob *b, const char *name) { return blob_find(b, 
 int main(int argc, char **argv) {
     const char *pfile = NULL, *ncase = "100000", *nbatch_s = "10", *stem = "omc_matrad_b200", *seeds = "97 33";
     double rel = 1.0e-3;
-    int device = 0, group = 0, rank = 0, world = 1;
+    int device = 0, group = 0, rank = 0, world = 1, ngpu = getenv("OMC_GPUS") ? atoi(getenv("OMC_GPUS")) : 1;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "-p") && i + 1 < argc) pfile = argv[++i];
         else if (!strcmp(argv[i], "-n") && i + 1 < argc) ncase = argv[++i];
@@ -47,8 +49,9 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[i], "-r") && i + 1 < argc) rank = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-w") && i + 1 < argc) world = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-s") && i + 1 < argc) seeds = argv[++i];
+        else if (!strcmp(argv[i], "-G") && i + 1 < argc) ngpu = atoi(argv[++i]);
         else {
-            printf("usage: %s -p problem.blob -n nHistories -b nbatch -t relDoseThreshold -o out_stem [-g beamlets per pass, default 64] [-d device] [-r rank -w world]\n",
+            printf("usage: %s -p problem.blob -n nHistories -b nbatch -t relDoseThreshold -o out_stem [-g beamlets per pass, default 64] [-d device] [-r rank -w world | -G ngpu]\n",
                    argv[0]);
             return 2;
         }
@@ -78,6 +81,50 @@ int main(int argc, char **argv) {
 
     printf("Number of voxels on each direction (X,Y,Z) : (%d, %d, %d)\n", g.isize, g.jsize, g.ksize);
     printf("Number of beamlets : %d (%d beams)\n", nbeamlets, s.nbeams);
+    if (ngpu > 1) {                                             /* the whole node behind one handle */
+        omc_gpu_multi m;
+        if (omc_gpu_multi_create(&m, ngpu, NULL)) { printf("No %d CUDA devices / no NCCL: this program has no CPU transport path.\n", ngpu); return EXIT_FAILURE; }
+#define MD(call) do { if (call) { printf("%s: %s\n", #call, omc_gpu_multi_last_error(m)); exit(EXIT_FAILURE); } } while (0)
+        MD(omc_gpu_multi_set_media(m, &t)); MD(omc_gpu_multi_set_geometry(m, &g)); MD(omc_gpu_multi_set_source_matrad(m, &s));
+        MD(omc_gpu_multi_set_vrt(m, nsplit));
+        int ixx = 97, jxx = 33;
+        sscanf(seeds, "%d %d", &ixx, &jxx);
+        MD(omc_gpu_multi_set_seed(m, ixx, jxx)); MD(omc_gpu_multi_set_option(m, "kernel", OMC_KERNEL_WAVEFRONT));
+        int nhist = atoi(ncase), nbatch = atoi(nbatch_s);
+        if (nbatch <= 0) { printf("Can not find 'nbatch' key on input file.\n"); return EXIT_FAILURE; }
+        if (nhist / nbatch == 0) nhist = nbatch;
+        nhist = (nhist / nbatch) * nbatch;
+        printf("Total number of particle histories: %d\nGPUs: %d\n", nhist, omc_gpu_multi_size(m));
+        if (group < 1) {
+            long long capn = (long long)(OMC_BEAMLET_GRID_BUDGET / ((double)(nvox + 1) * 4.0));
+            group = capn > OMC_BEAMLETS_PER_PASS ? OMC_BEAMLETS_PER_PASS : (capn < 1 ? 1 : (int)capn);
+        }
+        long long *jc = calloc((size_t)nbeamlets + 1, sizeof(long long)), tot = 0;
+        const double t0 = now_s();
+        printf("Execution time up to this point : %8.2f seconds\n", t0 - tbegin);
+        MD(omc_gpu_multi_run_beamlets(m, 0, nhist, nbatch, 0, nbeamlets, group, rel, dens, jc, &tot));
+        long long *ir = malloc((size_t)(tot ? tot : 1) * sizeof(long long));
+        double *val = malloc((size_t)(tot ? tot : 1) * sizeof(double));
+        MD(omc_gpu_multi_fetch_columns(m, ir, val));
+        const double t1 = now_s();
+        printf("Simulation finished\n");
+        printf("Beamlets computed: %d on %d GPUs, histories per second: %.4g, non-zeros: %lld (%.3f %% of the matrix)\n", nbeamlets,
+               omc_gpu_multi_size(m), (double)nbeamlets * nhist / (t1 - t0), tot, 100.0 * (double)tot / ((double)nvox * nbeamlets));
+        char *fn = malloc(strlen(stem) + 16);
+        sprintf(fn, "%s.csc", stem);
+        FILE *fp = fopen(fn, "wb");
+        if (!fp) { printf("Unable to open file: %s\n", fn); return EXIT_FAILURE; }
+        const long long hdr[3] = {nvox, nbeamlets, tot};
+        fwrite("OMCCSC1", 1, 8, fp);
+        fwrite(hdr, sizeof(long long), 3, fp);
+        fwrite(jc, sizeof(long long), (size_t)nbeamlets + 1, fp);
+        fwrite(ir, sizeof(long long), (size_t)tot, fp);
+        fwrite(val, sizeof(double), (size_t)tot, fp);
+        fclose(fp);
+        omc_gpu_multi_destroy(m);
+        printf("Total execution time : %8.5f seconds\n", now_s() - tbegin);
+        return EXIT_SUCCESS;
+    }
     if (omc_gpu_create(&gpu, device)) { printf("No CUDA device: this program has no CPU transport path.\n"); return EXIT_FAILURE; }
     if (omc_gpu_set_media(gpu, &t)) die("omc_gpu_set_media");
     if (omc_gpu_set_geometry(gpu, &g)) die("omc_gpu_set_geometry");

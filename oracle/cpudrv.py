@@ -176,7 +176,8 @@ class RefTransport(_CpuTransport):
     prefix = "ref_"
 
     def __init__(self, omp: bool = False, matrad: bool = False):
-        super().__init__(os.path.join(HERE, "_ref", "libompmc_ref_matrad.so") if matrad else ref_lib_path(omp))
+        super().__init__(os.path.join(HERE, "_ref", "libompmc_ref_matrad_omp.so" if omp else "libompmc_ref_matrad.so") if matrad
+                         else ref_lib_path(omp))
         if not matrad:
             self.lib.ref_init_from_inp.argtypes = [C.c_char_p]
             self.lib.ref_dump_problem.argtypes = [C.c_char_p]
@@ -222,5 +223,5 @@ def oracle_lib_path() -> str:
 
 def have_ref(omp: bool = False, matrad: bool = False) -> bool:
     if matrad:
-        return os.path.exists(os.path.join(HERE, "_ref", "libompmc_ref_matrad.so"))
+        return os.path.exists(os.path.join(HERE, "_ref", "libompmc_ref_matrad_omp.so" if omp else "libompmc_ref_matrad.so"))
     return os.path.exists(ref_lib_path(omp))

@@ -8,12 +8,14 @@ from ompmc_b200.api import GpuTransport
 from tests import sampler_cases as S
 prob, ph = S.problem_tissue4()
 g = GpuTransport(0); g.load_problem(prob); g.set_option('kernel', 1)
-N = 50000
+N = 20000
+out = {}
 for v in range(3):
-    out = {}
     for gi, grp in enumerate(S.MSDIST_GROUPS):
         inp = S.msdist_inputs(grp, N, False)
-        print('variant', v, 'group', gi, flush=True)
-        out[f'g{gi}'] = g.test_samplers(S.MSDIST | (v << 8), inp, first_history=10_000_000 * (gi + 1)).astype(np.float64)
-    np.savez_compressed(f'gpurun_out/msdist_diag_v{v}.npz', **out)
-    print('saved variant', v, flush=True)
+        o = g.test_samplers(S.MSDIST | (v << 8), inp, first_history=10_000_000 * (gi + 1))
+        out[f'v{v}_g{gi}_f'] = o[:, :6].astype(np.float32)
+        out[f'v{v}_g{gi}_omc'] = 1.0 - o[:, 6]
+    print('variant', v, 'done', flush=True)
+np.savez_compressed('gpurun_out/msdist_diag.npz', **out)
+print('saved')

@@ -7,7 +7,7 @@ from ompmc_b200.api import GpuTransport
 tag = sys.argv[1]
 n = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 20000000
 opts = dict(a.split('=') for a in sys.argv[2:] if '=' in a)
-prob, ph, w = bench.build_workload(opts.pop('workload', 'prostate6mv'))
+prob, ph, w = bench.build_workload(opts.pop('workload', 'prostate6mv'), int(opts.pop('nsplit', 1)))
 g = GpuTransport(0)
 g.load_problem(prob)
 g.set_option('kernel', 1)

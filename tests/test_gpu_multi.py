@@ -116,3 +116,43 @@ def test_reference_user_code_on_two_gpus(gpu):
     np.testing.assert_allclose(dose2, dose1, rtol=5e-4, atol=5e-4 * dose1.max())
     sel = dose1 > 0.2 * dose1.max()
     np.testing.assert_allclose(unc2[sel], unc1[sel], rtol=0.05, atol=2e-3)
+
+
+@pytest.mark.parametrize("n", [1, 2, 4])
+def test_beamlet_passes_over_devices_gathered_in_beamlet_order(gpu, n):
+    """omc_gpu_multi_run_beamlets(): passes of consecutive beamlets dealt to the devices, column slices gathered in beamlet order
+    (omc_matrad.c:1416-1477) -- against one device running the same passes; beamlet b owns the same history ids either way, so
+    the columns agree to the summation order of the fp32 dose atomics (entries at the threshold may fall on either side)."""
+    if ndev() < n:
+        pytest.skip(f"needs {n} GPUs")
+    from ompmc_b200.api import MultiGpuTransport
+    from tests.test_matrad import matrad_problem
+    prob, ph, nb = matrad_problem(nbix=(2, 2), angles=(0.0, 120.0, 250.0))          # 12 beamlets
+    gpu.load_problem(prob)
+    gpu.set_option("kernel", 1)
+    nh = 100000
+    ref = [gpu.run_beamlets(b0 * nh, nh, 4, b0, 4, 0.05, ph.med_densities) for b0 in (0, 4, 8)]
+    m = MultiGpuTransport(ndev=n)
+    try:
+        m.load_problem(prob)
+        m.set_option("kernel", 1)
+        jc, ir, val = m.run_beamlets(0, nh, 4, 0, nb, 0.05, ph.med_densities, per_pass=4)
+    finally:
+        m.close()
+    assert len(jc) == nb + 1 and jc[0] == 0 and jc[-1] == len(ir) == len(val)
+    for b in range(nb):
+        rjc, rir, rval = ref[b // 4]
+        k = b % 4
+        d0 = np.zeros(ph.nvox); d0[rir[rjc[k]:rjc[k + 1]]] = rval[rjc[k]:rjc[k + 1]]
+        r1 = ir[jc[b]:jc[b + 1]]
+        assert (np.diff(r1) > 0).all()
+        d1 = np.zeros(ph.nvox); d1[r1] = val[jc[b]:jc[b + 1]]
+        np.testing.assert_allclose(d1, d0, rtol=2e-3, atol=0.051 * d0.max())
+        assert abs(d1.sum() - d0.sum()) < 2e-3 * d0.sum()
+
+
+def test_column_gather_of_one_rank_is_the_identity(gpu):
+    mine = {0: (np.array([1, 5, 9], dtype=np.int64), np.array([0.5, 0.25, 1.0])), 1: (np.zeros(0, dtype=np.int64), np.zeros(0)),
+            2: (np.array([7], dtype=np.int64), np.array([2.0]))}
+    jc, ir, val = gpu.comm_gather_columns(3, mine)
+    assert jc.tolist() == [0, 3, 3, 4] and ir.tolist() == [1, 5, 9, 7] and val.tolist() == [0.5, 0.25, 1.0, 2.0]

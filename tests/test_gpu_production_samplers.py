@@ -34,9 +34,28 @@ def pair(gpu, oracle_lib):
     return gpu, oracle_lib, prob, ph
 
 
+def ks_distance_tol(a, b, rel=2e-4, abs_=2e-7):
+    """Two-sample Kolmogorov-Smirnov distance that forgives a shift of the abscissa by rel * |x| + abs_.
+
+    The step observables are NOT continuous: mscat() takes the tabulated u values without interpolation, u = 0 among
+    them, and the no-scattering amplitude puts 1-30 % of the mass exactly on the axis, so the distributions carry atoms of a few
+    per cent.  The production samplers place those atoms where fp32 arithmetic puts them (relative 1e-6 from the oracle's fp64
+    positions); a plain KS distance then reports the MASS of the atom, whatever the sample size.  Here F_a is compared with F_b
+    evaluated a tolerance to the right (and vice versa), which is the plain statistic for continuous parts and ignores shifts
+    far below any physical scale (angles, path lengths: 2e-4 relative)."""
+    a, b = np.sort(a), np.sort(b)
+    x = np.concatenate([a, b])
+    tol = rel * np.abs(x) + abs_
+    d1 = np.searchsorted(a, x - tol, side="right") / len(a) - np.searchsorted(b, x + tol, side="right") / len(b)
+    d2 = np.searchsorted(b, x - tol, side="right") / len(b) - np.searchsorted(a, x + tol, side="right") / len(a)
+    return max(float(d1.max()), float(d2.max()), 0.0)
+
+
 def ks_same(a, b, what):
-    r = stats.ks_2samp(a, b)
-    assert r.pvalue > KS_P, f"{what}: KS D = {r.statistic:.5f}, p = {r.pvalue:.2e}"
+    d = ks_distance_tol(a, b)
+    n = len(a) * len(b) / (len(a) + len(b))
+    pvalue = float(stats.kstwobign.sf(d * np.sqrt(n)))
+    assert pvalue > KS_P, f"{what}: KS D = {d:.5f}, p = {pvalue:.2e}"
     se = np.sqrt(a.var() / len(a) + b.var() / len(b))
     if se > 0:
         assert abs(a.mean() - b.mean()) < 4.5 * se + 1e-7 * abs(b.mean()), f"{what}: means {a.mean():.8g} vs {b.mean():.8g} (se {se:.3g})"

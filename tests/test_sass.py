@@ -49,9 +49,11 @@ def test_dose_scoring_instructions(sass):
 
 
 def test_step_kernels_keep_their_state_in_registers(sass):
-    # the condensed-history / boundary-crossing / step-size kernels: a handful of local accesses at most (call frames of the rare
-    # out-of-line samplers); the first version of the CH kernel executed 12.6 % LDL + STL
-    for k, limit in (("ech", 16), ("ebca", 24), ("esize", 4)):
+    # the condensed-history / boundary-crossing / step-size kernels: a few dozen STATIC local accesses at most (call frames of the
+    # rare out-of-line samplers, plus the spills of the 80-register cap = 6 resident blocks per SM, measured 1.303e8 against
+    # 1.243e8 histories/s with 96 registers and no spills); the first version of the CH kernel EXECUTED 12.6 % LDL + STL
+    #  because its generator state lived in local memory
+    for k, limit in (("ech", 48), ("ebca", 24), ("esize", 24)):
         n = count(sass[k], r"\b(LDL|STL)\b")
         total = count(sass[k], r"/\*[0-9a-f]{4}\*/")
         assert n <= limit, f"{k}: {n} local-memory instructions of {total}"
