@@ -306,7 +306,7 @@ static int wave_run(omc_gpu_handle h, bool start, long long first, long long nhi
             c.target = target;
             c.hist_next = (unsigned long long)first; c.hist_end = (unsigned long long)(first + nhist);
             c.hist_split = (unsigned long long)first; c.grid_new = (unsigned)g_new; c.old_done = 1;
-            const unsigned first_room = target / (unsigned)(P.nsplit > 1 ? P.nsplit : 1);   // (splitting multiplies the population)
+            const unsigned first_room = target / (unsigned)(P.nsplit > 1 ? 16 * P.nsplit : 1);  // (splitting: see advance_kernel)
             c.n_src = (unsigned)((unsigned long long)nhist < (unsigned long long)first_room ? nhist : first_room);
             CK(cudaMemcpyAsync(h->ctl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
             CK(cudaStreamSynchronize(h->stream));               // (c is a stack object)

@@ -373,6 +373,9 @@ __device__ __forceinline__ int woodcock_flight(const DevProblem &P, Rng &g, Part
     return 0;
 }
 
+// (Measured and rejected, round 2: LANE REFILL -- a warp owning 256 photons, a lane taking the next one as soon as its flight
+// ends, two tentative collisions per Philox block.  The flight loop then runs with nearly all lanes instead of 10 of 32, but the
+// per-lane record loads are scattered and the loop carries the whole photon state: 1.105e8 against 1.299e8 histories/s.)
 __device__ void photon_chunk_wc(const DevProblem &P, const WaveArgs &A, const BatchSel &BS, int par, unsigned i, unsigned n, Tally &t) {
     if (i >= n) return;
     WaveCtl *ctl = A.ctl;
@@ -1049,9 +1052,14 @@ __global__ void advance_kernel(const __grid_constant__ DevProblem P, WaveCtl *c)
     // photon splitting multiplies the particles a history puts into the queues: a photon record in flight is a ray that will
     // still release up to nsplit interaction sites over its next waves, so it counts as nsplit particles when the next
     // injection is sized (counting it as one let the population overshoot the queue capacity at nsplit = 20)
-    const unsigned ns = (unsigned)(P.nsplit > 1 ? P.nsplit : 1);
+    // (2 nsplit: the surviving scattered photon is split again at its next flight, so a history at nsplit = 20 has ~40 charged
+    // particles alive within a few waves of each other -- measured 836 electron steps per history against 42 without splitting)
+    const unsigned ns = (unsigned)(P.nsplit > 1 ? 2 * P.nsplit : 1);
     const unsigned long long load = (unsigned long long)live + (unsigned long long)(ns - 1u) * c->n_p[nxt].v;
-    const unsigned room = (unsigned)(((load < c->target) ? c->target - load : 0ull) / ns);
+    // With splitting the secondaries of an injection show up over the following waves (and their number per history depends on
+    // the cut-offs: delta rays down to AE), so the pool is filled by an eighth of the estimated room per wave -- the controller
+    // sees what a history really costs before it has committed the whole pool (the queues hold twice the target).
+    const unsigned room = (unsigned)(((load < c->target) ? c->target - load : 0ull) / ns) / (P.nsplit > 1 ? 8u : 1u);
     c->n_src = (unsigned)(left < (unsigned long long)room ? left : (unsigned long long)room);
     c->live = live;
     if (c->has_old) {                                          // nothing of the previous batch was met in this wave: it is complete
@@ -1116,9 +1124,9 @@ __global__ void rearm_kernel(WaveCtl *c, unsigned long long first, unsigned long
     c->old_done = c->has_old ? 0u : 1u;
     c->old_seen.v = 0;
     c->old_last = c->live;                                     // (not counted yet: the first wave of the new batch will)
-    const unsigned ns = nsplit > 1u ? nsplit : 1u;                // (a split ray in flight counts as nsplit particles, see advance_kernel)
+    const unsigned ns = nsplit > 1u ? 2u * nsplit : 1u;           // (a split ray in flight counts as 2 nsplit particles, see advance_kernel)
     const unsigned long long load = (unsigned long long)c->live + (unsigned long long)(ns - 1u) * c->n_p[c->parity].v;
-    const unsigned room = (unsigned)(((load < c->target) ? c->target - load : 0ull) / ns);
+    const unsigned room = (unsigned)(((load < c->target) ? c->target - load : 0ull) / ns) / (nsplit > 1u ? 8u : 1u);
     c->n_src = (unsigned)(nhist < (unsigned long long)room ? nhist : (unsigned long long)room);
 }
 void launch_rearm(WaveCtl *ctl, unsigned long long first, unsigned long long nhist, unsigned nsplit, cudaStream_t s) {

@@ -78,7 +78,12 @@ def msdist_observables(out, tustep_ref=None, d0=(0.0, 0.0, 1.0)):
     cost = dirf @ d0
     dperp = dirf - np.outer(cost, d0)
     # correlation between the lateral displacement and the lateral direction (PRESTA-II couples them)
-    corr = np.einsum("ij,ij->i", perp, dperp) / np.maximum(rperp * np.linalg.norm(dperp, axis=1), 1e-300)
+    # (undefined for a step without deflection -- 1 to 30 % of the steps sit exactly on the axis: there both vectors are rounding
+    # noise, 1e-17 in fp64 and 1e-8 in fp32, and their "angle" is garbage; such steps get corr = 0 on both sides)
+    dn = np.linalg.norm(dperp, axis=1)
+    scale_len = np.median(ustep) if tustep_ref is None else tustep_ref
+    ok = (rperp > 1e-6 * scale_len) & (dn > 1e-6)
+    corr = np.where(ok, np.einsum("ij,ij->i", perp, dperp) / np.where(ok, rperp * dn, 1.0), 0.0)
     # azimuth of the final direction around d0
     e1 = np.cross(d0, [1.0, 0.0, 0.0]) if abs(d0[0]) < 0.9 else np.cross(d0, [0.0, 1.0, 0.0])
     e1 /= np.linalg.norm(e1)
