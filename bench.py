@@ -124,6 +124,28 @@ class quiet_stdout:
         return False
 
 
+class stdout_to_stderr:
+    """NCCL prints its version banner on stdout when the first communicator comes up (NCCL_DEBUG=VERSION on the GPU boxes);
+    stdout must carry exactly one JSON line, so the communicator set-up runs with fd 1 pointing at stderr."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -222,7 +244,9 @@ def run_matrad(args) -> None:
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+            dist.barrier()
     if rank == 0:
         builder.build()
     if world > 1:
@@ -236,9 +260,11 @@ def run_matrad(args) -> None:
     tr.load_problem(prob)
     tr.set_option("kernel", 1)
     if world > 1:
-        box = [tr.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        tr.comm_init(rank, world, box[0])
+        with stdout_to_stderr():
+            box = [tr.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            tr.comm_init(rank, world, box[0])
+            tr.comm_sum([1.0])
     stream = torch.cuda.ExternalStream(tr.stream_ptr(), device=f"cuda:{local}")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
 
@@ -398,7 +424,9 @@ def main() -> None:
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+            dist.barrier()
     if rank == 0:
         builder.build()
     if world > 1:
@@ -417,9 +445,11 @@ def main() -> None:
         # NCCL inside the library (include/ompmc_b200.h, multi-GPU): rank 0 makes the unique id, torch.distributed only carries
         # its 128 bytes to the other ranks.  From here on run_batch() shards every batch over the ranks and sums the completed
         # batch grids on a side stream before accumEndep(); torch takes no part in the data path.
-        box = [tr.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        tr.comm_init(rank, world, box[0])
+        with stdout_to_stderr():
+            box = [tr.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            tr.comm_init(rank, world, box[0])
+            tr.comm_sum([1.0])                                # first collective of the library's communicator
 
     def barrier():
         torch.cuda.synchronize()

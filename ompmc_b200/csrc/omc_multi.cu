@@ -61,18 +61,22 @@ int omc_gpu_multi_create(omc_gpu_multi *out, int ndev, const int *device_ids) {
     }
     if (ndev <= 0) ndev = have;
     omc_gpu_multi m = new omc_gpu_multi_ctx();
-    for (int i = 0; i < ndev; i++) {
-        const int d = device_ids ? device_ids[i] : i;
-        omc_gpu_handle h = nullptr;
-        const int rc = omc_gpu_create(&h, d);
-        if (rc) {
-            for (omc_gpu_handle x : m->h) omc_gpu_destroy(x);
+    m->h.assign((size_t)ndev, nullptr);
+    for (int i = 0; i < ndev; i++) m->dev.push_back(device_ids ? device_ids[i] : i);
+    // every device's context comes up on its own thread (a CUDA context costs ~0.5 s; eight in a row was most of the start-up)
+    std::vector<int> crc((size_t)ndev, 0);
+    {
+        std::vector<std::thread> th;
+        for (int i = 0; i < ndev; i++) th.emplace_back([&, i] { crc[(size_t)i] = omc_gpu_create(&m->h[(size_t)i], m->dev[(size_t)i]); });
+        for (auto &t : th) t.join();
+    }
+    for (int i = 0; i < ndev; i++)
+        if (crc[(size_t)i]) {
+            const int rc = crc[(size_t)i];
+            for (omc_gpu_handle x : m->h) if (x) omc_gpu_destroy(x);
             delete m;
             return rc;
         }
-        m->h.push_back(h);
-        m->dev.push_back(d);
-    }
     if (ndev > 1) {
         char id[128];
         int rc = omc_gpu_comm_unique_id(id);
@@ -201,6 +205,7 @@ int omc_gpu_multi_run_beamlets(omc_gpu_multi m, long long first_history, int nhi
     if (nb < 1) { m->err = "beamlet range out of bounds"; return 2; }
     if (per_pass <= 0) per_pass = OMC_BEAMLETS_PER_PASS;
     const int ndev = (int)m->h.size();
+    if ((nb + per_pass - 1) / per_pass < ndev) per_pass = (nb + ndev - 1) / ndev;     // fewer passes than devices: smaller passes, every device busy
     const int npass = (nb + per_pass - 1) / per_pass;
     struct Pass {
         std::vector<long long> jc, ir;
