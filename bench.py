@@ -46,10 +46,12 @@ WORKLOADS = {
 }
 
 
-def build_workload(name: str, nsplit: int = 1):
+def build_workload(name: str, nsplit: int = 1, voxel_mm: float = 0.0):
     w = WORKLOADS[name]
     media = P.load_blob(P.golden(w["media"]))
     ph = w["phantom"]()
+    if voxel_mm > 0.0:                       # BASELINE config 5: the same phantom resampled to 2 mm / 1 mm voxels (any ratio)
+        ph = P.resample_phantom_to(ph, (voxel_mm / 10.0,) * 3)
     prob = P.build_problem(media, ph, ecut=w["ecut"], pcut=0.010, collimator=w["coll"], ssd=w["ssd"],
                            cdfinv=(media["cdfinv1_" + w["spectrum"]], media["cdfinv2_" + w["spectrum"]]), nsplit=nsplit)
     return prob, ph, w
@@ -185,7 +187,7 @@ def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    prob, ph, w = build_workload(args.workload, args.nsplit)
+    prob, ph, w = build_workload(args.workload, args.nsplit, args.voxel_mm)
     with quiet_stdout():
         tr, kind = cpu_reference_transport(prob)
         cores = tr.num_threads()
@@ -432,7 +434,7 @@ def main() -> None:
     if world > 1:
         dist.barrier()
 
-    prob, ph, w = build_workload(args.workload, args.nsplit)
+    prob, ph, w = build_workload(args.workload, args.nsplit, args.voxel_mm)
     tr = GpuTransport(local)
     tr.load_problem(prob)
     kernel = DEFAULT_KERNEL if args.kernel < 0 else args.kernel
@@ -548,7 +550,8 @@ def main() -> None:
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "mixed f64/f32" if kernel == 1 else "f64",
             "data": "synthetic",
-            "config": {"workload": args.workload, "desc": w["desc"], "hist_per_step_per_gpu": H, "nsplit": args.nsplit,
+            "config": {"workload": args.workload, "desc": w["desc"] + (f", resampled to {args.voxel_mm:g} mm voxels ({ph.isize}x{ph.jsize}x{ph.ksize})" if args.voxel_mm > 0 else ""),
+                       "hist_per_step_per_gpu": H, "nsplit": args.nsplit,
                        "kernel": {0: "lockstep", 1: "wavefront"}[kernel], "rng": "philox4x32-10 per history",
                        "l2": "256 MiB buffer written between steps (L2 flush)", "spinms": "synthetic (McKinley-Feshbach)"},
             "clocks": clocks, "gpu_launches": int(cnt["kernel_launches"]),

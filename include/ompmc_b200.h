@@ -261,6 +261,9 @@ int omc_gpu_get_history_records(omc_gpu_handle h, omc_history_record *out, long 
  * batch at once and waits for them only when that dose grid is needed again, one batch later.  Every rank must issue the
  * same sequence of batch calls.  score.ensrc and the work counters stay per rank (omc_gpu_comm_sum adds host values up).
  */
+/* the sharding rule itself (pure host arithmetic, no device needed): rank r of `world` owns [*lo, *lo + *count) of the batch
+ * [first, first + nhist); contiguous slices in rank order, the first nhist % world ranks get one history more */
+int omc_gpu_shard_range(long long first, long long nhist, int rank, int world, long long *lo, long long *count);
 int omc_gpu_comm_unique_id(char *id128 /* [128] out */);
 int omc_gpu_comm_init(omc_gpu_handle h, int rank, int world, const char *id128);   /* world == 1: drops the communicator */
 int omc_gpu_comm_rank(omc_gpu_handle h);

@@ -94,7 +94,7 @@ EXPORTS = ["omc_gpu_create", "omc_gpu_destroy", "omc_gpu_last_error", "omc_gpu_s
            "omc_gpu_get_batch_grid", "omc_gpu_accumulate_results", "omc_gpu_write_3ddose", "omc_gpu_test_format", "omc_gpu_run_beamlets", "omc_gpu_fetch_columns", "omc_gpu_reset_tallies", "omc_gpu_device_ptrs", "omc_gpu_stream", "omc_gpu_get_counters",
            "omc_gpu_get_history_records", "omc_gpu_test_geometry", "omc_gpu_test_rng", "omc_gpu_test_particles", "omc_gpu_test_samplers",
            "omc_gpu_abi_sizeof",
-           "omc_gpu_comm_unique_id", "omc_gpu_comm_init", "omc_gpu_comm_rank", "omc_gpu_comm_size", "omc_gpu_comm_sum", "omc_gpu_comm_gather_columns",
+           "omc_gpu_shard_range", "omc_gpu_comm_unique_id", "omc_gpu_comm_init", "omc_gpu_comm_rank", "omc_gpu_comm_size", "omc_gpu_comm_sum", "omc_gpu_comm_gather_columns",
            "omc_gpu_multi_create", "omc_gpu_multi_destroy", "omc_gpu_multi_size", "omc_gpu_multi_device", "omc_gpu_multi_last_error",
            "omc_gpu_multi_set_media", "omc_gpu_multi_set_geometry", "omc_gpu_multi_set_source_dosxyz", "omc_gpu_multi_set_source_matrad",
            "omc_gpu_multi_set_vrt", "omc_gpu_multi_set_seed", "omc_gpu_multi_set_option", "omc_gpu_multi_reset_tallies",
@@ -143,6 +143,7 @@ def load_library() -> C.CDLL:
     lib.omc_gpu_test_particles.argtypes = [H, C.c_int] + [C.c_void_p] * 5 + [C.c_longlong, C.c_void_p]
     lib.omc_gpu_test_samplers.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]
     # multi-GPU
+    lib.omc_gpu_shard_range.argtypes = [C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     lib.omc_gpu_comm_unique_id.argtypes = [C.c_char_p]
     lib.omc_gpu_comm_init.argtypes = [H, C.c_int, C.c_int, C.c_char_p]
     lib.omc_gpu_comm_rank.argtypes = [H]; lib.omc_gpu_comm_size.argtypes = [H]
@@ -171,6 +172,15 @@ def load_library() -> C.CDLL:
                                                C.c_void_p, C.POINTER(C.c_longlong)]
     lib.omc_gpu_multi_fetch_columns.argtypes = [H, C.c_void_p, C.c_void_p]
     return lib
+
+
+def shard_range_c(first: int, n: int, rank: int, world: int) -> tuple[int, int]:
+    """omc_gpu_shard_range(): the slice of a batch that omc_gpu_run_batch() gives rank `rank` (host arithmetic, no GPU needed)."""
+    lib = load_library()
+    lo, cnt = C.c_longlong(0), C.c_longlong(0)
+    if lib.omc_gpu_shard_range(int(first), int(n), int(rank), int(world), C.byref(lo), C.byref(cnt)) != 0:
+        raise ValueError("omc_gpu_shard_range: bad arguments")
+    return lo.value, cnt.value
 
 
 _NCCL_PRELOADED = False

@@ -949,9 +949,7 @@ int omc_gpu_accum_batch(omc_gpu_handle h) {
 // this rank's contiguous slice of the batch's history ids (the first nhist % world ranks get one more)
 static void shard_range(omc_gpu_handle h, long long &first, long long &nhist) {
     if (h->world <= 1) return;
-    const long long base = nhist / h->world, extra = nhist % h->world, r = h->rank;
-    first += r * base + (r < extra ? r : extra);
-    nhist = base + (r < extra ? 1 : 0);
+    omc_gpu_shard_range(first, nhist, h->rank, h->world, &first, &nhist);
 }
 
 int omc_gpu_start_batch(omc_gpu_handle h, long long first, long long nhist, int ibeamlet) {
@@ -1304,6 +1302,14 @@ int omc_gpu_device_ptrs(omc_gpu_handle h, void **endep, void **accum, void **acc
 }
 
 // ---- multi-GPU: NCCL inside the library ------------------------------------------------------------------------
+int omc_gpu_shard_range(long long first, long long nhist, int rank, int world, long long *lo, long long *count) {
+    if (!lo || !count || world < 1 || rank < 0 || rank >= world || nhist < 0) return 2;
+    const long long base = nhist / world, extra = nhist % world, r = rank;
+    *lo = first + r * base + (r < extra ? r : extra);
+    *count = base + (r < extra ? 1 : 0);
+    return 0;
+}
+
 int omc_gpu_comm_unique_id(char *id128) {
     if (!id128) return 2;
     NcclApi &N = nccl_api();

@@ -23,7 +23,10 @@ rank, world = dist.get_rank(), dist.get_world_size()
 prob, ph, cfg = golden_problem("golden_water700_6MV")
 tr = OracleTransport(); tr.set_num_threads(1); tr.load_problem(prob); tr.set_rng("philox")
 tr.accum_batch = tr.accum_endep
+from ompmc_b200.api import shard_range_c
 for ib in range(3):
+    # (the slice the C library would take on this rank: same rule)
+    assert shard_range_c(100 + ib * 401, 401, rank, world) == odist.shard_range(100 + ib * 401, 401, rank, world)
     odist.run_batch_sharded(tr, 100 + ib * 401, 401, rank, world, odist.allreduce_cpu_grid)
 a, a2, _ = tr.get_accum()
 np.savez(%(out)r + f".{rank}.npz", a=a, a2=a2)
@@ -32,9 +35,13 @@ dist.destroy_process_group()
 
 
 def test_shard_range_partitions():
-    for n in (0, 1, 7, 401, 1000):
+    """The Python rule and the rule INSIDE the library (omc_gpu_shard_range: what omc_gpu_run_batch() applies on every rank of an
+    NCCL communicator, include/ompmc_b200.h) are the same partition."""
+    from ompmc_b200.api import shard_range_c
+    for n in (0, 1, 7, 401, 1000, 67108864 * 8 + 5):
         for world in (1, 2, 3, 8):
             parts = [odist.shard_range(50, n, r, world) for r in range(world)]
+            assert parts == [shard_range_c(50, n, r, world) for r in range(world)]
             assert sum(p[1] for p in parts) == n
             pos = 50
             for lo, cnt in parts:
