@@ -57,3 +57,20 @@ def test_no_cpu_fallback(lib):
 def test_sm100a_cubin_present():
     out = __import__("subprocess").run(["cuobjdump", "-lelf", api.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_multi_gpu_entry_points_without_a_device():
+    """The multi-GPU layer has no CPU path either: omc_gpu_multi_create() reports "no CUDA device" (rc 3) where there is none;
+    the host-only helpers work without one (sharding rule, NCCL id when an NCCL is installed)."""
+    import ctypes as C
+    import torch
+    lib = api.load_library()
+    lo, cnt = C.c_longlong(0), C.c_longlong(0)
+    assert lib.omc_gpu_shard_range(100, 10, 3, 4, C.byref(lo), C.byref(cnt)) == 0 and (lo.value, cnt.value) == (108, 2)
+    assert lib.omc_gpu_shard_range(0, 10, 4, 4, C.byref(lo), C.byref(cnt)) != 0          # rank out of range
+    assert lib.omc_gpu_shard_range(0, -1, 0, 1, C.byref(lo), C.byref(cnt)) != 0
+    if not torch.cuda.is_available():
+        m = C.c_void_p()
+        assert lib.omc_gpu_multi_create(C.byref(m), 2, None) == 3 and not m.value
+        with __import__("pytest").raises(api.OmcGpuError):
+            api.MultiGpuTransport(ndev=2)
