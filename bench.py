@@ -439,6 +439,9 @@ def main() -> None:
     tr.load_problem(prob)
     kernel = DEFAULT_KERNEL if args.kernel < 0 else args.kernel
     tr.set_option("kernel", kernel)
+    for kv in filter(None, os.environ.get("OMC_BENCH_OPTIONS", "").split(",")):      # tuning experiments: "check_every=16,pool_size=..."
+        k, v = kv.split("=")
+        tr.set_option(k.strip(), int(v))
     tr.reset_tallies()
     H = args.hist_per_step
     stream = torch.cuda.ExternalStream(tr.stream_ptr(), device=f"cuda:{local}")
@@ -534,7 +537,11 @@ def main() -> None:
     e2e_s = time.perf_counter() - t0
 
     times = torch.tensor([ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=f"cuda:{local}")
+    per_rank = None
     if world > 1:
+        parts = [torch.zeros_like(times) for _ in range(world)]
+        dist.all_gather(parts, times)
+        per_rank = [round(float(p[0]) / args.steps, 2) for p in parts]      # each rank's own ms per step (skew diagnostic)
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms, e2e_ms, kernel_ms = (float(x) for x in times.tolist())
     if rank != 0:
@@ -557,6 +564,7 @@ def main() -> None:
             "clocks": clocks, "gpu_launches": int(cnt["kernel_launches"]),
             "e2e": {"value": e2e_value, "unit": "histories/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "host_buffers": "pinned" if pinned else "pageable"},
+            "ms_per_step_per_rank": per_rank,
             "sigma_rel_above_half_dmax": sigma, "histories_scored": int(nb * H * world),
             "time_to_1pct_sigma_s": (nb * H * world / value) * (sigma / 0.01) ** 2}
 

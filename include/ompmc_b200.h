@@ -176,16 +176,13 @@ int omc_gpu_run_histories(omc_gpu_handle h, long long first_history, long long n
 /* accumEndep() (omc_dosxyz.c:696-717): accum += e, accum2 += e*e, zero the batch grid. */
 int omc_gpu_accum_batch(omc_gpu_handle h);
 /* One iteration of the reference batch loop ({initHistory(); shower();} x nhist + accumEndep(), omc_dosxyz.c:1237-1263).
- * With the wavefront kernels consecutive calls are PIPELINED over a ring of four dose grids: the call returns when all its
- * histories have been started; its tail keeps running underneath the next calls (each particle scores into the grid of the
- * batch its history id belongs to), and a batch is accumulated -- in batch order -- by the first later call that finds it
- * gone from the particle queues, or by whichever call reads results (get_tallies, accumulate_results, synchronize...).  At
- * most four batches are alive together: a fifth start first waits for the oldest one.  (A batch of any size pays ~20 ms of
- * ramp-up and of tail for its longest particle lineages; with the ring that latency is hidden behind the next batches, so
- * batches of 1e6 histories run at the rate of large ones instead of one batch per tail.)
+ * With the wavefront kernels consecutive calls are PIPELINED: the call returns when all its histories have been
+ * started and every earlier batch is complete and accumulated; the tail of this batch keeps running underneath the
+ * next call (each particle scores into the grid of the batch its history id belongs to) and is completed and
+ * accumulated by the next call or by whichever call reads results (get_tallies, accumulate_results, synchronize...).
  * Pipelining attributes a particle in flight to its batch by its history id, so consecutive batches overlap only when
  * their id ranges ASCEND (first_history >= the end of the previous range, as in the reference's loop, where batch k owns
- * ids [k * nperbatch, (k+1) * nperbatch)); a call whose range starts lower first completes the batches in flight. */
+ * ids [k * nperbatch, (k+1) * nperbatch)); a call whose range starts lower first completes the batch in flight. */
 int omc_gpu_run_batch(omc_gpu_handle h, long long first_history, long long nhist, int ibeamlet);
 /* The same pipelining with the accumulation left to the caller (multi-GPU: the batch grid is summed over ranks before
  * accumEndep() squares it): start_batch returns when its histories are all started and the PREVIOUS started batch is

@@ -8,7 +8,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <deque>
 #include <string>
 #include <vector>
 
@@ -72,19 +71,19 @@ struct omc_gpu_ctx {
     nccl_comm_t comm = nullptr;
     int rank = 0, world = 1;
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_done[WAVE_RING] = {}, ev_free[WAVE_RING] = {};
-    bool grid_wait[WAVE_RING] = {};              // grid g may be scored into only after ev_free[g]
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    bool grid_wait[2] = {false, false};          // grid g may be scored into only after ev_free[g]
     unsigned long long reduces = 0;
     unsigned pool_target = 1u << 23;   // particles kept in flight (B200: 2 Mi 1.03e8, 4 Mi 1.07e8, 8 Mi 1.09e8 histories/s)
     unsigned pool_cap = 0, pool_cap_opt = 0;
-    int max_cross = 16, check_every = 32;   // waves per CUDA graph / status check (B200, 4e7-history call: 8 -> 1.271e8, 16 -> 1.290e8, 32 -> 1.309e8)
+    int max_cross = 16, check_every = 16;
     int photon_tracking = 1;      // 0: voxel-to-voxel march as in photon(); 1: Woodcock flight when nsplit == 1
     int max_virtual = 8;          // Woodcock: tentative collisions per photon per wave
     unsigned long long waves = 0;
     int trace = 0, use_graph = 1, overlap = 1, source_kind = 0, lookahead = 1;
     cudaStream_t stream2 = nullptr, stream3 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork3 = nullptr, ev_join3 = nullptr;
-    unsigned drain_threshold = 4096;     // measured on B200 (round-2 kernels, 4e7-history call): 4 Ki 1.314e8, 8 Ki 1.290e8, 32 Ki 1.253e8 histories/s
+    unsigned drain_threshold = 8192;     // measured on B200 (16M-history call): 0 -> 183.5 ms, 8 Ki -> 182.4, 32 Ki -> 193.9, 128 Ki -> 223.5
     // omc_gpu_accumulate_results scratch
     double *res_dens = nullptr, *res_dose = nullptr, *res_unc = nullptr;
     int res_nreg = -1;
@@ -96,12 +95,10 @@ struct omc_gpu_ctx {
     unsigned *fmt_nfb_dev = nullptr, *fmt_nfb_host = nullptr;
     cudaEvent_t fmt_ev[2] = {nullptr, nullptr};
     // batch pipelining (see wave_run)
-    std::deque<int> inflight;      // dose grids of the batches alive in the queues, oldest first (the last one = being injected)
-    unsigned done_seen[WAVE_RING] = {};   // WaveCtl::done_cnt as of the batches retired so far
-    int last_ibeamlet = -1;
+    int run_grid = -1, last_ibeamlet = -1;
     long long hist_hi = 0;         // end of the history-id range of the batch in flight (pipelining needs ascending ids)
     std::vector<int> done_q;
-    bool auto_acc[WAVE_RING] = {};
+    bool auto_acc[2] = {false, false};
     bool pipeline_next = false, pipeline_auto = false;   // how the next omc_gpu_run_histories() body is to run (set by the callers below)
     // multi-beamlet pass (omc_gpu_run_beamlets)
     float *mb_grid = nullptr;
@@ -204,19 +201,17 @@ static int alloc_estep_queue(omc_gpu_handle h, EStepQueue &q, unsigned cap) {
 }
 
 // ---- wavefront driver -------------------------------------------------------------------------------
-// WAVE_RING dose grids (fp32 chunk grid + fp64 batch grid each) let the NEXT batches start while the tails of the previous
-// ones are still in the queues: a particle scores into the grid of the batch its history id belongs to (WaveCtl::bstart /
-// bgrid).  h->inflight = grids of the batches alive in the queues, oldest first; h->done_q = grids of completed batches that
-// have not been accumulated yet (accumEndep), oldest first.  Batches are RETIRED IN ORDER (a newer batch whose particles
-// are gone first waits for the older one), so every rank of a multi-GPU run issues its collectives in the same order.
-
+// Two dose grids (fp32 chunk grid + fp64 batch grid each) let the NEXT batch start while the tail of the previous
+// one is still in the queues: a particle scores into the grid of the batch its history id belongs to
+// (WaveCtl::hist_split).  h->run_grid = grid of the batch whose tail is in flight (-1: queues empty);
+// h->done_q = grids of completed batches that have not been accumulated yet (accumEndep), oldest first.
 static int wave_prepare(omc_gpu_handle h) {
     const unsigned target = h->pool_target;
     const unsigned cap = h->pool_cap_opt ? h->pool_cap_opt : 2u * target + 65536u;
     if (h->pool_cap != cap) {
         free_pool(h->wave_bufs);
         h->pool_cap = 0;
-        h->inflight.clear();                      // (whatever was in flight is gone with the queues)
+        h->run_grid = -1;                         // (whatever was in flight is gone with the queues)
         for (int i = 0; i < 2; i++) {
             if (alloc_queue(h, h->wq.p[i], cap, true)) return 1;
             if (alloc_queue(h, h->wq.e[i], cap, false, true)) return 1;
@@ -289,49 +284,42 @@ static void drop_graph(omc_gpu_handle h) {
     h->graph_key.clear();
 }
 
-enum { WAVE_START = 0, WAVE_FINISH = 1, WAVE_RETIRE = 2 };
-
-// mode WAVE_START : inject histories [first, first+nhist) into dose grid g_new and return once all of them are started
-//                   (`lockstep`: and every earlier batch has left the queues -- the contract of omc_gpu_start_batch(), whose
-//                   caller drives the collectives and needs every rank to complete batch k-1 inside its start of batch k);
-//                   the tail of the new batch stays in the queues.
-//      WAVE_FINISH: run what is in the queues to the end (waves, then drain_kernel for the last few particles).
-//      WAVE_RETIRE: run waves until the OLDEST alive batch has left the queues (a full ring before a start).
-static int wave_run(omc_gpu_handle h, int mode, long long first, long long nhist, int ibeamlet, int g_new, bool lockstep = false) {
+// start == true : inject histories [first, first+nhist) and return once all of them are started AND the previous batch
+//                 (if its tail was in flight) is complete; the tail of the new batch stays in the queues.
+// start == false: run what is in the queues to the end (waves, then drain_kernel for the last few particles).
+// g_new: dose grid of the new batch (start only).
+static int wave_run(omc_gpu_handle h, bool start, long long first, long long nhist, int ibeamlet, int g_new) {
     DevProblem &P = h->P;
-    const bool start = (mode == WAVE_START);
-    if (!start && h->inflight.empty()) return 0;
+    if (!start && h->run_grid < 0) return 0;
     if (wave_prepare(h)) return 1;
     const unsigned target = h->pool_target;
+    int g_old = h->run_grid;
+    bool old_pending = false;
     if (start) {
         if (h->grid_wait[g_new]) {                              // the grid's previous batch is still being summed over the ranks
             CK(cudaStreamWaitEvent(h->stream, h->ev_free[g_new], 0));
             h->grid_wait[g_new] = false;
         }
-        if (h->inflight.empty()) {                              // empty pipeline
+        if (g_old < 0) {                                        // empty pipeline
             WaveCtl c;
             memset(&c, 0, sizeof c);
             c.target = target;
             c.hist_next = (unsigned long long)first; c.hist_end = (unsigned long long)(first + nhist);
-            c.nalive = 1; c.bgrid[0] = (unsigned)g_new;
-            for (int j = 0; j < WAVE_RING; j++) c.bstart[j] = ~0ull;
-            c.bstart[0] = (unsigned long long)first;
-            for (int g = 0; g < WAVE_RING; g++) h->done_seen[g] = 0;
+            c.hist_split = (unsigned long long)first; c.grid_new = (unsigned)g_new; c.old_done = 1;
             const unsigned first_room = target / (unsigned)(P.nsplit > 1 ? 16 * P.nsplit : 1);  // (splitting: see advance_kernel)
             c.n_src = (unsigned)((unsigned long long)nhist < (unsigned long long)first_room ? nhist : first_room);
             CK(cudaMemcpyAsync(h->ctl, &c, sizeof c, cudaMemcpyHostToDevice, h->stream));
             CK(cudaStreamSynchronize(h->stream));               // (c is a stack object)
-        } else {                                                // older batches still in flight: the new one joins the ring
-            if ((int)h->inflight.size() >= WAVE_RING) return fail(h, "internal: dose-grid ring is full");
-            launch_rearm(h->ctl, (unsigned long long)first, (unsigned long long)nhist, (unsigned)P.nsplit, (unsigned)g_new, h->stream);
+        } else {                                                // previous batch still in flight: it becomes "old"
+            launch_rearm(h->ctl, (unsigned long long)first, (unsigned long long)nhist, (unsigned)P.nsplit, h->stream);
+            old_pending = true;
         }
-        h->inflight.push_back(g_new);
         h->last_ibeamlet = ibeamlet;
     } else {
         const WaveCtl &s0 = *h->ctl_host;                       // status as of the last check
         if (s0.live == 0 && s0.n_src == 0 && s0.hist_next >= s0.hist_end) {
-            while (!h->inflight.empty()) { grid_done(h, h->inflight.front()); h->inflight.pop_front(); }
-            return 0;
+            h->run_grid = -1;
+            return grid_done(h, g_old);
         }
         ibeamlet = h->last_ibeamlet;
     }
@@ -393,11 +381,13 @@ static int wave_run(omc_gpu_handle h, int mode, long long first, long long nhist
         // histories per batch a hot voxel's fp32 sum reaches 1e4 MeV, where one ulp is 1e-3 MeV.  (Between two graph launches
         // nothing else runs on this stream, so the plain read-add-zero of flush_kernel is safe.)
         if (!h->mb_active && ((wave / every) & 3ull) == 3ull) {
-            for (int g : h->inflight) {
-                const size_t off = (size_t)g * P.nreg;
-                launch_flush(P.endep32 + off, P.endep + off, P.nreg, h->stream);
-                h->launches += 1;
-            }
+            const int gs[2] = {start ? g_new : g_old, (start && old_pending) ? g_old : -1};
+            for (int g : gs)
+                if (g >= 0) {
+                    const size_t off = (size_t)g * P.nreg;
+                    launch_flush(P.endep32 + off, P.endep + off, P.nreg, h->stream);
+                    h->launches += 1;
+                }
         }
         CK(cudaMemcpyAsync(h->ctl_slot[slot], h->ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaEventRecord(h->ev_stat[slot], h->stream));
@@ -409,9 +399,9 @@ static int wave_run(omc_gpu_handle h, int mode, long long first, long long nhist
             examined += 1;
             const WaveCtl &s = *h->ctl_host;
             if (h->trace)
-                fprintf(stderr, "wave %llu live %u n_src %u P %u E %u IP %u IE %u hist_next %llu alive %u oldest seen %u\n",
+                fprintf(stderr, "wave %llu live %u n_src %u P %u E %u IP %u IE %u hist_next %llu old %u/%u\n",
                         (unsigned long long)examined * every, s.live, s.n_src, s.n_p[s.parity].v, s.n_e[s.parity].v, s.n_ip[s.parity].v,
-                        s.n_ie[s.parity].v, s.hist_next, s.nalive, s.last_seen0);
+                        s.n_ie[s.parity].v, s.hist_next, s.has_old, s.old_done);
             if (s.overflow.v) {
                 h->err = "particle queue overflow on the device: increase option pool_size";
                 rc = 7; done = true;
@@ -419,23 +409,18 @@ static int wave_run(omc_gpu_handle h, int mode, long long first, long long nhist
             }
             const bool exhausted = s.hist_next >= s.hist_end && s.n_src == 0;
             ahead = h->lookahead && !exhausted && s.live > (1u << 18);
-            // retire, in order, the older batches that have left the queues: their grids are final
-            while (h->inflight.size() > 1 && s.done_cnt[h->inflight.front()] != h->done_seen[h->inflight.front()]) {
-                const int g = h->inflight.front();
-                h->done_seen[g] = s.done_cnt[g];
-                grid_done(h, g);
-                h->inflight.pop_front();
+            if (old_pending && s.old_done) {                    // the previous batch has left the queues: its grid is final
+                grid_done(h, g_old);
+                old_pending = false;
             }
-            if (mode == WAVE_START) {
-                // the tail of the new batch stays in flight: a batch is never completed by the call that starts it
-                if (exhausted && (!lockstep || h->inflight.size() == 1)) done = true;
-            } else if (mode == WAVE_RETIRE) {
-                if ((int)h->inflight.size() < WAVE_RING || (exhausted && s.live == 0)) done = true;
+            if (start) {
+                // the tail of the new batch stays in flight; it is always the NEXT call that completes a batch, even an
+                // already empty one, so that every rank of a multi-GPU run sees the same sequence of completed batches
+                if (exhausted && !old_pending) done = true;
             } else if (exhausted && s.live == 0) {
                 done = true;
-            } else if (exhausted && s.live <= h->drain_threshold && P.nsplit == 1 && !h->mb_active && h->inflight.size() == 1) {
-                // (split photons in flight cannot be handed over; the drain scores into ONE fp64 grid: not per beamlet, and
-                // only once a single batch is left)
+            } else if (exhausted && s.live <= h->drain_threshold && P.nsplit == 1 && !h->mb_active) {
+                // (split photons in flight cannot be handed over; the drain scores into ONE fp64 grid, not per beamlet)
                 drained = true; done = true;
             }
         }
@@ -445,12 +430,9 @@ static int wave_run(omc_gpu_handle h, int mode, long long first, long long nhist
         CK(cudaEventSynchronize(h->ev_stat[(issued - 1) & 1]));
         memcpy(h->ctl_host, h->ctl_slot[(issued - 1) & 1], sizeof(WaveCtl));
     }
-    if (rc) { h->inflight.clear(); return rc; }
-    if (mode != WAVE_FINISH) {
-        if (h->ctl_host->live == 0 && h->ctl_host->n_src == 0 && h->ctl_host->hist_next >= h->ctl_host->hist_end && mode == WAVE_RETIRE) {
-            while (!h->inflight.empty()) { grid_done(h, h->inflight.front()); h->inflight.pop_front(); }
-            memset(h->ctl_host, 0, sizeof(WaveCtl));
-        }
+    if (rc) { h->run_grid = -1; return rc; }
+    if (start) {
+        h->run_grid = g_new;
         CK(cudaGetLastError());
         return 0;
     }
@@ -459,20 +441,19 @@ static int wave_run(omc_gpu_handle h, int mode, long long first, long long nhist
         const int par = (int)h->ctl_host->parity;
         const PartQueue *q[4] = {&h->wq.p[par], &h->wq.e[par], &h->wq.ip[par], &h->wq.ie[par]};
         const unsigned *cnt[4] = {&h->ctl->n_p[par].v, &h->ctl->n_e[par].v, &h->ctl->n_ip[par].v, &h->ctl->n_ie[par].v};
-        if (drain_queues(h, q, cnt, h->inflight.front())) return 1;
+        if (drain_queues(h, q, cnt, g_old)) return 1;
     }
     memset(h->ctl_host, 0, sizeof(WaveCtl));                    // (status: nothing alive any more)
-    while (!h->inflight.empty()) { grid_done(h, h->inflight.front()); h->inflight.pop_front(); }
+    h->run_grid = -1;
+    grid_done(h, g_old);
     CK(cudaGetLastError());
     return 0;
 }
 
 static int free_grid(omc_gpu_handle h) {
-    for (int g = 0; g < WAVE_RING; g++) {
-        bool busy = in_done(h, g);
-        for (int f : h->inflight) busy |= (f == g);
-        if (!busy) return g;
-    }
+    const int busy = h->run_grid;
+    for (int g = 0; g < 2; g++)
+        if (g != busy && !in_done(h, g)) return g;
     return -1;
 }
 
@@ -511,8 +492,8 @@ static int accum_done(omc_gpu_handle h, bool only_auto) {
 
 // complete whatever is in flight and settle the accumulations owed by omc_gpu_run_batch()
 static int flush_all(omc_gpu_handle h) {
-    if (!h->inflight.empty()) {
-        int rc = wave_run(h, WAVE_FINISH, 0, 0, -1, -1);
+    if (h->run_grid >= 0) {
+        int rc = wave_run(h, false, 0, 0, -1, -1);
         if (rc) return rc;
     }
     return accum_done(h, true);
@@ -529,28 +510,21 @@ static int run_wavefront(omc_gpu_handle h, long long first, long long nhist, int
         if (!h->done_q.empty()) { g = h->done_q.back(); h->done_q.pop_back(); }
         else g = 0;
     } else {
-        // A particle in flight is attributed to its batch by its history id (WaveCtl::bstart): a batch that re-uses or
-        // lowers ids cannot share the queues with the tails of the previous ones -- complete those first.
-        if (!h->inflight.empty() && first < h->hist_hi) {
-            int rc = wave_run(h, WAVE_FINISH, 0, 0, -1, -1);
-            if (rc) return rc;
-            if (auto_acc && (rc = accum_done(h, true))) return rc;
-        }
-        if (!auto_acc && h->done_q.size() + h->inflight.size() >= 2)   // (the caller-driven form keeps its two-batch contract)
-            return fail(h, "two batches are waiting for omc_gpu_accum_batch(): accumulate before starting another one");
-        if ((int)h->inflight.size() >= WAVE_RING || free_grid(h) < 0) {   // ring full: the oldest batch has to leave the queues first
-            int rc = wave_run(h, WAVE_RETIRE, 0, 0, -1, -1);
+        // A particle in flight is attributed to the previous or to the new batch by `history id < first` (WaveCtl::hist_split):
+        // a batch that re-uses or lowers ids cannot share the queues with the tail of the previous one -- complete that first.
+        if (h->run_grid >= 0 && first < h->hist_hi) {
+            int rc = wave_run(h, false, 0, 0, -1, -1);
             if (rc) return rc;
             if (auto_acc && (rc = accum_done(h, true))) return rc;
         }
         g = free_grid(h);
-        if (g < 0) return fail(h, "every dose grid is waiting for omc_gpu_accum_batch(): accumulate before starting another batch");
+        if (g < 0) return fail(h, "two batches are waiting for omc_gpu_accum_batch(): accumulate before starting another one");
     }
     h->auto_acc[g] = auto_acc;
-    int rc = wave_run(h, WAVE_START, first, nhist, ibeamlet, g, pipelined && !auto_acc);
+    int rc = wave_run(h, true, first, nhist, ibeamlet, g);
     if (rc) return rc;
     h->hist_hi = first + nhist;
-    if (!pipelined) rc = wave_run(h, WAVE_FINISH, 0, 0, -1, -1);
+    if (!pipelined) rc = wave_run(h, false, 0, 0, -1, -1);
     return rc;
 }
 
@@ -597,7 +571,7 @@ void omc_gpu_destroy(omc_gpu_handle h) {
     if (h->comm) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->side) {
         cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side);
-        for (int i = 0; i < WAVE_RING; i++) { cudaEventDestroy(h->ev_done[i]); cudaEventDestroy(h->ev_free[i]); }
+        for (int i = 0; i < 2; i++) { cudaEventDestroy(h->ev_done[i]); cudaEventDestroy(h->ev_free[i]); }
     }
     cudaFree(h->ctl);
     if (h->ctl_host) cudaFreeHost(h->ctl_host);
@@ -784,8 +758,8 @@ int omc_gpu_set_geometry(omc_gpu_handle h, const omc_geometry *g) {
     if (h->tally_nreg != P.nreg) {
         cudaFree(P.endep); cudaFree(P.endep32); cudaFree(h->accum); cudaFree(h->accum2);
         P.endep = nullptr; P.endep32 = nullptr; h->accum = h->accum2 = nullptr;
-        CK(cudaMalloc((void **)&P.endep, (size_t)WAVE_RING * P.nreg * sizeof(double)));      // one batch grid per ring slot (pipelining), grid g at g * nreg
-        CK(cudaMalloc((void **)&P.endep32, (size_t)WAVE_RING * P.nreg * sizeof(float)));
+        CK(cudaMalloc((void **)&P.endep, (size_t)2 * P.nreg * sizeof(double)));      // two batch grids (pipelining), grid g at g * nreg
+        CK(cudaMalloc((void **)&P.endep32, (size_t)2 * P.nreg * sizeof(float)));
         CK(cudaMalloc((void **)&h->accum, (size_t)P.nreg * sizeof(double)));
         CK(cudaMalloc((void **)&h->accum2, (size_t)P.nreg * sizeof(double)));
         h->tally_nreg = P.nreg;
@@ -959,8 +933,8 @@ int omc_gpu_run_histories(omc_gpu_handle h, long long first, long long nhist, in
 int omc_gpu_accum_batch(omc_gpu_handle h) {
     if (!h || !h->have_geom) return 2;
     CK(cudaSetDevice(h->device));
-    if (h->done_q.empty() && !h->inflight.empty()) {           // the batches that were started are still in flight: complete them
-        int rc = wave_run(h, WAVE_FINISH, 0, 0, -1, -1);
+    if (h->done_q.empty() && h->run_grid >= 0) {               // the batch that was started is still in flight: complete it
+        int rc = wave_run(h, false, 0, 0, -1, -1);
         if (rc) return rc;
     }
     if (h->done_q.empty()) {                                   // nothing was run: accumEndep() of an empty batch grid
@@ -991,7 +965,7 @@ int omc_gpu_start_batch(omc_gpu_handle h, long long first, long long nhist, int 
 int omc_gpu_finish_batches(omc_gpu_handle h) {
     if (!h || !h->have_geom) return 2;
     CK(cudaSetDevice(h->device));
-    if (!h->inflight.empty()) return wave_run(h, WAVE_FINISH, 0, 0, -1, -1);
+    if (h->run_grid >= 0) return wave_run(h, false, 0, 0, -1, -1);
     return 0;
 }
 
@@ -1237,8 +1211,8 @@ int omc_gpu_run_beamlets(omc_gpu_handle h, long long first, int nhist, int nbatc
     h->mb_active = true;
     h->mb_first = (unsigned long long)first; h->mb_per = (unsigned)nhist; h->mb_n = (unsigned)nb; h->mb_ib0 = ib0;
     h->auto_acc[0] = false;
-    rc = wave_run(h, WAVE_START, first, (long long)nhist * nb, ib0, 0);
-    if (!rc) rc = wave_run(h, WAVE_FINISH, 0, 0, -1, -1);
+    rc = wave_run(h, true, first, (long long)nhist * nb, ib0, 0);
+    if (!rc) rc = wave_run(h, false, 0, 0, -1, -1);
     h->mb_active = false;
     h->done_q.clear();                                          // (the two batch grids were not used)
     if (rc) return rc;
@@ -1298,8 +1272,8 @@ int omc_gpu_reset_tallies(omc_gpu_handle h, int which) {
     const size_t n = (size_t)h->P.nreg;
     if (h->side) CK(cudaStreamSynchronize(h->side));
     if (which == 0) {                       // everything starts over: particles still in flight are dropped with their grids
-        h->inflight.clear(); h->done_q.clear();
-        for (int g = 0; g < WAVE_RING; g++) { h->auto_acc[g] = false; h->grid_wait[g] = false; }
+        h->run_grid = -1; h->done_q.clear(); h->auto_acc[0] = h->auto_acc[1] = false;
+        h->grid_wait[0] = h->grid_wait[1] = false;
         if (h->ctl_host) memset(h->ctl_host, 0, sizeof(WaveCtl));
     } else {                                // omc_matrad.c:1482 zeroes accum_endep between beamlets: settle what is owed first
         int rc = flush_all(h);
@@ -1308,8 +1282,8 @@ int omc_gpu_reset_tallies(omc_gpu_handle h, int which) {
     CK(cudaMemsetAsync(h->accum, 0, n * sizeof(double), h->stream));
     if (which == 0) {
         CK(cudaMemsetAsync(h->accum2, 0, n * sizeof(double), h->stream));
-        CK(cudaMemsetAsync(h->P.endep, 0, WAVE_RING * n * sizeof(double), h->stream));
-        CK(cudaMemsetAsync(h->P.endep32, 0, WAVE_RING * n * sizeof(float), h->stream));
+        CK(cudaMemsetAsync(h->P.endep, 0, 2 * n * sizeof(double), h->stream));
+        CK(cudaMemsetAsync(h->P.endep32, 0, 2 * n * sizeof(float), h->stream));
         CK(cudaMemsetAsync(h->P.ensrc, 0, sizeof(double), h->stream));
         CK(cudaMemsetAsync(h->P.counters, 0, sizeof(Counters), h->stream));
         h->launches = 0;
@@ -1349,7 +1323,7 @@ int omc_gpu_comm_unique_id(char *id128) {
 int omc_gpu_comm_init(omc_gpu_handle h, int rank, int world, const char *id128) {
     if (!h || !id128) return 2;
     if (world < 1 || rank < 0 || rank >= world) return fail(h, "omc_gpu_comm_init: rank / world out of range");
-    if (!h->inflight.empty() || !h->done_q.empty()) return fail(h, "omc_gpu_comm_init: batches are in flight");
+    if (h->run_grid >= 0 || !h->done_q.empty()) return fail(h, "omc_gpu_comm_init: batches are in flight");
     CK(cudaSetDevice(h->device));
     if (h->comm) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
     h->rank = rank; h->world = world;
@@ -1362,7 +1336,7 @@ int omc_gpu_comm_init(omc_gpu_handle h, int rank, int world, const char *id128) 
     if (e) { h->comm = nullptr; h->world = 1; h->rank = 0; h->err = std::string("ncclCommInitRank: ") + N.GetErrorString(e); return 8; }
     if (!h->side) {
         CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-        for (int i = 0; i < WAVE_RING; i++) {
+        for (int i = 0; i < 2; i++) {
             CK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
         }

@@ -44,26 +44,19 @@ struct alignas(256) PadU {
     unsigned v;
 };
 
-// Dose grids = statistical batches that may be alive in the particle queues together (batch pipelining, see omc_capi.cu).
-constexpr int WAVE_RING = 4;
-
 struct WaveCtl {
     PadU n_p[2], n_e[2], n_ip[2], n_ie[2];       // queue fill counts, [parity]: cur = parity, next = parity ^ 1
     PadU n_ch, n_bca;                            // step-class queues, filled and drained inside one wave
     PadU tk[5];                                  // chunk tickets per class (misc_kernel)
     PadU overflow, drain_ticket;
-    PadU seen[WAVE_RING];                        // particles of alive batch j (0 = oldest) met by the consumers of this wave
+    PadU old_seen;                               // particles of the PREVIOUS batch met by the consumers of this wave
     unsigned n_src;                              // histories injected by the current wave
     unsigned parity, target, live, waves;
-    // Batch pipelining: up to WAVE_RING batches are alive in the queues, the newest one being injected while the tails of the
-    // older ones are still in flight.  A particle belongs to the alive batch whose id range holds its history id (ranges
-    // ascend) and scores into that batch's dose grid; the consumers count the particles of every older batch they meet, and
-    // a batch that a whole wave did not meet has left the queues (advance_kernel: done_cnt of its grid goes up by one).
-    unsigned nalive;                             // alive batches, j = 0 oldest ... nalive-1 = the one being injected
-    unsigned bgrid[WAVE_RING];                   // dose grid of alive batch j
-    unsigned done_cnt[WAVE_RING];                // per dose GRID: batches scored into it that have left the queues (monotone)
-    unsigned last_seen0;                         // stragglers of the oldest alive batch in the last wave (trace)
-    unsigned long long bstart[WAVE_RING];        // first history id of alive batch j; ~0 for j >= nalive
+    // batch pipelining: histories with id < hist_split belong to the previous batch, whose tail is still in flight
+    // while this batch is injected; they score into dose grid (grid_new ^ 1), everything else into grid_new
+    unsigned has_old, old_done, grid_new;
+    unsigned old_last;                           // old_seen of the last completed wave (how many stragglers the old batch has left)
+    unsigned long long hist_split;
     unsigned long long hist_next, hist_end;
 };
 
@@ -135,6 +128,6 @@ struct FormatFallback {
 void launch_format(int mode, const double *src, long long n, const Pow10 *tab, char *out, FormatFallback *fb, unsigned *nfb, unsigned fb_cap,
                    cudaStream_t stream);
 // start the next batch while the tail of the previous one is still in the queues (see WaveCtl::hist_split)
-void launch_rearm(WaveCtl *ctl, unsigned long long first, unsigned long long nhist, unsigned nsplit, unsigned grid, cudaStream_t s);
+void launch_rearm(WaveCtl *ctl, unsigned long long first, unsigned long long nhist, unsigned nsplit, cudaStream_t s);
 
 }  // namespace omc

@@ -158,12 +158,11 @@ struct WaveArgs {
     int mb_ib0;
 };
 
-// Which dose grid a particle scores into (batch pipelining, WaveCtl::bstart / bgrid), wave-uniform part
+// Which of the two dose grids a particle scores into (batch pipelining, WaveCtl::hist_split), wave-uniform part
 struct BatchSel {
-    unsigned long long b1, b2, b3;               // first history ids of alive batches 1..3 (~0 when not alive)
-    unsigned grids;                              // dose grids of alive batches 0..3, 8 bits each
-    unsigned nalive;
-    float *base;
+    unsigned long long split;
+    float *g_new, *g_old;
+    unsigned has_old;
     // multi-beamlet pass: one grid per beamlet, beamlet = (history id - mb_first) / mb_per
     float *mb_grid;
     unsigned long long mb_first;
@@ -171,18 +170,14 @@ struct BatchSel {
     double mb_inv;
     size_t nreg;
     __device__ __forceinline__ void init(const DevProblem &P, const WaveCtl *c, const WaveArgs &A) {
-        static_assert(WAVE_RING == 4, "BatchSel holds three boundaries");
-        nalive = c->nalive;
-        b1 = c->bstart[1]; b2 = c->bstart[2]; b3 = c->bstart[3];
-        grids = c->bgrid[0] | (c->bgrid[1] << 8) | (c->bgrid[2] << 16) | (c->bgrid[3] << 24);
-        base = P.endep32;
+        split = c->hist_split; has_old = c->has_old;
+        g_new = P.endep32 + (size_t)c->grid_new * P.nreg;
+        g_old = P.endep32 + (size_t)(c->grid_new ^ 1u) * P.nreg;
         mb_grid = A.mb_grid; mb_first = A.mb_first; mb_per = A.mb_per; nreg = (size_t)P.nreg;
         mb_inv = A.mb_per ? 1.0 / (double)A.mb_per : 0.0;
     }
-    // alive batch of a history id: 0 = oldest ... nalive - 1 = the one being injected
-    __device__ __forceinline__ int index(uint32_t h0, uint32_t h1) const {
-        const unsigned long long id = (((unsigned long long)h1) << 32) | h0;
-        return (int)(id >= b1) + (int)(id >= b2) + (int)(id >= b3);
+    __device__ __forceinline__ bool is_old(uint32_t h0, uint32_t h1) const {
+        return has_old && ((((unsigned long long)h1) << 32) | h0) < split;
     }
     // index of the beamlet that owns a history id (multi-beamlet pass)
     __device__ __forceinline__ unsigned beamlet_of(uint32_t h0, uint32_t h1) const {
@@ -192,17 +187,15 @@ struct BatchSel {
         else if ((unsigned long long)q * mb_per > x) q -= 1u;
         return q;
     }
-    __device__ __forceinline__ float *grid(int bi, uint32_t h0, uint32_t h1) const {
+    __device__ __forceinline__ float *grid(bool old, uint32_t h0, uint32_t h1) const {
         if (mb_grid != nullptr) return mb_grid + (size_t)beamlet_of(h0, h1) * nreg;
-        return base + (size_t)((grids >> (8 * bi)) & 0xffu) * nreg;
+        return old ? g_old : g_new;
     }
-    // consumers count the particles of every OLDER batch they meet (bi < 0: no particle); zero in a whole wave = that batch
-    // has left the queues.  All lanes of `mask` must call this together.
-    __device__ __forceinline__ void count(WaveCtl *c, unsigned mask, int bi) const {
-        for (unsigned j = 0; j + 1u < nalive; j++) {
-            const unsigned m = __ballot_sync(mask, bi == (int)j);
-            if (m && (threadIdx.x & 31) == __ffs(mask) - 1) atomicAdd(&c->seen[j].v, (unsigned)__popc(m));
-        }
+    // consumers count the previous batch's particles they meet; zero in a whole wave = that batch is complete
+    __device__ __forceinline__ void count(WaveCtl *c, unsigned mask, bool old) const {
+        if (!has_old) return;
+        const unsigned m = __ballot_sync(mask, old);
+        if (m && (threadIdx.x & 31) == __ffs(mask) - 1) atomicAdd(&c->old_seen.v, (unsigned)__popc(m));
     }
 };
 
@@ -238,9 +231,9 @@ __device__ void photon_chunk(const DevProblem &P, const WaveArgs &A, const Batch
     WaveCtl *ctl = A.ctl;
     Part p; Rng g; double dpmfp; int tag;
     q_load(A.Q.p[par], i, p, g, P, dpmfp, tag);
-    const int bi = BS.index(g.h0, g.h1);
-    BS.count(ctl, __activemask(), bi);
-    float *dg = BS.grid(bi, g.h0, g.h1);
+    const bool old = BS.is_old(g.h0, g.h1);
+    BS.count(ctl, __activemask(), old);
+    float *dg = BS.grid(old, g.h0, g.h1);
     RegionRec R = load_region_w(P, p.ir);
     // uniform photon splitting, :1903-1945: the record is the ray of nsplit copies of weight wt/nsplit whose
     // interaction depths are stratified (eta'_k = eta'_0 - k/nsplit); copy `isplit` is the one in flight.
@@ -396,9 +389,9 @@ __device__ void photon_chunk_wc(const DevProblem &P, const WaveArgs &A, const Ba
         const uint4 r = q.rng[i];
         g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
     }
-    const int bi = BS.index(g.h0, g.h1);
-    BS.count(ctl, __activemask(), bi);
-    float *dg = BS.grid(bi, g.h0, g.h1);
+    const bool old = BS.is_old(g.h0, g.h1);
+    BS.count(ctl, __activemask(), old);
+    float *dg = BS.grid(old, g.h0, g.h1);
     if (p.ir == 0) return;                                     // outside the phantom: howfar() discards (idisc)
     {   // cut-off test of photon() :1884 (a flight that spans several waves repeats it, harmlessly)
         double rhof; int med;
@@ -423,7 +416,7 @@ __device__ void p_interact_chunk(const DevProblem &P, const WaveArgs &A, const B
         const uint4 r = A.Q.ip[par].rng[i];
         g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
     }
-    BS.count(ctl, __activemask(), BS.index(g.h0, g.h1));
+    BS.count(ctl, __activemask(), BS.is_old(g.h0, g.h1));
     const RegionRec R = load_region_w(P, p.ir);
     const int imed = R.med;
     const float rho_f = (float)R.rhof;
@@ -475,7 +468,7 @@ __device__ void e_interact_chunk(const DevProblem &P, const WaveArgs &A, const B
         const uint4 r = A.Q.ie[par].rng[i];
         g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
     }
-    BS.count(ctl, __activemask(), BS.index(g.h0, g.h1));
+    BS.count(ctl, __activemask(), BS.is_old(g.h0, g.h1));
     double rho_d; int imed;
     load_region_rm(P, p.ir, rho_d, imed);
     const float rho_f = (float)rho_d;
@@ -934,7 +927,7 @@ __global__ void __launch_bounds__(NT, OMC_MB_ESIZE) esize_kernel(const __grid_co
         const unsigned i = base + lane;
         Part p; Rng g; EStep e;
         int cls = CLS_NONE, st = 0;
-        int bi = -1;
+        bool old = false;
         if (i < n) {
             int tag;
             q_load_part(q, i, p, tag);
@@ -943,11 +936,11 @@ __global__ void __launch_bounds__(NT, OMC_MB_ESIZE) esize_kernel(const __grid_co
                 const int2 rm = q.rm[i];
                 const uint4 r = q.rng[i];
                 g.seed_blocks(P.seed0, P.seed1, r.x, r.y, r.z, r.w);
-                bi = BS.index(r.x, r.y);
-                cls = estep_size(P, BS.grid(bi, r.x, r.y), g, p, e, t, st, rm);
+                old = BS.is_old(r.x, r.y);
+                cls = estep_size(P, BS.grid(old, r.x, r.y), g, p, e, t, st, rm);
             }
         }
-        BS.count(ctl, 0xffffffffu, bi);
+        BS.count(ctl, 0xffffffffu, old);
         // one reservation per (warp, class): lane 0 asks for the CH slots, lane 1 for the BCA slots, together.
         // (The return of these two atomics is the kernel's top stall site -- 24 % of the samples in the round-2 capture.  Measured
         // and rejected: warp-private regions of the step queue, no atomics at all, the step kernels reading region by region:
@@ -988,7 +981,7 @@ __global__ void __launch_bounds__(NT, (CLS == 1 ? OMC_MB_ECH : OMC_MB_EBCA)) edo
         if (i < n) {
             es_get<OMC_WAVE_F32 && OMC_CH_BLOCK_RNG>(S, (CLS == CLS_CH) ? i : 2u * S.cap - 1u - i, p, g, e, P);
             if (i + stride < n) es_prefetch(S, (CLS == CLS_CH) ? i + stride : 2u * S.cap - 1u - (i + stride));
-            st = estep_do(P, BS.grid(BS.index(g.h0, g.h1), g.h0, g.h1), g, p, e, CLS, t, rho_new, med_new);
+            st = estep_do(P, BS.grid(BS.is_old(g.h0, g.h1), g.h0, g.h1), g, p, e, CLS, t, rho_new, med_new);
         }
         const unsigned m_e = __ballot_sync(0xffffffffu, st == 0), m_i = __ballot_sync(0xffffffffu, st > 0);
         unsigned b = 0;
@@ -1073,25 +1066,10 @@ __global__ void advance_kernel(const __grid_constant__ DevProblem P, WaveCtl *c)
     const unsigned room = (unsigned)(((load < c->target) ? c->target - load : 0ull) / ns) / (P.nsplit > 1 ? 8u : 1u);
     c->n_src = (unsigned)(left < (unsigned long long)room ? left : (unsigned long long)room);
     c->live = live;
-    if (c->nalive > 1) {
-        // an older batch that no consumer met in this wave has left the queues: its grid is final (the host retires the
-        // batches in order); the alive list closes up
-        const unsigned na = c->nalive;
-        unsigned w = 0;
-        c->last_seen0 = c->seen[0].v;
-        for (unsigned j = 0; j + 1u < na; j++) {
-            if (c->seen[j].v == 0) {
-                c->done_cnt[c->bgrid[j]] += 1u;
-            } else {
-                c->bstart[w] = c->bstart[j]; c->bgrid[w] = c->bgrid[j];
-                w++;
-            }
-            c->seen[j].v = 0;
-        }
-        c->bstart[w] = c->bstart[na - 1u]; c->bgrid[w] = c->bgrid[na - 1u];
-        w++;
-        for (unsigned j = w; j < (unsigned)WAVE_RING; j++) c->bstart[j] = ~0ull;
-        c->nalive = w;
+    if (c->has_old) {                                          // nothing of the previous batch was met in this wave: it is complete
+        if (c->old_seen.v == 0) { c->has_old = 0; c->old_done = 1; }
+        c->old_last = c->old_seen.v;
+        c->old_seen.v = 0;
     }
     c->tk[0].v = c->tk[1].v = c->tk[2].v = c->tk[3].v = c->tk[4].v = 0;
     c->parity = (unsigned)nxt;
@@ -1142,26 +1120,21 @@ void launch_wave(const DevProblem &P, WaveCtl *ctl, const WaveQueues &Q, const W
 
 // Next batch into the running pipeline: new history range, the dose grids swap roles, whatever is still alive
 // belongs to the previous batch (ids below `first`).
-__global__ void rearm_kernel(WaveCtl *c, unsigned long long first, unsigned long long nhist, unsigned nsplit, unsigned grid) {
+__global__ void rearm_kernel(WaveCtl *c, unsigned long long first, unsigned long long nhist, unsigned nsplit) {
     if (blockIdx.x || threadIdx.x) return;
-    c->hist_next = first; c->hist_end = first + nhist;
-    if (c->live == 0) {                                        // nothing alive: every batch in the list is complete
-        for (unsigned j = 0; j < c->nalive; j++) c->done_cnt[c->bgrid[j]] += 1u;
-        c->nalive = 0;
-    }
-    // (the host starts a batch only while the ring has room: nalive < WAVE_RING here)
-    c->bstart[c->nalive] = first; c->bgrid[c->nalive] = grid;
-    c->nalive += 1u;
-    for (unsigned j = c->nalive; j < (unsigned)WAVE_RING; j++) c->bstart[j] = ~0ull;
-    for (unsigned j = 0; j < (unsigned)WAVE_RING; j++) c->seen[j].v = 0;
-    c->last_seen0 = c->live;                                   // (not counted yet: the first wave of the new batch will)
+    c->hist_next = first; c->hist_end = first + nhist; c->hist_split = first;
+    c->grid_new ^= 1u;
+    c->has_old = (c->live > 0) ? 1u : 0u;
+    c->old_done = c->has_old ? 0u : 1u;
+    c->old_seen.v = 0;
+    c->old_last = c->live;                                     // (not counted yet: the first wave of the new batch will)
     const unsigned ns = nsplit > 1u ? 2u * nsplit : 1u;           // (a split ray in flight counts as 2 nsplit particles, see advance_kernel)
     const unsigned long long load = (unsigned long long)c->live + (unsigned long long)(ns - 1u) * c->n_p[c->parity].v;
     const unsigned room = (unsigned)(((load < c->target) ? c->target - load : 0ull) / ns) / (nsplit > 1u ? 8u : 1u);
     c->n_src = (unsigned)(nhist < (unsigned long long)room ? nhist : (unsigned long long)room);
 }
-void launch_rearm(WaveCtl *ctl, unsigned long long first, unsigned long long nhist, unsigned nsplit, unsigned grid, cudaStream_t s) {
-    rearm_kernel<<<1, 32, 0, s>>>(ctl, first, nhist, nsplit, grid);
+void launch_rearm(WaveCtl *ctl, unsigned long long first, unsigned long long nhist, unsigned nsplit, cudaStream_t s) {
+    rearm_kernel<<<1, 32, 0, s>>>(ctl, first, nhist, nsplit);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -34,7 +34,7 @@ def run_batches(tr, nb, per):
         a, a2, e = tr.get_tallies()
         return a[1:], a2[1:], e, tr.counters()
     finally:
-        tr.set_option("drain_threshold", 4096)
+        tr.set_option("drain_threshold", 8192)
 
 
 def same_statistics(ref, got, nb):

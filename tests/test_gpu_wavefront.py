@@ -166,7 +166,7 @@ def test_wavefront_scheduling_independence(gpu):
         gpu.reset_tallies()
         gpu.run_histories(0, 50000)
         runs.append((gpu.get_endep()[1:], gpu.counters()))
-    gpu.set_option("drain_threshold", 4096)
+    gpu.set_option("drain_threshold", 8192)
     assert runs[0][1] == runs[1][1]
     np.testing.assert_allclose(runs[0][0], runs[1][0], rtol=2e-4, atol=1e-4 * g0.max())
     assert abs(runs[0][0].sum() - g0.sum()) < 0.01 * g0.sum()
@@ -214,7 +214,7 @@ def test_batch_pipelining_matches_serial_batches(gpu):
         with pytest.raises(OmcGpuError):
             gpu.start_batch(2000, 1000)
     finally:
-        gpu.set_option("pool_size", 1 << 23); gpu.set_option("drain_threshold", 4096)
+        gpu.set_option("pool_size", 1 << 23); gpu.set_option("drain_threshold", 8192)
         gpu.reset_tallies()
     for a, b, e in ((a1, b1, e1), (a2, b2, e2)):
         assert abs(e - e0) <= 1e-9 * e0
