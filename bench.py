@@ -17,6 +17,12 @@ the batch grid is summed over ranks by NCCL inside the library before accumEndep
 
 Prints ONE JSON line on rank 0.  `--impl reference` times the unmodified reference (oracle/_ref, all
 host threads, its own RANMAR generator) on bounded samples of the same workload.
+
+Other workloads of BASELINE.json (not the default line): `--workload matrad_prostate` = config 4 (a step = one pass of 64
+beamlets x --hist-per-beamlet histories per GPU through omc_gpu_run_beamlets(); e2e adds the fetch of every pass's columns
+and the in-library gather of all ranks' columns), `--voxel-mm 2|1` = config 5's resampled grids, `--nsplit 20` = the
+splitting of the reference's shipped input file, `--workload tg119_6mv | water6mv` = configs 3 and 2.  OMC_BENCH_OPTIONS
+("check_every=16,pool_size=...") passes tuning options to the library for A/B runs.
 """
 from __future__ import annotations
 
