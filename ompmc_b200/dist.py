@@ -1,4 +1,9 @@
-"""Multi-GPU plumbing: one process per GPU, histories sharded by id range, batch grid all-reduced.
+"""Multi-GPU plumbing, caller-driven form: one process per GPU, histories sharded by id range, batch grid all-reduced.
+
+Since round 2 the PRODUCT path for several GPUs lives inside the C library (omc_gpu_comm_init / omc_gpu_multi_*,
+include/ompmc_b200.h: the same sharding rule -- omc_gpu_shard_range -- and the same all-reduce-before-accumEndep, on a side
+stream); bench.py uses that.  This module keeps the form in which the CALLER owns the collective (any torch.distributed
+backend on the pointers of omc_gpu_device_ptrs()), which is also what the world-size-2 gloo tests run on CPU.
 
 The reference's only parallelism is the OpenMP ``parallel for`` over the histories of one batch with
 a shared dose grid (omc_dosxyz.c:1252-1259, :690-691).  Here every rank transports a contiguous slice
